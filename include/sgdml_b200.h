@@ -1,0 +1,157 @@
+/*
+ * sgdml_b200 -- C ABI of the B200-native engine for sGDML's two dense hot paths
+ * (SURVEY.md section 8).  Plain pointers and sizes only; no torch / C++ types.
+ *
+ * Conventions
+ *  - All arrays are C-order (row-major) float64 / int64, exactly as NumPy hands them over.
+ *  - Every data pointer may be a HOST pointer or a DEVICE pointer of the current CUDA
+ *    device; the library detects which (cudaPointerGetAttributes) and stages host
+ *    buffers through device memory itself (H2D / D2H inside the call).
+ *  - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).  Calls
+ *    with host outputs synchronise that stream before returning; calls whose outputs
+ *    are device pointers are asynchronous on `stream`.
+ *  - Return value: 0 = ok; > 0 = LAPACK-style `info` (leading minor of that order is not
+ *    positive definite); < 0 = error (-(cudaError_t) for CUDA errors, <= -1000 for
+ *    argument errors).  sgdml_b200_last_error() returns a message for the calling thread.
+ *  - Notation: N atoms, D = N(N-1)/2 descriptor size, M training points, S permutations.
+ *    Pair order d <-> (a,b), a > b, is np.tril_indices(N,-1) (reference desc.py:109-110).
+ *
+ * Each entry point cites the reference interface it replaces (paths relative to
+ * /root/reference/sgdml/).  The reference is pure Python: there is no FFI to bind to,
+ * the seam is its `use_torch` engine objects (train.py:1412-1482, predict.py:358-421);
+ * INTEGRATION.md shows the ctypes stubs a maintainer would add there.
+ */
+#ifndef SGDML_B200_H
+#define SGDML_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SGDML_B200_ABI_VERSION 1
+
+#define SGDML_B200_OK 0
+#define SGDML_B200_ERR_ARG (-1000)
+#define SGDML_B200_ERR_UNSUPPORTED (-1001)
+#define SGDML_B200_ERR_NO_DEVICE (-1002)
+
+int sgdml_b200_abi_version(void);
+const char* sgdml_b200_last_error(void);
+/* Number of visible CUDA devices (0 => every compute entry point fails loudly). */
+int sgdml_b200_device_count(void);
+
+/* ---------------------------------------------------------------- representation */
+
+/* Desc.perm + tril_perms_lin: utils/desc.py:509-539, train.py:897-904.  Host integer
+ * routine, bit-exact.  perms (S,N) int64 -> out (S*D,) int64,
+ * out[d*S + p] = d(perms[p][a], perms[p][b]) + p*D for d = d(a,b). */
+int sgdml_b200_tril_perms_lin(const int64_t* perms, int64_t n_perms, int64_t n_atoms, int64_t* out);
+
+/* Desc.from_R: utils/desc.py:80-239, 288-365 (no lattice).  R (n_geo, 3N) ->
+ * R_desc (n_geo, D), R_d_desc (n_geo, D, 3). */
+int sgdml_b200_desc_from_R(const double* R, int64_t n_geo, int64_t n_atoms, double* R_desc,
+                           double* R_d_desc, void* stream);
+
+/* Desc.d_desc_dot_vec: utils/desc.py:368-385.  R_d_desc (n_geo, D, 3), vecs (n_geo, 3N)
+ * -> out (n_geo, D). */
+int sgdml_b200_d_desc_dot_vec(const double* R_d_desc, const double* vecs, int64_t n_geo,
+                              int64_t n_atoms, double* out, void* stream);
+
+/* Desc.vec_dot_d_desc: utils/desc.py:388-408.  R_d_desc (n_geo, D, 3), vecs (n_geo, D)
+ * -> out (n_geo, 3N). */
+int sgdml_b200_vec_dot_d_desc(const double* R_d_desc, const double* vecs, int64_t n_geo,
+                              int64_t n_atoms, double* out, void* stream);
+
+/* ---------------------------------------------------------------- predictor (path b) */
+
+typedef struct sgdml_b200_model sgdml_b200_model;
+
+/* GDMLPredict.__init__ / GDMLTorchPredict.__init__: predict.py:249-463,
+ * torchtools.py:401-593.  The engine keeps device copies of the (unpermuted) model;
+ * permutations are applied to the query inside the kernel, never as an M*S cache
+ * (predict.py:426-441 builds that cache on the CPU).
+ *   R_desc          (M, D)  -- NOTE: the .npz model stores it transposed (D, M), train.py:807
+ *   R_d_desc_alpha  (M, D)
+ *   tril_perms_lin  (S*D,)
+ *   sig as stored in the model; std, c as GDMLPredict uses them (predict.py:1286-1288). */
+int sgdml_b200_model_create(sgdml_b200_model** out, int64_t n_atoms, int64_t n_train,
+                            int64_t n_perms, const double* R_desc, const double* R_d_desc_alpha,
+                            const int64_t* tril_perms_lin, double sig, double std, double c);
+int sgdml_b200_model_destroy(sgdml_b200_model* model);
+
+/* GDMLPredict.predict(R): predict.py:1146-1294 (+ _predict_wkr predict.py:84-245).
+ * R (B, 3N) -> E (B,) [may be NULL], F (B, 3N); outputs scaled: F*std, E*std + c. */
+int sgdml_b200_predict(sgdml_b200_model* model, const double* R, int64_t n_geo, double* E,
+                       double* F, void* stream);
+
+/* GDMLPredict.set_R_desc / set_R_d_desc: predict.py:511-549.  Caches the training
+ * descriptor Jacobians (M, D, 3) on the device so that set_alphas and the training-point
+ * evaluation need no host data. */
+int sgdml_b200_model_set_R_d_desc(sgdml_b200_model* model, const double* R_d_desc);
+
+/* GDMLPredict.set_alphas: predict.py:551-601 / torchtools.py:760-875.
+ * alphas_F (3NM,) -> R_d_desc_alpha = J_m alpha_m on the device. */
+int sgdml_b200_model_set_alphas(sgdml_b200_model* model, const double* alphas_F, void* stream);
+
+/* GDMLPredict.predict() with R=None (training points from the cached descriptors):
+ * predict.py:1219-1235; the K.v operator of the iterative solver (iterative.py:183-204)
+ * and _recov_int_const (train.py:1136-1147).  Evaluates training points
+ * [m_begin, m_end).  scaled != 0: outputs scaled as sgdml_b200_predict; scaled == 0:
+ * raw sums (std = 1, c = 0), i.e. F = (K v)[m_begin*3N : m_end*3N] for alphas = v. */
+int sgdml_b200_predict_train(sgdml_b200_model* model, int64_t m_begin, int64_t m_end, int scaled,
+                             double* E, double* F, void* stream);
+
+/* Reads back R_d_desc_alpha (M, D) -- the `R_d_desc_alpha` key of the model file
+ * (train.py:791, 808). */
+int sgdml_b200_model_get_R_d_desc_alpha(sgdml_b200_model* model, double* out);
+
+/* ---------------------------------------------------------------- assembly (path a) */
+
+/* GDMLTrain._assemble_kernel_mat / GDMLTorchAssemble.forward: train.py:1260-1535,
+ * train.py:97-232, torchtools.py:110-392 (force-force blocks).
+ *   K[i*3N + r, c] = scale * K_ref[i*3N + r, col_idxs[c]],  K is (3NM, n_cols), row
+ *   stride ldk (>= n_cols).  col_idxs == NULL: all 3NM columns (n_cols must be 3NM);
+ *   otherwise a sorted, duplicate-free int64 list (train.py:1341-1345).
+ *   scale = -1 gives the matrix the analytic solver factorises (analytic.py:65). */
+int sgdml_b200_assemble(const double* R_desc, const double* R_d_desc, const int64_t* tril_perms_lin,
+                        int64_t n_atoms, int64_t n_train, int64_t n_perms, double sig,
+                        const int64_t* col_idxs, int64_t n_cols, double scale, double* K,
+                        int64_t ldk, void* stream);
+
+/* ---------------------------------------------------------------- dense solve (path a) */
+
+/* scipy.linalg.cho_factor (LAPACK dpotrf) as used by analytic.py:94-96 and
+ * iterative.py:447-449.  A (n, n) symmetric, row stride lda; only the LOWER triangle
+ * (row-major) is read and overwritten with L (A = L L^T).  Returns info > 0 if the
+ * leading minor of order info is not positive definite (analytic.py:101 catches the
+ * resulting LinAlgError). */
+int sgdml_b200_potrf(double* A, int64_t n, int64_t lda, void* stream);
+
+/* scipy.linalg.cho_solve (dpotrs), analytic.py:97-99: solves L L^T X = B in place.
+ * L from sgdml_b200_potrf; B (n, nrhs) row-major with row stride ldb. */
+int sgdml_b200_potrs(const double* L, int64_t n, int64_t lda, double* B, int64_t nrhs,
+                     int64_t ldb, void* stream);
+
+/* Analytic.solve core, analytic.py:65-99: given Kneg = -K_ref (n, n) (device or host;
+ * overwritten), adds lam to the diagonal, factorises, and returns
+ * alphas = -(Kneg + lam I)^-1 y. */
+int sgdml_b200_solve_analytic(double* Kneg, int64_t n, int64_t lda, double lam, const double* y,
+                              double* alphas, void* stream);
+
+/* C = alpha * A * B^T + beta * C on the FP64 tensor pipe (the building block of potrf's
+ * trailing update; exported for tests and benchmarks).  A (m, k) lda, B (n, k) ldb,
+ * C (m, n) ldc, all row-major device or host. */
+int sgdml_b200_dgemm_nt(int64_t m, int64_t n, int64_t k, double alpha, const double* A,
+                        int64_t lda, const double* B, int64_t ldb, double beta, double* C,
+                        int64_t ldc, void* stream);
+
+/* Test / tuning hook: selects the GEMM kernel used by dgemm_nt and potrf's trailing update.
+ * 0 = 128x128 DMMA tiles (default), 1 = 128x64 DMMA tiles, 2 = scalar FMA reference kernel. */
+int sgdml_b200_set_gemm_variant(int variant);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SGDML_B200_H */

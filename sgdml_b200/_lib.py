@@ -1,0 +1,125 @@
+"""ctypes binding of the engine's C ABI (include/sgdml_b200.h).
+
+The shared library is built in-tree by ``__graft_entry__.build()`` (or ``make -C
+sgdml_b200/csrc``).  There is no CPU fallback: if the library is missing, or no CUDA
+device is visible, every compute call raises.
+"""
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'libsgdml_b200.so')
+
+_lib = None
+
+c_double_p = C.POINTER(C.c_double)
+c_int64_p = C.POINTER(C.c_int64)
+c_void_p = C.c_void_p
+i64 = C.c_int64
+
+# name -> (restype, argtypes); mirrors include/sgdml_b200.h one to one
+SIGNATURES = {
+    'sgdml_b200_abi_version': (C.c_int, []),
+    'sgdml_b200_last_error': (C.c_char_p, []),
+    'sgdml_b200_device_count': (C.c_int, []),
+    'sgdml_b200_tril_perms_lin': (C.c_int, [c_void_p, i64, i64, c_void_p]),
+    'sgdml_b200_desc_from_R': (C.c_int, [c_void_p, i64, i64, c_void_p, c_void_p, c_void_p]),
+    'sgdml_b200_d_desc_dot_vec': (C.c_int, [c_void_p, c_void_p, i64, i64, c_void_p, c_void_p]),
+    'sgdml_b200_vec_dot_d_desc': (C.c_int, [c_void_p, c_void_p, i64, i64, c_void_p, c_void_p]),
+    'sgdml_b200_model_create': (
+        C.c_int,
+        [C.POINTER(c_void_p), i64, i64, i64, c_void_p, c_void_p, c_void_p, C.c_double, C.c_double, C.c_double],
+    ),
+    'sgdml_b200_model_destroy': (C.c_int, [c_void_p]),
+    'sgdml_b200_predict': (C.c_int, [c_void_p, c_void_p, i64, c_void_p, c_void_p, c_void_p]),
+    'sgdml_b200_model_set_R_d_desc': (C.c_int, [c_void_p, c_void_p]),
+    'sgdml_b200_model_set_alphas': (C.c_int, [c_void_p, c_void_p, c_void_p]),
+    'sgdml_b200_predict_train': (C.c_int, [c_void_p, i64, i64, C.c_int, c_void_p, c_void_p, c_void_p]),
+    'sgdml_b200_model_get_R_d_desc_alpha': (C.c_int, [c_void_p, c_void_p]),
+    'sgdml_b200_assemble': (
+        C.c_int,
+        [c_void_p, c_void_p, c_void_p, i64, i64, i64, C.c_double, c_void_p, i64, C.c_double, c_void_p, i64, c_void_p],
+    ),
+    'sgdml_b200_potrf': (C.c_int, [c_void_p, i64, i64, c_void_p]),
+    'sgdml_b200_potrs': (C.c_int, [c_void_p, i64, i64, c_void_p, i64, i64, c_void_p]),
+    'sgdml_b200_solve_analytic': (C.c_int, [c_void_p, i64, i64, C.c_double, c_void_p, c_void_p, c_void_p]),
+    'sgdml_b200_dgemm_nt': (
+        C.c_int,
+        [i64, i64, i64, C.c_double, c_void_p, i64, c_void_p, i64, C.c_double, c_void_p, i64, c_void_p],
+    ),
+    'sgdml_b200_set_gemm_variant': (C.c_int, [C.c_int]),
+}
+
+
+class EngineError(RuntimeError):
+    pass
+
+
+def lib():
+    """Loads libsgdml_b200.so (once).  Fails loudly if it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise EngineError(
+                'sgdml_b200: %s not found -- build it with `python -c "import __graft_entry__ as g; g.build()"` '
+                'or `make -C sgdml_b200/csrc`.  There is no CPU fallback.' % LIB_PATH
+            )
+        handle = C.CDLL(LIB_PATH)
+        for name, (restype, argtypes) in SIGNATURES.items():
+            fn = getattr(handle, name)
+            fn.restype = restype
+            fn.argtypes = argtypes
+        _lib = handle
+    return _lib
+
+
+def last_error():
+    msg = lib().sgdml_b200_last_error()
+    return msg.decode() if msg else ''
+
+
+def check(rc, what):
+    """Maps C-ABI return codes onto the exceptions the reference's callers catch:
+    info > 0 -> np.linalg.LinAlgError('... not positive definite') (analytic.py:101,
+    iterative.py:451-459); CUDA OOM -> RuntimeError('... out of memory')
+    (torchtools.py:352)."""
+    if rc == 0:
+        return
+    msg = last_error()
+    if rc > 0:
+        raise np.linalg.LinAlgError(msg or '%d-th leading minor of the array is not positive definite' % rc)
+    if rc == -2:  # cudaErrorMemoryAllocation
+        raise RuntimeError('CUDA out of memory in %s: %s' % (what, msg))
+    raise EngineError('%s failed (rc=%d): %s' % (what, rc, msg))
+
+
+def ptr(x):
+    """Address of a NumPy array (host) or torch tensor (host or CUDA), or None."""
+    if x is None:
+        return None
+    if isinstance(x, np.ndarray):
+        if not x.flags['C_CONTIGUOUS']:
+            raise ValueError('array must be C-contiguous')
+        return x.ctypes.data
+    # torch tensor
+    if not x.is_contiguous():
+        raise ValueError('tensor must be contiguous')
+    return x.data_ptr()
+
+
+def current_stream():
+    """cudaStream_t of torch's current stream (so that the engine's kernels are ordered
+    with torch work and visible to torch.cuda.Event timing)."""
+    import torch
+
+    if not torch.cuda.is_available():
+        return None
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def require_gpu():
+    if lib().sgdml_b200_device_count() < 1:
+        raise EngineError('sgdml_b200: no CUDA device visible; this engine has no CPU fallback')

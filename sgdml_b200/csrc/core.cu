@@ -1,0 +1,105 @@
+// Error plumbing, host/device staging and misc entry points of the sgdml_b200 C ABI.
+#include "common.cuh"
+
+namespace sgdml {
+
+static thread_local std::string g_last_error;
+
+void set_last_error(const std::string& msg) { g_last_error = msg; }
+
+int fail_cuda(cudaError_t e, const char* what, const char* file, int line) {
+  char buf[512];
+  snprintf(buf, sizeof(buf), "CUDA error %d (%s) in `%s` at %s:%d", (int)e, cudaGetErrorString(e), what, file, line);
+  g_last_error = buf;
+  // leave no sticky "last error" behind for the next call's launch checks
+  cudaGetLastError();
+  return -(int)e;
+}
+
+int fail_arg(const char* what) {
+  g_last_error = std::string("invalid argument: requirement `") + what + "` violated";
+  return SGDML_B200_ERR_ARG;
+}
+
+int require_device() {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0) {
+    cudaGetLastError();
+    g_last_error =
+        "sgdml_b200: no CUDA device visible -- this engine has no CPU fallback (B200 / sm_100a required)";
+    return SGDML_B200_ERR_NO_DEVICE;
+  }
+  return 0;
+}
+
+bool is_device_ptr(const void* p) {
+  if (p == nullptr) return false;
+  cudaPointerAttributes attr;
+  cudaError_t e = cudaPointerGetAttributes(&attr, p);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return attr.type == cudaMemoryTypeDevice || attr.type == cudaMemoryTypeManaged;
+}
+
+Staged::~Staged() {
+  if (owns_ && dev_) cudaFree(dev_);
+}
+
+int Staged::init(const void* user, size_t bytes, bool copy_in, cudaStream_t s) {
+  user_ = const_cast<void*>(user);
+  bytes_ = bytes;
+  if (user == nullptr || bytes == 0) {
+    dev_ = nullptr;
+    owns_ = false;
+    return 0;
+  }
+  if (is_device_ptr(user)) {
+    dev_ = user_;
+    owns_ = false;
+    return 0;
+  }
+  SG_CUDA(cudaMalloc(&dev_, bytes));
+  owns_ = true;
+  if (copy_in) SG_CUDA(cudaMemcpyAsync(dev_, user, bytes, cudaMemcpyHostToDevice, s));
+  return 0;
+}
+
+int Staged::finish(cudaStream_t s) {
+  if (owns_ && dev_ && user_) SG_CUDA(cudaMemcpyAsync(user_, dev_, bytes_, cudaMemcpyDeviceToHost, s));
+  return 0;
+}
+
+int num_sms() {
+  static int cached[64] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+  if (dev < 0 || dev >= 64) return 148;
+  if (cached[dev] == 0) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    cached[dev] = n;
+  }
+  return cached[dev];
+}
+
+}  // namespace sgdml
+
+extern "C" {
+
+int sgdml_b200_abi_version(void) { return SGDML_B200_ABI_VERSION; }
+
+const char* sgdml_b200_last_error(void) { return sgdml::g_last_error.c_str(); }
+
+int sgdml_b200_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+}  // extern "C"

@@ -1,0 +1,788 @@
+// Path (b): batched analytic energy/force prediction (SURVEY.md section 8 rows a-P, a-PT,
+// a-M) -- reference sgdml/predict.py:84-245 (_predict_wkr), predict.py:424-441 (permuted
+// caches), predict.py:551-601 (set_alphas), predict.py:1286-1288 (output scaling),
+// torchtools.py:877-1046 (_forward).
+//
+// B200 design (not a port of either reference engine):
+//  * Permutations are applied to the QUERY, never to the model: with e = perm_p[d],
+//      delta_p[d] = x[d] - X_m[perm_p[d]]  ==  q_p[e] - X_m[e],  q_p[e] = x[pinv_p[e]],
+//    so query b becomes S "virtual rows" q_{b,p} and the model stays an (M, D) pair of
+//    matrices Xc (centred descriptors) and JA (= R_d_desc_alpha).  The reference
+//    materialises an (M*S, D) permuted cache on the CPU (predict.py:426-437) and a
+//    (B, M*S, D) temporary on the GPU (torchtools.py:964-966).
+//  * The sum over training points is two GEMM-shaped contractions around an elementwise
+//    Matern-5/2 transform -- the same shape as attention -- and both run on the FP64
+//    tensor pipe (mma.sync m8n8k4.f64, SASS DMMA; tcgen05 has no f64 kind):
+//      GEMM1: S1 = Q Xc^T, S2 = Q JA^T                      (contraction over D)
+//      n^2 = |q|^2 + |Xc_m|^2 - 2 S1,  a = S2 - Xc_m.JA_m,  c1, c2 = Matern factors
+//      GEMM2: G = (sum_m c1) Q - C1 Xc - C2 JA             (contraction over M)
+//    G (BQ x DP) lives in registers for the whole sweep over M; Xc/JA tiles arrive through
+//    a double-buffered cp.async.bulk (TMA engine) + mbarrier pipeline from L2.
+//  * A small finishing kernel folds the S virtual rows back (F_desc[d] = sum_p
+//    G_p[perm_p[d]]), applies J_x^T (predict.py:240-243) and the std / c scaling.
+#include <algorithm>
+#include <cmath>
+
+#include "common.cuh"
+#include "desc.cuh"
+
+namespace sgdml {
+
+// ============================================================== tile configuration
+template <int DP_, int BQ_, int BM_, int W1Q_, int W1M_, int W1K_, int W2Q_, int W2D_>
+struct PCfg {
+  static constexpr int DP = DP_;        // padded descriptor size (multiple of 8)
+  static constexpr int DS = DP_ + 4;    // row stride of Q / Xc / JA tiles (== 4 or 12 mod 16: conflict-free DMMA frags)
+  static constexpr int BQ = BQ_;        // virtual query rows per CTA
+  static constexpr int BM = BM_;        // training points per pipeline stage
+  static constexpr int CS = BM_ + 4;    // row stride of the S/C tiles
+  static constexpr int W1Q = W1Q_, W1M = W1M_, W1K = W1K_;  // GEMM1 warp grid (rows, cols, split-k)
+  static constexpr int W2Q = W2Q_, W2D = W2D_;              // GEMM2 warp grid (rows, cols)
+  static constexpr int NT = 256;
+  static constexpr int TR1 = BQ / (8 * W1Q);
+  static constexpr int TC1 = BM / (8 * W1M);
+  static constexpr int KS1 = DP / 4 / W1K;  // k-steps per warp in GEMM1
+  static constexpr int TR2 = BQ / (8 * W2Q);
+  static constexpr int TD2 = DP / (8 * W2D);
+  static constexpr int EPT = BQ * BM / NT;  // epilogue-1 elements per thread
+  static_assert(W1Q * W1M * W1K == 8 && W2Q * W2D == 8, "8 warps");
+  static_assert(BQ % (8 * W1Q) == 0 && BM % (8 * W1M) == 0 && (DP / 4) % W1K == 0, "GEMM1 tiling");
+  static_assert(BQ % (8 * W2Q) == 0 && DP % (8 * W2D) == 0, "GEMM2 tiling");
+  static_assert(BM == 8 || BM == 16 || BM == 32, "row reduction uses shuffles inside one warp");
+  static_assert((BQ * BM) % NT == 0, "epilogue mapping");
+  // shared memory carve-up (in doubles)
+  static constexpr int OFF_Q = 0;
+  static constexpr int OFF_X = OFF_Q + BQ * DS;           // [2][BM*DS]
+  static constexpr int OFF_JA = OFF_X + 2 * BM * DS;      // [2][BM*DS]
+  static constexpr int OFF_MM = OFF_JA + 2 * BM * DS;     // [2][BM]
+  static constexpr int OFF_XJA = OFF_MM + 2 * BM;         // [2][BM]
+  static constexpr int OFF_P = OFF_XJA + 2 * BM;          // [W1K][2][BQ*CS]; set 0 becomes C1/C2
+  static constexpr int OFF_QQ = OFF_P + W1K * 2 * BQ * CS;
+  static constexpr int OFF_CSUM = OFF_QQ + BQ;
+  static constexpr int OFF_E = OFF_CSUM + BQ;
+  static constexpr int OFF_BAR = OFF_E + BQ;              // 2 x uint64
+  static constexpr int SMEM_DOUBLES = OFF_BAR + 2;
+  static constexpr size_t SMEM_BYTES = (size_t)SMEM_DOUBLES * 8;
+  static_assert(SMEM_BYTES <= 232448, "exceeds 227 KB of shared memory");
+  static_assert((BM * DS * 8) % 16 == 0 && (BM * 8) % 16 == 0, "bulk copy granularity");
+};
+
+struct PredictArgs {
+  // model (device)
+  const double* Xc;     // (Mpad, DS) centred descriptors, zero padded
+  const double* JA;     // (Mpad, DS) R_d_desc_alpha, zero padded
+  const double* mm;     // (Mpad) |Xc_m|^2
+  const double* xja;    // (Mpad) Xc_m . JA_m
+  const double* mu;     // (DP) centre
+  const int* pinv;      // (S, D) inverse descriptor perms
+  int D, M, S, Mpad;
+  double sig;
+  // queries
+  const double* xq;     // (B, D) query descriptors
+  int64_t n_rows;       // B*S virtual rows
+  // outputs
+  double* G;            // (n_rows, DP)
+  double* Erow;         // (n_rows)
+};
+
+// ============================================================== main kernel
+template <class C>
+__global__ void __launch_bounds__(256, 1) k_predict_main(const PredictArgs p) {
+  extern __shared__ __align__(128) double smem[];
+  double* Qs = smem + C::OFF_Q;
+  double* Xs = smem + C::OFF_X;
+  double* JAs = smem + C::OFF_JA;
+  double* mms = smem + C::OFF_MM;
+  double* xjas = smem + C::OFF_XJA;
+  double* Ps = smem + C::OFF_P;
+  double* qq = smem + C::OFF_QQ;
+  double* csum_s = smem + C::OFF_CSUM;
+  double* E_s = smem + C::OFF_E;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::OFF_BAR);
+
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5, lane = tid & 31;
+  const int lr = lane >> 2, lc = lane & 3;  // fragment row / k (or col pair) index
+  const int64_t r0 = (int64_t)blockIdx.x * C::BQ;
+  const int n_tiles = p.Mpad / C::BM;
+  constexpr uint32_t STAGE_BYTES = (uint32_t)((2 * C::BM * C::DS + 2 * C::BM) * 8);
+
+  if (tid == 0) {
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+
+  auto issue_tile = [&](int t) {
+    const int s = t & 1;
+    const int64_t m0 = (int64_t)t * C::BM;
+    mbar_arrive_expect_tx(&bars[s], STAGE_BYTES);
+    bulk_g2s(Xs + s * C::BM * C::DS, p.Xc + m0 * C::DS, C::BM * C::DS * 8, &bars[s]);
+    bulk_g2s(JAs + s * C::BM * C::DS, p.JA + m0 * C::DS, C::BM * C::DS * 8, &bars[s]);
+    bulk_g2s(mms + s * C::BM, p.mm + m0, C::BM * 8, &bars[s]);
+    bulk_g2s(xjas + s * C::BM, p.xja + m0, C::BM * 8, &bars[s]);
+  };
+  if (tid == 0) {
+    issue_tile(0);
+    if (n_tiles > 1) issue_tile(1);
+  }
+
+  // ---- build the Q tile: Q[r][e] = x_b[pinv_p[e]] - mu[e]  (row r <-> (b, p) = divmod(r0 + r, S))
+  for (int idx = tid; idx < C::BQ * C::DS; idx += C::NT) {
+    const int r = idx / C::DS, e = idx - r * C::DS;
+    const int64_t row = r0 + r;
+    double v = 0.0;
+    if (row < p.n_rows && e < p.D) {
+      const int64_t b = row / p.S;
+      const int pp = (int)(row - b * p.S);
+      v = p.xq[b * p.D + p.pinv[pp * p.D + e]] - p.mu[e];
+    }
+    Qs[idx] = v;
+  }
+  if (tid < C::BQ) {
+    csum_s[tid] = 0.0;
+    E_s[tid] = 0.0;
+  }
+  __syncthreads();
+  for (int r = warp; r < C::BQ; r += 8) {
+    double s = 0.0;
+    for (int e = lane; e < C::DP; e += 32) {
+      const double v = Qs[r * C::DS + e];
+      s = fma(v, v, s);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) qq[r] = s;
+  }
+  __syncthreads();
+
+  // GEMM1 warp coordinates
+  const int w1k = warp % C::W1K;
+  const int w1m = (warp / C::W1K) % C::W1M;
+  const int w1q = warp / (C::W1K * C::W1M);
+  const int row1 = w1q * (C::TR1 * 8);
+  const int col1 = w1m * (C::TC1 * 8);
+  const int k1 = w1k * C::KS1 * 4;
+  // GEMM2 warp coordinates
+  const int w2d = warp % C::W2D;
+  const int w2q = warp / C::W2D;
+  const int row2 = w2q * (C::TR2 * 8);
+  const int dcol2 = w2d * (C::TD2 * 8);
+
+  double accG[C::TR2][C::TD2][2];
+#pragma unroll
+  for (int i = 0; i < C::TR2; ++i)
+#pragma unroll
+    for (int j = 0; j < C::TD2; ++j) accG[i][j][0] = accG[i][j][1] = 0.0;
+
+  double csum_part[C::EPT], E_part[C::EPT];
+#pragma unroll
+  for (int j = 0; j < C::EPT; ++j) csum_part[j] = E_part[j] = 0.0;
+
+  const double sig = p.sig;
+  const double sig_inv = 1.0 / sig;
+  const double k_base = 5.0 / (3.0 * sig * sig * sig);  // predict.py:195 mat52_base_fact
+  const double k_diag = 5.0 / sig;                      // predict.py:196 diag_scale_fact
+
+  for (int t = 0; t < n_tiles; ++t) {
+    const int s = t & 1;
+    const double* Xt = Xs + s * C::BM * C::DS;
+    const double* JAt = JAs + s * C::BM * C::DS;
+    mbar_wait(&bars[s], (uint32_t)((t >> 1) & 1));
+
+    // ---------------- GEMM1: partial S1 = Q Xc^T, S2 = Q JA^T over this warp's k-range
+    {
+      double a1[C::TR1][C::TC1][2], a2[C::TR1][C::TC1][2];
+#pragma unroll
+      for (int i = 0; i < C::TR1; ++i)
+#pragma unroll
+        for (int j = 0; j < C::TC1; ++j) a1[i][j][0] = a1[i][j][1] = a2[i][j][0] = a2[i][j][1] = 0.0;
+      const double* qa = Qs + (row1 + lr) * C::DS + k1 + lc;
+      const double* xb = Xt + (col1 + lr) * C::DS + k1 + lc;
+      const double* jb = JAt + (col1 + lr) * C::DS + k1 + lc;
+#pragma unroll 2
+      for (int ks = 0; ks < C::KS1; ++ks) {
+        double fa[C::TR1], fx[C::TC1], fj[C::TC1];
+#pragma unroll
+        for (int i = 0; i < C::TR1; ++i) fa[i] = qa[i * 8 * C::DS + ks * 4];
+#pragma unroll
+        for (int j = 0; j < C::TC1; ++j) {
+          fx[j] = xb[j * 8 * C::DS + ks * 4];
+          fj[j] = jb[j * 8 * C::DS + ks * 4];
+        }
+#pragma unroll
+        for (int i = 0; i < C::TR1; ++i)
+#pragma unroll
+          for (int j = 0; j < C::TC1; ++j) {
+            dmma884(a1[i][j][0], a1[i][j][1], fa[i], fx[j]);
+            dmma884(a2[i][j][0], a2[i][j][1], fa[i], fj[j]);
+          }
+      }
+      double* P1 = Ps + (w1k * 2 + 0) * C::BQ * C::CS;
+      double* P2 = Ps + (w1k * 2 + 1) * C::BQ * C::CS;
+#pragma unroll
+      for (int i = 0; i < C::TR1; ++i)
+#pragma unroll
+        for (int j = 0; j < C::TC1; ++j) {
+          const int off = (row1 + i * 8 + lr) * C::CS + col1 + j * 8 + 2 * lc;
+          *reinterpret_cast<double2*>(P1 + off) = make_double2(a1[i][j][0], a1[i][j][1]);
+          *reinterpret_cast<double2*>(P2 + off) = make_double2(a2[i][j][0], a2[i][j][1]);
+        }
+    }
+    __syncthreads();
+
+    // ---------------- elementwise Matern-5/2 transform (predict.py:199-217), in place
+    {
+      const double* mmt = mms + s * C::BM;
+      const double* xjat = xjas + s * C::BM;
+#pragma unroll
+      for (int j = 0; j < C::EPT; ++j) {
+        const int e = tid + j * C::NT;
+        const int r = e / C::BM, mc = e % C::BM;
+        const int off = r * C::CS + mc;
+        double s1 = Ps[off], s2 = Ps[C::BQ * C::CS + off];
+#pragma unroll
+        for (int wk = 1; wk < C::W1K; ++wk) {
+          s1 += Ps[(wk * 2 + 0) * C::BQ * C::CS + off];
+          s2 += Ps[(wk * 2 + 1) * C::BQ * C::CS + off];
+        }
+        const double n2 = fmax(qq[r] + mmt[mc] - 2.0 * s1, 0.0);
+        const double nrm = sqrt(5.0 * n2);        // sqrt5 * |delta|   (predict.py:204)
+        const double a = s2 - xjat[mc];           // delta . JA        (predict.py:208-210)
+        const double base = exp(-nrm * sig_inv) * k_base;  // predict.py:206-207
+        const double c1 = a * base * k_diag;      // predict.py:212
+        const double c2 = base * (nrm + sig);     // predict.py:213
+        csum_part[j] += c1;
+        E_part[j] = fma(a, c2, E_part[j]);        // predict.py:217
+        Ps[off] = c1;
+        Ps[C::BQ * C::CS + off] = c2;
+      }
+    }
+    __syncthreads();
+
+    // ---------------- GEMM2: accG += C1 Xc + C2 JA (contraction over the BM points)
+    {
+      const double* c1a = Ps + (row2 + lr) * C::CS + lc;
+      const double* c2a = c1a + C::BQ * C::CS;
+      const double* xb = Xt + lc * C::DS + dcol2 + lr;
+      const double* jb = JAt + lc * C::DS + dcol2 + lr;
+#pragma unroll 2
+      for (int ks = 0; ks < C::BM / 4; ++ks) {
+        double f1[C::TR2], f2[C::TR2], fx[C::TD2], fj[C::TD2];
+#pragma unroll
+        for (int i = 0; i < C::TR2; ++i) {
+          f1[i] = c1a[i * 8 * C::CS + ks * 4];
+          f2[i] = c2a[i * 8 * C::CS + ks * 4];
+        }
+#pragma unroll
+        for (int j = 0; j < C::TD2; ++j) {
+          fx[j] = xb[ks * 4 * C::DS + j * 8];
+          fj[j] = jb[ks * 4 * C::DS + j * 8];
+        }
+#pragma unroll
+        for (int i = 0; i < C::TR2; ++i)
+#pragma unroll
+          for (int j = 0; j < C::TD2; ++j) {
+            dmma884(accG[i][j][0], accG[i][j][1], f1[i], fx[j]);
+            dmma884(accG[i][j][0], accG[i][j][1], f2[i], fj[j]);
+          }
+      }
+    }
+    __syncthreads();
+    if (tid == 0 && t + 2 < n_tiles) issue_tile(t + 2);
+  }
+
+  // ---- reduce csum / E over the BM threads that share a row
+#pragma unroll
+  for (int j = 0; j < C::EPT; ++j) {
+    double cs = csum_part[j], es = E_part[j];
+#pragma unroll
+    for (int o = C::BM / 2; o > 0; o >>= 1) {
+      cs += __shfl_xor_sync(0xffffffffu, cs, o);
+      es += __shfl_xor_sync(0xffffffffu, es, o);
+    }
+    const int e = tid + j * C::NT;
+    if (e % C::BM == 0) {
+      csum_s[e / C::BM] = cs;
+      E_s[e / C::BM] = es;
+    }
+  }
+  __syncthreads();
+
+  // ---- G = (sum_m c1) Q - (C1 Xc + C2 JA)
+#pragma unroll
+  for (int i = 0; i < C::TR2; ++i) {
+    const int r = row2 + i * 8 + lr;
+    const int64_t row = r0 + r;
+    if (row < p.n_rows) {
+      const double cs = csum_s[r];
+#pragma unroll
+      for (int j = 0; j < C::TD2; ++j) {
+        const int col = dcol2 + j * 8 + 2 * lc;
+        const double g0 = cs * Qs[r * C::DS + col] - accG[i][j][0];
+        const double g1 = cs * Qs[r * C::DS + col + 1] - accG[i][j][1];
+        *reinterpret_cast<double2*>(p.G + row * C::DP + col) = make_double2(g0, g1);
+      }
+    }
+  }
+  if (tid < C::BQ && r0 + tid < p.n_rows) p.Erow[r0 + tid] = E_s[tid];
+}
+
+// ============================================================== finishing kernel
+// F_desc[d] = sum_p G[b*S+p][perm_p[d]];  F = J_x^T F_desc (predict.py:240-243);
+// E = sum_p Erow;  outputs scaled by std, E += c (predict.py:1286-1288).
+__global__ void __launch_bounds__(128) k_predict_finish(const double* __restrict__ G, const double* __restrict__ Erow,
+                                                        const double* __restrict__ gq, const int* __restrict__ perm,
+                                                        int n_atoms, int D, int DP, int S, double std, double c,
+                                                        double* __restrict__ E, double* __restrict__ F) {
+  extern __shared__ double fd[];  // D
+  const int64_t b = blockIdx.x;
+  for (int d = threadIdx.x; d < D; d += blockDim.x) {
+    double s = 0.0;
+    for (int pp = 0; pp < S; ++pp) s += G[(b * S + pp) * DP + perm[pp * D + d]];
+    fd[d] = s;
+  }
+  __syncthreads();
+  const double* g = gq + b * (int64_t)D * 3;
+  for (int idx = threadIdx.x; idx < 3 * n_atoms; idx += blockDim.x) {
+    const int k = idx / 3, cc = idx - 3 * k;
+    double s = 0.0;
+    for (int o = 0; o < n_atoms; ++o) {
+      if (o == k) continue;
+      if (o > k) {
+        const int d = pair_index(o, k);
+        s += g[d * 3 + cc] * fd[d];
+      } else {
+        const int d = pair_index(k, o);
+        s -= g[d * 3 + cc] * fd[d];
+      }
+    }
+    F[b * 3 * n_atoms + idx] = s * std;
+  }
+  if (E != nullptr && threadIdx.x == 0) {
+    double s = 0.0;
+    for (int pp = 0; pp < S; ++pp) s += Erow[b * S + pp];
+    E[b] = s * std + c;
+  }
+}
+
+// ============================================================== model maintenance kernels
+__global__ void k_col_mean(const double* __restrict__ X, int M, int D, double* __restrict__ mu, int DP) {
+  // one block per column
+  const int d = blockIdx.x;
+  __shared__ double red[256];
+  double s = 0.0;
+  if (d < D)
+    for (int m = threadIdx.x; m < M; m += blockDim.x) s += X[(int64_t)m * D + d];
+  red[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0 && d < DP) mu[d] = (d < D) ? red[0] / (double)M : 0.0;
+}
+
+// src (M, D) -> dst (Mpad, DS) zero padded, optionally centred
+__global__ void k_pad_rows(const double* __restrict__ src, const double* __restrict__ mu, int M, int D, int Mpad,
+                           int DS, double* __restrict__ dst) {
+  int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (int64_t)Mpad * DS) return;
+  const int m = (int)(idx / DS), d = (int)(idx - (int64_t)m * DS);
+  double v = 0.0;
+  if (m < M && d < D) v = src[(int64_t)m * D + d] - (mu ? mu[d] : 0.0);
+  dst[idx] = v;
+}
+
+// JA[m][d] = g_{m,d} . (alpha_{m,b} - alpha_{m,a})  (desc.py:368-385), written into the padded layout
+__global__ void k_set_alphas(const double* __restrict__ R_d_desc, const double* __restrict__ alphas, int M, int D,
+                             int n_atoms, int DS, double* __restrict__ JA) {
+  int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (int64_t)M * D) return;
+  const int m = (int)(idx / D), d = (int)(idx - (int64_t)m * D);
+  int a, b;
+  pair_from_d(d, a, b);
+  const double* v = alphas + (int64_t)m * 3 * n_atoms;
+  const double* g = R_d_desc + idx * 3;
+  double s = g[0] * (v[3 * b + 0] - v[3 * a + 0]);
+  s += g[1] * (v[3 * b + 1] - v[3 * a + 1]);
+  s += g[2] * (v[3 * b + 2] - v[3 * a + 2]);
+  JA[(int64_t)m * DS + d] = s;
+}
+
+// mm[m] = |Xc_m|^2, xja[m] = Xc_m . JA_m ; one warp per row
+__global__ void k_row_dots(const double* __restrict__ Xc, const double* __restrict__ JA, int Mpad, int DS,
+                           double* __restrict__ mm, double* __restrict__ xja) {
+  const int m = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (m >= Mpad) return;
+  double s1 = 0.0, s2 = 0.0;
+  for (int d = lane; d < DS; d += 32) {
+    const double x = Xc[(int64_t)m * DS + d];
+    s1 = fma(x, x, s1);
+    s2 = fma(x, JA[(int64_t)m * DS + d], s2);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+    s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+  }
+  if (lane == 0) {
+    if (mm) mm[m] = s1;
+    xja[m] = s2;
+  }
+}
+
+__global__ void k_unpad_rows(const double* __restrict__ src, int M, int D, int DS, double* __restrict__ dst) {
+  int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (int64_t)M * D) return;
+  const int m = (int)(idx / D), d = (int)(idx - (int64_t)m * D);
+  dst[idx] = src[(int64_t)m * DS + d];
+}
+
+}  // namespace sgdml
+
+using namespace sgdml;
+
+// ============================================================== model object
+struct sgdml_b200_model {
+  int N = 0, D = 0, M = 0, S = 0;
+  int DP = 0, DS = 0, BM = 0, BQ = 0, Mpad = 0, cfg = -1;
+  int device = 0;
+  double sig = 0, std = 1, c = 0;
+  double *X = nullptr;    // (M, D) raw descriptors (training-point queries)
+  double *Xc = nullptr, *JA = nullptr, *mm = nullptr, *xja = nullptr, *mu = nullptr;
+  int *perm = nullptr, *pinv = nullptr;  // (S, D)
+  double* R_d_desc = nullptr;            // (M, D, 3), optional
+  // workspace for up to ws_geo queries
+  int64_t ws_geo = 0;
+  double *ws_xq = nullptr, *ws_gq = nullptr, *ws_G = nullptr, *ws_Erow = nullptr, *ws_R = nullptr, *ws_E = nullptr,
+         *ws_F = nullptr;
+};
+
+namespace {
+
+// tile configurations: <DP, BQ, BM, W1Q, W1M, W1K, W2Q, W2D>
+using Cfg40 = PCfg<40, 128, 32, 4, 2, 1, 8, 1>;
+using Cfg72 = PCfg<72, 64, 32, 4, 2, 1, 8, 1>;
+using Cfg112 = PCfg<112, 64, 16, 4, 1, 2, 4, 2>;
+using Cfg160 = PCfg<160, 32, 16, 2, 1, 4, 2, 4>;
+using Cfg224 = PCfg<224, 32, 16, 2, 1, 4, 2, 4>;
+using Cfg256 = PCfg<256, 32, 8, 2, 1, 4, 2, 4>;
+
+struct CfgInfo {
+  int DP, BQ, BM;
+};
+const CfgInfo kCfgs[] = {{40, 128, 32}, {72, 64, 32}, {112, 64, 16}, {160, 32, 16}, {224, 32, 16}, {256, 32, 8}};
+const int kNumCfgs = 6;
+
+template <class C>
+int launch_main_t(const PredictArgs& a, cudaStream_t s) {
+  static bool configured[64] = {false};
+  int dev = 0;
+  SG_CUDA(cudaGetDevice(&dev));
+  if (dev >= 0 && dev < 64 && !configured[dev]) {
+    SG_CUDA(cudaFuncSetAttribute(k_predict_main<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES));
+    configured[dev] = true;
+  }
+  const int64_t grid = (a.n_rows + C::BQ - 1) / C::BQ;
+  k_predict_main<C><<<(unsigned)grid, C::NT, C::SMEM_BYTES, s>>>(a);
+  SG_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int launch_main(int cfg, const PredictArgs& a, cudaStream_t s) {
+  switch (cfg) {
+    case 0: return launch_main_t<Cfg40>(a, s);
+    case 1: return launch_main_t<Cfg72>(a, s);
+    case 2: return launch_main_t<Cfg112>(a, s);
+    case 3: return launch_main_t<Cfg160>(a, s);
+    case 4: return launch_main_t<Cfg224>(a, s);
+    case 5: return launch_main_t<Cfg256>(a, s);
+  }
+  return fail_arg("no predictor tile configuration for this descriptor size");
+}
+
+void free_ws(sgdml_b200_model* m) {
+  cudaFree(m->ws_xq);
+  cudaFree(m->ws_gq);
+  cudaFree(m->ws_G);
+  cudaFree(m->ws_Erow);
+  cudaFree(m->ws_R);
+  cudaFree(m->ws_E);
+  cudaFree(m->ws_F);
+  m->ws_xq = m->ws_gq = m->ws_G = m->ws_Erow = m->ws_R = m->ws_E = m->ws_F = nullptr;
+  m->ws_geo = 0;
+}
+
+int ensure_ws(sgdml_b200_model* m, int64_t n_geo) {
+  if (n_geo <= m->ws_geo) return 0;
+  free_ws(m);
+  SG_CUDA(cudaMalloc(&m->ws_xq, sizeof(double) * n_geo * m->D));
+  SG_CUDA(cudaMalloc(&m->ws_gq, sizeof(double) * n_geo * m->D * 3));
+  SG_CUDA(cudaMalloc(&m->ws_G, sizeof(double) * n_geo * m->S * m->DP));
+  SG_CUDA(cudaMalloc(&m->ws_Erow, sizeof(double) * n_geo * m->S));
+  SG_CUDA(cudaMalloc(&m->ws_R, sizeof(double) * n_geo * 3 * m->N));
+  SG_CUDA(cudaMalloc(&m->ws_E, sizeof(double) * n_geo));
+  SG_CUDA(cudaMalloc(&m->ws_F, sizeof(double) * n_geo * 3 * m->N));
+  m->ws_geo = n_geo;
+  return 0;
+}
+
+// queries per chunk: bounds the G workspace (rows * DP * 8 bytes) to ~256 MB
+int64_t chunk_geos(const sgdml_b200_model* m) {
+  int64_t rows = (int64_t)(256ll << 20) / ((int64_t)m->DP * 8);
+  int64_t g = rows / m->S;
+  if (g < 1) g = 1;
+  if (g > 65536) g = 65536;
+  return g;
+}
+
+// Runs the predictor on n_geo queries whose descriptors (xq, gq) are on the device.
+int run_queries(sgdml_b200_model* m, const double* xq, const double* gq, int64_t n_geo, double std, double c,
+                double* E_dev, double* F_dev, cudaStream_t s) {
+  PredictArgs a;
+  a.Xc = m->Xc;
+  a.JA = m->JA;
+  a.mm = m->mm;
+  a.xja = m->xja;
+  a.mu = m->mu;
+  a.pinv = m->pinv;
+  a.D = m->D;
+  a.M = m->M;
+  a.S = m->S;
+  a.Mpad = m->Mpad;
+  a.sig = m->sig;
+  a.xq = xq;
+  a.n_rows = n_geo * m->S;
+  a.G = m->ws_G;
+  a.Erow = m->ws_Erow;
+  SG_TRY(launch_main(m->cfg, a, s));
+  k_predict_finish<<<(unsigned)n_geo, 128, sizeof(double) * m->D, s>>>(m->ws_G, m->ws_Erow, gq, m->perm, m->N, m->D,
+                                                                        m->DP, m->S, std, c, E_dev, F_dev);
+  SG_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int refresh_row_dots(sgdml_b200_model* m, bool with_mm, cudaStream_t s) {
+  k_row_dots<<<ceil_div(m->Mpad, 8), 256, 0, s>>>(m->Xc, m->JA, m->Mpad, m->DS, with_mm ? m->mm : nullptr, m->xja);
+  SG_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int sgdml_b200_model_create(sgdml_b200_model** out, int64_t n_atoms, int64_t n_train, int64_t n_perms,
+                            const double* R_desc, const double* R_d_desc_alpha, const int64_t* tril_perms_lin,
+                            double sig, double std, double c) {
+  SG_TRY(require_device());
+  SG_ARG(out != nullptr && R_desc != nullptr && R_d_desc_alpha != nullptr && tril_perms_lin != nullptr);
+  SG_ARG(n_atoms >= 2 && n_train >= 1 && n_perms >= 1 && sig > 0);
+  const int64_t D = n_atoms * (n_atoms - 1) / 2;
+  int cfg = -1;
+  for (int i = 0; i < kNumCfgs; ++i)
+    if (D <= kCfgs[i].DP) {
+      cfg = i;
+      break;
+    }
+  if (cfg < 0) {
+    set_last_error("sgdml_b200_model_create: descriptor size D > 256 (N > 23 atoms) is not supported by the fused "
+                   "predictor yet");
+    return SGDML_B200_ERR_UNSUPPORTED;
+  }
+  sgdml_b200_model* m = new sgdml_b200_model();
+  m->N = (int)n_atoms;
+  m->D = (int)D;
+  m->M = (int)n_train;
+  m->S = (int)n_perms;
+  m->cfg = cfg;
+  m->DP = kCfgs[cfg].DP;
+  m->DS = m->DP + 4;
+  m->BQ = kCfgs[cfg].BQ;
+  m->BM = kCfgs[cfg].BM;
+  m->Mpad = (int)((n_train + m->BM - 1) / m->BM * m->BM);
+  m->sig = sig;
+  m->std = std;
+  m->c = c;
+  cudaGetDevice(&m->device);
+
+  // integer tables on the host (bit-exact), then to the device
+  std::vector<int64_t> lin((size_t)(n_perms * D));
+  if (is_device_ptr(tril_perms_lin)) {
+    cudaError_t e = cudaMemcpy(lin.data(), tril_perms_lin, sizeof(int64_t) * lin.size(), cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) {
+      delete m;
+      return fail_cuda(e, "copy tril_perms_lin", __FILE__, __LINE__);
+    }
+  } else {
+    std::copy(tril_perms_lin, tril_perms_lin + lin.size(), lin.begin());
+  }
+  std::vector<int> perm((size_t)(n_perms * D)), pinv((size_t)(n_perms * D), -1);
+  for (int64_t pp = 0; pp < n_perms; ++pp)
+    for (int64_t d = 0; d < D; ++d) {
+      const int64_t e = lin[(size_t)(d * n_perms + pp)] - pp * D;  // train.py:903-904
+      if (e < 0 || e >= D || pinv[(size_t)(pp * D + e)] != -1) {
+        delete m;
+        return fail_arg("tril_perms_lin must encode S permutations of 0..D-1");
+      }
+      perm[(size_t)(pp * D + d)] = (int)e;
+      pinv[(size_t)(pp * D + e)] = (int)d;
+    }
+
+  int rc = 0;
+  auto body = [&]() -> int {
+    cudaStream_t s = 0;
+    SG_CUDA(cudaMalloc(&m->perm, sizeof(int) * perm.size()));
+    SG_CUDA(cudaMalloc(&m->pinv, sizeof(int) * pinv.size()));
+    SG_CUDA(cudaMemcpy(m->perm, perm.data(), sizeof(int) * perm.size(), cudaMemcpyHostToDevice));
+    SG_CUDA(cudaMemcpy(m->pinv, pinv.data(), sizeof(int) * pinv.size(), cudaMemcpyHostToDevice));
+    SG_CUDA(cudaMalloc(&m->X, sizeof(double) * n_train * D));
+    SG_CUDA(cudaMalloc(&m->Xc, sizeof(double) * m->Mpad * m->DS));
+    SG_CUDA(cudaMalloc(&m->JA, sizeof(double) * m->Mpad * m->DS));
+    SG_CUDA(cudaMalloc(&m->mm, sizeof(double) * m->Mpad));
+    SG_CUDA(cudaMalloc(&m->xja, sizeof(double) * m->Mpad));
+    SG_CUDA(cudaMalloc(&m->mu, sizeof(double) * m->DS));
+    SG_CUDA(cudaMemset(m->mu, 0, sizeof(double) * m->DS));
+    Staged sJA;
+    SG_CUDA(cudaMemcpy(m->X, R_desc, sizeof(double) * n_train * D, cudaMemcpyDefault));
+    SG_TRY(sJA.init(R_d_desc_alpha, sizeof(double) * n_train * D, true, s));
+    k_col_mean<<<m->DP, 256, 0, s>>>(m->X, m->M, m->D, m->mu, m->DP);
+    SG_CUDA(cudaGetLastError());
+    const int64_t tot = (int64_t)m->Mpad * m->DS;
+    k_pad_rows<<<ceil_div(tot, 256), 256, 0, s>>>(m->X, m->mu, m->M, m->D, m->Mpad, m->DS, m->Xc);
+    SG_CUDA(cudaGetLastError());
+    k_pad_rows<<<ceil_div(tot, 256), 256, 0, s>>>((const double*)sJA.dev(), nullptr, m->M, m->D, m->Mpad, m->DS,
+                                                  m->JA);
+    SG_CUDA(cudaGetLastError());
+    SG_TRY(refresh_row_dots(m, true, s));
+    SG_CUDA(cudaStreamSynchronize(s));
+    return 0;
+  };
+  rc = body();
+  if (rc != 0) {
+    sgdml_b200_model_destroy(m);
+    return rc;
+  }
+  *out = m;
+  return 0;
+}
+
+int sgdml_b200_model_destroy(sgdml_b200_model* m) {
+  if (m == nullptr) return 0;
+  cudaFree(m->X);
+  cudaFree(m->Xc);
+  cudaFree(m->JA);
+  cudaFree(m->mm);
+  cudaFree(m->xja);
+  cudaFree(m->mu);
+  cudaFree(m->perm);
+  cudaFree(m->pinv);
+  cudaFree(m->R_d_desc);
+  free_ws(m);
+  delete m;
+  return 0;
+}
+
+int sgdml_b200_predict(sgdml_b200_model* m, const double* R, int64_t n_geo, double* E, double* F, void* stream) {
+  SG_TRY(require_device());
+  SG_ARG(m != nullptr && R != nullptr && F != nullptr && n_geo >= 0);
+  if (n_geo == 0) return 0;
+  cudaStream_t s = (cudaStream_t)stream;
+  const int64_t chunk = std::min<int64_t>(chunk_geos(m), n_geo);
+  SG_TRY(ensure_ws(m, chunk));
+  const bool R_dev = is_device_ptr(R), F_dev = is_device_ptr(F), E_dev = (E != nullptr) && is_device_ptr(E);
+  const int dimi = 3 * m->N;
+  for (int64_t g0 = 0; g0 < n_geo; g0 += chunk) {
+    const int64_t ng = std::min<int64_t>(chunk, n_geo - g0);
+    const double* Rd = R + g0 * dimi;
+    if (!R_dev) {
+      SG_CUDA(cudaMemcpyAsync(m->ws_R, Rd, sizeof(double) * ng * dimi, cudaMemcpyHostToDevice, s));
+      Rd = m->ws_R;
+    }
+    SG_TRY(launch_desc_from_R(Rd, ng, m->N, m->ws_xq, m->ws_gq, s));
+    double* Fd = F_dev ? F + g0 * dimi : m->ws_F;
+    double* Ed = (E == nullptr) ? nullptr : (E_dev ? E + g0 : m->ws_E);
+    SG_TRY(run_queries(m, m->ws_xq, m->ws_gq, ng, m->std, m->c, Ed, Fd, s));
+    if (!F_dev) SG_CUDA(cudaMemcpyAsync(F + g0 * dimi, Fd, sizeof(double) * ng * dimi, cudaMemcpyDeviceToHost, s));
+    if (E != nullptr && !E_dev) SG_CUDA(cudaMemcpyAsync(E + g0, Ed, sizeof(double) * ng, cudaMemcpyDeviceToHost, s));
+  }
+  if (!R_dev || !F_dev || (E != nullptr && !E_dev)) SG_CUDA(cudaStreamSynchronize(s));
+  return 0;
+}
+
+int sgdml_b200_model_set_R_d_desc(sgdml_b200_model* m, const double* R_d_desc) {
+  SG_TRY(require_device());
+  SG_ARG(m != nullptr && R_d_desc != nullptr);
+  const size_t bytes = sizeof(double) * (size_t)m->M * m->D * 3;
+  if (m->R_d_desc == nullptr) SG_CUDA(cudaMalloc(&m->R_d_desc, bytes));
+  SG_CUDA(cudaMemcpy(m->R_d_desc, R_d_desc, bytes, cudaMemcpyDefault));
+  return 0;
+}
+
+int sgdml_b200_model_set_alphas(sgdml_b200_model* m, const double* alphas_F, void* stream) {
+  SG_TRY(require_device());
+  SG_ARG(m != nullptr && alphas_F != nullptr);
+  if (m->R_d_desc == nullptr) {
+    set_last_error("sgdml_b200_model_set_alphas: call sgdml_b200_model_set_R_d_desc first (predict.py:575)");
+    return SGDML_B200_ERR_ARG;
+  }
+  cudaStream_t s = (cudaStream_t)stream;
+  Staged sA;
+  SG_TRY(sA.init(alphas_F, sizeof(double) * (size_t)m->M * 3 * m->N, true, s));
+  const int64_t tot = (int64_t)m->M * m->D;
+  k_set_alphas<<<ceil_div(tot, 256), 256, 0, s>>>(m->R_d_desc, (const double*)sA.dev(), m->M, m->D, m->N, m->DS,
+                                                  m->JA);
+  SG_CUDA(cudaGetLastError());
+  SG_TRY(refresh_row_dots(m, false, s));
+  if (sA.staged()) SG_CUDA(cudaStreamSynchronize(s));
+  return 0;
+}
+
+int sgdml_b200_predict_train(sgdml_b200_model* m, int64_t m_begin, int64_t m_end, int scaled, double* E, double* F,
+                             void* stream) {
+  SG_TRY(require_device());
+  SG_ARG(m != nullptr && F != nullptr);
+  SG_ARG(m_begin >= 0 && m_end <= m->M && m_begin <= m_end);
+  if (m->R_d_desc == nullptr) {
+    set_last_error("sgdml_b200_predict_train: call sgdml_b200_model_set_R_d_desc first (predict.py:1223-1229)");
+    return SGDML_B200_ERR_ARG;
+  }
+  const int64_t n_geo = m_end - m_begin;
+  if (n_geo == 0) return 0;
+  cudaStream_t s = (cudaStream_t)stream;
+  const int64_t chunk = std::min<int64_t>(chunk_geos(m), n_geo);
+  SG_TRY(ensure_ws(m, chunk));
+  const bool F_dev = is_device_ptr(F), E_dev = (E != nullptr) && is_device_ptr(E);
+  const int dimi = 3 * m->N;
+  const double std = scaled ? m->std : 1.0, c = scaled ? m->c : 0.0;
+  for (int64_t g0 = 0; g0 < n_geo; g0 += chunk) {
+    const int64_t ng = std::min<int64_t>(chunk, n_geo - g0);
+    const double* xq = m->X + (m_begin + g0) * m->D;
+    const double* gq = m->R_d_desc + (m_begin + g0) * m->D * 3;
+    double* Fd = F_dev ? F + g0 * dimi : m->ws_F;
+    double* Ed = (E == nullptr) ? nullptr : (E_dev ? E + g0 : m->ws_E);
+    SG_TRY(run_queries(m, xq, gq, ng, std, c, Ed, Fd, s));
+    if (!F_dev) SG_CUDA(cudaMemcpyAsync(F + g0 * dimi, Fd, sizeof(double) * ng * dimi, cudaMemcpyDeviceToHost, s));
+    if (E != nullptr && !E_dev) SG_CUDA(cudaMemcpyAsync(E + g0, Ed, sizeof(double) * ng, cudaMemcpyDeviceToHost, s));
+  }
+  if (!F_dev || (E != nullptr && !E_dev)) SG_CUDA(cudaStreamSynchronize(s));
+  return 0;
+}
+
+int sgdml_b200_model_get_R_d_desc_alpha(sgdml_b200_model* m, double* out) {
+  SG_TRY(require_device());
+  SG_ARG(m != nullptr && out != nullptr);
+  Staged sO;
+  SG_TRY(sO.init(out, sizeof(double) * (size_t)m->M * m->D, false, 0));
+  const int64_t tot = (int64_t)m->M * m->D;
+  k_unpad_rows<<<ceil_div(tot, 256), 256, 0, 0>>>(m->JA, m->M, m->D, m->DS, (double*)sO.dev());
+  SG_CUDA(cudaGetLastError());
+  SG_TRY(sO.finish(0));
+  SG_CUDA(cudaStreamSynchronize(0));
+  return 0;
+}
+
+}  // extern "C"

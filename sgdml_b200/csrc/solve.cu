@@ -1,0 +1,678 @@
+// Path (a), dense solve (SURVEY.md section 8 row a-S1): FP64 Cholesky factorisation and
+// triangular solves replacing scipy.linalg.cho_factor / cho_solve (LAPACK dpotrf/dpotrs) in
+// sgdml/solvers/analytic.py:94-99 and iterative.py:447-449.
+//
+// B200 design.  K stays in HBM from assembly to the solve (the reference round-trips every
+// block-column through the host, torchtools.py:233).  Blocked right-looking Cholesky on the
+// lower triangle of the row-major matrix, panel width NB = 128:
+//   1. k_potf2_tile   one CTA factorises the 128 x 128 diagonal block in shared memory;
+//   2. k_trsm_strip   64-row strips of the panel solve X L11^T = P by true substitution
+//                     (no explicit inverse: diagonal blocks of sGDML kernels have condition
+//                     numbers ~1e11, lam = 1e-10) and also emit -X into a workspace;
+//   3. k_gemm_nt      trailing update C += (-X) X^T on the FP64 tensor pipe (mma.sync
+//                     m8n8k4.f64 -> SASS DMMA; tcgen05 has no f64 kind), lower tiles only,
+//                     4-stage cp.async pipeline, fragment-major shared-memory tiles.
+// FP64 throughout: TF32/BF16 factorisations cannot deliver 1e-6 forces at cond ~4e11.
+#include <algorithm>
+#include <cmath>
+
+#include "common.cuh"
+
+namespace sgdml {
+
+constexpr int NB = 128;  // Cholesky panel width
+
+// ====================================================================== GEMM  C (+)= A B^T
+template <int BM_, int BN_, int WM_, int WN_>
+struct GCfg {
+  static constexpr int BM = BM_, BN = BN_, WM = WM_, WN = WN_;
+  static constexpr int BK = 16, STAGES = 4, NT = 256;
+  static constexpr int TR = BM / (8 * WM), TC = BN / (8 * WN);
+  static constexpr int A_DBL = BM * BK, B_DBL = BN * BK;
+  static constexpr size_t SMEM_BYTES = (size_t)STAGES * (A_DBL + B_DBL) * 8;
+  static_assert(WM * WN == 8, "8 warps");
+  static_assert(BM % (8 * WM) == 0 && BN % (8 * WN) == 0, "warp tiling");
+  static_assert((BM * 8) % NT == 0 && (BN * 8) % NT == 0, "loader mapping");
+  static_assert(BM % BN == 0, "triangular enumeration assumes BM = r BN");
+};
+
+struct GemmArgs {
+  int64_t m, n, k;
+  const double* A;
+  int64_t lda;
+  const double* B;
+  int64_t ldb;
+  double* C;
+  int64_t ldc;
+  double alpha, beta;
+  int mode;  // 0: C = alpha A B^T + beta C ; 1: C += A B^T (accumulators start from C)
+  int tri;   // 1: C square, only tiles touching the lower triangle are computed
+  const int* abort_flag;  // optional: skip all work when *abort_flag != 0
+};
+
+// shared-memory tile layout: [k/4][row][4] so that one DMMA fragment (8 rows x 4 k) is 256
+// contiguous bytes -> conflict-free LDS.64
+template <class G>
+__global__ void __launch_bounds__(256) k_gemm_nt(const GemmArgs p) {
+  extern __shared__ __align__(128) double gsm[];
+  if (p.abort_flag != nullptr && *p.abort_flag != 0) return;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int lr = lane >> 2, lc = lane & 3;
+
+  // ---- tile coordinates
+  int64_t ti, tj;
+  if (p.tri) {
+    constexpr int r = G::BM / G::BN;
+    const int64_t b = blockIdx.x;
+    int64_t t = (int64_t)((sqrt(8.0 * (double)b / r + 1.0) - 1.0) * 0.5);
+    while (r * (t + 1) * (t + 2) / 2 <= b) ++t;
+    while (r * t * (t + 1) / 2 > b) --t;
+    ti = t;
+    tj = b - r * t * (t + 1) / 2;
+  } else {
+    const int64_t ntn = (p.n + G::BN - 1) / G::BN;
+    ti = blockIdx.x / ntn;
+    tj = blockIdx.x - ti * ntn;
+  }
+  const int64_t m0 = ti * G::BM, n0 = tj * G::BN;
+  if (m0 >= p.m || n0 >= p.n) return;
+
+  const int wm = warp / G::WN, wn = warp % G::WN;
+  const int row0 = wm * G::TR * 8, col0 = wn * G::TC * 8;
+
+  double acc[G::TR][G::TC][2];
+  if (p.mode == 1) {
+#pragma unroll
+    for (int i = 0; i < G::TR; ++i) {
+      const int64_t r = m0 + row0 + i * 8 + lr;
+#pragma unroll
+      for (int j = 0; j < G::TC; ++j) {
+        const int64_t c = n0 + col0 + j * 8 + 2 * lc;
+        double2 v = make_double2(0.0, 0.0);
+        if (r < p.m && c + 1 < p.n)
+          v = *reinterpret_cast<const double2*>(p.C + r * p.ldc + c);
+        else if (r < p.m && c < p.n)
+          v.x = p.C[r * p.ldc + c];
+        acc[i][j][0] = v.x;
+        acc[i][j][1] = v.y;
+      }
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < G::TR; ++i)
+#pragma unroll
+      for (int j = 0; j < G::TC; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+  }
+
+  const int KT = (int)((p.k + G::BK - 1) / G::BK);
+  auto load_tile = [&](int kt) {
+    double* As = gsm + (size_t)(kt % G::STAGES) * (G::A_DBL + G::B_DBL);
+    double* Bs = As + G::A_DBL;
+    const int64_t k0 = (int64_t)kt * G::BK;
+#pragma unroll
+    for (int q = 0; q < G::BM * 8 / G::NT; ++q) {
+      const int op = tid + q * G::NT;
+      const int row = op >> 3, kp = op & 7;
+      const bool ok = (m0 + row < p.m) && (k0 + 2 * kp < p.k);
+      const double* src = ok ? p.A + (m0 + row) * p.lda + k0 + 2 * kp : p.A;
+      cp_async16_pred(As + ((kp >> 1) * G::BM + row) * 4 + (kp & 1) * 2, src, ok);
+    }
+#pragma unroll
+    for (int q = 0; q < G::BN * 8 / G::NT; ++q) {
+      const int op = tid + q * G::NT;
+      const int row = op >> 3, kp = op & 7;
+      const bool ok = (n0 + row < p.n) && (k0 + 2 * kp < p.k);
+      const double* src = ok ? p.B + (n0 + row) * p.ldb + k0 + 2 * kp : p.B;
+      cp_async16_pred(Bs + ((kp >> 1) * G::BN + row) * 4 + (kp & 1) * 2, src, ok);
+    }
+  };
+
+#pragma unroll
+  for (int s = 0; s < G::STAGES - 1; ++s) {
+    if (s < KT) load_tile(s);
+    cp_async_commit();
+  }
+  for (int kt = 0; kt < KT; ++kt) {
+    cp_async_wait<G::STAGES - 2>();
+    __syncthreads();
+    if (kt + G::STAGES - 1 < KT) load_tile(kt + G::STAGES - 1);
+    cp_async_commit();
+    const double* As = gsm + (size_t)(kt % G::STAGES) * (G::A_DBL + G::B_DBL);
+    const double* Bs = As + G::A_DBL;
+#pragma unroll
+    for (int ks = 0; ks < G::BK / 4; ++ks) {
+      double fa[G::TR], fb[G::TC];
+#pragma unroll
+      for (int i = 0; i < G::TR; ++i) fa[i] = As[(ks * G::BM + row0 + i * 8 + lr) * 4 + lc];
+#pragma unroll
+      for (int j = 0; j < G::TC; ++j) fb[j] = Bs[(ks * G::BN + col0 + j * 8 + lr) * 4 + lc];
+#pragma unroll
+      for (int i = 0; i < G::TR; ++i)
+#pragma unroll
+        for (int j = 0; j < G::TC; ++j) dmma884(acc[i][j][0], acc[i][j][1], fa[i], fb[j]);
+    }
+  }
+  cp_async_wait<0>();
+
+  // ---- epilogue
+#pragma unroll
+  for (int i = 0; i < G::TR; ++i) {
+    const int64_t r = m0 + row0 + i * 8 + lr;
+    if (r >= p.m) continue;
+#pragma unroll
+    for (int j = 0; j < G::TC; ++j) {
+      const int64_t c = n0 + col0 + j * 8 + 2 * lc;
+      if (c >= p.n) continue;
+      double* dst = p.C + r * p.ldc + c;
+      double v0 = acc[i][j][0], v1 = acc[i][j][1];
+      if (p.mode == 0) {
+        v0 *= p.alpha;
+        v1 *= p.alpha;
+        if (p.beta != 0.0) {
+          v0 += p.beta * dst[0];
+          if (c + 1 < p.n) v1 += p.beta * dst[1];
+        }
+      }
+      if (c + 1 < p.n)
+        *reinterpret_cast<double2*>(dst) = make_double2(v0, v1);
+      else
+        dst[0] = v0;
+    }
+  }
+}
+
+// slow reference path for unaligned / odd shapes (also the on-GPU cross-check in tests)
+__global__ void k_gemm_nt_naive(const GemmArgs p) {
+  if (p.abort_flag != nullptr && *p.abort_flag != 0) return;
+  const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= p.n) return;
+  for (int64_t r = blockIdx.y; r < p.m; r += gridDim.y) {
+    if (p.tri && c > r) continue;
+    double s = 0.0;
+    for (int64_t kk = 0; kk < p.k; ++kk) s = fma(p.A[r * p.lda + kk], p.B[c * p.ldb + kk], s);
+    double* dst = p.C + r * p.ldc + c;
+    if (p.mode == 1)
+      *dst += s;
+    else
+      *dst = p.alpha * s + (p.beta != 0.0 ? p.beta * *dst : 0.0);
+  }
+}
+
+using GBig = GCfg<128, 128, 2, 4>;
+using GTall = GCfg<128, 64, 4, 2>;
+
+static int g_gemm_variant = 0;  // 0: 128x128 tiles (1 CTA/SM), 1: 128x64 tiles (2 CTAs/SM)
+
+template <class G>
+static int launch_gemm_t(const GemmArgs& a, cudaStream_t s) {
+  static bool configured[64] = {false};
+  int dev = 0;
+  SG_CUDA(cudaGetDevice(&dev));
+  if (dev >= 0 && dev < 64 && !configured[dev]) {
+    SG_CUDA(cudaFuncSetAttribute(k_gemm_nt<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM_BYTES));
+    configured[dev] = true;
+  }
+  int64_t blocks;
+  const int64_t ntm = (a.m + G::BM - 1) / G::BM, ntn = (a.n + G::BN - 1) / G::BN;
+  if (a.tri)
+    blocks = (int64_t)(G::BM / G::BN) * ntm * (ntm + 1) / 2;
+  else
+    blocks = ntm * ntn;
+  if (blocks == 0) return 0;
+  k_gemm_nt<G><<<(unsigned)blocks, G::NT, G::SMEM_BYTES, s>>>(a);
+  SG_CUDA(cudaGetLastError());
+  return 0;
+}
+
+static bool gemm_fast_ok(const GemmArgs& a) {
+  auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+  return (a.lda % 2 == 0) && (a.ldb % 2 == 0) && (a.ldc % 2 == 0) && (a.k % 2 == 0) && al16(a.A) && al16(a.B) &&
+         al16(a.C);
+}
+
+int launch_gemm(const GemmArgs& a, cudaStream_t s) {
+  if (a.m <= 0 || a.n <= 0) return 0;
+  if (g_gemm_variant == 2 || !gemm_fast_ok(a)) {
+    dim3 grid((unsigned)((a.n + 127) / 128), (unsigned)std::min<int64_t>(a.m, 65535));
+    k_gemm_nt_naive<<<grid, 128, 0, s>>>(a);
+    SG_CUDA(cudaGetLastError());
+    return 0;
+  }
+  if (g_gemm_variant == 1) return launch_gemm_t<GTall>(a, s);
+  return launch_gemm_t<GBig>(a, s);
+}
+
+// ====================================================================== potf2 on one tile
+// Factorises the nb x nb (nb <= 128) diagonal block at A (row stride lda) in shared memory.
+// info: set to (k0 + j + 1) if the pivot j is not positive (LAPACK dpotrf convention).
+__global__ void __launch_bounds__(512) k_potf2_tile(double* __restrict__ A, int64_t lda, int nb, int64_t k0,
+                                                    int* __restrict__ info) {
+  extern __shared__ double T[];  // nb x (NB+1)
+  constexpr int LD = NB + 1;
+  if (*info != 0) return;
+  const int tid = threadIdx.x, nt = blockDim.x;
+  for (int idx = tid; idx < nb * nb; idx += nt) {
+    const int i = idx / nb, j = idx - i * nb;
+    T[i * LD + j] = (j <= i) ? A[(int64_t)i * lda + j] : 0.0;
+  }
+  __shared__ int bad;
+  if (tid == 0) bad = 0;
+  __syncthreads();
+  for (int j = 0; j < nb; ++j) {
+    const double ajj = T[j * LD + j];
+    if (!(ajj > 0.0)) {  // also catches NaN
+      if (tid == 0) bad = j + 1;
+      break;  // uniform: every thread reads the same ajj
+    }
+    const double d = sqrt(ajj);
+    const double dinv = 1.0 / d;
+    __syncthreads();  // everyone has read ajj before it is overwritten
+    for (int i = j + 1 + tid; i < nb; i += nt) T[i * LD + j] *= dinv;
+    if (tid == 0) T[j * LD + j] = d;
+    __syncthreads();
+    const int rem = nb - j - 1;
+    for (int idx = tid; idx < rem * rem; idx += nt) {
+      const int ii = idx / rem, ll = idx - ii * rem;
+      if (ll <= ii) {
+        const int i = j + 1 + ii, l = j + 1 + ll;
+        T[i * LD + l] = fma(-T[i * LD + j], T[l * LD + j], T[i * LD + l]);
+      }
+    }
+    __syncthreads();
+  }
+  __syncthreads();
+  if (bad != 0) {
+    if (tid == 0) *info = (int)(k0 + bad);
+    return;
+  }
+  for (int idx = tid; idx < nb * nb; idx += nt) {
+    const int i = idx / nb, j = idx - i * nb;
+    if (j <= i) A[(int64_t)i * lda + j] = T[i * LD + j];
+  }
+}
+
+// ====================================================================== panel TRSM strips
+// Solves X L11^T = P for a strip of RS rows of the panel P (rows x kb, kb <= NB) below the
+// diagonal block L11 (kb x kb, lower), by blocked forward substitution in shared memory.
+// Writes X over P and -X into W (row stride NB) for the trailing update.
+constexpr int RS = 64;   // rows per strip
+constexpr int SB = 32;   // substitution block
+__global__ void __launch_bounds__(256) k_trsm_strip(double* __restrict__ A, int64_t lda, int64_t k0, int kb,
+                                                    int64_t n, double* __restrict__ W,
+                                                    const int* __restrict__ info) {
+  extern __shared__ __align__(16) double tsm[];
+  constexpr int LD = NB + 4;  // == 4 mod 16: conflict-free DMMA fragment loads
+  double* L = tsm;            // NB x LD
+  double* X = L + NB * LD;    // RS x LD
+  if (*info != 0) return;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int lr = lane >> 2, lc = lane & 3;
+  const int64_t r0 = k0 + kb + (int64_t)blockIdx.x * RS;
+  const int rows = (int)min((int64_t)RS, n - r0);
+  const double* L11 = A + k0 * lda + k0;
+  double* P = A + r0 * lda + k0;
+
+  for (int idx = tid; idx < NB * NB; idx += 256) {
+    const int i = idx / NB, j = idx - i * NB;
+    L[i * LD + j] = (i < kb && j <= i) ? L11[(int64_t)i * lda + j] : ((i == j) ? 1.0 : 0.0);
+  }
+  for (int idx = tid; idx < RS * NB; idx += 256) {
+    const int i = idx / NB, j = idx - i * NB;
+    X[i * LD + j] = (i < rows && j < kb) ? P[(int64_t)i * lda + j] : 0.0;
+  }
+  __syncthreads();
+
+  for (int jb = 0; jb < NB / SB; ++jb) {
+    const int c0 = jb * SB;
+    if (c0 >= kb) break;
+    if (jb > 0) {
+      // X[:, c0:c0+SB] -= X[:, 0:c0] * L[c0:c0+SB, 0:c0]^T ; warp w owns rows 8w..8w+7
+      double acc[SB / 8][2];
+#pragma unroll
+      for (int j = 0; j < SB / 8; ++j) acc[j][0] = acc[j][1] = 0.0;
+      const double* xa = X + (warp * 8 + lr) * LD + lc;
+      const double* lb = L + (c0 + lr) * LD + lc;
+      for (int ks = 0; ks < c0 / 4; ++ks) {
+        const double fa = xa[ks * 4];
+#pragma unroll
+        for (int j = 0; j < SB / 8; ++j) dmma884(acc[j][0], acc[j][1], fa, lb[j * 8 * LD + ks * 4]);
+      }
+#pragma unroll
+      for (int j = 0; j < SB / 8; ++j) {
+        double* dst = X + (warp * 8 + lr) * LD + c0 + j * 8 + 2 * lc;
+        dst[0] -= acc[j][0];
+        dst[1] -= acc[j][1];
+      }
+    }
+    __syncthreads();
+    // substitution inside the SB x SB diagonal block: thread r < RS owns row r
+    if (tid < RS) {
+      double x[SB];
+#pragma unroll
+      for (int c = 0; c < SB; ++c) x[c] = X[tid * LD + c0 + c];
+#pragma unroll
+      for (int c = 0; c < SB; ++c) {
+        const double xc = x[c] / L[(c0 + c) * LD + c0 + c];
+        x[c] = xc;
+#pragma unroll
+        for (int l = c + 1; l < SB; ++l) x[l] = fma(-xc, L[(c0 + l) * LD + c0 + c], x[l]);
+      }
+#pragma unroll
+      for (int c = 0; c < SB; ++c) X[tid * LD + c0 + c] = x[c];
+    }
+    __syncthreads();
+  }
+
+  for (int idx = tid; idx < RS * NB; idx += 256) {
+    const int i = idx / NB, j = idx - i * NB;
+    if (i < rows && j < kb) {
+      const double v = X[i * LD + j];
+      P[(int64_t)i * lda + j] = v;
+      W[(r0 + i) * NB + j] = -v;
+    }
+  }
+}
+
+// ====================================================================== triangular solves
+// forward:  z_blk = L_kk^-1 r_blk ; backward: x_blk = L_kk^-T r_blk ; one CTA, nb <= 128.
+// B is (n, nrhs) row-major with row stride ldb; each thread owns one right-hand side.
+__global__ void __launch_bounds__(128) k_trsv_diag(const double* __restrict__ A, int64_t lda, int64_t k0, int nb,
+                                                   double* __restrict__ B, int64_t nrhs, int64_t ldb, int backward) {
+  extern __shared__ double Ls[];  // nb x (NB+1)
+  constexpr int LD = NB + 1;
+  const double* Lkk = A + k0 * lda + k0;
+  for (int idx = threadIdx.x; idx < nb * nb; idx += blockDim.x) {
+    const int i = idx / nb, j = idx - i * nb;
+    Ls[i * LD + j] = (j <= i) ? Lkk[(int64_t)i * lda + j] : 0.0;
+  }
+  __syncthreads();
+  for (int64_t rhs = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; rhs < nrhs;
+       rhs += (int64_t)gridDim.x * blockDim.x) {
+    double* b = B + k0 * ldb + rhs;
+    if (!backward) {
+      for (int i = 0; i < nb; ++i) {
+        double s = b[(int64_t)i * ldb];
+        for (int j = 0; j < i; ++j) s = fma(-Ls[i * LD + j], b[(int64_t)j * ldb], s);
+        b[(int64_t)i * ldb] = s / Ls[i * LD + i];
+      }
+    } else {
+      for (int i = nb - 1; i >= 0; --i) {
+        double s = b[(int64_t)i * ldb];
+        for (int j = i + 1; j < nb; ++j) s = fma(-Ls[j * LD + i], b[(int64_t)j * ldb], s);
+        b[(int64_t)i * ldb] = s / Ls[i * LD + i];
+      }
+    }
+  }
+}
+
+// single right-hand side: cooperative substitution by one CTA (nb <= 128), the common case
+__global__ void __launch_bounds__(128) k_trsv_diag1(const double* __restrict__ A, int64_t lda, int64_t k0, int nb,
+                                                    double* __restrict__ b, int64_t ldb, int backward) {
+  extern __shared__ double Ls[];  // nb x (NB+1) + nb
+  constexpr int LD = NB + 1;
+  double* x = Ls + NB * LD;
+  const double* Lkk = A + k0 * lda + k0;
+  const int tid = threadIdx.x;
+  for (int idx = tid; idx < nb * nb; idx += blockDim.x) {
+    const int i = idx / nb, j = idx - i * nb;
+    Ls[i * LD + j] = (j <= i) ? Lkk[(int64_t)i * lda + j] : 0.0;
+  }
+  if (tid < nb) x[tid] = b[(k0 + tid) * ldb];
+  __syncthreads();
+  if (!backward) {
+    // column-oriented: after x_j is final, eliminate it from the rows below
+    for (int j = 0; j < nb; ++j) {
+      if (tid == j) x[j] = x[j] / Ls[j * LD + j];
+      __syncthreads();
+      if (tid > j && tid < nb) x[tid] = fma(-Ls[tid * LD + j], x[j], x[tid]);
+      __syncthreads();
+    }
+  } else {
+    for (int j = nb - 1; j >= 0; --j) {
+      if (tid == j) x[j] = x[j] / Ls[j * LD + j];
+      __syncthreads();
+      if (tid < j) x[tid] = fma(-Ls[j * LD + tid], x[j], x[tid]);
+      __syncthreads();
+    }
+  }
+  if (tid < nb) b[(k0 + tid) * ldb] = x[tid];
+}
+
+// forward update: B[k0+nb:, :] -= L[k0+nb:, k0:k0+nb] * B[k0:k0+nb, :]   (one warp per row)
+__global__ void __launch_bounds__(256) k_trsv_update_fwd(const double* __restrict__ A, int64_t lda, int64_t k0,
+                                                         int nb, int64_t n, double* __restrict__ B, int64_t nrhs,
+                                                         int64_t ldb) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = k0 + nb + (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= n) return;
+  const double* Lr = A + row * lda + k0;
+  for (int64_t rhs = 0; rhs < nrhs; ++rhs) {
+    double s = 0.0;
+    for (int j = lane; j < nb; j += 32) s = fma(Lr[j], B[(k0 + j) * ldb + rhs], s);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) B[row * ldb + rhs] -= s;
+  }
+}
+
+// backward update: B[0:k0, :] -= L[k0:k0+nb, 0:k0]^T * B[k0:k0+nb, :]   (one thread per column j)
+__global__ void __launch_bounds__(256) k_trsv_update_bwd(const double* __restrict__ A, int64_t lda, int64_t k0,
+                                                         int nb, double* __restrict__ B, int64_t nrhs, int64_t ldb) {
+  const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= k0) return;
+  for (int64_t rhs = 0; rhs < nrhs; ++rhs) {
+    double s = 0.0;
+    for (int r = 0; r < nb; ++r) s = fma(A[(k0 + r) * lda + j], B[(k0 + r) * ldb + rhs], s);
+    B[j * ldb + rhs] -= s;
+  }
+}
+
+__global__ void k_add_diag(double* __restrict__ A, int64_t n, int64_t lda, double lam) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) A[i * lda + i] += lam;
+}
+
+__global__ void k_negate_copy(const double* __restrict__ src, double* __restrict__ dst, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = -src[i];
+}
+
+// ---------------------------------------------------------------------- host drivers (device pointers)
+int potrf_device(double* A, int64_t n, int64_t lda, int* info_host, cudaStream_t s) {
+  int* d_info = nullptr;
+  double* W = nullptr;
+  SG_CUDA(cudaMalloc(&d_info, sizeof(int)));
+  cudaError_t e = cudaMalloc(&W, sizeof(double) * (size_t)n * NB);
+  if (e != cudaSuccess) {
+    cudaFree(d_info);
+    return fail_cuda(e, "cudaMalloc(panel workspace)", __FILE__, __LINE__);
+  }
+  auto body = [&]() -> int {
+    SG_CUDA(cudaMemsetAsync(d_info, 0, sizeof(int), s));
+    const size_t potf2_smem = sizeof(double) * NB * (NB + 1);
+    const size_t trsm_smem = sizeof(double) * (NB + RS) * (NB + 4);
+    SG_CUDA(cudaFuncSetAttribute(k_potf2_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)potf2_smem));
+    SG_CUDA(cudaFuncSetAttribute(k_trsm_strip, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)trsm_smem));
+    for (int64_t k0 = 0; k0 < n; k0 += NB) {
+      const int kb = (int)std::min<int64_t>(NB, n - k0);
+      k_potf2_tile<<<1, 512, potf2_smem, s>>>(A + k0 * lda + k0, lda, kb, k0, d_info);
+      SG_CUDA(cudaGetLastError());
+      const int64_t rem = n - k0 - kb;
+      if (rem <= 0) break;
+      k_trsm_strip<<<(unsigned)((rem + RS - 1) / RS), 256, trsm_smem, s>>>(A, lda, k0, kb, n, W, d_info);
+      SG_CUDA(cudaGetLastError());
+      GemmArgs g;
+      g.m = rem;
+      g.n = rem;
+      g.k = kb;
+      g.A = W + (k0 + kb) * NB;  // -X
+      g.lda = NB;
+      g.B = A + (k0 + kb) * lda + k0;  // X
+      g.ldb = lda;
+      g.C = A + (k0 + kb) * lda + (k0 + kb);
+      g.ldc = lda;
+      g.alpha = 1.0;
+      g.beta = 1.0;
+      g.mode = 1;
+      g.tri = 1;
+      g.abort_flag = d_info;
+      SG_TRY(launch_gemm(g, s));
+    }
+    SG_CUDA(cudaMemcpyAsync(info_host, d_info, sizeof(int), cudaMemcpyDeviceToHost, s));
+    SG_CUDA(cudaStreamSynchronize(s));
+    return 0;
+  };
+  int rc = body();
+  cudaFree(d_info);
+  cudaFree(W);
+  return rc;
+}
+
+int potrs_device(const double* L, int64_t n, int64_t lda, double* B, int64_t nrhs, int64_t ldb, cudaStream_t s) {
+  const size_t smem = sizeof(double) * (NB * (NB + 1) + NB);
+  SG_CUDA(cudaFuncSetAttribute(k_trsv_diag, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  SG_CUDA(cudaFuncSetAttribute(k_trsv_diag1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  // forward: L z = b
+  for (int64_t k0 = 0; k0 < n; k0 += NB) {
+    const int nb = (int)std::min<int64_t>(NB, n - k0);
+    if (nrhs == 1)
+      k_trsv_diag1<<<1, 128, smem, s>>>(L, lda, k0, nb, B, ldb, 0);
+    else
+      k_trsv_diag<<<(unsigned)std::min<int64_t>((nrhs + 127) / 128, 1024), 128, smem, s>>>(L, lda, k0, nb, B, nrhs, ldb,
+                                                                                          0);
+    SG_CUDA(cudaGetLastError());
+    const int64_t rem = n - k0 - nb;
+    if (rem > 0) {
+      k_trsv_update_fwd<<<(unsigned)((rem + 7) / 8), 256, 0, s>>>(L, lda, k0, nb, n, B, nrhs, ldb);
+      SG_CUDA(cudaGetLastError());
+    }
+  }
+  // backward: L^T x = z
+  const int64_t last = ((n - 1) / NB) * NB;
+  for (int64_t k0 = last; k0 >= 0; k0 -= NB) {
+    const int nb = (int)std::min<int64_t>(NB, n - k0);
+    if (nrhs == 1)
+      k_trsv_diag1<<<1, 128, smem, s>>>(L, lda, k0, nb, B, ldb, 1);
+    else
+      k_trsv_diag<<<(unsigned)std::min<int64_t>((nrhs + 127) / 128, 1024), 128, smem, s>>>(L, lda, k0, nb, B, nrhs, ldb,
+                                                                                          1);
+    SG_CUDA(cudaGetLastError());
+    if (k0 > 0) {
+      k_trsv_update_bwd<<<(unsigned)((k0 + 255) / 256), 256, 0, s>>>(L, lda, k0, nb, B, nrhs, ldb);
+      SG_CUDA(cudaGetLastError());
+    }
+  }
+  return 0;
+}
+
+}  // namespace sgdml
+
+using namespace sgdml;
+
+extern "C" {
+
+int sgdml_b200_potrf(double* A, int64_t n, int64_t lda, void* stream) {
+  SG_TRY(require_device());
+  SG_ARG(A != nullptr && n >= 1 && lda >= n);
+  cudaStream_t s = (cudaStream_t)stream;
+  Staged sA;
+  SG_TRY(sA.init(A, sizeof(double) * (size_t)n * lda, true, s));
+  int info = 0;
+  SG_TRY(potrf_device((double*)sA.dev(), n, lda, &info, s));
+  SG_TRY(sA.finish(s));
+  if (sA.staged()) SG_CUDA(cudaStreamSynchronize(s));
+  if (info > 0) {
+    char buf[160];
+    snprintf(buf, sizeof(buf), "%d-th leading minor of the array is not positive definite", info);
+    set_last_error(buf);
+  }
+  return info;
+}
+
+int sgdml_b200_potrs(const double* L, int64_t n, int64_t lda, double* B, int64_t nrhs, int64_t ldb, void* stream) {
+  SG_TRY(require_device());
+  SG_ARG(L != nullptr && B != nullptr && n >= 1 && lda >= n && nrhs >= 1 && ldb >= nrhs);
+  cudaStream_t s = (cudaStream_t)stream;
+  Staged sL, sB;
+  SG_TRY(sL.init(L, sizeof(double) * (size_t)n * lda, true, s));
+  SG_TRY(sB.init(B, sizeof(double) * (size_t)n * ldb, true, s));
+  SG_TRY(potrs_device((const double*)sL.dev(), n, lda, (double*)sB.dev(), nrhs, ldb, s));
+  SG_TRY(sB.finish(s));
+  if (sL.staged() || sB.staged()) SG_CUDA(cudaStreamSynchronize(s));
+  return 0;
+}
+
+int sgdml_b200_solve_analytic(double* Kneg, int64_t n, int64_t lda, double lam, const double* y, double* alphas,
+                              void* stream) {
+  SG_TRY(require_device());
+  SG_ARG(Kneg != nullptr && y != nullptr && alphas != nullptr && n >= 1 && lda >= n);
+  cudaStream_t s = (cudaStream_t)stream;
+  Staged sK, sY, sX;
+  SG_TRY(sK.init(Kneg, sizeof(double) * (size_t)n * lda, true, s));
+  SG_TRY(sY.init(y, sizeof(double) * (size_t)n, true, s));
+  SG_TRY(sX.init(alphas, sizeof(double) * (size_t)n, false, s));
+  double* K = (double*)sK.dev();
+  k_add_diag<<<ceil_div(n, 256), 256, 0, s>>>(K, n, lda, lam);  // analytic.py:82
+  SG_CUDA(cudaGetLastError());
+  int info = 0;
+  SG_TRY(potrf_device(K, n, lda, &info, s));  // analytic.py:94-96
+  if (info > 0) {
+    char buf[160];
+    snprintf(buf, sizeof(buf), "%d-th leading minor of the array is not positive definite", info);
+    set_last_error(buf);
+    return info;
+  }
+  double* tmp = nullptr;
+  SG_CUDA(cudaMalloc(&tmp, sizeof(double) * (size_t)n));
+  auto body = [&]() -> int {
+    SG_CUDA(cudaMemcpyAsync(tmp, sY.dev(), sizeof(double) * (size_t)n, cudaMemcpyDeviceToDevice, s));
+    SG_TRY(potrs_device(K, n, lda, tmp, 1, 1, s));  // analytic.py:97-99
+    k_negate_copy<<<ceil_div(n, 256), 256, 0, s>>>(tmp, (double*)sX.dev(), n);
+    SG_CUDA(cudaGetLastError());
+    SG_TRY(sX.finish(s));
+    SG_CUDA(cudaStreamSynchronize(s));
+    return 0;
+  };
+  int rc = body();
+  cudaFree(tmp);
+  return rc;
+}
+
+int sgdml_b200_dgemm_nt(int64_t m, int64_t n, int64_t k, double alpha, const double* A, int64_t lda, const double* B,
+                        int64_t ldb, double beta, double* C, int64_t ldc, void* stream) {
+  SG_TRY(require_device());
+  SG_ARG(A != nullptr && B != nullptr && C != nullptr && m >= 1 && n >= 1 && k >= 1);
+  SG_ARG(lda >= k && ldb >= k && ldc >= n);
+  cudaStream_t s = (cudaStream_t)stream;
+  Staged sA, sB, sC;
+  SG_TRY(sA.init(A, sizeof(double) * (size_t)m * lda, true, s));
+  SG_TRY(sB.init(B, sizeof(double) * (size_t)n * ldb, true, s));
+  SG_TRY(sC.init(C, sizeof(double) * (size_t)m * ldc, true, s));
+  GemmArgs g;
+  g.m = m;
+  g.n = n;
+  g.k = k;
+  g.A = (const double*)sA.dev();
+  g.lda = lda;
+  g.B = (const double*)sB.dev();
+  g.ldb = ldb;
+  g.C = (double*)sC.dev();
+  g.ldc = ldc;
+  g.alpha = alpha;
+  g.beta = beta;
+  g.mode = 0;
+  g.tri = 0;
+  g.abort_flag = nullptr;
+  SG_TRY(launch_gemm(g, s));
+  SG_TRY(sC.finish(s));
+  if (sA.staged() || sB.staged() || sC.staged()) SG_CUDA(cudaStreamSynchronize(s));
+  return 0;
+}
+
+// test / tuning hook: 0 = 128x128 tiles, 1 = 128x64 tiles, 2 = naive kernel
+int sgdml_b200_set_gemm_variant(int v) {
+  g_gemm_variant = v;
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,98 @@
+"""``Analytic`` -- closed-form solver (reference sgdml/solvers/analytic.py:37-159) on the B200.
+
+Assembly writes -K straight into HBM (scale = -1, analytic.py:65), lam is added to the
+diagonal, and the FP64 Cholesky factorisation + two triangular solves run on the device
+(analytic.py:82-99).  A non-positive-definite matrix surfaces as
+``np.linalg.LinAlgError('... not positive definite')`` exactly like SciPy's, so callers'
+``except`` clauses keep working; the reference's LU fallback (analytic.py:101-114) is then
+run on the host from a freshly assembled matrix.
+"""
+
+import logging
+import timeit
+from functools import partial
+
+import numpy as np
+
+from .. import _lib
+
+DONE = 1
+NOT_DONE = 0
+
+
+class Analytic(object):
+    def __init__(self, gdml_train, desc, callback=None):
+        self.log = logging.getLogger(__name__)
+        self.gdml_train = gdml_train
+        self.desc = desc
+        self.callback = callback
+        self.timings = {}
+
+    def solve(self, task, R_desc, R_d_desc, tril_perms_lin, y):
+        """analytic.py:49-151 -> alphas (3NM,)."""
+        import torch
+
+        sig = task['sig']
+        lam = task['lam']
+        if task.get('use_E_cstr', False):
+            raise NotImplementedError('use_E_cstr is out of scope (SURVEY.md section 2 row 22)')
+
+        n_train = R_d_desc.shape[0]
+        if self.callback is not None:
+            self.callback = partial(self.callback, disp_str='Assembling kernel matrix')
+            self.callback(0, 100)
+
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        ev[0].record()
+        K, n = self.gdml_train._assemble_kernel_mat_device(
+            R_desc, R_d_desc, tril_perms_lin, sig, scale=-1.0
+        )  # analytic.py:65 (flip sign to make convex)
+        ev[1].record()
+
+        if self.callback is not None:
+            self.callback = partial(self.callback, disp_str='Solving linear system (Cholesky factorization)')
+            self.callback(NOT_DONE)
+
+        start = timeit.default_timer()
+        y = np.ascontiguousarray(y, dtype=np.float64)
+        alphas = np.empty(n)
+        try:
+            _lib.check(
+                _lib.lib().sgdml_b200_solve_analytic(
+                    K.data_ptr(), n, K.shape[1], float(lam), _lib.ptr(y), _lib.ptr(alphas), _lib.current_stream()
+                ),
+                'solve_analytic',
+            )
+        except np.linalg.LinAlgError:
+            # analytic.py:101-114: try a solver that makes fewer assumptions (host LU, as the reference)
+            self.log.warning('Cholesky factorisation failed (matrix not positive definite); falling back to LU.')
+            import scipy.linalg
+
+            del K
+            K, n = self.gdml_train._assemble_kernel_mat_device(R_desc, R_d_desc, tril_perms_lin, sig, scale=-1.0)
+            Kh = K[:, :n].cpu().numpy()
+            Kh[np.diag_indices_from(Kh)] += lam
+            alphas = -scipy.linalg.solve(Kh, y, overwrite_a=True, check_finite=False)
+        ev[2].record()
+        torch.cuda.synchronize()
+        self.timings = {
+            'assemble_s': ev[0].elapsed_time(ev[1]) * 1e-3,
+            'solve_s': ev[1].elapsed_time(ev[2]) * 1e-3,
+        }
+        del K
+
+        if self.callback is not None:
+            dur_s = timeit.default_timer() - start
+            self.callback(
+                DONE,
+                disp_str='Training on {:,} points'.format(n_train),
+                sec_disp_str='took {:.1f} s'.format(dur_s) if dur_s >= 0.1 else '',
+            )
+        return alphas
+
+    @staticmethod
+    def est_memory_requirement(n_train, n_atoms):
+        """Device bytes: K once (factorised in place; the reference needs ~3x, analytic.py:153-159)
+        plus the panel workspace and vectors."""
+        n = n_train * 3 * n_atoms
+        return n * n * 8 + n * 128 * 8 + 4 * n * 8

@@ -1,0 +1,235 @@
+"""``GDMLTrain`` -- the reference's training API (sgdml/train.py:305-1258) on the B200 engine.
+
+Hot path only: ``train(task)``, ``create_model``, ``_recov_int_const`` and
+``_assemble_kernel_mat`` keep the reference's names, arguments and model/.npz layout
+(train.py:793-830).  Task creation / sampling / permutation discovery stay the reference's
+own host code (out of scope): a task dict produced by
+``sgdml.train.GDMLTrain.create_task`` is a valid input here.
+
+K is assembled directly in HBM, negated and regularised in place and factorised there; the
+reference's torch engine copies every block-column to the host (torchtools.py:233) and
+always factorises on the CPU (analytic.py:94).
+"""
+
+import logging
+import timeit
+
+import numpy as np
+
+from . import _lib
+from .desc import Desc, tril_perms_lin as _tril_perms_lin
+from .predict import GDMLPredict
+from .solvers.analytic import Analytic
+
+__version__ = '0.1.0'
+
+
+def _torch():
+    import torch
+
+    return torch
+
+
+class GDMLTrain(object):
+    def __init__(self, max_memory=None, max_processes=None, use_torch=False):
+        """train.py:306-361.  `max_memory` [GB] caps the device memory the analytic solver
+        may use (default: what is free on the current GPU); `max_processes` / `use_torch`
+        are accepted for signature compatibility."""
+        self.log = logging.getLogger(__name__)
+        _lib.require_gpu()
+        self._max_memory = max_memory
+        self._max_processes = max_processes
+        self._use_torch = use_torch
+
+    # ------------------------------------------------------------------ model assembly
+    def create_model(self, task, solver, R_desc, R_d_desc, tril_perms_lin, std, alphas_F, alphas_E=None):
+        """train.py:727-832: same keys, shapes and dtypes as the reference model dict."""
+        n_train, dim_d = R_d_desc.shape[:2]
+        n_atoms = int((1 + np.sqrt(8 * dim_d + 1)) / 2)
+        desc = Desc(n_atoms, max_processes=self._max_processes)
+        dim_i = desc.dim_i
+        R_d_desc_alpha = desc.d_desc_dot_vec(R_d_desc, alphas_F.reshape(-1, dim_i))  # train.py:791
+
+        model = {
+            'type': 'm',
+            'code_version': __version__,
+            'dataset_name': task['dataset_name'],
+            'dataset_theory': task['dataset_theory'],
+            'solver_name': solver,
+            'z': task['z'],
+            'idxs_train': task['idxs_train'],
+            'md5_train': task['md5_train'],
+            'idxs_valid': task['idxs_valid'],
+            'md5_valid': task['md5_valid'],
+            'n_test': 0,
+            'md5_test': None,
+            'f_err': {'mae': np.nan, 'rmse': np.nan},
+            'R_desc': R_desc.T,  # train.py:807 (transposed)
+            'R_d_desc_alpha': R_d_desc_alpha,
+            'c': 0.0,
+            'std': std,
+            'sig': task['sig'],
+            'lam': task['lam'],
+            'alphas_F': alphas_F,
+            'perms': task['perms'],
+            'tril_perms_lin': tril_perms_lin,
+            'use_E': task['use_E'],
+        }
+        if task['use_E']:
+            model['e_err'] = {'mae': np.nan, 'rmse': np.nan}
+            if task['use_E_cstr']:
+                model['alphas_E'] = alphas_E
+        if 'lattice' in task:
+            model['lattice'] = task['lattice']
+        if 'r_unit' in task and 'e_unit' in task:
+            model['r_unit'] = task['r_unit']
+            model['e_unit'] = task['e_unit']
+        return model
+
+    # ------------------------------------------------------------------ training
+    def train(self, task, save_progr_callback=None, callback=None):
+        """train.py:836-1088.  Returns the model dict."""
+        task = dict(task)
+        if task.get('use_E_cstr', False):
+            raise NotImplementedError('use_E_cstr is out of scope (SURVEY.md section 2 row 22)')
+        if 'lattice' in task:
+            raise NotImplementedError('periodic boundary conditions are out of scope (SURVEY.md section 2 row 21)')
+
+        n_train, n_atoms = task['R_train'].shape[:2]
+        desc = Desc(n_atoms, max_processes=self._max_processes)
+
+        tril_perms_lin = _tril_perms_lin(task['perms'])  # train.py:897-904
+
+        R = np.ascontiguousarray(task['R_train'], dtype=np.float64).reshape(n_train, -1)
+        R_desc, R_d_desc = desc.from_R(R)  # train.py:926-935
+        if n_train == 1:
+            R_desc, R_d_desc = R_desc[None], R_d_desc[None]
+
+        y = np.asarray(task['F_train'], dtype=np.float64).ravel().copy()  # train.py:939-947
+        y_std = np.std(y)
+        y /= y_std
+
+        est_bytes_analytic = Analytic.est_memory_requirement(n_train, n_atoms)
+        free_bytes, _total = _torch().cuda.mem_get_info()
+        max_bytes = free_bytes if self._max_memory is None else min(free_bytes, self._max_memory * 1024**3)
+        if est_bytes_analytic > max_bytes:
+            raise NotImplementedError(
+                'K needs {:.1f} GB but only {:.1f} GB of HBM are available: the iterative solver '
+                '(solvers/iterative.py:473-825) is not part of this round'.format(
+                    est_bytes_analytic / 2**30, max_bytes / 2**30
+                )
+            )
+
+        analytic = Analytic(self, desc, callback=callback)
+        alphas = analytic.solve(task, R_desc, R_d_desc, tril_perms_lin, y)
+        self.timings = dict(analytic.timings)
+
+        model = self.create_model(task, 'analytic', R_desc, R_d_desc, tril_perms_lin, y_std, alphas)
+
+        if model['use_E']:  # train.py:1074-1086
+            model['c'] = self._recov_int_const(model, task, R_desc=R_desc, R_d_desc=R_d_desc)
+        return model
+
+    def _recov_int_const(self, model, task, R_desc=None, R_d_desc=None):
+        """train.py:1090-1258: c = mean(E_ref - E_pred) over the training points.  The
+        reference's dataset self-diagnostics (sign / correlation / scale warnings,
+        train.py:1150-1255) are kept."""
+        gdml_predict = GDMLPredict(model, max_memory=self._max_memory, max_processes=self._max_processes)
+        gdml_predict.set_R_desc(R_desc)
+        gdml_predict.set_R_d_desc(R_d_desc)
+        E_pred, _ = gdml_predict.predict()
+        E_ref = np.squeeze(task['E_train'])
+
+        e_fact = np.linalg.lstsq(np.column_stack((E_pred, np.ones(E_ref.shape))), E_ref, rcond=-1)[0][0]
+        corrcoef = np.corrcoef(E_ref, E_pred)[0, 1]
+        if np.sign(e_fact) == -1:
+            self.log.warning('The provided dataset may contain gradients instead of force labels (flipped sign).')
+        if corrcoef < 0.95:
+            self.log.warning(
+                'Potentially inconsistent energy labels detected (correlation coefficient {:.2f}).'.format(corrcoef)
+            )
+        if np.abs(e_fact - 1) > 1e-1:
+            self.log.warning(
+                'Potentially inconsistent scales in energy vs. force labels detected (factor ~{:.2f}).'.format(e_fact)
+            )
+        return np.sum(E_ref - E_pred) / E_ref.shape[0]  # train.py:1258
+
+    # ------------------------------------------------------------------ kernel matrix
+    def _assemble_kernel_mat_device(self, R_desc, R_d_desc, tril_perms_lin, sig, col_idxs=None, scale=1.0, ldk=None):
+        """K (or scale*K) assembled into a new CUDA tensor of shape (3NM, ldk); only the first
+        n_cols columns are meaningful.  col_idxs: None | sorted unique int array."""
+        torch = _torch()
+        R_desc = np.ascontiguousarray(R_desc, dtype=np.float64)
+        R_d_desc = np.ascontiguousarray(R_d_desc, dtype=np.float64)
+        tril_perms_lin = np.ascontiguousarray(tril_perms_lin, dtype=np.int64)
+        n_train, dim_d = R_d_desc.shape[:2]
+        n_atoms = int((1 + np.sqrt(8 * dim_d + 1)) / 2)
+        n_perms = len(tril_perms_lin) // dim_d
+        n = n_train * 3 * n_atoms
+        if col_idxs is None:
+            n_cols, cols = n, None
+        else:
+            cols = np.ascontiguousarray(col_idxs, dtype=np.int64)
+            n_cols = len(cols)
+        if ldk is None:
+            ldk = (n_cols + 1) // 2 * 2  # even row stride keeps the DMMA GEMM on its aligned path
+        K = torch.empty((n, ldk), dtype=torch.float64, device='cuda')
+        _lib.check(
+            _lib.lib().sgdml_b200_assemble(
+                _lib.ptr(R_desc),
+                _lib.ptr(R_d_desc),
+                _lib.ptr(tril_perms_lin),
+                n_atoms,
+                n_train,
+                n_perms,
+                float(sig),
+                _lib.ptr(cols),
+                n_cols,
+                float(scale),
+                K.data_ptr(),
+                ldk,
+                _lib.current_stream(),
+            ),
+            'assemble',
+        )
+        return K, n_cols
+
+    def _assemble_kernel_mat(
+        self,
+        R_desc,
+        R_d_desc,
+        tril_perms_lin,
+        sig,
+        desc,
+        use_E_cstr=False,
+        col_idxs=np.s_[:],
+        alloc_extra_rows=0,
+        callback=None,
+    ):
+        """train.py:1260-1535: returns K as a host array of shape (3NM + alloc_extra_rows, n_cols)
+        in the reference's sign convention.  (The analytic path does not use this host copy.)"""
+        if use_E_cstr:
+            raise NotImplementedError('use_E_cstr is out of scope (SURVEY.md section 2 row 22)')
+        n_train, dim_d = R_d_desc.shape[:2]
+        dim_i = 3 * int((1 + np.sqrt(8 * dim_d + 1)) / 2)
+        K_n_rows = n_train * dim_i
+        if isinstance(col_idxs, slice):
+            cols = np.arange(K_n_rows)[col_idxs]
+            if len(cols) == K_n_rows:
+                cols = None
+        else:
+            cols = np.asarray(col_idxs, dtype=np.int64)
+            assert len(cols) == len(set(cols.tolist()))  # train.py:1337
+            assert np.array_equal(cols, np.sort(cols))  # train.py:1341-1345
+        if cols is not None and len(cols) > K_n_rows:
+            raise ValueError('Columns indexed beyond range.')  # train.py:1349-1350
+        if callback is not None:
+            callback(0, 100)
+        start = timeit.default_timer()
+        Kd, n_cols = self._assemble_kernel_mat_device(R_desc, R_d_desc, tril_perms_lin, sig, col_idxs=cols)
+        K = np.empty((K_n_rows + alloc_extra_rows, n_cols))
+        K[:K_n_rows, :] = Kd[:, :n_cols].cpu().numpy()
+        if callback is not None:
+            dur_s = timeit.default_timer() - start
+            callback(1, 1, sec_disp_str='took {:.1f} s'.format(dur_s) if dur_s >= 0.1 else '')
+        return K

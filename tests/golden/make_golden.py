@@ -1,0 +1,110 @@
+"""Generates the golden fixtures under tests/golden/ by running the UNMODIFIED reference
+(stefanch/sGDML v1.0.3, commit a6ae5e8) on seeded synthetic inputs.
+
+The reference ships no tests or golden vectors of its own, so its
+own outputs are the pin.  Run in the build container only (the reference is not on the
+GPU box):
+
+    cp -r /root/reference/sgdml baseline/_ref/          # writable copy (predict.py:1046-1074)
+    PYTHONPATH=baseline/_ref:. python tests/golden/make_golden.py
+
+Each fixture holds the inputs (geometries, labels, perms, sig, lam, query geometries) and
+the reference outputs of every hot-path stage: tril_perms_lin (Desc.perm / train.py:897-904),
+R_desc / R_d_desc (Desc.from_R), K (_assemble_kernel_mat, NumPy engine, 1 process), alphas_F,
+R_d_desc_alpha, std, c (GDMLTrain.train, analytic solver) and E, F (GDMLPredict.predict,
+NumPy engine) on query geometries and on the training geometries.
+"""
+
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, 'baseline', '_ref'))
+
+import importlib.util  # noqa: E402
+
+_spec = importlib.util.spec_from_file_location('synth', os.path.join(ROOT, 'sgdml_b200', 'synth.py'))
+synth = importlib.util.module_from_spec(_spec)
+_spec.loader.exec_module(synth)
+
+import sgdml  # noqa: E402  (the reference)
+from sgdml.predict import GDMLPredict  # noqa: E402
+from sgdml.train import GDMLTrain  # noqa: E402
+from sgdml.utils.desc import Desc  # noqa: E402
+
+assert sgdml.__version__ == '1.0.3'
+
+CASES = {
+    # name: (n_atoms, n_train, n_rotors, n_swaps, sig, n_query)
+    'n9_m16_s6': (9, 16, 1, 1, 20, 12),  # ethanol-like (BASELINE config 1, reduced M)
+    'n5_m10_s1': (5, 10, 0, 0, 10, 6),  # no symmetries
+    'n12_m8_s12': (12, 8, 1, 2, 30, 5),  # larger group, D = 66
+    'n21_m6_s6': (21, 6, 1, 1, 20, 4),  # aspirin-size descriptor (BASELINE config 2, reduced M)
+}
+
+
+def main():
+    gdml_train = GDMLTrain(max_processes=1, use_torch=False)  # one instance per process (train.py:336-342)
+    for name, (N, M, n_rot, n_swap, sig, n_query) in CASES.items():
+        perms = synth.rotor_swap_group(N, n_rot, n_swap)
+        task = synth.make_task(N, M, perms, sig)
+        desc = Desc(N, max_processes=1)
+
+        tril_perms = np.array([Desc.perm(p) for p in task['perms']])
+        tril_perms_lin = (tril_perms + np.arange(len(perms))[:, None] * desc.dim).flatten('F')
+
+        R = task['R_train'].reshape(M, -1)
+        R_desc, R_d_desc = desc.from_R(R, max_processes=1)
+        K = gdml_train._assemble_kernel_mat(R_desc, R_d_desc, tril_perms_lin, sig, desc)
+
+        model = gdml_train.train(task)
+        assert np.array_equal(model['tril_perms_lin'], tril_perms_lin)
+
+        predictor = GDMLPredict(model, max_processes=1, use_torch=False)
+        R_query = synth.geometries(N, n_query, 1).reshape(n_query, -1)
+        E_q, F_q = predictor.predict(R_query)
+        E_t, F_t = predictor.predict(R)
+
+        # K.v identity inputs: a fixed random vector through the reference's matrix
+        rng = np.random.default_rng(5)
+        v = rng.standard_normal(K.shape[0])
+        Kv = K @ v
+
+        out = os.path.join(HERE, name + '.npz')
+        np.savez_compressed(
+            out,
+            reference_version=sgdml.__version__,
+            n_atoms=N,
+            perms=perms,
+            sig=sig,
+            lam=task['lam'],
+            z=task['z'],
+            R_train=task['R_train'],
+            F_train=task['F_train'],
+            E_train=task['E_train'],
+            tril_perms_lin=tril_perms_lin,
+            R_desc=R_desc,
+            R_d_desc=R_d_desc,
+            K=K,
+            alphas_F=model['alphas_F'],
+            R_d_desc_alpha=model['R_d_desc_alpha'],
+            model_R_desc=model['R_desc'],
+            std=model['std'],
+            c=model['c'],
+            R_query=R_query,
+            E_query=E_q,
+            F_query=F_q,
+            E_train_pred=E_t,
+            F_train_pred=F_t,
+            v=v,
+            Kv=Kv,
+        )
+        print(name, 'K', K.shape, 'size %.0f KB' % (os.path.getsize(out) / 1024))
+
+
+if __name__ == '__main__':
+    main()
