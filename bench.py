@@ -1,0 +1,503 @@
+#!/usr/bin/env python
+"""Benchmark of the sGDML hot paths on B200 (contract: see the task's bench.py section).
+
+Metric (BASELINE.json): force predictions/s (the `value`) and K-assembly + solve wall-time
+(the `train` object), on BASELINE config 2 -- synthetic aspirin, 21 atoms, 1000 training
+points, 6 permutations, sigma 20 -- unless --workload says otherwise.
+
+A "step" is one pass of the prediction path over one batch of `--batch` synthetic query
+geometries per GPU.  `value` times K steps with inputs resident in HBM; `e2e` times the same
+steps through the public API ``GDMLPredict.predict`` with HOST buffers (pinned), host<->device
+copies inside the timed region.  The training path (GDMLTrain.train: descriptors, assembly of
+K in HBM, FP64 Cholesky, model, integration constant) runs once on rank 0 before the
+prediction steps, produces the model they use, and is reported under `train`.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl engine|reference]
+    torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+"""
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (config key in sgdml_b200.synth.CONFIGS, BASELINE.json config it stands for)
+    'aspirin': ('aspirin', 'configs[1]: aspirin 21 atoms, 1000 train, 6 perms (synthetic, SURVEY 8d)'),
+    'ethanol': ('ethanol', 'configs[0]: ethanol 9 atoms, 200 train, 6 perms (synthetic, SURVEY 8d)'),
+}
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='engine', choices=['engine', 'reference'])
+    ap.add_argument('--workload', default='aspirin', choices=sorted(WORKLOADS))
+    ap.add_argument('--batch', type=int, default=65536, help='query geometries per GPU per step')
+    ap.add_argument('--n-train', type=int, default=None, help='override the number of training points')
+    ap.add_argument('--no-train', action='store_true', help='skip the training leg (random-coefficient model)')
+    ap.add_argument('--cpu-seconds', type=float, default=15.0, help='target duration of the cpu_baseline sample')
+    ap.add_argument('--ref-batch', type=int, default=None, help='queries per step of the reference arm')
+    return ap.parse_args()
+
+
+# --------------------------------------------------------------------------- clocks
+class ClockSampler(object):
+    """Samples nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+
+    Q = (
+        'index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
+        'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+        'clocks_event_reasons.sw_power_cap'
+    )
+
+    def __init__(self, gpu_index):
+        self.gpu_index = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ['nvidia-smi', '-i', str(self.gpu_index), '--query-gpu=' + self.Q, '--format=csv,noheader,nounits', '-lms', '100'],
+                stdout=subprocess.PIPE,
+                stderr=subprocess.DEVNULL,
+                text=True,
+            )
+            self.thread = threading.Thread(target=self._reader, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _reader(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, power, reasons = [], [], [], set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for r in self.rows:
+            f = [x.strip() for x in r.split(',')]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1]))
+                smax.append(float(f[2]))
+                power.append(float(f[3]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, f[4:8]):
+                if val.lower().startswith('active'):
+                    reasons.add(nm)
+        if not sm:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['no samples']}
+        # "under load": samples in the upper half of the observed power range
+        thr = 0.5 * (max(power) + min(power))
+        load = [s for s, p in zip(sm, power) if p >= thr] or sm
+        return {
+            'sm_mhz': float(np.median(load)),
+            'sm_max_mhz': float(max(smax)),
+            'power_w_max': float(max(power)),
+            'samples': len(sm),
+            'reasons': sorted(reasons),
+        }
+
+
+# --------------------------------------------------------------------------- workload
+def workload_cfg(args):
+    from sgdml_b200 import synth
+
+    cfg = dict(synth.CONFIGS[WORKLOADS[args.workload][0]])
+    if args.n_train is not None:
+        cfg['n_train'] = args.n_train
+    return cfg
+
+
+def algorithmic_flops_per_query(cfg, S):
+    N = cfg['n_atoms']
+    D = N * (N - 1) // 2
+    return 9.0 * cfg['n_train'] * S * D  # W_P = 9 M S D
+
+
+# --------------------------------------------------------------------------- reference arm (CPU)
+def oracle_random_model(cfg, perms):
+    """Random-coefficient model of the workload's shape built with the ORACLE (CPU) code:
+    prediction cost does not depend on the coefficient values."""
+    from oracle import desc as odesc
+    from sgdml_b200 import synth
+
+    N, M = cfg['n_atoms'], cfg['n_train']
+    R = synth.geometries(N, M, 0).reshape(M, -1)
+    rng = np.random.default_rng(99)
+    alphas = rng.standard_normal(M * 3 * N)
+    x, g = odesc.from_R(R)
+    return {
+        'type': 'm',
+        'z': np.ones(N, dtype=np.int64),
+        'R_desc': x.T.copy(),
+        'R_d_desc_alpha': odesc.d_desc_dot_vec(g, alphas.reshape(M, -1)),
+        'alphas_F': alphas,
+        'c': 0.0,
+        'std': 1.0,
+        'sig': cfg['sig'],
+        'lam': 1e-10,
+        'perms': perms,
+        'tril_perms_lin': odesc.tril_perms_lin(perms),
+        'use_E': True,
+    }
+
+
+def cpu_predict_rate(model, cfg, n_queries, n_procs, seed=1):
+    from oracle import predict as opredict
+    from sgdml_b200 import synth
+
+    Rq = synth.geometries(cfg['n_atoms'], n_queries, seed).reshape(n_queries, -1)
+    t0 = time.perf_counter()
+    opredict.predict_parallel(model, Rq, n_procs)
+    return n_queries / (time.perf_counter() - t0)
+
+
+def run_reference(args):
+    """`--impl reference`: the reference's own CPU algorithm for the prediction path (the
+    oracle port of predict.py:84-245, one geometry per worker task like its bulk_mp mode) on all
+    host threads.  Under torchrun only rank 0 works."""
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    from sgdml_b200 import synth
+
+    cfg = workload_cfg(args)
+    perms = synth.rotor_swap_group(cfg['n_atoms'], cfg['n_rotors'], cfg['n_swaps'])
+    model = oracle_random_model(cfg, perms)
+    cores = os.cpu_count() or 1
+    # calibrate the per-step sample so that warmup + steps stay within a few minutes
+    rate1 = cpu_predict_rate(model, cfg, 8, 1)
+    per_step = args.ref_batch or int(max(cores, min(4096, rate1 * cores * 0.5 * 4.0)))  # ~4 s per step
+    for _ in range(args.warmup):
+        cpu_predict_rate(model, cfg, per_step, cores, seed=7)
+    t0 = time.perf_counter()
+    for k in range(args.steps):
+        cpu_predict_rate(model, cfg, per_step, cores, seed=11 + k)
+    dt = time.perf_counter() - t0
+    value = per_step * args.steps / dt
+    S = len(perms)
+    line = {
+        'impl': 'reference',
+        'metric': 'force_predictions_per_s',
+        'value': value,
+        'unit': 'predictions/s',
+        'n_gpus': args.gpus,
+        'steps': args.steps,
+        'warmup': args.warmup,
+        'ms_per_step': 1e3 * dt / args.steps,
+        'higher_is_better': True,
+        'scaling': 'weak',
+        'vs_baseline': None,
+        'dtype': 'f64',
+        'data': 'synthetic',
+        'config': {
+            'workload': WORKLOADS[args.workload][1],
+            'n_atoms': cfg['n_atoms'],
+            'n_train': cfg['n_train'],
+            'n_perms': S,
+            'sig': cfg['sig'],
+            'batch_per_step': per_step,
+        },
+        'cpu_baseline': {
+            'value': value,
+            'unit': 'predictions/s',
+            'cores': cores,
+            'kind': 'port',
+            'sample': '%d steps x %d query geometries, NumPy oracle port, fork pool over all host threads' % (args.steps, per_step),
+        },
+        'e2e': {'value': value, 'unit': 'predictions/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
+    }
+    print(json.dumps(line))
+
+
+# --------------------------------------------------------------------------- engine arm
+def run_engine(args):
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+
+    import sgdml_b200
+    from sgdml_b200 import _lib, synth
+
+    L = _lib.lib()
+    cfg = workload_cfg(args)
+    N, M = cfg['n_atoms'], cfg['n_train']
+    D = N * (N - 1) // 2
+    perms = synth.rotor_swap_group(N, cfg['n_rotors'], cfg['n_swaps'])
+    S = len(perms)
+    n = 3 * N * M
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------- training leg (rank 0), model broadcast to the other ranks
+    train_info = None
+    task = synth.make_task(N, M, perms, cfg['sig'])
+    trainer = sgdml_b200.GDMLTrain()
+    if args.no_train:
+        model = synth.random_model(N, M, perms, cfg['sig'])
+    else:
+        alphas_t = torch.empty(n + 2, dtype=torch.float64, device='cuda')
+        if rank == 0:
+            # warm-up: a small training run (kernel load, context, allocator)
+            trainer.train(synth.make_task(N, min(M, 40), perms, cfg['sig']))
+            torch.cuda.synchronize()
+            L.sgdml_b200_profile_reset()
+            t0 = time.perf_counter()
+            model0 = trainer.train(task)
+            torch.cuda.synchronize()
+            train_s = time.perf_counter() - t0
+            snap = _lib.profile_snapshot()
+            tm = trainer.timings
+            hbm_peak, hbm_src = measured_peak('hbm_gbs', 6650.0)
+            fp64_peak = fp64_peak_tflops(L)
+            asm_bytes = 8.0 * n * n + 8.0 * M * 4 * D
+            train_info = {
+                'metric': 'K-assembly+solve wall-time',
+                'unit': 's',
+                'higher_is_better': False,
+                'n': n,
+                'K_bytes': 8 * n * n,
+                'total_s': train_s,
+                'assemble_s': tm['assemble_s'],
+                'solve_s': tm['solve_s'],
+                'what': 'GDMLTrain.train(task): host R/F/E in -> model dict out (descriptors, K assembly in HBM, '
+                'FP64 Cholesky + 2 triangular solves, R_d_desc_alpha, integration constant)',
+                'gpu_launches': int(sum(v[2] for v in snap.values())),
+                'roofline_assemble': {
+                    'bound': 'hbm',
+                    'achieved': asm_bytes / tm['assemble_s'] * 1e-9,
+                    'peak': hbm_peak,
+                    'unit': 'GB/s',
+                    'frac': asm_bytes / tm['assemble_s'] * 1e-9 / hbm_peak,
+                    'peak_source': hbm_src,
+                    'algorithmic_bytes': asm_bytes,
+                },
+                'roofline_solve': {
+                    'bound': 'fp64-tensor (DMMA)',
+                    'achieved': (n**3 / 3.0) / tm['solve_s'] * 1e-12,
+                    'peak': fp64_peak,
+                    'unit': 'TFLOP/s',
+                    'frac': (n**3 / 3.0) / tm['solve_s'] * 1e-12 / fp64_peak,
+                    'peak_source': 'live DMMA m8n8k4 probe (sgdml_b200_fp64_peak_tflops); MEASURED_PEAKS.json has no FP64 entry',
+                    'algorithmic_flops': n**3 / 3.0,
+                    'note': 'whole solve (potf2 + TRSM strips + DMMA trailing updates + 2 triangular solves) over n^3/3',
+                },
+            }
+            alphas_t[:n] = torch.from_numpy(model0['alphas_F']).cuda()
+            alphas_t[n] = float(model0['c'])
+            alphas_t[n + 1] = float(model0['std'])
+        if world > 1:
+            dist.broadcast(alphas_t, src=0)
+        if rank == 0:
+            model = model0
+        else:
+            host = alphas_t.cpu().numpy()
+            desc = sgdml_b200.desc.Desc(N)
+            R_desc, R_d_desc = desc.from_R(task['R_train'].reshape(M, -1))
+            from sgdml_b200.desc import tril_perms_lin
+
+            model = trainer.create_model(task, 'analytic', R_desc, R_d_desc, tril_perms_lin(perms), float(host[n + 1]), host[:n].copy())
+            model['c'] = float(host[n])
+
+    predictor = sgdml_b200.GDMLPredict(model)
+
+    # ---------------- prediction steps, inputs resident in HBM
+    B = args.batch
+    Rq_host = synth.geometries(N, B, 1 + rank).reshape(B, -1)
+    Rq_dev = torch.from_numpy(Rq_host).cuda()
+    for _ in range(max(args.warmup, 3)):
+        predictor.predict(Rq_dev)
+    L.sgdml_b200_profile_reset()
+    sampler = ClockSampler(local_rank)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        E_dev, F_dev = predictor.predict(Rq_dev)
+    e1.record()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    dt = torch.tensor([e0.elapsed_time(e1) * 1e-3], dtype=torch.float64, device='cuda')
+    if world > 1:
+        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+    dt = float(dt.item())
+    launches_timed = int(sum(v[2] for v in _lib.profile_snapshot().values()))
+    value = world * B * args.steps / dt
+
+    # ---------------- end to end through the public API with pinned HOST buffers
+    R_pin = torch.from_numpy(Rq_host).pin_memory()
+    for _ in range(2):
+        predictor.predict(R_pin)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        E_h, F_h = predictor.predict(R_pin)
+        _ = float(E_h[0])  # the step's result is read on the host
+    torch.cuda.synchronize()
+    dt_e2e = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device='cuda')
+    barrier()
+    if world > 1:
+        dist.all_reduce(dt_e2e, op=dist.ReduceOp.MAX)
+    dt_e2e = float(dt_e2e.item())
+    e2e_value = world * B * args.steps / dt_e2e
+
+    # parity spot check of the benchmarked path (tiny, after the timed regions)
+    assert np.allclose(F_h[:8].numpy(), F_dev[:8].cpu().numpy(), rtol=0, atol=0), 'host and device paths disagree'
+
+    # ---------------- roofline of the dominant kernel (rank 0): device time of k_predict_main
+    roofline = None
+    cpu_baseline = None
+    if rank == 0:
+        L.sgdml_b200_profile_reset()
+        L.sgdml_b200_profile_enable(1)
+        reps = 3
+        for _ in range(reps):
+            predictor.predict(Rq_dev)
+        torch.cuda.synchronize()
+        L.sgdml_b200_profile_enable(0)
+        snap = _lib.profile_snapshot()
+        main_ms, main_scopes, main_launches = snap['predict_main']
+        aux_ms = snap['predict_aux'][0] + snap['desc'][0]
+        flops_step = algorithmic_flops_per_query(cfg, S) * B
+        t_step = main_ms * 1e-3 / reps
+        fp64_peak = fp64_peak_tflops(L)
+        achieved = flops_step / t_step * 1e-12
+        roofline = {
+            'bound': 'tensor',
+            'pipe': 'fp64 tensor pipe (mma.sync.m8n8k4.f64 -> DMMA); tcgen05 has no f64 kind',
+            'kernel': 'k_predict_main',
+            'achieved': achieved,
+            'peak': fp64_peak,
+            'unit': 'TFLOP/s',
+            'frac': achieved / fp64_peak,
+            'peak_source': 'live DMMA m8n8k4 probe (sgdml_b200_fp64_peak_tflops), burst; MEASURED_PEAKS.json carries only HBM and bf16 peaks',
+            'algorithmic_flops_per_step': flops_step,
+            'kernel_ms_per_step': t_step * 1e3,
+            'launches_per_step': main_launches / reps,
+            'kernel_share_of_step': main_ms / max(main_ms + aux_ms, 1e-9),
+            'traffic': None,
+        }
+        if world == 1:
+            cores = os.cpu_count() or 1
+            cmodel = oracle_random_model(cfg, perms)
+            rate1 = cpu_predict_rate(cmodel, cfg, 8, 1)
+            nq = int(max(cores, min(200000, rate1 * cores * 0.5 * args.cpu_seconds)))
+            cpu_predict_rate(cmodel, cfg, cores, cores)  # warm the pool / page in
+            rate = cpu_predict_rate(cmodel, cfg, nq, cores)
+            cpu_baseline = {
+                'value': rate,
+                'unit': 'predictions/s',
+                'cores': cores,
+                'kind': 'port',
+                'sample': '%d query geometries of the same workload, NumPy oracle port of predict.py:84-245, fork pool over all host threads'
+                % nq,
+            }
+
+    if rank == 0:
+        line = {
+            'metric': 'force_predictions_per_s',
+            'value': value,
+            'unit': 'predictions/s',
+            'n_gpus': world,
+            'steps': args.steps,
+            'warmup': max(args.warmup, 3),
+            'ms_per_step': 1e3 * dt / args.steps,
+            'higher_is_better': True,
+            'scaling': 'weak',
+            'vs_baseline': None,
+            'dtype': 'f64',
+            'data': 'synthetic',
+            'config': {
+                'workload': WORKLOADS[args.workload][1],
+                'n_atoms': N,
+                'n_train': M,
+                'n_perms': S,
+                'sig': cfg['sig'],
+                'batch_per_gpu_per_step': B,
+                'parallelism': 'query batch sharded over %d GPU(s), model replicated, no data-path collective' % world,
+                'l2': 'no explicit flush: each step streams %.0f MB of per-row workspace (> 126 MB L2); the %.1f MB model '
+                'is L2-resident by design' % (B * S * 224 * 8 * 2 / 1e6 if D > 160 else B * S * 40 * 8 * 2 / 1e6, 2 * M * D * 8 / 1e6),
+                'model': 'trained by the engine in this run' if not args.no_train else 'random coefficients',
+            },
+            'e2e': {
+                'value': e2e_value,
+                'unit': 'predictions/s',
+                'h2d_bytes_per_step': B * 3 * N * 8,
+                'd2h_bytes_per_step': B * (3 * N + 1) * 8,
+                'what': 'GDMLPredict.predict(pinned host R) -> host E, F; copies inside the timed region',
+            },
+            'gpu_launches': launches_timed,
+            'clocks': clocks,
+            'roofline': roofline,
+            'cpu_baseline': cpu_baseline,
+            'train': train_info,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def measured_peak(key, fallback):
+    path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    try:
+        with open(path) as f:
+            return float(json.load(f)[key]), 'MEASURED_PEAKS.json (%s, of measured)' % key
+    except Exception:
+        return fallback, 'fallback from B200_PROFILING.md (of fallback)'
+
+
+def fp64_peak_tflops(L):
+    import ctypes
+
+    v = ctypes.c_double()
+    rc = L.sgdml_b200_fp64_peak_tflops(ctypes.byref(v))
+    if rc != 0 or not (v.value > 0):
+        raise RuntimeError('fp64 peak probe failed')
+    return v.value
+
+
+def main():
+    args = parse_args()
+    if args.impl == 'reference':
+        run_reference(args)
+    else:
+        run_engine(args)
+
+
+if __name__ == '__main__':
+    main()

@@ -147,6 +147,23 @@ int sgdml_b200_dgemm_nt(int64_t m, int64_t n, int64_t k, double alpha, const dou
                         int64_t lda, const double* B, int64_t ldb, double beta, double* C,
                         int64_t ldc, void* stream);
 
+/* ---------------------------------------------------------------- launch accounting / profiling
+ * Kernel families: 0 predictor main kernel, 1 predictor auxiliary kernels, 2 K assembly,
+ * 3 DMMA GEMM (Cholesky trailing update), 4 potf2 diagonal tiles, 5 panel TRSM strips,
+ * 6 triangular solves, 7 descriptor kernels, 8 misc.
+ * `launches` counts kernel launches per family since the last reset (always on).  With
+ * profiling enabled, the library brackets each family's launches with CUDA events on the
+ * launching stream and accumulates the device time (this synchronises; benchmarks enable it
+ * only for the roofline measurement, never inside a throughput-timed region). */
+int sgdml_b200_profile_enable(int on);
+int sgdml_b200_profile_reset(void);
+int sgdml_b200_profile_get(int family, double* total_ms, int64_t* scopes, int64_t* launches);
+
+/* FP64 tensor-pipe peak of the current device, measured live with a register-resident
+ * mma.sync.m8n8k4.f64 loop (TFLOP/s); the roofline denominator for the FP64 kernels
+ * (MEASURED_PEAKS.json only carries HBM and bf16 numbers). */
+int sgdml_b200_fp64_peak_tflops(double* tflops);
+
 /* Test / tuning hook: selects the GEMM kernel used by dgemm_nt and potrf's trailing update.
  * 0 = 128x128 DMMA tiles (default), 1 = 128x64 DMMA tiles, 2 = scalar FMA reference kernel. */
 int sgdml_b200_set_gemm_variant(int variant);

@@ -51,6 +51,10 @@ SIGNATURES = {
         [i64, i64, i64, C.c_double, c_void_p, i64, c_void_p, i64, C.c_double, c_void_p, i64, c_void_p],
     ),
     'sgdml_b200_set_gemm_variant': (C.c_int, [C.c_int]),
+    'sgdml_b200_profile_enable': (C.c_int, [C.c_int]),
+    'sgdml_b200_profile_reset': (C.c_int, []),
+    'sgdml_b200_profile_get': (C.c_int, [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    'sgdml_b200_fp64_peak_tflops': (C.c_int, [C.POINTER(C.c_double)]),
 }
 
 
@@ -123,3 +127,20 @@ def current_stream():
 def require_gpu():
     if lib().sgdml_b200_device_count() < 1:
         raise EngineError('sgdml_b200: no CUDA device visible; this engine has no CPU fallback')
+
+
+KERNEL_FAMILIES = ['predict_main', 'predict_aux', 'assemble', 'gemm', 'potf2', 'trsm', 'trsv', 'desc', 'misc']
+
+
+def profile_snapshot():
+    """{family: (device_ms_total, timed_scopes, launches)} since the last reset."""
+    out = {}
+    for i, name in enumerate(KERNEL_FAMILIES):
+        ms, sc, ln = C.c_double(), C.c_int64(), C.c_int64()
+        lib().sgdml_b200_profile_get(i, C.byref(ms), C.byref(sc), C.byref(ln))
+        out[name] = (ms.value, sc.value, ln.value)
+    return out
+
+
+def launches_total():
+    return sum(v[2] for v in profile_snapshot().values())

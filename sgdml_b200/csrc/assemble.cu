@@ -391,8 +391,12 @@ extern "C" int sgdml_b200_assemble(const double* R_desc, const double* R_d_desc,
     // rows on grid.y (<= 65535), column tiles on grid.x
     SG_ARG(M <= 65535);
     dim3 grid((unsigned)ceil_div(nJ, TJ), (unsigned)M);
-    k_assemble<<<grid, 256, smem, s>>>(a);
-    SG_CUDA(cudaGetLastError());
+    {
+      ProfScope ps(KID_ASSEMBLE, s);
+      k_assemble<<<grid, 256, smem, s>>>(a);
+      SG_CUDA(cudaGetLastError());
+      count_launch(KID_ASSEMBLE);
+    }
     SG_TRY(sK.finish(s));
     // the integer tables are read by the kernel: wait before freeing them
     SG_CUDA(cudaStreamSynchronize(s));

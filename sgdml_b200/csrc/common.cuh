@@ -65,6 +65,25 @@ inline int ceil_div(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 
 int num_sms();
 
+// ------------------------------------------------------------------ launch accounting / profiling
+// Kernel families (ids of sgdml_b200_profile_get).
+enum KernelId { KID_PREDICT_MAIN = 0, KID_PREDICT_AUX = 1, KID_ASSEMBLE = 2, KID_GEMM = 3, KID_POTF2 = 4,
+                KID_TRSM = 5, KID_TRSV = 6, KID_DESC = 7, KID_MISC = 8, KID_COUNT = 9 };
+void count_launch(int kid, int n = 1);
+// When profiling is enabled, ProfScope records CUDA events around a launch sequence on `s`
+// and adds the elapsed device time to the family's total (synchronises at scope exit).
+bool profiling_enabled();
+class ProfScope {
+ public:
+  ProfScope(int kid, cudaStream_t s);
+  ~ProfScope();
+
+ private:
+  int kid_;
+  cudaStream_t s_;
+  cudaEvent_t e0_ = nullptr, e1_ = nullptr;
+};
+
 // ------------------------------------------------------------------ device helpers
 #ifdef __CUDACC__
 

@@ -85,9 +85,62 @@ int num_sms() {
   return cached[dev];
 }
 
+// ---- launch accounting / profiling
+static long long g_launches[KID_COUNT] = {0};
+static double g_prof_ms[KID_COUNT] = {0};
+static long long g_prof_n[KID_COUNT] = {0};
+static int g_prof_enabled = 0;
+
+void count_launch(int kid, int n) {
+  if (kid >= 0 && kid < KID_COUNT) g_launches[kid] += n;
+}
+bool profiling_enabled() { return g_prof_enabled != 0; }
+
+ProfScope::ProfScope(int kid, cudaStream_t s) : kid_(kid), s_(s) {
+  if (!g_prof_enabled) return;
+  if (cudaEventCreate(&e0_) != cudaSuccess || cudaEventCreate(&e1_) != cudaSuccess) {
+    e0_ = e1_ = nullptr;
+    return;
+  }
+  cudaEventRecord(e0_, s_);
+}
+ProfScope::~ProfScope() {
+  if (e0_ == nullptr || e1_ == nullptr) return;
+  cudaEventRecord(e1_, s_);
+  if (cudaEventSynchronize(e1_) == cudaSuccess) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, e0_, e1_) == cudaSuccess) {
+      g_prof_ms[kid_] += ms;
+      g_prof_n[kid_] += 1;
+    }
+  }
+  cudaEventDestroy(e0_);
+  cudaEventDestroy(e1_);
+}
+
 }  // namespace sgdml
 
 extern "C" {
+
+int sgdml_b200_profile_enable(int on) {
+  sgdml::g_prof_enabled = on;
+  return 0;
+}
+int sgdml_b200_profile_reset(void) {
+  for (int i = 0; i < sgdml::KID_COUNT; ++i) {
+    sgdml::g_prof_ms[i] = 0;
+    sgdml::g_prof_n[i] = 0;
+    sgdml::g_launches[i] = 0;
+  }
+  return 0;
+}
+int sgdml_b200_profile_get(int kid, double* total_ms, int64_t* scopes, int64_t* launches) {
+  if (kid < 0 || kid >= sgdml::KID_COUNT) return SGDML_B200_ERR_ARG;
+  if (total_ms) *total_ms = sgdml::g_prof_ms[kid];
+  if (scopes) *scopes = sgdml::g_prof_n[kid];
+  if (launches) *launches = sgdml::g_launches[kid];
+  return 0;
+}
 
 int sgdml_b200_abi_version(void) { return SGDML_B200_ABI_VERSION; }
 

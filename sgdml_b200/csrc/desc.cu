@@ -84,8 +84,10 @@ int launch_desc_from_R(const double* R, int64_t n_geo, int n_atoms, double* R_de
   if (n_geo == 0) return 0;
   const int D = n_atoms * (n_atoms - 1) / 2;
   int64_t total = n_geo * D;
+  ProfScope ps(KID_DESC, s);
   k_desc_from_R<<<ceil_div(total, 256), 256, 0, s>>>(R, n_geo, n_atoms, D, R_desc, R_d_desc);
   SG_CUDA(cudaGetLastError());
+  count_launch(KID_DESC);
   return 0;
 }
 
@@ -96,6 +98,7 @@ int launch_d_desc_dot_vec(const double* R_d_desc, const double* vecs, int64_t n_
   int64_t total = n_geo * D;
   k_d_desc_dot_vec<<<ceil_div(total, 256), 256, 0, s>>>(R_d_desc, vecs, n_geo, n_atoms, D, out, out_stride);
   SG_CUDA(cudaGetLastError());
+  count_launch(KID_DESC);
   return 0;
 }
 
@@ -106,6 +109,7 @@ int launch_vec_dot_d_desc(const double* R_d_desc, const double* vecs, int64_t n_
   int64_t total = n_geo * 3 * n_atoms;
   k_vec_dot_d_desc<<<ceil_div(total, 256), 256, 0, s>>>(R_d_desc, vecs, n_geo, n_atoms, D, vec_stride, out);
   SG_CUDA(cudaGetLastError());
+  count_launch(KID_DESC);
   return 0;
 }
 

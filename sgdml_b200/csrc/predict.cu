@@ -558,16 +558,25 @@ int run_queries(sgdml_b200_model* m, const double* xq, const double* gq, int64_t
   a.n_rows = n_geo * m->S;
   a.G = m->ws_G;
   a.Erow = m->ws_Erow;
-  SG_TRY(launch_main(m->cfg, a, s));
-  k_predict_finish<<<(unsigned)n_geo, 128, sizeof(double) * m->D, s>>>(m->ws_G, m->ws_Erow, gq, m->perm, m->N, m->D,
-                                                                        m->DP, m->S, std, c, E_dev, F_dev);
-  SG_CUDA(cudaGetLastError());
+  {
+    ProfScope ps(KID_PREDICT_MAIN, s);
+    SG_TRY(launch_main(m->cfg, a, s));
+    count_launch(KID_PREDICT_MAIN);
+  }
+  {
+    ProfScope ps(KID_PREDICT_AUX, s);
+    k_predict_finish<<<(unsigned)n_geo, 128, sizeof(double) * m->D, s>>>(m->ws_G, m->ws_Erow, gq, m->perm, m->N, m->D,
+                                                                          m->DP, m->S, std, c, E_dev, F_dev);
+    SG_CUDA(cudaGetLastError());
+    count_launch(KID_PREDICT_AUX);
+  }
   return 0;
 }
 
 int refresh_row_dots(sgdml_b200_model* m, bool with_mm, cudaStream_t s) {
   k_row_dots<<<ceil_div(m->Mpad, 8), 256, 0, s>>>(m->Xc, m->JA, m->Mpad, m->DS, with_mm ? m->mm : nullptr, m->xja);
   SG_CUDA(cudaGetLastError());
+  count_launch(KID_PREDICT_AUX);
   return 0;
 }
 
@@ -736,6 +745,7 @@ int sgdml_b200_model_set_alphas(sgdml_b200_model* m, const double* alphas_F, voi
   k_set_alphas<<<ceil_div(tot, 256), 256, 0, s>>>(m->R_d_desc, (const double*)sA.dev(), m->M, m->D, m->N, m->DS,
                                                   m->JA);
   SG_CUDA(cudaGetLastError());
+  count_launch(KID_PREDICT_AUX);
   SG_TRY(refresh_row_dots(m, false, s));
   if (sA.staged()) SG_CUDA(cudaStreamSynchronize(s));
   return 0;

@@ -219,8 +219,10 @@ static int launch_gemm_t(const GemmArgs& a, cudaStream_t s) {
   else
     blocks = ntm * ntn;
   if (blocks == 0) return 0;
+  ProfScope ps(KID_GEMM, s);
   k_gemm_nt<G><<<(unsigned)blocks, G::NT, G::SMEM_BYTES, s>>>(a);
   SG_CUDA(cudaGetLastError());
+  count_launch(KID_GEMM);
   return 0;
 }
 
@@ -234,8 +236,10 @@ int launch_gemm(const GemmArgs& a, cudaStream_t s) {
   if (a.m <= 0 || a.n <= 0) return 0;
   if (g_gemm_variant == 2 || !gemm_fast_ok(a)) {
     dim3 grid((unsigned)((a.n + 127) / 128), (unsigned)std::min<int64_t>(a.m, 65535));
+    ProfScope ps(KID_GEMM, s);
     k_gemm_nt_naive<<<grid, 128, 0, s>>>(a);
     SG_CUDA(cudaGetLastError());
+    count_launch(KID_GEMM);
     return 0;
   }
   if (g_gemm_variant == 1) return launch_gemm_t<GTall>(a, s);
@@ -477,6 +481,25 @@ __global__ void k_negate_copy(const double* __restrict__ src, double* __restrict
   if (i < n) dst[i] = -src[i];
 }
 
+// FP64 tensor-pipe peak probe: 8 independent accumulator pairs per warp, register operands only
+__global__ void __launch_bounds__(256) k_dmma_peak(double* out, int iters, double a, double b) {
+  double c0[8], c1[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    c0[i] = i;
+    c1[i] = -i;
+  }
+  const double ra = a + threadIdx.x * 1e-12, rb = b;
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) dmma884(c0[i], c1[i], ra, rb);
+  }
+  double s = 0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s += c0[i] + c1[i];
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
 // ---------------------------------------------------------------------- host drivers (device pointers)
 int potrf_device(double* A, int64_t n, int64_t lda, int* info_host, cudaStream_t s) {
   int* d_info = nullptr;
@@ -495,12 +518,20 @@ int potrf_device(double* A, int64_t n, int64_t lda, int* info_host, cudaStream_t
     SG_CUDA(cudaFuncSetAttribute(k_trsm_strip, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)trsm_smem));
     for (int64_t k0 = 0; k0 < n; k0 += NB) {
       const int kb = (int)std::min<int64_t>(NB, n - k0);
-      k_potf2_tile<<<1, 512, potf2_smem, s>>>(A + k0 * lda + k0, lda, kb, k0, d_info);
-      SG_CUDA(cudaGetLastError());
+      {
+        ProfScope ps(KID_POTF2, s);
+        k_potf2_tile<<<1, 512, potf2_smem, s>>>(A + k0 * lda + k0, lda, kb, k0, d_info);
+        SG_CUDA(cudaGetLastError());
+        count_launch(KID_POTF2);
+      }
       const int64_t rem = n - k0 - kb;
       if (rem <= 0) break;
-      k_trsm_strip<<<(unsigned)((rem + RS - 1) / RS), 256, trsm_smem, s>>>(A, lda, k0, kb, n, W, d_info);
-      SG_CUDA(cudaGetLastError());
+      {
+        ProfScope ps(KID_TRSM, s);
+        k_trsm_strip<<<(unsigned)((rem + RS - 1) / RS), 256, trsm_smem, s>>>(A, lda, k0, kb, n, W, d_info);
+        SG_CUDA(cudaGetLastError());
+        count_launch(KID_TRSM);
+      }
       GemmArgs g;
       g.m = rem;
       g.n = rem;
@@ -529,6 +560,8 @@ int potrf_device(double* A, int64_t n, int64_t lda, int* info_host, cudaStream_t
 }
 
 int potrs_device(const double* L, int64_t n, int64_t lda, double* B, int64_t nrhs, int64_t ldb, cudaStream_t s) {
+  ProfScope ps(KID_TRSV, s);
+  count_launch(KID_TRSV, (int)(4 * ((n + NB - 1) / NB) - 2));
   const size_t smem = sizeof(double) * (NB * (NB + 1) + NB);
   SG_CUDA(cudaFuncSetAttribute(k_trsv_diag, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   SG_CUDA(cudaFuncSetAttribute(k_trsv_diag1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -614,6 +647,7 @@ int sgdml_b200_solve_analytic(double* Kneg, int64_t n, int64_t lda, double lam, 
   double* K = (double*)sK.dev();
   k_add_diag<<<ceil_div(n, 256), 256, 0, s>>>(K, n, lda, lam);  // analytic.py:82
   SG_CUDA(cudaGetLastError());
+  count_launch(KID_MISC, 2);
   int info = 0;
   SG_TRY(potrf_device(K, n, lda, &info, s));  // analytic.py:94-96
   if (info > 0) {
@@ -666,6 +700,34 @@ int sgdml_b200_dgemm_nt(int64_t m, int64_t n, int64_t k, double alpha, const dou
   SG_TRY(launch_gemm(g, s));
   SG_TRY(sC.finish(s));
   if (sA.staged() || sB.staged() || sC.staged()) SG_CUDA(cudaStreamSynchronize(s));
+  return 0;
+}
+
+int sgdml_b200_fp64_peak_tflops(double* tflops) {
+  SG_TRY(require_device());
+  SG_ARG(tflops != nullptr);
+  double* out = nullptr;
+  const int grid = num_sms() * 4, iters = 1 << 14;
+  SG_CUDA(cudaMalloc(&out, sizeof(double) * (size_t)grid * 256));
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  double best = 0.0;
+  for (int rep = 0; rep < 5; ++rep) {
+    cudaEventRecord(e0, 0);
+    k_dmma_peak<<<grid, 256>>>(out, iters, 1.0000001, 1e-9);
+    cudaEventRecord(e1, 0);
+    cudaEventSynchronize(e1);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    const double tf = 2.0 * 256.0 * 8.0 * iters * 8.0 * grid / (ms * 1e-3) * 1e-12;
+    if (rep > 0 && tf > best) best = tf;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(out);
+  SG_CUDA(cudaGetLastError());
+  *tflops = best;
   return 0;
 }
 

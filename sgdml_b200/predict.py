@@ -145,7 +145,8 @@ class GDMLPredict(object):
     def predict(self, R=None, return_E=True):
         """predict.py:1146-1294.  R (B, 3N) [or (3N,)] float64 -> (E (B,), F (B, 3N)) or (F,).
         With R=None the cached training descriptors are evaluated (predict.py:1219-1235).
-        NumPy in -> NumPy out; CUDA torch tensor in -> CUDA torch tensors out (no copies)."""
+        NumPy in -> NumPy out; torch tensor in (CUDA, or pinned/pageable host) -> torch tensors out on the
+        same device (CUDA tensors are used in place, no copies)."""
         L = _lib.lib()
         dim_i = 3 * self.n_atoms
         if R is None:
@@ -167,9 +168,9 @@ class GDMLPredict(object):
             R = np.ascontiguousarray(R, dtype=np.float64)
             if R.ndim == 1:
                 R = R[None, :]  # predict.py:1183-1184
-            R = R.reshape(R.shape[0], -1)
-            if R.shape[1] != dim_i:
+            if R.size % dim_i != 0 or (R.ndim == 2 and R.shape[1] != dim_i):
                 raise ValueError('R must have 3*n_atoms columns')
+            R = R.reshape(-1, dim_i)
             n = R.shape[0]
             F = np.empty((n, dim_i))
             E = np.empty(n) if return_E else None
@@ -180,8 +181,9 @@ class GDMLPredict(object):
                 raise ValueError('torch inputs must be float64')
             R = R.contiguous().reshape(-1, dim_i) if R.dim() != 1 else R.contiguous().reshape(1, dim_i)
             n = R.shape[0]
-            F = torch.empty((n, dim_i), dtype=torch.float64, device=R.device)
-            E = torch.empty((n,), dtype=torch.float64, device=R.device) if return_E else None
+            pin = (not R.is_cuda) and R.is_pinned()  # pinned host tensor in -> pinned host tensors out
+            F = torch.empty((n, dim_i), dtype=torch.float64, device=R.device, pin_memory=pin)
+            E = torch.empty((n,), dtype=torch.float64, device=R.device, pin_memory=pin) if return_E else None
         _lib.check(
             L.sgdml_b200_predict(self._handle, _lib.ptr(R), n, _lib.ptr(E), _lib.ptr(F), _lib.current_stream()),
             'predict',

@@ -1,0 +1,384 @@
+"""GPU parity tests proper: every hot-path entry point of the C ABI against the oracle and
+against the reference's golden outputs.  Tolerances: integer work bit-exact; floating point
+far inside the 1e-6 relative bound of BASELINE.json's north_star (stated per test)."""
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+from conftest import golden_model, golden_task, rel_err  # noqa: E402
+
+import oracle  # noqa: E402,F401
+from oracle import assemble as oassemble  # noqa: E402
+from oracle import desc as odesc  # noqa: E402
+from oracle import predict as opredict  # noqa: E402
+from oracle import solve as osolve  # noqa: E402
+from oracle import train as otrain  # noqa: E402
+
+
+@pytest.fixture(scope='module')
+def eng():
+    import sgdml_b200
+    from sgdml_b200 import _lib
+
+    _lib.require_gpu()
+    return sgdml_b200
+
+
+def _oracle_model(N, M, perms, sig, seed=0, alpha_scale=1.0):
+    """Random-coefficient model built with the ORACLE's descriptor code (no GPU involved)."""
+    from sgdml_b200 import synth
+
+    R = synth.geometries(N, M, seed).reshape(M, -1)
+    rng = np.random.default_rng(seed + 99)
+    alphas = alpha_scale * rng.standard_normal(M * 3 * N)
+    x, g = odesc.from_R(R)
+    return (
+        {
+            'type': 'm',
+            'z': np.ones(N, dtype=np.int64),
+            'R_desc': x.T.copy(),
+            'R_d_desc_alpha': odesc.d_desc_dot_vec(g, alphas.reshape(M, -1)),
+            'alphas_F': alphas,
+            'c': 0.37,
+            'std': 1.7,
+            'sig': sig,
+            'lam': 1e-10,
+            'perms': np.asarray(perms, dtype=np.int64),
+            'tril_perms_lin': odesc.tril_perms_lin(perms),
+            'use_E': True,
+        },
+        x,
+        g,
+    )
+
+
+# --------------------------------------------------------------------------- representation
+def test_tril_perms_lin_bit_exact(eng, golden):
+    from sgdml_b200.desc import Desc, tril_perms_lin
+
+    out = tril_perms_lin(golden['perms'])
+    assert out.dtype == np.int64
+    assert np.array_equal(out, golden['tril_perms_lin'])
+    D = golden['R_desc'].shape[1]
+    for p_idx, p in enumerate(golden['perms']):
+        assert np.array_equal(Desc.perm(p), golden['tril_perms_lin'].reshape(D, -1)[:, p_idx] - p_idx * D)
+
+
+def test_descriptor_golden(eng, golden):
+    from sgdml_b200.desc import Desc
+
+    N = int(golden['n_atoms'])
+    M = golden['R_train'].shape[0]
+    d = Desc(N)
+    x, g = d.from_R(golden['R_train'].reshape(M, -1))
+    assert rel_err(x, golden['R_desc']) < 1e-14
+    assert rel_err(g, golden['R_d_desc']) < 1e-14
+    # single geometry returns (D,), (D, 3) like desc.py:329-330
+    x1, g1 = d.from_R(golden['R_train'][0].reshape(-1))
+    assert x1.shape == (d.dim,) and g1.shape == (d.dim, 3)
+    rng = np.random.default_rng(1)
+    v = rng.standard_normal((M, 3 * N))
+    assert rel_err(d.d_desc_dot_vec(golden['R_d_desc'], v), odesc.d_desc_dot_vec(golden['R_d_desc'], v)) < 1e-13
+    w = rng.standard_normal((M, d.dim))
+    assert rel_err(d.vec_dot_d_desc(golden['R_d_desc'], w), odesc.vec_dot_d_desc(golden['R_d_desc'], w)) < 1e-13
+
+
+# --------------------------------------------------------------------------- predictor
+def test_predict_golden(eng, golden):
+    """E, F within 1e-6 rel of the reference NumPy path (north_star); we demand 1e-10."""
+    p = eng.GDMLPredict(golden_model(golden))
+    E, F = p.predict(golden['R_query'])
+    assert rel_err(F, golden['F_query']) < 1e-10
+    assert rel_err(E, golden['E_query']) < 1e-10
+    M = golden['R_train'].shape[0]
+    E, F = p.predict(golden['R_train'].reshape(M, -1))  # self terms (delta = 0)
+    assert rel_err(F, golden['F_train_pred']) < 1e-10
+    assert rel_err(E, golden['E_train_pred']) < 1e-10
+    (F2,) = p.predict(golden['R_query'][0], return_E=False)  # 1-D input gets a leading axis
+    assert F2.shape == (1, golden['R_query'].shape[1])
+    assert rel_err(F2[0], golden['F_query'][0]) < 1e-10
+
+
+@pytest.mark.parametrize(
+    'N,M,rot,swap,sig',
+    [
+        (3, 5, 1, 0, 5),  # D = 3, S = 3
+        (4, 70, 0, 2, 10),  # D = 6, S = 4, M not a multiple of any tile
+        (9, 200, 1, 1, 20),  # BASELINE config 1 shape
+        (12, 33, 1, 2, 30),  # D = 66 -> DP 72
+        (15, 40, 2, 0, 30),  # D = 105 -> DP 112
+        (18, 21, 1, 1, 40),  # D = 153 -> DP 160
+        (21, 50, 1, 1, 20),  # BASELINE config 2 descriptor, D = 210 -> DP 224
+        (23, 19, 0, 1, 20),  # D = 253 -> DP 256
+    ],
+)
+def test_predict_vs_oracle_shapes(eng, N, M, rot, swap, sig):
+    from sgdml_b200 import synth
+
+    perms = synth.rotor_swap_group(N, rot, swap)
+    model, _, _ = _oracle_model(N, M, perms, sig, seed=N)
+    B = 37
+    Rq = synth.geometries(N, B, 1).reshape(B, -1)
+    E_ref, F_ref = opredict.Predictor(model).predict(Rq)
+    p = eng.GDMLPredict(model)
+    E, F = p.predict(Rq)
+    assert rel_err(F, F_ref) < 1e-10
+    assert rel_err(E, E_ref) < 1e-10
+
+
+def test_predict_torch_device_tensors(eng):
+    import torch
+    from sgdml_b200 import synth
+
+    N, M = 9, 64
+    perms = synth.rotor_swap_group(N, 1, 1)
+    model, _, _ = _oracle_model(N, M, perms, 20)
+    Rq = synth.geometries(N, 300, 1).reshape(300, -1)
+    p = eng.GDMLPredict(model)
+    E_h, F_h = p.predict(Rq)
+    E_d, F_d = p.predict(torch.from_numpy(Rq).cuda())
+    assert E_d.is_cuda and F_d.is_cuda
+    assert np.array_equal(E_d.cpu().numpy(), E_h) and np.array_equal(F_d.cpu().numpy(), F_h)
+
+
+def test_permutation_equivariance(eng):
+    """F(R[:, p, :]) == F(R)[:, p, :] and E invariant for every perm of the model group."""
+    from sgdml_b200 import synth
+
+    N, M = 9, 50
+    perms = synth.rotor_swap_group(N, 1, 1)
+    model, _, _ = _oracle_model(N, M, perms, 20)
+    p = eng.GDMLPredict(model)
+    R = synth.geometries(N, 8, 3)
+    E0, F0 = p.predict(R.reshape(8, -1))
+    for pm in perms:
+        E1, F1 = p.predict(R[:, pm, :].reshape(8, -1))
+        assert rel_err(E1, E0) < 1e-12
+        assert rel_err(F1.reshape(8, N, 3), F0.reshape(8, N, 3)[:, pm, :]) < 1e-11
+
+
+def test_force_is_minus_energy_gradient(eng):
+    from sgdml_b200 import synth
+
+    N, M = 6, 30
+    perms = synth.rotor_swap_group(N, 1, 0)
+    model, _, _ = _oracle_model(N, M, perms, 10)
+    p = eng.GDMLPredict(model)
+    R = synth.geometries(N, 1, 4).reshape(1, -1)
+    _, F = p.predict(R)
+    h = 1e-5
+    Rp = np.repeat(R, 6 * N, axis=0)
+    for k in range(3 * N):
+        Rp[2 * k, k] += h
+        Rp[2 * k + 1, k] -= h
+    E, _ = p.predict(Rp)
+    grad = (E[0::2] - E[1::2]) / (2 * h)
+    assert rel_err(-grad, F[0]) < 1e-7
+
+
+def test_kv_identity_and_set_alphas(eng, golden):
+    """K @ v == predict_train(alphas = v) (iterative.py:183-204), via set_R_d_desc / set_alphas."""
+    m = golden_model(golden)
+    p = eng.GDMLPredict(m)
+    p.set_R_desc(golden['R_desc'])
+    p.set_R_d_desc(golden['R_d_desc'])
+    p.set_alphas(golden['v'])
+    Kv = p.kmatvec_train().ravel()
+    assert rel_err(Kv, golden['Kv']) < 1e-10
+    ja = p.get_R_d_desc_alpha()
+    N = int(golden['n_atoms'])
+    assert rel_err(ja, odesc.d_desc_dot_vec(golden['R_d_desc'], golden['v'].reshape(-1, 3 * N))) < 1e-13
+    # a slice of training points
+    M = golden['R_desc'].shape[0]
+    part = p.kmatvec_train(1, M - 1).ravel()
+    assert rel_err(part, golden['Kv'][3 * N : (M - 1) * 3 * N]) < 1e-10
+    # back to the trained coefficients: predict() with R=None == reference prediction on training points
+    p.set_alphas(golden['alphas_F'])
+    E, F = p.predict()
+    assert rel_err(F, golden['F_train_pred']) < 1e-10
+    assert rel_err(E, golden['E_train_pred']) < 1e-10
+
+
+def test_predict_empty_and_errors(eng, golden):
+    p = eng.GDMLPredict(golden_model(golden))
+    N = int(golden['n_atoms'])
+    E, F = p.predict(np.empty((0, 3 * N)))
+    assert E.shape == (0,) and F.shape == (0, 3 * N)
+    with pytest.raises(ValueError):
+        p.predict(np.zeros((2, 3 * N + 1)))
+    with pytest.raises(RuntimeError):
+        eng.GDMLPredict(golden_model(golden)).predict()  # no cached training descriptors
+    bad = golden_model(golden)
+    bad['type'] = 'd'
+    with pytest.raises(ValueError):
+        eng.GDMLPredict(bad)
+
+
+# --------------------------------------------------------------------------- assembly
+def test_assemble_golden(eng, golden):
+    from sgdml_b200.desc import Desc
+
+    N = int(golden['n_atoms'])
+    t = eng.GDMLTrain()
+    K = t._assemble_kernel_mat(golden['R_desc'], golden['R_d_desc'], golden['tril_perms_lin'], int(golden['sig']), Desc(N))
+    assert K.shape == golden['K'].shape
+    assert rel_err(K, golden['K']) < 1e-12
+    assert rel_err(K, K.T) < 1e-13  # symmetric
+
+
+def test_assemble_col_subsets(eng, golden):
+    from sgdml_b200.desc import Desc
+
+    N = int(golden['n_atoms'])
+    n = golden['K'].shape[0]
+    t = eng.GDMLTrain()
+    args = (golden['R_desc'], golden['R_d_desc'], golden['tril_perms_lin'], int(golden['sig']), Desc(N))
+    K = t._assemble_kernel_mat(*args, col_idxs=np.s_[: 2 * 3 * N])  # block-boundary slice (train.py:1357-1374)
+    assert rel_err(K, golden['K'][:, : 6 * N]) < 1e-12
+    cols = np.unique(np.random.default_rng(0).integers(0, n, size=23))  # index list (train.py:1376-1407)
+    K = t._assemble_kernel_mat(*args, col_idxs=cols, alloc_extra_rows=5)
+    assert K.shape == (n + 5, len(cols))
+    assert rel_err(K[:n], golden['K'][:, cols]) < 1e-12
+
+
+@pytest.mark.parametrize('N,M,rot,swap,sig', [(3, 4, 1, 0, 5), (7, 9, 1, 1, 15), (10, 5, 2, 1, 20)])
+def test_assemble_vs_oracle(eng, N, M, rot, swap, sig):
+    from sgdml_b200 import synth
+    from sgdml_b200.desc import Desc
+
+    perms = synth.rotor_swap_group(N, rot, swap)
+    R = synth.geometries(N, M, 2).reshape(M, -1)
+    x, g = odesc.from_R(R)
+    lin = odesc.tril_perms_lin(perms)
+    K_ref = oassemble.assemble(x, g, lin, sig)
+    K = eng.GDMLTrain()._assemble_kernel_mat(x, g, lin, sig, Desc(N))
+    assert rel_err(K, K_ref) < 1e-12
+
+
+# --------------------------------------------------------------------------- dense solve
+@pytest.mark.parametrize('variant', [0, 1, 2])
+@pytest.mark.parametrize('m,n,k', [(128, 128, 128), (300, 200, 64), (257, 129, 130), (64, 1000, 16), (33, 17, 7)])
+def test_dgemm_nt(eng, variant, m, n, k):
+    from sgdml_b200 import _lib
+
+    L = _lib.lib()
+    rng = np.random.default_rng(m + n + k)
+    A = rng.standard_normal((m, k))
+    B = rng.standard_normal((n, k))
+    C = rng.standard_normal((m, n))
+    ref = 0.75 * A @ B.T - 1.25 * C
+    L.sgdml_b200_set_gemm_variant(variant)
+    try:
+        _lib.check(L.sgdml_b200_dgemm_nt(m, n, k, 0.75, _lib.ptr(A), k, _lib.ptr(B), k, -1.25, _lib.ptr(C), n, None), 'dgemm')
+    finally:
+        L.sgdml_b200_set_gemm_variant(0)
+    assert rel_err(C, ref) < 1e-13
+
+
+@pytest.mark.parametrize('variant', [0, 1])
+@pytest.mark.parametrize('n', [64, 128, 200, 513, 1400])
+def test_potrf_potrs(eng, variant, n):
+    import scipy.linalg
+    from sgdml_b200 import _lib
+
+    L = _lib.lib()
+    rng = np.random.default_rng(n)
+    X = rng.standard_normal((n, n + 20))
+    A = X @ X.T + 1e-3 * np.eye(n)
+    b = rng.standard_normal((n, 3))
+    Af = A.copy()
+    L.sgdml_b200_set_gemm_variant(variant)
+    try:
+        _lib.check(L.sgdml_b200_potrf(_lib.ptr(Af), n, n, None), 'potrf')
+    finally:
+        L.sgdml_b200_set_gemm_variant(0)
+    Lg = np.tril(Af)
+    Lr = scipy.linalg.cholesky(A, lower=True)
+    assert rel_err(Lg, Lr) < 1e-10
+    assert rel_err(Lg @ Lg.T, A) < 1e-13
+    x = b.copy()
+    _lib.check(L.sgdml_b200_potrs(_lib.ptr(Af), n, n, _lib.ptr(x), 3, 3, None), 'potrs')
+    assert rel_err(A @ x, b) < 1e-9
+    x1 = np.ascontiguousarray(b[:, 0])
+    _lib.check(L.sgdml_b200_potrs(_lib.ptr(Af), n, n, _lib.ptr(x1), 1, 1, None), 'potrs')
+    assert rel_err(x1, x[:, 0]) < 1e-12
+
+
+def test_potrf_not_positive_definite(eng):
+    from sgdml_b200 import _lib
+
+    n = 300
+    rng = np.random.default_rng(0)
+    X = rng.standard_normal((n, n))
+    A = X @ X.T + np.eye(n)
+    A[170, 170] = -1.0  # leading minor of order 171 fails
+    rc = _lib.lib().sgdml_b200_potrf(_lib.ptr(A.copy()), n, n, None)
+    assert rc == 171
+    with pytest.raises(np.linalg.LinAlgError, match='not positive definite'):
+        _lib.check(rc, 'potrf')
+
+
+def test_solve_analytic_golden(eng, golden):
+    """alphas = -(-K + lam I)^-1 y (analytic.py:65-99) from the reference's own K."""
+    from sgdml_b200 import _lib
+
+    task = golden_task(golden)
+    y, _ = otrain.labels(task)
+    n = golden['K'].shape[0]
+    Kneg = -golden['K'].copy()
+    alphas = np.empty(n)
+    _lib.check(
+        _lib.lib().sgdml_b200_solve_analytic(_lib.ptr(Kneg), n, n, float(golden['lam']), _lib.ptr(y), _lib.ptr(alphas), None),
+        'solve_analytic',
+    )
+    # the system has cond ~1e11: compare the residual and the predictions, not alphas digit by digit
+    A = -golden['K'] + float(golden['lam']) * np.eye(n)
+    assert np.linalg.norm(A @ (-alphas) - y) < 1e-9 * np.linalg.norm(y)
+    assert rel_err(alphas, golden['alphas_F']) < 1e-3
+
+
+# --------------------------------------------------------------------------- end to end
+def test_train_end_to_end_golden(eng, golden):
+    """GDMLTrain.train(task) -> model -> GDMLPredict.predict == reference train + predict within 1e-6."""
+    task = golden_task(golden)
+    model = eng.GDMLTrain().train(task)
+    assert np.array_equal(model['tril_perms_lin'], golden['tril_perms_lin'])
+    assert model['R_desc'].shape == golden['model_R_desc'].shape  # (D, M) transposed layout
+    assert rel_err(model['R_desc'], golden['model_R_desc']) < 1e-14
+    assert abs(model['std'] - float(golden['std'])) < 1e-13
+    assert abs(model['c'] - float(golden['c'])) < 1e-6 * max(1.0, abs(float(golden['c'])))
+    p = eng.GDMLPredict(model)
+    E, F = p.predict(golden['R_query'])
+    assert rel_err(F, golden['F_query']) < 1e-6
+    assert rel_err(E, golden['E_query']) < 1e-6
+
+
+def test_train_ethanol_config_vs_oracle(eng):
+    """BASELINE config 1 (9 atoms, 200 training points, 6 perms): engine-trained model vs
+    oracle-trained model, predictions on 100 query geometries within 1e-6."""
+    from sgdml_b200 import synth
+
+    task = synth.make_config_task('ethanol')
+    model = eng.GDMLTrain().train(task)
+    ref = otrain.train(task)
+    Rq = synth.geometries(9, 100, 1).reshape(100, -1)
+    E_ref, F_ref = opredict.Predictor(ref).predict(Rq)
+    E, F = eng.GDMLPredict(model).predict(Rq)
+    assert rel_err(F, F_ref) < 1e-6
+    assert rel_err(E, E_ref) < 1e-6
+
+
+def test_model_npz_roundtrip(eng, golden, tmp_path):
+    """The model dict survives np.savez_compressed / np.load like the reference's (cli.py:1098, io.py:404)."""
+    task = golden_task(golden)
+    model = eng.GDMLTrain().train(task)
+    path = tmp_path / 'model.npz'
+    np.savez_compressed(path, **model)
+    with np.load(path, allow_pickle=True) as f:
+        loaded = {k: f[k] for k in f.files}
+    assert str(loaded['type']) == 'm' and loaded['R_desc'].shape == model['R_desc'].shape
+    E0, F0 = eng.GDMLPredict(model).predict(golden['R_query'])
+    E1, F1 = eng.GDMLPredict(loaded).predict(golden['R_query'])
+    assert np.array_equal(F0, F1) and np.array_equal(E0, E1)
