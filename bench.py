@@ -36,6 +36,14 @@ WORKLOADS = {
 }
 
 
+T0 = time.perf_counter()
+
+
+def log(msg):
+    sys.stderr.write('[bench %7.1fs] %s\n' % (time.perf_counter() - T0, msg))
+    sys.stderr.flush()
+
+
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
@@ -47,6 +55,7 @@ def parse_args():
     ap.add_argument('--n-train', type=int, default=None, help='override the number of training points')
     ap.add_argument('--no-train', action='store_true', help='skip the training leg (random-coefficient model)')
     ap.add_argument('--cpu-seconds', type=float, default=15.0, help='target duration of the cpu_baseline sample')
+    ap.add_argument('--no-cpu-baseline', action='store_true', help='skip the cpu_baseline leg (profiling runs)')
     ap.add_argument('--ref-batch', type=int, default=None, help='queries per step of the reference arm')
     return ap.parse_args()
 
@@ -165,14 +174,25 @@ def oracle_random_model(cfg, perms):
     }
 
 
-def cpu_predict_rate(model, cfg, n_queries, n_procs, seed=1):
-    from oracle import predict as opredict
-    from sgdml_b200 import synth
+class CpuPredictor(object):
+    """The CPU arm: oracle port of predict.py:84-245 on a persistent pool over the host threads."""
 
-    Rq = synth.geometries(cfg['n_atoms'], n_queries, seed).reshape(n_queries, -1)
-    t0 = time.perf_counter()
-    opredict.predict_parallel(model, Rq, n_procs)
-    return n_queries / (time.perf_counter() - t0)
+    def __init__(self, model, cfg, n_procs):
+        from oracle import predict as opredict
+
+        self.cfg = cfg
+        self.pp = opredict.ParallelPredictor(model, n_procs)
+
+    def rate(self, n_queries, seed=1):
+        from sgdml_b200 import synth
+
+        Rq = synth.geometries(self.cfg['n_atoms'], n_queries, seed).reshape(n_queries, -1)
+        t0 = time.perf_counter()
+        self.pp.predict(Rq)
+        return n_queries / (time.perf_counter() - t0)
+
+    def close(self):
+        self.pp.close()
 
 
 def run_reference(args):
@@ -188,15 +208,18 @@ def run_reference(args):
     perms = synth.rotor_swap_group(cfg['n_atoms'], cfg['n_rotors'], cfg['n_swaps'])
     model = oracle_random_model(cfg, perms)
     cores = os.cpu_count() or 1
-    # calibrate the per-step sample so that warmup + steps stay within a few minutes
-    rate1 = cpu_predict_rate(model, cfg, 8, 1)
-    per_step = args.ref_batch or int(max(cores, min(4096, rate1 * cores * 0.5 * 4.0)))  # ~4 s per step
+    cpu = CpuPredictor(model, cfg, cores)
+    # calibrate the per-step sample (~4 s per step) so that warmup + steps stay within a few minutes
+    cpu.rate(cores, seed=3)  # spin the pool up
+    rate_probe = cpu.rate(4 * cores, seed=5)
+    per_step = args.ref_batch or int(max(cores, min(200000, rate_probe * 4.0)))
     for _ in range(args.warmup):
-        cpu_predict_rate(model, cfg, per_step, cores, seed=7)
+        cpu.rate(per_step, seed=7)
     t0 = time.perf_counter()
     for k in range(args.steps):
-        cpu_predict_rate(model, cfg, per_step, cores, seed=11 + k)
+        cpu.rate(per_step, seed=11 + k)
     dt = time.perf_counter() - t0
+    cpu.close()
     value = per_step * args.steps / dt
     S = len(perms)
     line = {
@@ -226,7 +249,7 @@ def run_reference(args):
             'unit': 'predictions/s',
             'cores': cores,
             'kind': 'port',
-            'sample': '%d steps x %d query geometries, NumPy oracle port, fork pool over all host threads' % (args.steps, per_step),
+            'sample': '%d steps x %d query geometries, NumPy oracle port, process pool over all host threads (1 BLAS thread each)' % (args.steps, per_step),
         },
         'e2e': {'value': value, 'unit': 'predictions/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
@@ -272,13 +295,16 @@ def run_engine(args):
         alphas_t = torch.empty(n + 2, dtype=torch.float64, device='cuda')
         if rank == 0:
             # warm-up: a small training run (kernel load, context, allocator)
+            log('warm-up training run')
             trainer.train(synth.make_task(N, min(M, 40), perms, cfg['sig']))
+            log('timed training run: n = %d' % n)
             torch.cuda.synchronize()
             L.sgdml_b200_profile_reset()
             t0 = time.perf_counter()
             model0 = trainer.train(task)
             torch.cuda.synchronize()
             train_s = time.perf_counter() - t0
+            log('training done in %.3f s (%s)' % (train_s, trainer.timings))
             snap = _lib.profile_snapshot()
             tm = trainer.timings
             hbm_peak, hbm_src = measured_peak('hbm_gbs', 6650.0)
@@ -333,6 +359,7 @@ def run_engine(args):
             model['c'] = float(host[n])
 
     predictor = sgdml_b200.GDMLPredict(model)
+    log('predictor ready; batch %d' % args.batch)
 
     # ---------------- prediction steps, inputs resident in HBM
     B = args.batch
@@ -358,6 +385,7 @@ def run_engine(args):
     dt = float(dt.item())
     launches_timed = int(sum(v[2] for v in _lib.profile_snapshot().values()))
     value = world * B * args.steps / dt
+    log('device-resident steps done: %.3e predictions/s' % value)
 
     # ---------------- end to end through the public API with pinned HOST buffers
     R_pin = torch.from_numpy(Rq_host).pin_memory()
@@ -375,6 +403,7 @@ def run_engine(args):
         dist.all_reduce(dt_e2e, op=dist.ReduceOp.MAX)
     dt_e2e = float(dt_e2e.item())
     e2e_value = world * B * args.steps / dt_e2e
+    log('e2e steps done: %.3e predictions/s' % e2e_value)
 
     # parity spot check of the benchmarked path (tiny, after the timed regions)
     assert np.allclose(F_h[:8].numpy(), F_dev[:8].cpu().numpy(), rtol=0, atol=0), 'host and device paths disagree'
@@ -412,19 +441,24 @@ def run_engine(args):
             'kernel_share_of_step': main_ms / max(main_ms + aux_ms, 1e-9),
             'traffic': None,
         }
-        if world == 1:
+        log('roofline probe done')
+        if world == 1 and not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
             cmodel = oracle_random_model(cfg, perms)
-            rate1 = cpu_predict_rate(cmodel, cfg, 8, 1)
-            nq = int(max(cores, min(200000, rate1 * cores * 0.5 * args.cpu_seconds)))
-            cpu_predict_rate(cmodel, cfg, cores, cores)  # warm the pool / page in
-            rate = cpu_predict_rate(cmodel, cfg, nq, cores)
+            cpu = CpuPredictor(cmodel, cfg, cores)
+            cpu.rate(cores, seed=3)  # spin the pool up
+            rate_probe = cpu.rate(4 * cores, seed=5)
+            nq = int(max(cores, min(400000, rate_probe * args.cpu_seconds)))
+            log('cpu baseline: %d queries on %d threads (probe rate %.1f/s)' % (nq, cores, rate_probe))
+            rate = cpu.rate(nq)
+            cpu.close()
+            log('cpu baseline done: %.1f predictions/s' % rate)
             cpu_baseline = {
                 'value': rate,
                 'unit': 'predictions/s',
                 'cores': cores,
                 'kind': 'port',
-                'sample': '%d query geometries of the same workload, NumPy oracle port of predict.py:84-245, fork pool over all host threads'
+                'sample': '%d query geometries of the same workload, NumPy oracle port of predict.py:84-245, process pool over all host threads (1 BLAS thread each)'
                 % nq,
             }
 

@@ -99,6 +99,12 @@ _WKR_PRED = None
 
 def _mp_init(model):
     global _WKR_PRED
+    try:  # one BLAS thread per worker process: the pool itself covers the host threads
+        from threadpoolctl import threadpool_limits
+
+        threadpool_limits(limits=1)
+    except Exception:
+        pass
     _WKR_PRED = Predictor(model)
 
 
@@ -106,13 +112,40 @@ def _mp_predict(R_chunk):
     return _WKR_PRED.predict(R_chunk)
 
 
+class ParallelPredictor(object):
+    """Bulk prediction over all host threads -- the reference's ``bulk_mp`` mode
+    (predict.py:1237-1257): a pool of worker processes, whole geometries per task.  The pool is
+    created with the ``spawn`` start method (safe after CUDA initialisation in the parent)."""
+
+    def __init__(self, model, n_procs):
+        self.n_procs = max(int(n_procs), 1)
+        self.pool = None
+        if self.n_procs > 1:
+            self.pool = mp.get_context('spawn').Pool(self.n_procs, initializer=_mp_init, initargs=(model,))
+        else:
+            self.single = Predictor(model)
+
+    def predict(self, R):
+        R = np.asarray(R, dtype=np.float64)
+        if self.pool is None:
+            return self.single.predict(R)
+        n_chunks = max(1, min(len(R), self.n_procs * 4))
+        res = self.pool.map(_mp_predict, np.array_split(R, n_chunks), chunksize=1)
+        return np.concatenate([r[0] for r in res]), np.concatenate([r[1] for r in res])
+
+    def close(self):
+        if self.pool is not None:
+            self.pool.close()
+            self.pool.join()
+            self.pool = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+
 def predict_parallel(model, R, n_procs):
-    """Bulk prediction over all host cores: the reference's ``bulk_mp`` mode
-    (predict.py:1237-1257) -- one whole geometry per worker task."""
-    R = np.asarray(R, dtype=np.float64)
-    if n_procs <= 1:
-        return Predictor(model).predict(R)
-    chunks = np.array_split(R, min(len(R), n_procs * 4))
-    with mp.get_context('fork').Pool(n_procs, initializer=_mp_init, initargs=(model,)) as pool:
-        res = pool.map(_mp_predict, chunks)
-    return np.concatenate([r[0] for r in res]), np.concatenate([r[1] for r in res])
+    with ParallelPredictor(model, n_procs) as pp:
+        return pp.predict(R)
