@@ -163,6 +163,9 @@ int sgdml_b200_profile_get(int family, double* total_ms, int64_t* scopes, int64_
  * mma.sync.m8n8k4.f64 loop (TFLOP/s); the roofline denominator for the FP64 kernels
  * (MEASURED_PEAKS.json only carries HBM and bf16 numbers). */
 int sgdml_b200_fp64_peak_tflops(double* tflops);
+/* Same probe held for `seconds` (<= 30); reports the second half: the sustained figure for
+ * kernels timed inside a long step (clocks settle under the power cap). */
+int sgdml_b200_fp64_peak_tflops_sustained(double seconds, double* tflops);
 
 /* Test / tuning hook: selects the GEMM kernel used by dgemm_nt and potrf's trailing update.
  * 0 = 128x128 DMMA tiles (default), 1 = 128x64 DMMA tiles, 2 = scalar FMA reference kernel. */

@@ -55,6 +55,7 @@ SIGNATURES = {
     'sgdml_b200_profile_reset': (C.c_int, []),
     'sgdml_b200_profile_get': (C.c_int, [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     'sgdml_b200_fp64_peak_tflops': (C.c_int, [C.POINTER(C.c_double)]),
+    'sgdml_b200_fp64_peak_tflops_sustained': (C.c_int, [C.c_double, C.POINTER(C.c_double)]),
 }
 
 

@@ -29,8 +29,9 @@
 namespace sgdml {
 
 // ============================================================== tile configuration
-template <int DP_, int BQ_, int BM_, int W1Q_, int W1M_, int W1K_, int W2Q_, int W2D_>
+template <int DP_, int BQ_, int BM_, int W1Q_, int W1M_, int W1K_, int W2Q_, int W2D_, int MINB_ = 1>
 struct PCfg {
+  static constexpr int MINB = MINB_;    // CTAs per SM the kernel is compiled for
   static constexpr int DP = DP_;        // padded descriptor size (multiple of 8)
   static constexpr int DS = DP_ + 4;    // row stride of Q / Xc / JA tiles (== 4 or 12 mod 16: conflict-free DMMA frags)
   static constexpr int BQ = BQ_;        // virtual query rows per CTA
@@ -87,7 +88,7 @@ struct PredictArgs {
 
 // ============================================================== main kernel
 template <class C>
-__global__ void __launch_bounds__(256, 1) k_predict_main(const PredictArgs p) {
+__global__ void __launch_bounds__(256, C::MINB) k_predict_main(const PredictArgs p) {
   extern __shared__ __align__(128) double smem[];
   double* Qs = smem + C::OFF_Q;
   double* Xs = smem + C::OFF_X;
@@ -464,7 +465,9 @@ struct sgdml_b200_model {
 namespace {
 
 // tile configurations: <DP, BQ, BM, W1Q, W1M, W1K, W2Q, W2D>
-using Cfg40 = PCfg<40, 128, 32, 4, 2, 1, 8, 1>;
+// D <= 40: two co-resident CTAs per SM so that one CTA's transform / barriers / prologue overlap
+// the other's DMMA phases (the sweep over M is only a handful of tiles at ethanol size)
+using Cfg40 = PCfg<40, 64, 32, 4, 2, 1, 8, 1, 2>;
 using Cfg72 = PCfg<72, 64, 32, 4, 2, 1, 8, 1>;
 using Cfg112 = PCfg<112, 64, 16, 4, 1, 2, 4, 2>;
 using Cfg160 = PCfg<160, 32, 16, 2, 1, 4, 2, 4>;
@@ -474,7 +477,7 @@ using Cfg256 = PCfg<256, 32, 8, 2, 1, 4, 2, 4>;
 struct CfgInfo {
   int DP, BQ, BM;
 };
-const CfgInfo kCfgs[] = {{40, 128, 32}, {72, 64, 32}, {112, 64, 16}, {160, 32, 16}, {224, 32, 16}, {256, 32, 8}};
+const CfgInfo kCfgs[] = {{40, 64, 32}, {72, 64, 32}, {112, 64, 16}, {160, 32, 16}, {224, 32, 16}, {256, 32, 8}};
 const int kNumCfgs = 6;
 
 template <class C>

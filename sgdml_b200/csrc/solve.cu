@@ -62,13 +62,21 @@ __global__ void __launch_bounds__(256) k_gemm_nt(const GemmArgs p) {
   // ---- tile coordinates
   int64_t ti, tj;
   if (p.tri) {
+    // L2-friendly rasterisation of the lower triangle: super-tiles of GS x GS row tiles are
+    // enumerated in triangular order, tiles inside a super-tile row-major, so that the ~148
+    // co-resident CTAs share a small set of A and B operand panels.
     constexpr int r = G::BM / G::BN;
-    const int64_t b = blockIdx.x;
-    int64_t t = (int64_t)((sqrt(8.0 * (double)b / r + 1.0) - 1.0) * 0.5);
-    while (r * (t + 1) * (t + 2) / 2 <= b) ++t;
-    while (r * t * (t + 1) / 2 > b) --t;
-    ti = t;
-    tj = b - r * t * (t + 1) / 2;
+    constexpr int GS = 8;
+    constexpr int PER = GS * GS * r;
+    const int64_t sb = blockIdx.x / PER;
+    const int local = (int)(blockIdx.x - sb * PER);
+    int64_t t = (int64_t)((sqrt(8.0 * (double)sb + 1.0) - 1.0) * 0.5);
+    while ((t + 1) * (t + 2) / 2 <= sb) ++t;
+    while (t * (t + 1) / 2 > sb) --t;
+    const int64_t sj = sb - t * (t + 1) / 2;
+    ti = t * GS + local / (GS * r);
+    tj = sj * GS * r + local % (GS * r);
+    if (tj * G::BN >= (ti + 1) * G::BM) return;  // strictly above the diagonal
   } else {
     const int64_t ntn = (p.n + G::BN - 1) / G::BN;
     ti = blockIdx.x / ntn;
@@ -214,9 +222,10 @@ static int launch_gemm_t(const GemmArgs& a, cudaStream_t s) {
   }
   int64_t blocks;
   const int64_t ntm = (a.m + G::BM - 1) / G::BM, ntn = (a.n + G::BN - 1) / G::BN;
-  if (a.tri)
-    blocks = (int64_t)(G::BM / G::BN) * ntm * (ntm + 1) / 2;
-  else
+  if (a.tri) {
+    const int64_t sr = (ntm + 7) / 8;
+    blocks = sr * (sr + 1) / 2 * 64 * (G::BM / G::BN);
+  } else
     blocks = ntm * ntn;
   if (blocks == 0) return 0;
   ProfScope ps(KID_GEMM, s);
@@ -249,50 +258,88 @@ int launch_gemm(const GemmArgs& a, cudaStream_t s) {
 // ====================================================================== potf2 on one tile
 // Factorises the nb x nb (nb <= 128) diagonal block at A (row stride lda) in shared memory.
 // info: set to (k0 + j + 1) if the pivot j is not positive (LAPACK dpotrf convention).
-__global__ void __launch_bounds__(512) k_potf2_tile(double* __restrict__ A, int64_t lda, int nb, int64_t k0,
-                                                    int* __restrict__ info) {
-  extern __shared__ double T[];  // nb x (NB+1)
-  constexpr int LD = NB + 1;
-  if (*info != 0) return;
-  const int tid = threadIdx.x, nt = blockDim.x;
-  for (int idx = tid; idx < nb * nb; idx += nt) {
-    const int i = idx / nb, j = idx - i * nb;
-    T[i * LD + j] = (j <= i) ? A[(int64_t)i * lda + j] : 0.0;
-  }
+// Register-resident right-looking factorisation: thread (ty, tx) of a 32 x 32 grid owns the
+// 4 x 4 elements (ty + 32a, tx + 32b); per column only the pivot column travels through shared
+// memory (double buffered -> one barrier per column).
+__global__ void __launch_bounds__(1024) k_potf2_tile(double* __restrict__ A, int64_t lda, int nb, int64_t k0,
+                                                     int* __restrict__ info) {
+  __shared__ double colbuf[2][NB];
   __shared__ int bad;
+  if (*info != 0) return;
+  const int tid = threadIdx.x;
+  const int tx = tid & 31, ty = tid >> 5;
+  double a[4][4];
+#pragma unroll
+  for (int ai = 0; ai < 4; ++ai)
+#pragma unroll
+    for (int bi = 0; bi < 4; ++bi) {
+      const int i = ty + 32 * ai, l = tx + 32 * bi;
+      a[ai][bi] = (i < nb && l <= i) ? A[(int64_t)i * lda + l] : 0.0;
+    }
   if (tid == 0) bad = 0;
   __syncthreads();
-  for (int j = 0; j < nb; ++j) {
-    const double ajj = T[j * LD + j];
-    if (!(ajj > 0.0)) {  // also catches NaN
-      if (tid == 0) bad = j + 1;
-      break;  // uniform: every thread reads the same ajj
-    }
-    const double d = sqrt(ajj);
-    const double dinv = 1.0 / d;
-    __syncthreads();  // everyone has read ajj before it is overwritten
-    for (int i = j + 1 + tid; i < nb; i += nt) T[i * LD + j] *= dinv;
-    if (tid == 0) T[j * LD + j] = d;
-    __syncthreads();
-    const int rem = nb - j - 1;
-    for (int idx = tid; idx < rem * rem; idx += nt) {
-      const int ii = idx / rem, ll = idx - ii * rem;
-      if (ll <= ii) {
-        const int i = j + 1 + ii, l = j + 1 + ll;
-        T[i * LD + l] = fma(-T[i * LD + j], T[l * LD + j], T[i * LD + l]);
+  bool failed = false;
+#pragma unroll
+  for (int bj = 0; bj < 4; ++bj) {
+    if (failed) break;
+    for (int jj = 0; jj < 32; ++jj) {
+      const int j = bj * 32 + jj;
+      if (j >= nb) break;
+      double* cb = colbuf[j & 1];
+      if (tx == jj) {  // owners of column j publish it (raw values)
+#pragma unroll
+        for (int ai = 0; ai < 4; ++ai) {
+          const int i = ty + 32 * ai;
+          if (i >= j && i < nb) cb[i] = a[ai][bj];
+        }
+      }
+      __syncthreads();
+      const double ajj = cb[j];
+      if (!(ajj > 0.0)) {  // not positive definite (also catches NaN); uniform across the CTA
+        if (tid == 0) bad = j + 1;
+        failed = true;
+        break;
+      }
+      const double d = sqrt(ajj);
+      const double dinv = 1.0 / d;
+      double ci[4], cl[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int i = ty + 32 * q, l = tx + 32 * q;
+        ci[q] = (i > j && i < nb) ? cb[i] * dinv : 0.0;
+        cl[q] = (l > j && l < nb) ? cb[l] * dinv : 0.0;
+      }
+#pragma unroll
+      for (int ai = 0; ai < 4; ++ai)
+#pragma unroll
+        for (int bi = 0; bi < 4; ++bi) {
+          const int i = ty + 32 * ai, l = tx + 32 * bi;
+          if (l > j && l <= i) a[ai][bi] = fma(-ci[ai], cl[bi], a[ai][bi]);
+        }
+      if (tx == jj) {  // finalise column j in the owners' registers
+#pragma unroll
+        for (int ai = 0; ai < 4; ++ai) {
+          const int i = ty + 32 * ai;
+          if (i == j)
+            a[ai][bj] = d;
+          else if (i > j)
+            a[ai][bj] *= dinv;
+        }
       }
     }
-    __syncthreads();
   }
   __syncthreads();
   if (bad != 0) {
     if (tid == 0) *info = (int)(k0 + bad);
     return;
   }
-  for (int idx = tid; idx < nb * nb; idx += nt) {
-    const int i = idx / nb, j = idx - i * nb;
-    if (j <= i) A[(int64_t)i * lda + j] = T[i * LD + j];
-  }
+#pragma unroll
+  for (int ai = 0; ai < 4; ++ai)
+#pragma unroll
+    for (int bi = 0; bi < 4; ++bi) {
+      const int i = ty + 32 * ai, l = tx + 32 * bi;
+      if (i < nb && l <= i) A[(int64_t)i * lda + l] = a[ai][bi];
+    }
 }
 
 // ====================================================================== panel TRSM strips
@@ -302,7 +349,7 @@ __global__ void __launch_bounds__(512) k_potf2_tile(double* __restrict__ A, int6
 constexpr int RS = 64;   // rows per strip
 constexpr int SB = 32;   // substitution block
 __global__ void __launch_bounds__(256) k_trsm_strip(double* __restrict__ A, int64_t lda, int64_t k0, int kb,
-                                                    int64_t n, double* __restrict__ W,
+                                                    int64_t n, double* __restrict__ W, int64_t ldw, int wcol,
                                                     const int* __restrict__ info) {
   extern __shared__ __align__(16) double tsm[];
   constexpr int LD = NB + 4;  // == 4 mod 16: conflict-free DMMA fragment loads
@@ -372,7 +419,7 @@ __global__ void __launch_bounds__(256) k_trsm_strip(double* __restrict__ A, int6
     if (i < rows && j < kb) {
       const double v = X[i * LD + j];
       P[(int64_t)i * lda + j] = v;
-      W[(r0 + i) * NB + j] = -v;
+      W[(r0 + i) * ldw + wcol + j] = -v;
     }
   }
 }
@@ -409,37 +456,62 @@ __global__ void __launch_bounds__(128) k_trsv_diag(const double* __restrict__ A,
   }
 }
 
-// single right-hand side: cooperative substitution by one CTA (nb <= 128), the common case
-__global__ void __launch_bounds__(128) k_trsv_diag1(const double* __restrict__ A, int64_t lda, int64_t k0, int nb,
+// single right-hand side (the common case): the CTA stages the diagonal block in shared memory,
+// then ONE warp runs the substitution with the solution in registers (4 entries per lane) and
+// warp shuffles for the pivot broadcast -- no block-wide barrier per column.
+__global__ void __launch_bounds__(256) k_trsv_diag1(const double* __restrict__ A, int64_t lda, int64_t k0, int nb,
                                                     double* __restrict__ b, int64_t ldb, int backward) {
-  extern __shared__ double Ls[];  // nb x (NB+1) + nb
+  extern __shared__ double Ls[];  // NB x (NB+1)
   constexpr int LD = NB + 1;
-  double* x = Ls + NB * LD;
   const double* Lkk = A + k0 * lda + k0;
   const int tid = threadIdx.x;
-  for (int idx = tid; idx < nb * nb; idx += blockDim.x) {
-    const int i = idx / nb, j = idx - i * nb;
-    Ls[i * LD + j] = (j <= i) ? Lkk[(int64_t)i * lda + j] : 0.0;
+  for (int idx = tid; idx < NB * NB; idx += blockDim.x) {
+    const int i = idx / NB, j = idx - i * NB;
+    Ls[i * LD + j] = (i < nb && j <= i) ? Lkk[(int64_t)i * lda + j] : ((i == j) ? 1.0 : 0.0);
   }
-  if (tid < nb) x[tid] = b[(k0 + tid) * ldb];
   __syncthreads();
+  if (tid >= 32) return;
+  const int lane = tid;
+  double x[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int i = lane + 32 * q;
+    x[q] = (i < nb) ? b[(k0 + i) * ldb] : 0.0;
+  }
   if (!backward) {
-    // column-oriented: after x_j is final, eliminate it from the rows below
-    for (int j = 0; j < nb; ++j) {
-      if (tid == j) x[j] = x[j] / Ls[j * LD + j];
-      __syncthreads();
-      if (tid > j && tid < nb) x[tid] = fma(-Ls[tid * LD + j], x[j], x[tid]);
-      __syncthreads();
+#pragma unroll
+    for (int qj = 0; qj < 4; ++qj) {
+      for (int jj = 0; jj < 32; ++jj) {
+        const int j = qj * 32 + jj;
+        const double xj = __shfl_sync(0xffffffffu, x[qj], jj) / Ls[j * LD + j];
+        if (lane == jj) x[qj] = xj;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int i = lane + 32 * q;
+          if (i > j) x[q] = fma(-Ls[i * LD + j], xj, x[q]);
+        }
+      }
     }
   } else {
-    for (int j = nb - 1; j >= 0; --j) {
-      if (tid == j) x[j] = x[j] / Ls[j * LD + j];
-      __syncthreads();
-      if (tid < j) x[tid] = fma(-Ls[j * LD + tid], x[j], x[tid]);
-      __syncthreads();
+#pragma unroll
+    for (int qj = 3; qj >= 0; --qj) {
+      for (int jj = 31; jj >= 0; --jj) {
+        const int j = qj * 32 + jj;
+        const double xj = __shfl_sync(0xffffffffu, x[qj], jj) / Ls[j * LD + j];
+        if (lane == jj) x[qj] = xj;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int i = lane + 32 * q;
+          if (i < j) x[q] = fma(-Ls[j * LD + i], xj, x[q]);
+        }
+      }
     }
   }
-  if (tid < nb) b[(k0 + tid) * ldb] = x[tid];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int i = lane + 32 * q;
+    if (i < nb) b[(k0 + i) * ldb] = x[q];
+  }
 }
 
 // forward update: B[k0+nb:, :] -= L[k0+nb:, k0:k0+nb] * B[k0:k0+nb, :]   (one warp per row)
@@ -501,53 +573,84 @@ __global__ void __launch_bounds__(256) k_dmma_peak(double* out, int iters, doubl
 }
 
 // ---------------------------------------------------------------------- host drivers (device pointers)
+// Two-level blocking: inner panels of NB = 128 columns (potf2 tile + substitution strips), whose
+// trailing update is applied eagerly only inside the current outer block of NBO columns; the rest
+// of the matrix receives ONE lazy update per outer block with k = NBO, so every C tile is read and
+// written n/NBO times instead of n/NB times and the GEMM prologue/epilogue is amortised over 4x
+// more math.
+constexpr int NBO = 512;
+
 int potrf_device(double* A, int64_t n, int64_t lda, int* info_host, cudaStream_t s) {
   int* d_info = nullptr;
   double* W = nullptr;
   SG_CUDA(cudaMalloc(&d_info, sizeof(int)));
-  cudaError_t e = cudaMalloc(&W, sizeof(double) * (size_t)n * NB);
+  cudaError_t e = cudaMalloc(&W, sizeof(double) * (size_t)n * NBO);
   if (e != cudaSuccess) {
     cudaFree(d_info);
     return fail_cuda(e, "cudaMalloc(panel workspace)", __FILE__, __LINE__);
   }
   auto body = [&]() -> int {
     SG_CUDA(cudaMemsetAsync(d_info, 0, sizeof(int), s));
-    const size_t potf2_smem = sizeof(double) * NB * (NB + 1);
     const size_t trsm_smem = sizeof(double) * (NB + RS) * (NB + 4);
-    SG_CUDA(cudaFuncSetAttribute(k_potf2_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)potf2_smem));
     SG_CUDA(cudaFuncSetAttribute(k_trsm_strip, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)trsm_smem));
-    for (int64_t k0 = 0; k0 < n; k0 += NB) {
-      const int kb = (int)std::min<int64_t>(NB, n - k0);
-      {
-        ProfScope ps(KID_POTF2, s);
-        k_potf2_tile<<<1, 512, potf2_smem, s>>>(A + k0 * lda + k0, lda, kb, k0, d_info);
-        SG_CUDA(cudaGetLastError());
-        count_launch(KID_POTF2);
+    for (int64_t K0 = 0; K0 < n; K0 += NBO) {
+      const int64_t K1 = std::min<int64_t>(K0 + NBO, n);  // end of the outer block
+      for (int64_t k0 = K0; k0 < K1; k0 += NB) {
+        const int kb = (int)std::min<int64_t>(NB, n - k0);
+        {
+          ProfScope ps(KID_POTF2, s);
+          k_potf2_tile<<<1, 1024, 0, s>>>(A + k0 * lda + k0, lda, kb, k0, d_info);
+          SG_CUDA(cudaGetLastError());
+          count_launch(KID_POTF2);
+        }
+        const int64_t rem = n - k0 - kb;
+        if (rem <= 0) break;
+        {
+          ProfScope ps(KID_TRSM, s);
+          k_trsm_strip<<<(unsigned)((rem + RS - 1) / RS), 256, trsm_smem, s>>>(A, lda, k0, kb, n, W, NBO,
+                                                                              (int)(k0 - K0), d_info);
+          SG_CUDA(cudaGetLastError());
+          count_launch(KID_TRSM);
+        }
+        const int64_t cols_in = K1 - (k0 + kb);  // columns of the outer block still to be factorised
+        if (cols_in > 0) {
+          GemmArgs g;
+          g.m = rem;
+          g.n = cols_in;
+          g.k = kb;
+          g.A = W + (k0 + kb) * NBO + (k0 - K0);  // -X
+          g.lda = NBO;
+          g.B = A + (k0 + kb) * lda + k0;  // X rows of the outer block
+          g.ldb = lda;
+          g.C = A + (k0 + kb) * lda + (k0 + kb);
+          g.ldc = lda;
+          g.alpha = 1.0;
+          g.beta = 1.0;
+          g.mode = 1;
+          g.tri = 0;
+          g.abort_flag = d_info;
+          SG_TRY(launch_gemm(g, s));
+        }
       }
-      const int64_t rem = n - k0 - kb;
-      if (rem <= 0) break;
-      {
-        ProfScope ps(KID_TRSM, s);
-        k_trsm_strip<<<(unsigned)((rem + RS - 1) / RS), 256, trsm_smem, s>>>(A, lda, k0, kb, n, W, d_info);
-        SG_CUDA(cudaGetLastError());
-        count_launch(KID_TRSM);
+      const int64_t rem = n - K1;
+      if (rem > 0) {
+        GemmArgs g;
+        g.m = rem;
+        g.n = rem;
+        g.k = K1 - K0;
+        g.A = W + K1 * NBO;  // -X, all panels of the outer block
+        g.lda = NBO;
+        g.B = A + K1 * lda + K0;
+        g.ldb = lda;
+        g.C = A + K1 * lda + K1;
+        g.ldc = lda;
+        g.alpha = 1.0;
+        g.beta = 1.0;
+        g.mode = 1;
+        g.tri = 1;
+        g.abort_flag = d_info;
+        SG_TRY(launch_gemm(g, s));
       }
-      GemmArgs g;
-      g.m = rem;
-      g.n = rem;
-      g.k = kb;
-      g.A = W + (k0 + kb) * NB;  // -X
-      g.lda = NB;
-      g.B = A + (k0 + kb) * lda + k0;  // X
-      g.ldb = lda;
-      g.C = A + (k0 + kb) * lda + (k0 + kb);
-      g.ldc = lda;
-      g.alpha = 1.0;
-      g.beta = 1.0;
-      g.mode = 1;
-      g.tri = 1;
-      g.abort_flag = d_info;
-      SG_TRY(launch_gemm(g, s));
     }
     SG_CUDA(cudaMemcpyAsync(info_host, d_info, sizeof(int), cudaMemcpyDeviceToHost, s));
     SG_CUDA(cudaStreamSynchronize(s));
@@ -569,7 +672,7 @@ int potrs_device(const double* L, int64_t n, int64_t lda, double* B, int64_t nrh
   for (int64_t k0 = 0; k0 < n; k0 += NB) {
     const int nb = (int)std::min<int64_t>(NB, n - k0);
     if (nrhs == 1)
-      k_trsv_diag1<<<1, 128, smem, s>>>(L, lda, k0, nb, B, ldb, 0);
+      k_trsv_diag1<<<1, 256, smem, s>>>(L, lda, k0, nb, B, ldb, 0);
     else
       k_trsv_diag<<<(unsigned)std::min<int64_t>((nrhs + 127) / 128, 1024), 128, smem, s>>>(L, lda, k0, nb, B, nrhs, ldb,
                                                                                           0);
@@ -585,7 +688,7 @@ int potrs_device(const double* L, int64_t n, int64_t lda, double* B, int64_t nrh
   for (int64_t k0 = last; k0 >= 0; k0 -= NB) {
     const int nb = (int)std::min<int64_t>(NB, n - k0);
     if (nrhs == 1)
-      k_trsv_diag1<<<1, 128, smem, s>>>(L, lda, k0, nb, B, ldb, 1);
+      k_trsv_diag1<<<1, 256, smem, s>>>(L, lda, k0, nb, B, ldb, 1);
     else
       k_trsv_diag<<<(unsigned)std::min<int64_t>((nrhs + 127) / 128, 1024), 128, smem, s>>>(L, lda, k0, nb, B, nrhs, ldb,
                                                                                           1);
@@ -728,6 +831,43 @@ int sgdml_b200_fp64_peak_tflops(double* tflops) {
   cudaFree(out);
   SG_CUDA(cudaGetLastError());
   *tflops = best;
+  return 0;
+}
+
+// Sustained variant: keeps the DMMA pipe saturated for `seconds` (power-capped clocks settle
+// well below the burst clock on a 1 kW part) and reports the throughput of the second half.
+int sgdml_b200_fp64_peak_tflops_sustained(double seconds, double* tflops) {
+  SG_TRY(require_device());
+  SG_ARG(tflops != nullptr && seconds > 0.0 && seconds <= 30.0);
+  double* out = nullptr;
+  const int grid = num_sms() * 4, iters = 1 << 14;
+  SG_CUDA(cudaMalloc(&out, sizeof(double) * (size_t)grid * 256));
+  cudaEvent_t e0, e1, e2;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  cudaEventCreate(&e2);
+  // calibrate one launch
+  cudaEventRecord(e0, 0);
+  k_dmma_peak<<<grid, 256>>>(out, iters, 1.0000001, 1e-9);
+  cudaEventRecord(e1, 0);
+  cudaEventSynchronize(e1);
+  float ms1 = 1.f;
+  cudaEventElapsedTime(&ms1, e0, e1);
+  const int n_launch = (int)(seconds * 1e3 / ms1) + 2;
+  const int half = n_launch / 2;
+  for (int i = 0; i < half; ++i) k_dmma_peak<<<grid, 256>>>(out, iters, 1.0000001, 1e-9);
+  cudaEventRecord(e1, 0);
+  for (int i = half; i < n_launch; ++i) k_dmma_peak<<<grid, 256>>>(out, iters, 1.0000001, 1e-9);
+  cudaEventRecord(e2, 0);
+  cudaEventSynchronize(e2);
+  float ms = 1.f;
+  cudaEventElapsedTime(&ms, e1, e2);
+  *tflops = 2.0 * 256.0 * 8.0 * iters * 8.0 * grid * (double)(n_launch - half) / (ms * 1e-3) * 1e-12;
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaEventDestroy(e2);
+  cudaFree(out);
+  SG_CUDA(cudaGetLastError());
   return 0;
 }
 
