@@ -23,16 +23,20 @@ namespace sgdml {
 constexpr int NB = 128;  // Cholesky panel width
 
 // ====================================================================== GEMM  C (+)= A B^T
-template <int BM_, int BN_, int WM_, int WN_>
+template <int BM_, int BN_, int WM_, int WN_, int BK_, int STAGES_>
 struct GCfg {
   static constexpr int BM = BM_, BN = BN_, WM = WM_, WN = WN_;
-  static constexpr int BK = 16, STAGES = 4, NT = 256;
+  static constexpr int BK = BK_, STAGES = STAGES_, NT = 256;
+  static constexpr int KP = BK / 2;                 // 16-byte pairs per tile row
+  static constexpr int QA = BM * KP / NT, QB = BN * KP / NT;  // cp.async ops per thread per stage
+  static constexpr int KSTEPS = BK / 4;
   static constexpr int TR = BM / (8 * WM), TC = BN / (8 * WN);
   static constexpr int A_DBL = BM * BK, B_DBL = BN * BK;
   static constexpr size_t SMEM_BYTES = (size_t)STAGES * (A_DBL + B_DBL) * 8;
   static_assert(WM * WN == 8, "8 warps");
   static_assert(BM % (8 * WM) == 0 && BN % (8 * WN) == 0, "warp tiling");
-  static_assert((BM * 8) % NT == 0 && (BN * 8) % NT == 0, "loader mapping");
+  static_assert((BM * KP) % NT == 0 && (BN * KP) % NT == 0, "loader mapping");
+  static_assert(QA <= KSTEPS && QB <= KSTEPS, "one A and one B op per k-step at most");
   static_assert(BM % BN == 0, "triangular enumeration assumes BM = r BN");
 };
 
@@ -88,6 +92,39 @@ __global__ void __launch_bounds__(256) k_gemm_nt(const GemmArgs p) {
   const int wm = warp / G::WN, wn = warp % G::WN;
   const int row0 = wm * G::TR * 8, col0 = wn * G::TC * 8;
 
+  const int KT = (int)((p.k + G::BK - 1) / G::BK);
+  // one 16-byte cp.async of the A (or B) tile of k-tile `kt`: op index q of this thread
+  auto load_a = [&](int kt, int q) {
+    double* As = gsm + (size_t)(kt % G::STAGES) * (G::A_DBL + G::B_DBL);
+    const int64_t k0 = (int64_t)kt * G::BK;
+    const int op = tid + q * G::NT;
+    const int row = op / G::KP, kp = op % G::KP;
+    const bool ok = (m0 + row < p.m) && (k0 + 2 * kp < p.k);
+    const double* src = ok ? p.A + (m0 + row) * p.lda + k0 + 2 * kp : p.A;
+    cp_async16_pred(As + ((kp >> 1) * G::BM + row) * 4 + (kp & 1) * 2, src, ok);
+  };
+  auto load_b = [&](int kt, int q) {
+    double* Bs = gsm + (size_t)(kt % G::STAGES) * (G::A_DBL + G::B_DBL) + G::A_DBL;
+    const int64_t k0 = (int64_t)kt * G::BK;
+    const int op = tid + q * G::NT;
+    const int row = op / G::KP, kp = op % G::KP;
+    const bool ok = (n0 + row < p.n) && (k0 + 2 * kp < p.k);
+    const double* src = ok ? p.B + (n0 + row) * p.ldb + k0 + 2 * kp : p.B;
+    cp_async16_pred(Bs + ((kp >> 1) * G::BN + row) * 4 + (kp & 1) * 2, src, ok);
+  };
+
+  // pipeline prologue first, so that the C-tile loads below overlap with it
+#pragma unroll
+  for (int st = 0; st < G::STAGES - 1; ++st) {
+    if (st < KT) {
+#pragma unroll
+      for (int q = 0; q < G::QA; ++q) load_a(st, q);
+#pragma unroll
+      for (int q = 0; q < G::QB; ++q) load_b(st, q);
+    }
+    cp_async_commit();
+  }
+
   double acc[G::TR][G::TC][2];
   if (p.mode == 1) {
 #pragma unroll
@@ -112,43 +149,20 @@ __global__ void __launch_bounds__(256) k_gemm_nt(const GemmArgs p) {
       for (int j = 0; j < G::TC; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
   }
 
-  const int KT = (int)((p.k + G::BK - 1) / G::BK);
-  auto load_tile = [&](int kt) {
-    double* As = gsm + (size_t)(kt % G::STAGES) * (G::A_DBL + G::B_DBL);
-    double* Bs = As + G::A_DBL;
-    const int64_t k0 = (int64_t)kt * G::BK;
-#pragma unroll
-    for (int q = 0; q < G::BM * 8 / G::NT; ++q) {
-      const int op = tid + q * G::NT;
-      const int row = op >> 3, kp = op & 7;
-      const bool ok = (m0 + row < p.m) && (k0 + 2 * kp < p.k);
-      const double* src = ok ? p.A + (m0 + row) * p.lda + k0 + 2 * kp : p.A;
-      cp_async16_pred(As + ((kp >> 1) * G::BM + row) * 4 + (kp & 1) * 2, src, ok);
-    }
-#pragma unroll
-    for (int q = 0; q < G::BN * 8 / G::NT; ++q) {
-      const int op = tid + q * G::NT;
-      const int row = op >> 3, kp = op & 7;
-      const bool ok = (n0 + row < p.n) && (k0 + 2 * kp < p.k);
-      const double* src = ok ? p.B + (n0 + row) * p.ldb + k0 + 2 * kp : p.B;
-      cp_async16_pred(Bs + ((kp >> 1) * G::BN + row) * 4 + (kp & 1) * 2, src, ok);
-    }
-  };
-
-#pragma unroll
-  for (int s = 0; s < G::STAGES - 1; ++s) {
-    if (s < KT) load_tile(s);
-    cp_async_commit();
-  }
   for (int kt = 0; kt < KT; ++kt) {
     cp_async_wait<G::STAGES - 2>();
     __syncthreads();
-    if (kt + G::STAGES - 1 < KT) load_tile(kt + G::STAGES - 1);
-    cp_async_commit();
+    const bool more = (kt + G::STAGES - 1 < KT);
     const double* As = gsm + (size_t)(kt % G::STAGES) * (G::A_DBL + G::B_DBL);
     const double* Bs = As + G::A_DBL;
 #pragma unroll
-    for (int ks = 0; ks < G::BK / 4; ++ks) {
+    for (int ks = 0; ks < G::KSTEPS; ++ks) {
+      // the next stage's loads are spread over the k-steps: a burst of LDGSTS right after the
+      // barrier blocks the fragment LDS behind it in the LSU queue and starves the DMMA pipe
+      if (more) {
+        if (ks < G::QA) load_a(kt + G::STAGES - 1, ks);
+        if (ks < G::QB) load_b(kt + G::STAGES - 1, ks);
+      }
       double fa[G::TR], fb[G::TC];
 #pragma unroll
       for (int i = 0; i < G::TR; ++i) fa[i] = As[(ks * G::BM + row0 + i * 8 + lr) * 4 + lc];
@@ -159,6 +173,7 @@ __global__ void __launch_bounds__(256) k_gemm_nt(const GemmArgs p) {
 #pragma unroll
         for (int j = 0; j < G::TC; ++j) dmma884(acc[i][j][0], acc[i][j][1], fa[i], fb[j]);
     }
+    cp_async_commit();
   }
   cp_async_wait<0>();
 
@@ -206,8 +221,8 @@ __global__ void k_gemm_nt_naive(const GemmArgs p) {
   }
 }
 
-using GBig = GCfg<128, 128, 2, 4>;
-using GTall = GCfg<128, 64, 4, 2>;
+using GBig = GCfg<128, 128, 2, 4, 32, 3>;   // 196 KB smem, 1 CTA/SM
+using GTall = GCfg<128, 64, 4, 2, 16, 4>;   // 98 KB smem, 2 CTAs/SM
 
 static int g_gemm_variant = 0;  // 0: 128x128 tiles (1 CTA/SM), 1: 128x64 tiles (2 CTAs/SM)
 
@@ -578,12 +593,14 @@ __global__ void __launch_bounds__(256) k_dmma_peak(double* out, int iters, doubl
 // of the matrix receives ONE lazy update per outer block with k = NBO, so every C tile is read and
 // written n/NBO times instead of n/NB times and the GEMM prologue/epilogue is amortised over 4x
 // more math.
-constexpr int NBO = 512;
+constexpr int NBO_MAX = 1024;
 
 int potrf_device(double* A, int64_t n, int64_t lda, int* info_host, cudaStream_t s) {
   int* d_info = nullptr;
   double* W = nullptr;
   SG_CUDA(cudaMalloc(&d_info, sizeof(int)));
+  // outer block: wide for large matrices (fewer passes over C), narrower when n is small
+  const int NBO = (n >= 16384) ? NBO_MAX : ((n >= 4096) ? 512 : 256);
   cudaError_t e = cudaMalloc(&W, sizeof(double) * (size_t)n * NBO);
   if (e != cudaSuccess) {
     cudaFree(d_info);

@@ -95,4 +95,4 @@ class Analytic(object):
         """Device bytes: K once (factorised in place; the reference needs ~3x, analytic.py:153-159)
         plus the panel workspace and vectors."""
         n = n_train * 3 * n_atoms
-        return n * n * 8 + n * 512 * 8 + 4 * n * 8
+        return n * n * 8 + n * 1024 * 8 + 4 * n * 8
