@@ -177,11 +177,22 @@ __global__ void __launch_bounds__(256) k_gemm_nt(const GemmArgs p) {
   }
   cp_async_wait<0>();
 
-  // ---- epilogue
+  // ---- epilogue (mode 0 reads the old C values of a whole fragment row first, so that the
+  //      loads are independent instead of one exposed round trip per element)
 #pragma unroll
   for (int i = 0; i < G::TR; ++i) {
     const int64_t r = m0 + row0 + i * 8 + lr;
     if (r >= p.m) continue;
+    double old0[G::TC], old1[G::TC];
+    if (p.mode == 0 && p.beta != 0.0) {
+#pragma unroll
+      for (int j = 0; j < G::TC; ++j) {
+        const int64_t c = n0 + col0 + j * 8 + 2 * lc;
+        const double* src = p.C + r * p.ldc + c;
+        old0[j] = (c < p.n) ? src[0] : 0.0;
+        old1[j] = (c + 1 < p.n) ? src[1] : 0.0;
+      }
+    }
 #pragma unroll
     for (int j = 0; j < G::TC; ++j) {
       const int64_t c = n0 + col0 + j * 8 + 2 * lc;
@@ -192,8 +203,8 @@ __global__ void __launch_bounds__(256) k_gemm_nt(const GemmArgs p) {
         v0 *= p.alpha;
         v1 *= p.alpha;
         if (p.beta != 0.0) {
-          v0 += p.beta * dst[0];
-          if (c + 1 < p.n) v1 += p.beta * dst[1];
+          v0 += p.beta * old0[j];
+          v1 += p.beta * old1[j];
         }
       }
       if (c + 1 < p.n)
