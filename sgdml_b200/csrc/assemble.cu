@@ -33,39 +33,50 @@ struct AsmArgs {
   const int* jpts;         // (nJ) training point of each block-column
   const int64_t* dest;     // (nJ, 3N) destination column in K or -1
   int N, D, M, S, nJ, TJ;
+  unsigned mN, mNN, mPer;  // ceil(2^32 / d) for d = N, N*N, 5N
   double sig, scale;
   double* K;
   int64_t ldk;
 };
 
-__device__ __forceinline__ int pair_idx_any(int a, int b) { return a > b ? pair_index(a, b) : pair_index(b, a); }
-
-// expands compressed g (D,3) into the antisymmetric table G (N,N,3), zero diagonal
-__device__ void load_pair_table(const double* __restrict__ g, int N, double* __restrict__ G, int tid, int nt) {
-  for (int idx = tid; idx < N * N; idx += nt) {
-    const int a = idx / N, b = idx - a * N;
-    double v0 = 0.0, v1 = 0.0, v2 = 0.0;
-    if (a > b) {
-      const int d = pair_index(a, b);
-      v0 = g[d * 3 + 0];
-      v1 = g[d * 3 + 1];
-      v2 = g[d * 3 + 2];
-    } else if (b > a) {
-      const int d = pair_index(b, a);
-      v0 = -g[d * 3 + 0];
-      v1 = -g[d * 3 + 1];
-      v2 = -g[d * 3 + 2];
+// expands compressed g (D,3) into the antisymmetric table G (N,N,3), zero diagonal, and the
+// descriptor x (D) into the symmetric table X (N,N)
+__device__ void load_pair_tables(const double* __restrict__ g, const double* __restrict__ x, int N,
+                                 double* __restrict__ G, double* __restrict__ X, int warp, int lane, int nw) {
+  for (int a = warp; a < N; a += nw)
+    for (int b = lane; b < N; b += 32) {
+      double v0 = 0.0, v1 = 0.0, v2 = 0.0, xv = 0.0;
+      if (a != b) {
+        const int hi = a > b ? a : b, lo = a > b ? b : a;
+        const int d = pair_index(hi, lo);
+        const double sgn = a > b ? 1.0 : -1.0;
+        v0 = sgn * g[d * 3 + 0];
+        v1 = sgn * g[d * 3 + 1];
+        v2 = sgn * g[d * 3 + 2];
+        xv = x[d];
+      }
+      const int idx = a * N + b;
+      G[idx * 3 + 0] = v0;
+      G[idx * 3 + 1] = v1;
+      G[idx * 3 + 2] = v2;
+      X[idx] = xv;
     }
-    G[idx * 3 + 0] = v0;
-    G[idx * 3 + 1] = v1;
-    G[idx * 3 + 2] = v2;
-  }
 }
 
-__global__ void __launch_bounds__(256) k_assemble(const AsmArgs p) {
+// exact x / d for 0 <= x < 2^20, 1 <= d < 2^12 with m = ceil(2^32 / d): runtime integer division
+// compiles to an XU-pipe sequence that throttled the first version of this kernel
+__device__ __forceinline__ int fastdiv(int x, unsigned m) { return (int)__umulhi((unsigned)x, m); }
+
+constexpr int ASM_NI = 4;  // 3x3 atom-pair sub-blocks per thread (accumulators live in registers)
+
+// One CTA: row point i, a tile of TJ column points.  Permutations are the OUTER loop; for each
+// permutation the per-point vectors (delta table, u, v, diagonal sums) are rebuilt in shared
+// memory with unit-stride loops over atom tables, then every thread adds the permutation's
+// contribution to its 3x3 sub-blocks, which stay in registers until the single final store.
+__global__ void __launch_bounds__(256, 2) k_assemble(const AsmArgs p) {
   extern __shared__ __align__(16) double sm[];
-  const int N = p.N, D = p.D, S = p.S, TJ = p.TJ;
-  const int N3 = 3 * N, NN3 = N * N * 3;
+  const int N = p.N, S = p.S, TJ = p.TJ;
+  const int N3 = 3 * N, NN = N * N, NN3 = NN * 3;
   const int tid = threadIdx.x, nt = blockDim.x;
   const int warp = tid >> 5, lane = tid & 31, nw = nt >> 5;
 
@@ -73,149 +84,202 @@ __global__ void __launch_bounds__(256) k_assemble(const AsmArgs p) {
   const int jt0 = blockIdx.x * TJ;
   const int tj = min(TJ, p.nJ - jt0);
 
-  // shared layout
-  double* Gi = sm;                       // NN3
-  double* xi = Gi + NN3;                 // D
-  double* Gj = xi + D;                   // TJ*NN3
-  double* xj = Gj + TJ * NN3;            // TJ*D
-  double* del = xj + TJ * D;             // TJ*S*D
-  double* cc = del + TJ * S * D;         // TJ*S*2
-  double* u = cc + TJ * S * 2;           // TJ*S*N3
-  double* v = u + TJ * S * N3;           // TJ*S*N3
-  double* Dg = v + TJ * S * N3;          // TJ*S*3*N3
-  int* sP = reinterpret_cast<int*>(Dg + TJ * S * 3 * N3);  // S*N
-  int* sPi = sP + S * N;                                     // S*N
+  double* Gi = sm;                 // NN3
+  double* Xi = Gi + NN3;           // NN
+  double* Gj = Xi + NN;            // TJ*NN3
+  double* Xj = Gj + TJ * NN3;      // TJ*NN
+  double* Dl = Xj + TJ * NN;       // TJ*NN   delta table in the j frame (current permutation)
+  double* u = Dl + TJ * NN;        // TJ*N3
+  double* v = u + TJ * N3;         // TJ*N3
+  double* Dg = v + TJ * N3;        // TJ*3*N3
+  double* cc = Dg + TJ * 3 * N3;   // S*TJ*2
+  double* n2s = cc + S * TJ * 2;   // S*TJ  sum of squared deltas (each pair twice)
+  int* sP = reinterpret_cast<int*>(n2s + S * TJ);  // S*N
+  int* sPi = sP + S * N;                                // S*N
 
-  // ---- stage 0: pair tables and descriptors of i and of the tile's points
-  load_pair_table(p.R_d_desc + (int64_t)i * D * 3, N, Gi, tid, nt);
-  for (int d = tid; d < D; d += nt) xi[d] = p.R_desc[(int64_t)i * D + d];
+  load_pair_tables(p.R_d_desc + (int64_t)i * p.D * 3, p.R_desc + (int64_t)i * p.D, N, Gi, Xi, warp, lane, nw);
   for (int t = 0; t < tj; ++t) {
     const int j = p.jpts[jt0 + t];
-    load_pair_table(p.R_d_desc + (int64_t)j * D * 3, N, Gj + t * NN3, tid, nt);
-    for (int d = tid; d < D; d += nt) xj[t * D + d] = p.R_desc[(int64_t)j * D + d];
+    load_pair_tables(p.R_d_desc + (int64_t)j * p.D * 3, p.R_desc + (int64_t)j * p.D, N, Gj + t * NN3, Xj + t * NN, warp,
+                     lane, nw);
   }
   for (int idx = tid; idx < S * N; idx += nt) {
     sP[idx] = p.aperm[idx];
     sPi[idx] = p.apinv[idx];
   }
+  for (int idx = tid; idx < S * TJ; idx += nt) n2s[idx] = 0.0;
+
+  // this thread's output items: (t, a, b) = column point, row atom, column atom
+  int it_t[ASM_NI], it_a[ASM_NI], it_b[ASM_NI];
+  double acc[ASM_NI][9];
+#pragma unroll
+  for (int q = 0; q < ASM_NI; ++q) {
+    const int it = tid + q * nt;
+    const bool ok = it < tj * NN;
+    const int t = ok ? fastdiv(it, p.mNN) : 0;
+    const int ab = ok ? it - t * NN : 0;
+    it_t[q] = ok ? t : -1;
+    it_a[q] = fastdiv(ab, p.mN);
+    it_b[q] = ab - it_a[q] * N;
+#pragma unroll
+    for (int e = 0; e < 9; ++e) acc[q][e] = 0.0;
+  }
   __syncthreads();
 
-  // ---- stage A: delta_p, n_p -> c1, c2 ; one warp per (j, p)
   const double sig = p.sig;
   const double sig2 = sig * sig;
   const double inv_div = 1.0 / (3.0 * sig2 * sig2);  // 1/mat52_base_div (train.py:179)
-  for (int jp = warp; jp < tj * S; jp += nw) {
-    const int t = jp / S, pp = jp - t * S;
-    double s = 0.0;
-    for (int d = lane; d < D; d += 32) {
-      const double dl = xi[d] - xj[t * D + p.dperm[pp * D + d]];  // train.py:199
-      del[jp * D + d] = dl;
-      s = fma(dl, dl, s);
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    if (lane == 0) {
-      const double nrm = sqrt(5.0) * sqrt(s);            // train.py:201
-      const double base = exp(-nrm / sig) * inv_div * 5.0;  // train.py:202
-      cc[jp * 2 + 0] = base * 5.0;                       // c1 (train.py:211)
-      cc[jp * 2 + 1] = (sig2 + sig * nrm) * base;        // c2 (train.py:219)
-    }
-  }
-  __syncthreads();
 
-  // ---- stage B: u_p, v_p (3N each) and the diagonal sums Dg_p (9N) per (j, p)
-  {
-    const int per = N3 + N3 + 3 * N3;
-    for (int idx = tid; idx < tj * S * per; idx += nt) {
-      const int jp = idx / per;
-      int r = idx - jp * per;
-      const int t = jp / S, pp = jp - t * S;
-      const double* dl = del + jp * D;
-      const double* Gjt = Gj + t * NN3;
-      if (r < N3) {  // u_p[a][c]
-        const int a = r / 3, c = r - 3 * a;
-        double s = 0.0;
-        for (int g = 0; g < N; ++g)
-          if (g != a) s = fma(Gi[(a * N + g) * 3 + c], dl[pair_idx_any(a, g)], s);
-        u[jp * N3 + r] = -s;
-      } else if (r < 2 * N3) {  // v_p[b][c]
-        r -= N3;
-        const int b = r / 3, c = r - 3 * b;
-        const int pib = sPi[pp * N + b];
-        double s = 0.0;
-        for (int g = 0; g < N; ++g)
-          if (g != b) s = fma(Gjt[(b * N + g) * 3 + c], dl[pair_idx_any(pib, sPi[pp * N + g])], s);
-        v[jp * N3 + r] = -s;
-      } else {  // Dg_p[a][c][c']
-        r -= 2 * N3;
-        const int a = r / 9, c = (r - 9 * a) / 3, c2 = r - 9 * a - 3 * c;
-        const int pa = sP[pp * N + a];
-        double s = 0.0;
-        for (int g = 0; g < N; ++g)
-          if (g != a) s = fma(Gi[(a * N + g) * 3 + c], Gjt[(pa * N + sP[pp * N + g]) * 3 + c2], s);
-        Dg[jp * 3 * N3 + r] = s;
+  for (int pp = 0; pp < S; ++pp) {
+    const int* P = sP + pp * N;
+    const int* Pi = sPi + pp * N;
+    // ---- S1: delta table in the j frame, Dl[b][g] = x_i[d(P^-1 b, P^-1 g)] - x_j[d(b, g)]
+    //          (= delta_p[d(P^-1 b, P^-1 g)], train.py:199) and sum of squares; all warps, rows of
+    //          the (t, b) plane round-robin over warps, g over lanes
+    for (int t = 0; t < tj; ++t) {
+      double s2 = 0.0;
+      for (int e = tid; e < NN; e += nt) {
+        const int b = fastdiv(e, p.mN);
+        const int g = e - b * N;
+        const double dl = Xi[Pi[b] * N + Pi[g]] - Xj[t * NN + e];
+        Dl[t * NN + e] = dl;
+        s2 = fma(dl, dl, s2);
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+      if (lane == 0 && s2 != 0.0) atomicAdd(&n2s[pp * TJ + t], s2);
+    }
+    __syncthreads();
+
+    // ---- S2: u[a] = -sum_g G_i[a][g] Dl[Pa][Pg],  v[b] = -sum_g G_j[b][g] Dl[b][g],
+    //          Dg[a][c][c'] = sum_g G_i[a][g][c] G_j[Pa][Pg][c']      (units of 3 outputs each)
+    {
+      // Matern factors of this permutation (one thread per column point, from the tail of the CTA)
+      if (tid >= nt - tj) {
+        const int t = nt - 1 - tid;
+        const double nrm = sqrt(5.0) * sqrt(0.5 * n2s[pp * TJ + t]);  // every pair twice; train.py:201
+        const double base = exp(-nrm / sig) * inv_div * 5.0;          // train.py:202
+        cc[(pp * TJ + t) * 2 + 0] = base * 5.0;                       // c1 (train.py:211)
+        cc[(pp * TJ + t) * 2 + 1] = (sig2 + sig * nrm) * base;        // c2 (train.py:219)
+      }
+      const int per = 5 * N;  // N (u) + N (v) + 3N (Dg rows a,c)
+      for (int idx = tid; idx < tj * per; idx += nt) {
+        const int t = fastdiv(idx, p.mPer);
+        const int r = idx - t * per;
+        const double* Gjt = Gj + t * NN3;
+        const double* Dlt = Dl + t * NN;
+        if (r < N) {  // u[a][0..2]
+          const int a = r, pa = P[a];
+          const double* gi = Gi + a * N3;
+          const double* dl = Dlt + pa * N;
+          double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+          for (int g = 0; g < N; ++g) {
+            const double d = dl[P[g]];
+            s0 = fma(gi[g * 3 + 0], d, s0);
+            s1 = fma(gi[g * 3 + 1], d, s1);
+            s2 = fma(gi[g * 3 + 2], d, s2);
+          }
+          u[t * N3 + 3 * a + 0] = -s0;
+          u[t * N3 + 3 * a + 1] = -s1;
+          u[t * N3 + 3 * a + 2] = -s2;
+        } else if (r < 2 * N) {  // v[b][0..2]
+          const int b = r - N;
+          const double* gj = Gjt + b * N3;
+          const double* dl = Dlt + b * N;
+          double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+          for (int g = 0; g < N; ++g) {
+            const double d = dl[g];
+            s0 = fma(gj[g * 3 + 0], d, s0);
+            s1 = fma(gj[g * 3 + 1], d, s1);
+            s2 = fma(gj[g * 3 + 2], d, s2);
+          }
+          v[t * N3 + 3 * b + 0] = -s0;
+          v[t * N3 + 3 * b + 1] = -s1;
+          v[t * N3 + 3 * b + 2] = -s2;
+        } else {  // Dg[a][c][0..2]
+          const int ac = r - 2 * N;
+          const int a = (int)__umulhi((unsigned)ac, 0x55555556u), c = ac - 3 * a;
+          const double* gi = Gi + a * N3 + c;
+          const double* gj = Gjt + P[a] * N3;
+          double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+          for (int g = 0; g < N; ++g) {
+            const double x = gi[g * 3];
+            const double* y = gj + P[g] * 3;
+            s0 = fma(x, y[0], s0);
+            s1 = fma(x, y[1], s1);
+            s2 = fma(x, y[2], s2);
+          }
+          Dg[t * 3 * N3 + ac * 3 + 0] = s0;
+          Dg[t * 3 * N3 + ac * 3 + 1] = s1;
+          Dg[t * 3 * N3 + ac * 3 + 2] = s2;
+        }
       }
     }
-  }
-  __syncthreads();
+    __syncthreads();
 
-  // ---- stage C: 3x3 atom-pair sub-blocks
-  for (int it = tid; it < tj * N * N; it += nt) {
-    const int t = it / (N * N);
-    const int ab = it - t * N * N;
-    const int a = ab / N, b = ab - a * N;
-    const double* Gjt = Gj + t * NN3;
-    double acc[3][3];
+    // ---- S3: acc[a][b] += c1 u[a] (x) v[b] - c2 T[a][b]
 #pragma unroll
-    for (int c = 0; c < 3; ++c)
+    for (int q = 0; q < ASM_NI; ++q) {
+      const int t = it_t[q];
+      if (t < 0) continue;
+      const int a = it_a[q], b = it_b[q];
+      const double c1 = cc[(pp * TJ + t) * 2 + 0], c2 = cc[(pp * TJ + t) * 2 + 1];
+      const double* ua = u + t * N3 + 3 * a;
+      const double* vb = v + t * N3 + 3 * b;
+      const int pa = P[a];
+      double t0[3], t1[3];  // T[a][b] = t0[c] * t1[c'] (outer product) unless b == P a
+      if (b != pa) {
+        const double* gi = Gi + (a * N + Pi[b]) * 3;
+        const double* gj = Gj + t * NN3 + (pa * N + b) * 3;
 #pragma unroll
-      for (int c2 = 0; c2 < 3; ++c2) acc[c][c2] = 0.0;
-    for (int pp = 0; pp < S; ++pp) {
-      const int jp = t * S + pp;
-      const double c1 = cc[jp * 2 + 0], c2v = cc[jp * 2 + 1];
-      const double* ua = u + jp * N3 + 3 * a;
-      const double* vb = v + jp * N3 + 3 * b;
-      const int pa = sP[pp * N + a];
-      double tt[3][3];
-      if (b == pa) {
-        const double* dg = Dg + jp * 3 * N3 + 9 * a;
+        for (int c = 0; c < 3; ++c) {
+          t0[c] = c2 * gi[c];   // -c2 * (-gi (x) gj) = +c2 gi (x) gj
+          t1[c] = gj[c];
+        }
 #pragma unroll
-        for (int c = 0; c < 3; ++c)
+        for (int c = 0; c < 3; ++c) {
+          const double cu = c1 * ua[c];
 #pragma unroll
-          for (int c2 = 0; c2 < 3; ++c2) tt[c][c2] = dg[c * 3 + c2];
+          for (int c2i = 0; c2i < 3; ++c2i)
+            acc[q][c * 3 + c2i] = fma(t0[c], t1[c2i], fma(cu, vb[c2i], acc[q][c * 3 + c2i]));
+        }
       } else {
-        const int g = sPi[pp * N + b];
-        const double* gi = Gi + (a * N + g) * 3;
-        const double* gj = Gjt + (pa * N + b) * 3;
+        const double* dg = Dg + t * 3 * N3 + 9 * a;
 #pragma unroll
-        for (int c = 0; c < 3; ++c)
+        for (int c = 0; c < 3; ++c) {
+          const double cu = c1 * ua[c];
 #pragma unroll
-          for (int c2 = 0; c2 < 3; ++c2) tt[c][c2] = -gi[c] * gj[c2];
-      }
-#pragma unroll
-      for (int c = 0; c < 3; ++c) {
-        const double cu = c1 * ua[c];
-#pragma unroll
-        for (int c2 = 0; c2 < 3; ++c2) acc[c][c2] += cu * vb[c2] - c2v * tt[c][c2];
+          for (int c2i = 0; c2i < 3; ++c2i)
+            acc[q][c * 3 + c2i] = fma(-c2, dg[c * 3 + c2i], fma(cu, vb[c2i], acc[q][c * 3 + c2i]));
+        }
       }
     }
+    // (no barrier here: the next S1 only writes Dl / cc[pp+1]; u, v, Dg are rewritten after it)
+  }
+
+  // ---- single store of the finished 3x3 sub-blocks
+#pragma unroll
+  for (int q = 0; q < ASM_NI; ++q) {
+    const int t = it_t[q];
+    if (t < 0) continue;
+    const int a = it_a[q], b = it_b[q];
     const int64_t* dst = p.dest + (int64_t)(jt0 + t) * N3 + 3 * b;
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
       double* Krow = p.K + ((int64_t)i * N3 + 3 * a + c) * p.ldk;
 #pragma unroll
-      for (int c2 = 0; c2 < 3; ++c2) {
-        const int64_t col = dst[c2];
-        if (col >= 0) Krow[col] = p.scale * acc[c][c2];
+      for (int c2i = 0; c2i < 3; ++c2i) {
+        const int64_t col = dst[c2i];
+        if (col >= 0) Krow[col] = p.scale * acc[q][c * 3 + c2i];
       }
     }
   }
 }
 
 static size_t asm_smem_bytes(int N, int D, int S, int TJ) {
-  const size_t N3 = 3 * (size_t)N, NN3 = (size_t)N * N * 3;
-  size_t dbl = NN3 + D + (size_t)TJ * NN3 + (size_t)TJ * D + (size_t)TJ * S * D + (size_t)TJ * S * 2 +
-               2 * (size_t)TJ * S * N3 + (size_t)TJ * S * 3 * N3;
+  (void)D;
+  const size_t N3 = 3 * (size_t)N, NN = (size_t)N * N;
+  size_t dbl = NN * 3 + NN + (size_t)TJ * (NN * 3 + NN + NN + 2 * N3 + 3 * N3) + (size_t)S * TJ * 3;
   return dbl * 8 + 2 * (size_t)S * N * 4;
 }
 
@@ -328,15 +392,16 @@ extern "C" int sgdml_b200_assemble(const double* R_desc, const double* R_d_desc,
   }
   const int nJ = (int)jpts.size();
 
-  // ---- tile size from the shared-memory budget
+  // ---- tile size: at most ASM_NI 3x3 sub-blocks per thread, and shared memory small enough for
+  //      two co-resident CTAs per SM
   int TJ = 0;
   for (int t = 8; t >= 1; --t)
-    if (asm_smem_bytes(N, D, S, t) <= 200 * 1024) {
+    if ((int64_t)t * N * N <= (int64_t)ASM_NI * 256 && asm_smem_bytes(N, D, S, t) <= 110 * 1024) {
       TJ = t;
       break;
     }
   if (TJ == 0) {
-    set_last_error("sgdml_b200_assemble: (N, S) too large for the single-pass assembly kernel");
+    set_last_error("sgdml_b200_assemble: this kernel supports N <= 32 atoms (N*N <= 1024 sub-blocks per CTA)");
     return SGDML_B200_ERR_UNSUPPORTED;
   }
   TJ = std::min(TJ, nJ);
@@ -384,6 +449,9 @@ extern "C" int sgdml_b200_assemble(const double* R_desc, const double* R_d_desc,
     a.S = S;
     a.nJ = nJ;
     a.TJ = TJ;
+    a.mN = (unsigned)((0x100000000ull + N - 1) / N);
+    a.mNN = (unsigned)((0x100000000ull + (uint64_t)N * N - 1) / ((uint64_t)N * N));
+    a.mPer = (unsigned)((0x100000000ull + 5 * N - 1) / (5 * N));
     a.sig = sig;
     a.scale = scale;
     a.K = (double*)sK.dev();

@@ -29,8 +29,9 @@
 namespace sgdml {
 
 // ============================================================== tile configuration
-template <int DP_, int BQ_, int BM_, int W1Q_, int W1M_, int W1K_, int W2Q_, int W2D_, int MINB_ = 1>
+template <int DP_, int BQ_, int BM_, int W1Q_, int W1M_, int W1K_, int W2Q_, int W2D_, int MINB_ = 1, int W2S_ = 1>
 struct PCfg {
+  static constexpr int W2S = W2S_;      // 2: GEMM2 split by operand (warps 0-3: C1*Xc, warps 4-7: C2*JA)
   static constexpr int MINB = MINB_;    // CTAs per SM the kernel is compiled for
   static constexpr int DP = DP_;        // padded descriptor size (multiple of 8)
   static constexpr int DS = DP_ + 4;    // row stride of Q / Xc / JA tiles (== 4 or 12 mod 16: conflict-free DMMA frags)
@@ -46,7 +47,8 @@ struct PCfg {
   static constexpr int TR2 = BQ / (8 * W2Q);
   static constexpr int TD2 = DP / (8 * W2D);
   static constexpr int EPT = BQ * BM / NT;  // epilogue-1 elements per thread
-  static_assert(W1Q * W1M * W1K == 8 && W2Q * W2D == 8, "8 warps");
+  static_assert(W1Q * W1M * W1K == 8 && W2Q * W2D * W2S == 8 && (W2S == 1 || W2S == 2), "8 warps");
+  static_assert(W2S == 1 || W1K * 2 * BQ_ * (BM_ + 4) >= BQ_ * DP_, "combine scratch must fit in the S/C region");
   static_assert(BQ % (8 * W1Q) == 0 && BM % (8 * W1M) == 0 && (DP / 4) % W1K == 0, "GEMM1 tiling");
   static_assert(BQ % (8 * W2Q) == 0 && DP % (8 * W2D) == 0, "GEMM2 tiling");
   static_assert(BM == 8 || BM == 16 || BM == 32, "row reduction uses shuffles inside one warp");
@@ -85,6 +87,46 @@ struct PredictArgs {
   double* G;            // (n_rows, DP)
   double* Erow;         // (n_rows)
 };
+
+// ============================================================== Matern-5/2 factors
+// exp(-t) for t >= 0: Cody-Waite reduction + degree-12 Taylor polynomial (|r| <= ln2/2, truncation
+// 1.7e-16 relative) -- ~16 FP64-pipe instructions instead of the library exp's ~22; the FP64 pipe
+// is the kernel's bottleneck, so the transform is kept as lean as the 1e-6 force bound allows.
+__device__ __forceinline__ double exp_neg(double t) {
+  t = fmin(t, 708.0);
+  const double kf = rint(-t * 1.4426950408889634074);
+  double r = fma(kf, -6.93147180369123816490e-01, -t);
+  r = fma(kf, -1.90821492927058770002e-10, r);
+  double p = 2.08767569878680989792e-09;  // 1/12!
+  p = fma(p, r, 2.50521083854417187751e-08);
+  p = fma(p, r, 2.75573192239858906526e-07);
+  p = fma(p, r, 2.75573192239858906526e-06);
+  p = fma(p, r, 2.48015873015873015873e-05);
+  p = fma(p, r, 1.98412698412698412698e-04);
+  p = fma(p, r, 1.38888888888888888889e-03);
+  p = fma(p, r, 8.33333333333333333333e-03);
+  p = fma(p, r, 4.16666666666666666667e-02);
+  p = fma(p, r, 1.66666666666666666667e-01);
+  p = fma(p, r, 0.5);
+  p = fma(p, r, 1.0);
+  p = fma(p, r, 1.0);
+  const long long k = (long long)kf;
+  return p * __longlong_as_double((k + 1023) << 52);
+}
+
+struct MaternK {
+  double sig, sig_inv, k_base, k_diag;
+};
+// n2raw = |q|^2 + |x|^2 - 2 q.x (may be slightly negative), a = delta . JA  ->  c1, c2
+// (predict.py:204-213):  n = sqrt5 |delta|, base = exp(-n/sig) 5/(3 sig^3), c1 = a base 5/sig,
+// c2 = base (n + sig)
+__device__ __forceinline__ void matern52(double n2raw, double a, const MaternK& k, double& c1, double& c2) {
+  const double x = 5.0 * fmax(n2raw, 0.0);
+  const double nrm = (x > 0.0) ? x * rsqrt(x) : 0.0;
+  const double base = exp_neg(nrm * k.sig_inv) * k.k_base;
+  c1 = a * base * k.k_diag;
+  c2 = base * (nrm + k.sig);
+}
 
 // ============================================================== main kernel
 template <class C>
@@ -130,16 +172,31 @@ __global__ void __launch_bounds__(256, C::MINB) k_predict_main(const PredictArgs
   }
 
   // ---- build the Q tile: Q[r][e] = x_b[pinv_p[e]] - mu[e]  (row r <-> (b, p) = divmod(r0 + r, S))
-  for (int idx = tid; idx < C::BQ * C::DS; idx += C::NT) {
-    const int r = idx / C::DS, e = idx - r * C::DS;
-    const int64_t row = r0 + r;
-    double v = 0.0;
-    if (row < p.n_rows && e < p.D) {
-      const int64_t b = row / p.S;
-      const int pp = (int)(row - b * p.S);
-      v = p.xq[b * p.D + p.pinv[pp * p.D + e]] - p.mu[e];
+  {
+    const int64_t b_lo = r0 / p.S;
+    const int64_t row_hi = min(r0 + (int64_t)C::BQ, p.n_rows) - 1;
+    const int nb = (row_hi >= r0) ? (int)(row_hi / p.S - b_lo + 1) : 0;
+    const bool staged = (nb * p.D <= C::W1K * 2 * C::BQ * C::CS);
+    if (staged) {
+      // the tile's query descriptors are contiguous in xq: stage them in the (still unused) S/C
+      // region with coalesced loads, then gather from shared memory
+      const double* src = p.xq + b_lo * p.D;
+      for (int idx = tid; idx < nb * p.D; idx += C::NT) Ps[idx] = src[idx];
+      __syncthreads();
     }
-    Qs[idx] = v;
+#pragma unroll 4
+    for (int idx = tid; idx < C::BQ * C::DS; idx += C::NT) {
+      const int r = idx / C::DS, e = idx - r * C::DS;
+      const int64_t row = r0 + r;
+      double v = 0.0;
+      if (row < p.n_rows && e < p.D) {
+        const int64_t b = row / p.S;
+        const int pp = (int)(row - b * p.S);
+        const int d = p.pinv[pp * p.D + e];
+        v = (staged ? Ps[(int)(b - b_lo) * p.D + d] : p.xq[b * p.D + d]) - p.mu[e];
+      }
+      Qs[idx] = v;
+    }
   }
   if (tid < C::BQ) {
     csum_s[tid] = 0.0;
@@ -166,8 +223,10 @@ __global__ void __launch_bounds__(256, C::MINB) k_predict_main(const PredictArgs
   const int col1 = w1m * (C::TC1 * 8);
   const int k1 = w1k * C::KS1 * 4;
   // GEMM2 warp coordinates
-  const int w2d = warp % C::W2D;
-  const int w2q = warp / C::W2D;
+  constexpr int W2G = C::W2Q * C::W2D;  // warps per operand group
+  const int w2s = warp / W2G;           // 0: Xc (and JA when W2S == 1), 1: JA
+  const int w2d = (warp % W2G) % C::W2D;
+  const int w2q = (warp % W2G) / C::W2D;
   const int row2 = w2q * (C::TR2 * 8);
   const int dcol2 = w2d * (C::TD2 * 8);
 
@@ -177,22 +236,30 @@ __global__ void __launch_bounds__(256, C::MINB) k_predict_main(const PredictArgs
 #pragma unroll
     for (int j = 0; j < C::TD2; ++j) accG[i][j][0] = accG[i][j][1] = 0.0;
 
-  double csum_part[C::EPT], E_part[C::EPT];
+  // running row sums: split-k path -> per epilogue element; fused path -> per fragment row
+  constexpr int NPART = (C::W1K > 1) ? C::EPT : C::TR1;
+  double csum_part[NPART], E_part[NPART];
 #pragma unroll
-  for (int j = 0; j < C::EPT; ++j) csum_part[j] = E_part[j] = 0.0;
+  for (int j = 0; j < NPART; ++j) csum_part[j] = E_part[j] = 0.0;
 
-  const double sig = p.sig;
-  const double sig_inv = 1.0 / sig;
-  const double k_base = 5.0 / (3.0 * sig * sig * sig);  // predict.py:195 mat52_base_fact
-  const double k_diag = 5.0 / sig;                      // predict.py:196 diag_scale_fact
+  MaternK mk;
+  mk.sig = p.sig;
+  mk.sig_inv = 1.0 / p.sig;
+  mk.k_base = 5.0 / (3.0 * p.sig * p.sig * p.sig);  // predict.py:195 mat52_base_fact
+  mk.k_diag = 5.0 / p.sig;                          // predict.py:196 diag_scale_fact
+
+  double* C1s = Ps;
+  double* C2s = Ps + C::BQ * C::CS;
 
   for (int t = 0; t < n_tiles; ++t) {
     const int s = t & 1;
     const double* Xt = Xs + s * C::BM * C::DS;
     const double* JAt = JAs + s * C::BM * C::DS;
+    const double* mmt = mms + s * C::BM;
+    const double* xjat = xjas + s * C::BM;
     mbar_wait(&bars[s], (uint32_t)((t >> 1) & 1));
 
-    // ---------------- GEMM1: partial S1 = Q Xc^T, S2 = Q JA^T over this warp's k-range
+    // ---------------- GEMM1: S1 = Q Xc^T, S2 = Q JA^T (over this warp's k-range)
     {
       double a1[C::TR1][C::TC1][2], a2[C::TR1][C::TC1][2];
 #pragma unroll
@@ -220,23 +287,45 @@ __global__ void __launch_bounds__(256, C::MINB) k_predict_main(const PredictArgs
             dmma884(a2[i][j][0], a2[i][j][1], fa[i], fj[j]);
           }
       }
-      double* P1 = Ps + (w1k * 2 + 0) * C::BQ * C::CS;
-      double* P2 = Ps + (w1k * 2 + 1) * C::BQ * C::CS;
+      if constexpr (C::W1K == 1) {
+        // fused: Matern transform straight on the accumulator fragments (predict.py:199-217)
 #pragma unroll
-      for (int i = 0; i < C::TR1; ++i)
+        for (int i = 0; i < C::TR1; ++i) {
+          const int r = row1 + i * 8 + lr;
+          const double qr = qq[r];
 #pragma unroll
-        for (int j = 0; j < C::TC1; ++j) {
-          const int off = (row1 + i * 8 + lr) * C::CS + col1 + j * 8 + 2 * lc;
-          *reinterpret_cast<double2*>(P1 + off) = make_double2(a1[i][j][0], a1[i][j][1]);
-          *reinterpret_cast<double2*>(P2 + off) = make_double2(a2[i][j][0], a2[i][j][1]);
+          for (int j = 0; j < C::TC1; ++j) {
+            const int mc = col1 + j * 8 + 2 * lc;
+            double c1v[2], c2v[2];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              const double a = a2[i][j][h] - xjat[mc + h];
+              matern52(qr + mmt[mc + h] - 2.0 * a1[i][j][h], a, mk, c1v[h], c2v[h]);
+              csum_part[i] += c1v[h];
+              E_part[i] = fma(a, c2v[h], E_part[i]);
+            }
+            const int off = r * C::CS + mc;
+            *reinterpret_cast<double2*>(C1s + off) = make_double2(c1v[0], c1v[1]);
+            *reinterpret_cast<double2*>(C2s + off) = make_double2(c2v[0], c2v[1]);
+          }
         }
+      } else {
+        double* P1 = Ps + (w1k * 2 + 0) * C::BQ * C::CS;
+        double* P2 = Ps + (w1k * 2 + 1) * C::BQ * C::CS;
+#pragma unroll
+        for (int i = 0; i < C::TR1; ++i)
+#pragma unroll
+          for (int j = 0; j < C::TC1; ++j) {
+            const int off = (row1 + i * 8 + lr) * C::CS + col1 + j * 8 + 2 * lc;
+            *reinterpret_cast<double2*>(P1 + off) = make_double2(a1[i][j][0], a1[i][j][1]);
+            *reinterpret_cast<double2*>(P2 + off) = make_double2(a2[i][j][0], a2[i][j][1]);
+          }
+      }
     }
     __syncthreads();
 
-    // ---------------- elementwise Matern-5/2 transform (predict.py:199-217), in place
-    {
-      const double* mmt = mms + s * C::BM;
-      const double* xjat = xjas + s * C::BM;
+    if constexpr (C::W1K > 1) {
+      // ---------------- split-k: sum the partials, Matern transform in place
 #pragma unroll
       for (int j = 0; j < C::EPT; ++j) {
         const int e = tid + j * C::NT;
@@ -248,82 +337,129 @@ __global__ void __launch_bounds__(256, C::MINB) k_predict_main(const PredictArgs
           s1 += Ps[(wk * 2 + 0) * C::BQ * C::CS + off];
           s2 += Ps[(wk * 2 + 1) * C::BQ * C::CS + off];
         }
-        const double n2 = fmax(qq[r] + mmt[mc] - 2.0 * s1, 0.0);
-        const double nrm = sqrt(5.0 * n2);        // sqrt5 * |delta|   (predict.py:204)
-        const double a = s2 - xjat[mc];           // delta . JA        (predict.py:208-210)
-        const double base = exp(-nrm * sig_inv) * k_base;  // predict.py:206-207
-        const double c1 = a * base * k_diag;      // predict.py:212
-        const double c2 = base * (nrm + sig);     // predict.py:213
+        const double a = s2 - xjat[mc];
+        double c1, c2;
+        matern52(qq[r] + mmt[mc] - 2.0 * s1, a, mk, c1, c2);
         csum_part[j] += c1;
-        E_part[j] = fma(a, c2, E_part[j]);        // predict.py:217
-        Ps[off] = c1;
-        Ps[C::BQ * C::CS + off] = c2;
+        E_part[j] = fma(a, c2, E_part[j]);
+        C1s[off] = c1;
+        C2s[off] = c2;
       }
+      __syncthreads();
     }
-    __syncthreads();
 
     // ---------------- GEMM2: accG += C1 Xc + C2 JA (contraction over the BM points)
     {
-      const double* c1a = Ps + (row2 + lr) * C::CS + lc;
-      const double* c2a = c1a + C::BQ * C::CS;
+      const double* c1a = C1s + (row2 + lr) * C::CS + lc;
+      const double* c2a = C2s + (row2 + lr) * C::CS + lc;
       const double* xb = Xt + lc * C::DS + dcol2 + lr;
       const double* jb = JAt + lc * C::DS + dcol2 + lr;
+      if constexpr (C::W2S == 1) {
 #pragma unroll 2
-      for (int ks = 0; ks < C::BM / 4; ++ks) {
-        double f1[C::TR2], f2[C::TR2], fx[C::TD2], fj[C::TD2];
+        for (int ks = 0; ks < C::BM / 4; ++ks) {
+          double f1[C::TR2], f2[C::TR2], fx[C::TD2], fj[C::TD2];
 #pragma unroll
-        for (int i = 0; i < C::TR2; ++i) {
-          f1[i] = c1a[i * 8 * C::CS + ks * 4];
-          f2[i] = c2a[i * 8 * C::CS + ks * 4];
-        }
-#pragma unroll
-        for (int j = 0; j < C::TD2; ++j) {
-          fx[j] = xb[ks * 4 * C::DS + j * 8];
-          fj[j] = jb[ks * 4 * C::DS + j * 8];
-        }
-#pragma unroll
-        for (int i = 0; i < C::TR2; ++i)
+          for (int i = 0; i < C::TR2; ++i) {
+            f1[i] = c1a[i * 8 * C::CS + ks * 4];
+            f2[i] = c2a[i * 8 * C::CS + ks * 4];
+          }
 #pragma unroll
           for (int j = 0; j < C::TD2; ++j) {
-            dmma884(accG[i][j][0], accG[i][j][1], f1[i], fx[j]);
-            dmma884(accG[i][j][0], accG[i][j][1], f2[i], fj[j]);
+            fx[j] = xb[ks * 4 * C::DS + j * 8];
+            fj[j] = jb[ks * 4 * C::DS + j * 8];
           }
+#pragma unroll
+          for (int i = 0; i < C::TR2; ++i)
+#pragma unroll
+            for (int j = 0; j < C::TD2; ++j) {
+              dmma884(accG[i][j][0], accG[i][j][1], f1[i], fx[j]);
+              dmma884(accG[i][j][0], accG[i][j][1], f2[i], fj[j]);
+            }
+        }
+      } else {
+        const double* ca = w2s ? c2a : c1a;
+        const double* ob = w2s ? jb : xb;
+#pragma unroll 2
+        for (int ks = 0; ks < C::BM / 4; ++ks) {
+          double f[C::TR2], fo[C::TD2];
+#pragma unroll
+          for (int i = 0; i < C::TR2; ++i) f[i] = ca[i * 8 * C::CS + ks * 4];
+#pragma unroll
+          for (int j = 0; j < C::TD2; ++j) fo[j] = ob[ks * 4 * C::DS + j * 8];
+#pragma unroll
+          for (int i = 0; i < C::TR2; ++i)
+#pragma unroll
+            for (int j = 0; j < C::TD2; ++j) dmma884(accG[i][j][0], accG[i][j][1], f[i], fo[j]);
+        }
       }
     }
     __syncthreads();
     if (tid == 0 && t + 2 < n_tiles) issue_tile(t + 2);
   }
 
-  // ---- reduce csum / E over the BM threads that share a row
+  // ---- row sums csum[r] = sum_m c1, E[r] = sum_m a c2
+  if constexpr (C::W1K > 1) {
 #pragma unroll
-  for (int j = 0; j < C::EPT; ++j) {
-    double cs = csum_part[j], es = E_part[j];
+    for (int j = 0; j < C::EPT; ++j) {
+      double cs = csum_part[j], es = E_part[j];
 #pragma unroll
-    for (int o = C::BM / 2; o > 0; o >>= 1) {
-      cs += __shfl_xor_sync(0xffffffffu, cs, o);
-      es += __shfl_xor_sync(0xffffffffu, es, o);
+      for (int o = C::BM / 2; o > 0; o >>= 1) {
+        cs += __shfl_xor_sync(0xffffffffu, cs, o);
+        es += __shfl_xor_sync(0xffffffffu, es, o);
+      }
+      const int e = tid + j * C::NT;
+      if (e % C::BM == 0) {
+        csum_s[e / C::BM] = cs;
+        E_s[e / C::BM] = es;
+      }
     }
-    const int e = tid + j * C::NT;
-    if (e % C::BM == 0) {
-      csum_s[e / C::BM] = cs;
-      E_s[e / C::BM] = es;
+  } else {
+#pragma unroll
+    for (int i = 0; i < C::TR1; ++i) {
+      double cs = csum_part[i], es = E_part[i];
+      cs += __shfl_xor_sync(0xffffffffu, cs, 1);
+      es += __shfl_xor_sync(0xffffffffu, es, 1);
+      cs += __shfl_xor_sync(0xffffffffu, cs, 2);
+      es += __shfl_xor_sync(0xffffffffu, es, 2);
+      if (lc == 0) {  // W1M warps share a row: csum_s / E_s were zeroed before the sweep
+        atomicAdd(&csum_s[row1 + i * 8 + lr], cs);
+        atomicAdd(&E_s[row1 + i * 8 + lr], es);
+      }
+    }
+  }
+  if constexpr (C::W2S == 2) {
+    // the JA group parks its partial sums in the (now free) S/C region
+    if (w2s == 1) {
+#pragma unroll
+      for (int i = 0; i < C::TR2; ++i)
+#pragma unroll
+        for (int j = 0; j < C::TD2; ++j)
+          *reinterpret_cast<double2*>(Ps + (row2 + i * 8 + lr) * C::DP + dcol2 + j * 8 + 2 * lc) =
+              make_double2(accG[i][j][0], accG[i][j][1]);
     }
   }
   __syncthreads();
 
   // ---- G = (sum_m c1) Q - (C1 Xc + C2 JA)
+  if (C::W2S == 1 || w2s == 0) {
 #pragma unroll
-  for (int i = 0; i < C::TR2; ++i) {
-    const int r = row2 + i * 8 + lr;
-    const int64_t row = r0 + r;
-    if (row < p.n_rows) {
-      const double cs = csum_s[r];
+    for (int i = 0; i < C::TR2; ++i) {
+      const int r = row2 + i * 8 + lr;
+      const int64_t row = r0 + r;
+      if (row < p.n_rows) {
+        const double cs = csum_s[r];
 #pragma unroll
-      for (int j = 0; j < C::TD2; ++j) {
-        const int col = dcol2 + j * 8 + 2 * lc;
-        const double g0 = cs * Qs[r * C::DS + col] - accG[i][j][0];
-        const double g1 = cs * Qs[r * C::DS + col + 1] - accG[i][j][1];
-        *reinterpret_cast<double2*>(p.G + row * C::DP + col) = make_double2(g0, g1);
+        for (int j = 0; j < C::TD2; ++j) {
+          const int col = dcol2 + j * 8 + 2 * lc;
+          double g0 = cs * Qs[r * C::DS + col] - accG[i][j][0];
+          double g1 = cs * Qs[r * C::DS + col + 1] - accG[i][j][1];
+          if constexpr (C::W2S == 2) {
+            const double2 o = *reinterpret_cast<const double2*>(Ps + r * C::DP + col);
+            g0 -= o.x;
+            g1 -= o.y;
+          }
+          *reinterpret_cast<double2*>(p.G + row * C::DP + col) = make_double2(g0, g1);
+        }
       }
     }
   }
@@ -467,7 +603,7 @@ namespace {
 // tile configurations: <DP, BQ, BM, W1Q, W1M, W1K, W2Q, W2D>
 // D <= 40: two co-resident CTAs per SM so that one CTA's transform / barriers / prologue overlap
 // the other's DMMA phases (the sweep over M is only a handful of tiles at ethanol size)
-using Cfg40 = PCfg<40, 64, 32, 4, 2, 1, 8, 1, 2>;
+using Cfg40 = PCfg<40, 64, 32, 4, 2, 1, 4, 1, 2, 2>;
 using Cfg72 = PCfg<72, 64, 32, 4, 2, 1, 8, 1>;
 using Cfg112 = PCfg<112, 64, 16, 4, 1, 2, 4, 2>;
 using Cfg160 = PCfg<160, 32, 16, 2, 1, 4, 2, 4>;
