@@ -63,11 +63,11 @@ struct PCfg {
   static constexpr int OFF_QQ = OFF_P + W1K * 2 * BQ * CS;
   static constexpr int OFF_CSUM = OFF_QQ + BQ;
   static constexpr int OFF_E = OFF_CSUM + BQ;
-  static constexpr int OFF_BAR = OFF_E + BQ;              // 2 x uint64
-  static constexpr int SMEM_DOUBLES = OFF_BAR + 2;
+  static constexpr int OFF_BAR = OFF_E + BQ;              // 3 x uint64
+  static constexpr int SMEM_DOUBLES = OFF_BAR + 4;
   static constexpr size_t SMEM_BYTES = (size_t)SMEM_DOUBLES * 8;
   static_assert(SMEM_BYTES <= 232448, "exceeds 227 KB of shared memory");
-  static_assert((BM * DS * 8) % 16 == 0 && (BM * 8) % 16 == 0, "bulk copy granularity");
+  static_assert((BM * DS * 8) % 16 == 0 && (BM * 8) % 16 == 0 && (BQ * 8) % 16 == 0, "bulk copy granularity");
 };
 
 struct PredictArgs {
@@ -76,12 +76,11 @@ struct PredictArgs {
   const double* JA;     // (Mpad, DS) R_d_desc_alpha, zero padded
   const double* mm;     // (Mpad) |Xc_m|^2
   const double* xja;    // (Mpad) Xc_m . JA_m
-  const double* mu;     // (DP) centre
-  const int* pinv;      // (S, D) inverse descriptor perms
   int D, M, S, Mpad;
   double sig;
-  // queries
-  const double* xq;     // (B, D) query descriptors
+  // queries: virtual rows (b, p) prepared by k_query_rows
+  const double* Qg;     // (rows padded to BQ, DS)  q_{b,p}[e] = x_b[pinv_p[e]] - mu[e], zero padded
+  const double* qqg;    // (rows padded to BQ)      |q_{b,p}|^2
   int64_t n_rows;       // B*S virtual rows
   // outputs
   double* G;            // (n_rows, DP)
@@ -97,35 +96,38 @@ __device__ __forceinline__ double exp_neg(double t) {
   const double kf = rint(-t * 1.4426950408889634074);
   double r = fma(kf, -6.93147180369123816490e-01, -t);
   r = fma(kf, -1.90821492927058770002e-10, r);
-  double p = 2.08767569878680989792e-09;  // 1/12!
-  p = fma(p, r, 2.50521083854417187751e-08);
-  p = fma(p, r, 2.75573192239858906526e-07);
-  p = fma(p, r, 2.75573192239858906526e-06);
-  p = fma(p, r, 2.48015873015873015873e-05);
-  p = fma(p, r, 1.98412698412698412698e-04);
-  p = fma(p, r, 1.38888888888888888889e-03);
-  p = fma(p, r, 8.33333333333333333333e-03);
-  p = fma(p, r, 4.16666666666666666667e-02);
-  p = fma(p, r, 1.66666666666666666667e-01);
-  p = fma(p, r, 0.5);
-  p = fma(p, r, 1.0);
-  p = fma(p, r, 1.0);
+  // Estrin evaluation (dependency depth 5 instead of 12: the transform is latency-sensitive)
+  const double r2 = r * r;
+  const double a0 = 1.0 + r;
+  const double a1 = fma(1.66666666666666666667e-01, r, 0.5);
+  const double a2 = fma(8.33333333333333333333e-03, r, 4.16666666666666666667e-02);
+  const double a3 = fma(1.98412698412698412698e-04, r, 1.38888888888888888889e-03);
+  const double a4 = fma(2.75573192239858906526e-06, r, 2.48015873015873015873e-05);
+  const double a5 = fma(2.50521083854417187751e-08, r, 2.75573192239858906526e-07);
+  const double r4 = r2 * r2;
+  const double b0 = fma(a1, r2, a0);
+  const double b1 = fma(a3, r2, a2);
+  const double b2 = fma(a5, r2, a4);
+  const double r8 = r4 * r4;
+  const double d0 = fma(b1, r4, b0);
+  const double d1 = fma(2.08767569878680989792e-09, r4, b2);  // 1/12! r^12 term
+  const double pv = fma(d1, r8, d0);
   const long long k = (long long)kf;
-  return p * __longlong_as_double((k + 1023) << 52);
+  return pv * __longlong_as_double((k + 1023) << 52);
 }
 
 struct MaternK {
-  double sig, sig_inv, k_base, k_diag;
+  double sig, sig_inv, k_base, k_c1;  // k_c1 = k_base * 5/sig
 };
-// n2raw = |q|^2 + |x|^2 - 2 q.x (may be slightly negative), a = delta . JA  ->  c1, c2
-// (predict.py:204-213):  n = sqrt5 |delta|, base = exp(-n/sig) 5/(3 sig^3), c1 = a base 5/sig,
-// c2 = base (n + sig)
-__device__ __forceinline__ void matern52(double n2raw, double a, const MaternK& k, double& c1, double& c2) {
-  const double x = 5.0 * fmax(n2raw, 0.0);
-  const double nrm = (x > 0.0) ? x * rsqrt(x) : 0.0;
-  const double base = exp_neg(nrm * k.sig_inv) * k.k_base;
-  c1 = a * base * k.k_diag;
-  c2 = base * (nrm + k.sig);
+// x5 = 5 (|q|^2 + |x|^2 - 2 q.x) (may be slightly negative), a = delta . JA  ->  c1, c2
+// (predict.py:204-213):  n = sqrt(x5) = sqrt5 |delta|, base = exp(-n/sig) 5/(3 sig^3),
+// c1 = a base 5/sig, c2 = base (n + sig)
+__device__ __forceinline__ void matern52(double x5, double a, const MaternK& k, double& c1, double& c2) {
+  const double x = fmax(x5, 1e-300);   // n = 1e-150 stands in for 0: no branch, no 0 * inf
+  const double nrm = x * rsqrt(x);
+  const double e = exp_neg(nrm * k.sig_inv);
+  c1 = a * (e * k.k_c1);
+  c2 = (e * k.k_base) * (nrm + k.sig);
 }
 
 // ============================================================== main kernel
@@ -153,6 +155,7 @@ __global__ void __launch_bounds__(256, C::MINB) k_predict_main(const PredictArgs
   if (tid == 0) {
     mbar_init(&bars[0], 1);
     mbar_init(&bars[1], 1);
+    mbar_init(&bars[2], 1);
     fence_mbar_init();
   }
   __syncthreads();
@@ -167,53 +170,19 @@ __global__ void __launch_bounds__(256, C::MINB) k_predict_main(const PredictArgs
     bulk_g2s(xjas + s * C::BM, p.xja + m0, C::BM * 8, &bars[s]);
   };
   if (tid == 0) {
+    // the Q tile (BQ prepared virtual rows, contiguous) and its row norms: two bulk copies
+    mbar_arrive_expect_tx(&bars[2], (uint32_t)((C::BQ * C::DS + C::BQ) * 8));
+    bulk_g2s(Qs, p.Qg + r0 * C::DS, C::BQ * C::DS * 8, &bars[2]);
+    bulk_g2s(qq, p.qqg + r0, C::BQ * 8, &bars[2]);
     issue_tile(0);
     if (n_tiles > 1) issue_tile(1);
-  }
-
-  // ---- build the Q tile: Q[r][e] = x_b[pinv_p[e]] - mu[e]  (row r <-> (b, p) = divmod(r0 + r, S))
-  {
-    const int64_t b_lo = r0 / p.S;
-    const int64_t row_hi = min(r0 + (int64_t)C::BQ, p.n_rows) - 1;
-    const int nb = (row_hi >= r0) ? (int)(row_hi / p.S - b_lo + 1) : 0;
-    const bool staged = (nb * p.D <= C::W1K * 2 * C::BQ * C::CS);
-    if (staged) {
-      // the tile's query descriptors are contiguous in xq: stage them in the (still unused) S/C
-      // region with coalesced loads, then gather from shared memory
-      const double* src = p.xq + b_lo * p.D;
-      for (int idx = tid; idx < nb * p.D; idx += C::NT) Ps[idx] = src[idx];
-      __syncthreads();
-    }
-#pragma unroll 4
-    for (int idx = tid; idx < C::BQ * C::DS; idx += C::NT) {
-      const int r = idx / C::DS, e = idx - r * C::DS;
-      const int64_t row = r0 + r;
-      double v = 0.0;
-      if (row < p.n_rows && e < p.D) {
-        const int64_t b = row / p.S;
-        const int pp = (int)(row - b * p.S);
-        const int d = p.pinv[pp * p.D + e];
-        v = (staged ? Ps[(int)(b - b_lo) * p.D + d] : p.xq[b * p.D + d]) - p.mu[e];
-      }
-      Qs[idx] = v;
-    }
   }
   if (tid < C::BQ) {
     csum_s[tid] = 0.0;
     E_s[tid] = 0.0;
   }
   __syncthreads();
-  for (int r = warp; r < C::BQ; r += 8) {
-    double s = 0.0;
-    for (int e = lane; e < C::DP; e += 32) {
-      const double v = Qs[r * C::DS + e];
-      s = fma(v, v, s);
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    if (lane == 0) qq[r] = s;
-  }
-  __syncthreads();
+  mbar_wait(&bars[2], 0);
 
   // GEMM1 warp coordinates
   const int w1k = warp % C::W1K;
@@ -246,7 +215,7 @@ __global__ void __launch_bounds__(256, C::MINB) k_predict_main(const PredictArgs
   mk.sig = p.sig;
   mk.sig_inv = 1.0 / p.sig;
   mk.k_base = 5.0 / (3.0 * p.sig * p.sig * p.sig);  // predict.py:195 mat52_base_fact
-  mk.k_diag = 5.0 / p.sig;                          // predict.py:196 diag_scale_fact
+  mk.k_c1 = mk.k_base * 5.0 / p.sig;                // ... times predict.py:196 diag_scale_fact
 
   double* C1s = Ps;
   double* C2s = Ps + C::BQ * C::CS;
@@ -258,6 +227,9 @@ __global__ void __launch_bounds__(256, C::MINB) k_predict_main(const PredictArgs
     const double* mmt = mms + s * C::BM;
     const double* xjat = xjas + s * C::BM;
     mbar_wait(&bars[s], (uint32_t)((t >> 1) & 1));
+    // real training points in this tile: the zero-padded tail of the last tile is skipped
+    // (whole 8-point fragment columns in GEMM1, whole 4-point k-steps in GEMM2)
+    const int mvalid = min(C::BM, p.M - t * C::BM);
 
     // ---------------- GEMM1: S1 = Q Xc^T, S2 = Q JA^T (over this warp's k-range)
     {
@@ -280,33 +252,38 @@ __global__ void __launch_bounds__(256, C::MINB) k_predict_main(const PredictArgs
           fj[j] = jb[j * 8 * C::DS + ks * 4];
         }
 #pragma unroll
-        for (int i = 0; i < C::TR1; ++i)
+        for (int j = 0; j < C::TC1; ++j) {
+          if (col1 + j * 8 < mvalid) {  // warp-uniform
 #pragma unroll
-          for (int j = 0; j < C::TC1; ++j) {
-            dmma884(a1[i][j][0], a1[i][j][1], fa[i], fx[j]);
-            dmma884(a2[i][j][0], a2[i][j][1], fa[i], fj[j]);
+            for (int i = 0; i < C::TR1; ++i) {
+              dmma884(a1[i][j][0], a1[i][j][1], fa[i], fx[j]);
+              dmma884(a2[i][j][0], a2[i][j][1], fa[i], fj[j]);
+            }
           }
+        }
       }
       if constexpr (C::W1K == 1) {
         // fused: Matern transform straight on the accumulator fragments (predict.py:199-217)
 #pragma unroll
-        for (int i = 0; i < C::TR1; ++i) {
-          const int r = row1 + i * 8 + lr;
-          const double qr = qq[r];
+        for (int j = 0; j < C::TC1; ++j) {
+          const int mc = col1 + j * 8 + 2 * lc;
+          if (col1 + j * 8 < mvalid) {  // warp-uniform: fragment columns of real training points
+            const double m5a = 5.0 * mmt[mc], m5b = 5.0 * mmt[mc + 1];
+            const double xa = xjat[mc], xb2 = xjat[mc + 1];
 #pragma unroll
-          for (int j = 0; j < C::TC1; ++j) {
-            const int mc = col1 + j * 8 + 2 * lc;
-            double c1v[2], c2v[2];
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-              const double a = a2[i][j][h] - xjat[mc + h];
-              matern52(qr + mmt[mc + h] - 2.0 * a1[i][j][h], a, mk, c1v[h], c2v[h]);
-              csum_part[i] += c1v[h];
-              E_part[i] = fma(a, c2v[h], E_part[i]);
+            for (int i = 0; i < C::TR1; ++i) {
+              const int r = row1 + i * 8 + lr;
+              const double q5 = 5.0 * qq[r];
+              double c1a_, c2a_, c1b_, c2b_;
+              const double aa = a2[i][j][0] - xa, ab = a2[i][j][1] - xb2;
+              matern52(fma(-10.0, a1[i][j][0], q5 + m5a), aa, mk, c1a_, c2a_);
+              matern52(fma(-10.0, a1[i][j][1], q5 + m5b), ab, mk, c1b_, c2b_);
+              csum_part[i] += c1a_ + c1b_;
+              E_part[i] = fma(aa, c2a_, fma(ab, c2b_, E_part[i]));
+              const int off = r * C::CS + mc;
+              *reinterpret_cast<double2*>(C1s + off) = make_double2(c1a_, c1b_);
+              *reinterpret_cast<double2*>(C2s + off) = make_double2(c2a_, c2b_);
             }
-            const int off = r * C::CS + mc;
-            *reinterpret_cast<double2*>(C1s + off) = make_double2(c1v[0], c1v[1]);
-            *reinterpret_cast<double2*>(C2s + off) = make_double2(c2v[0], c2v[1]);
           }
         }
       } else {
@@ -339,7 +316,7 @@ __global__ void __launch_bounds__(256, C::MINB) k_predict_main(const PredictArgs
         }
         const double a = s2 - xjat[mc];
         double c1, c2;
-        matern52(qq[r] + mmt[mc] - 2.0 * s1, a, mk, c1, c2);
+        matern52(fma(-10.0, s1, 5.0 * (qq[r] + mmt[mc])), a, mk, c1, c2);
         csum_part[j] += c1;
         E_part[j] = fma(a, c2, E_part[j]);
         C1s[off] = c1;
@@ -354,9 +331,10 @@ __global__ void __launch_bounds__(256, C::MINB) k_predict_main(const PredictArgs
       const double* c2a = C2s + (row2 + lr) * C::CS + lc;
       const double* xb = Xt + lc * C::DS + dcol2 + lr;
       const double* jb = JAt + lc * C::DS + dcol2 + lr;
+      const int ks_end = (mvalid + 3) >> 2;
       if constexpr (C::W2S == 1) {
 #pragma unroll 2
-        for (int ks = 0; ks < C::BM / 4; ++ks) {
+        for (int ks = 0; ks < ks_end; ++ks) {
           double f1[C::TR2], f2[C::TR2], fx[C::TD2], fj[C::TD2];
 #pragma unroll
           for (int i = 0; i < C::TR2; ++i) {
@@ -380,7 +358,7 @@ __global__ void __launch_bounds__(256, C::MINB) k_predict_main(const PredictArgs
         const double* ca = w2s ? c2a : c1a;
         const double* ob = w2s ? jb : xb;
 #pragma unroll 2
-        for (int ks = 0; ks < C::BM / 4; ++ks) {
+        for (int ks = 0; ks < ks_end; ++ks) {
           double f[C::TR2], fo[C::TD2];
 #pragma unroll
           for (int i = 0; i < C::TR2; ++i) f[i] = ca[i * 8 * C::CS + ks * 4];
@@ -464,6 +442,36 @@ __global__ void __launch_bounds__(256, C::MINB) k_predict_main(const PredictArgs
     }
   }
   if (tid < C::BQ && r0 + tid < p.n_rows) p.Erow[r0 + tid] = E_s[tid];
+}
+
+// ============================================================== query rows
+// One warp per virtual row (b, p): Qg[row][e] = x_b[pinv_p[e]] - mu[e] (zero beyond D and beyond the
+// last real row, so that every main-kernel tile is one contiguous bulk copy) and qq[row] = |Qg[row]|^2.
+__global__ void __launch_bounds__(256) k_query_rows(const double* __restrict__ xq, const int* __restrict__ pinv,
+                                                    const double* __restrict__ mu, int D, int DS, int S,
+                                                    int64_t n_rows, int64_t n_rows_pad, double* __restrict__ Qg,
+                                                    double* __restrict__ qqg) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= n_rows_pad) return;
+  double s = 0.0;
+  if (row < n_rows) {
+    const int64_t b = row / S;
+    const int pp = (int)(row - b * S);
+    const double* x = xq + b * D;
+    const int* pi = pinv + pp * D;
+    for (int e = lane; e < DS; e += 32) {
+      double v = 0.0;
+      if (e < D) v = x[pi[e]] - mu[e];
+      Qg[row * DS + e] = v;
+      s = fma(v, v, s);
+    }
+  } else {
+    for (int e = lane; e < DS; e += 32) Qg[row * DS + e] = 0.0;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane == 0) qqg[row] = s;
 }
 
 // ============================================================== finishing kernel
@@ -592,10 +600,14 @@ struct sgdml_b200_model {
   double *Xc = nullptr, *JA = nullptr, *mm = nullptr, *xja = nullptr, *mu = nullptr;
   int *perm = nullptr, *pinv = nullptr;  // (S, D)
   double* R_d_desc = nullptr;            // (M, D, 3), optional
-  // workspace for up to ws_geo queries
-  int64_t ws_geo = 0;
-  double *ws_xq = nullptr, *ws_gq = nullptr, *ws_G = nullptr, *ws_Erow = nullptr, *ws_R = nullptr, *ws_E = nullptr,
-         *ws_F = nullptr;
+  // two workspace slots (slot 1 and the side streams are only used by the host-I/O pipeline)
+  struct WS {
+    int64_t geo = 0;
+    double *xq = nullptr, *gq = nullptr, *G = nullptr, *Erow = nullptr, *R = nullptr, *E = nullptr, *F = nullptr,
+           *Qg = nullptr, *qq = nullptr;
+  } ws[2];
+  cudaStream_t pipe_stream[2] = {nullptr, nullptr};
+  cudaEvent_t pipe_event[3] = {nullptr, nullptr, nullptr};
 };
 
 namespace {
@@ -644,28 +656,53 @@ int launch_main(int cfg, const PredictArgs& a, cudaStream_t s) {
 }
 
 void free_ws(sgdml_b200_model* m) {
-  cudaFree(m->ws_xq);
-  cudaFree(m->ws_gq);
-  cudaFree(m->ws_G);
-  cudaFree(m->ws_Erow);
-  cudaFree(m->ws_R);
-  cudaFree(m->ws_E);
-  cudaFree(m->ws_F);
-  m->ws_xq = m->ws_gq = m->ws_G = m->ws_Erow = m->ws_R = m->ws_E = m->ws_F = nullptr;
-  m->ws_geo = 0;
+  for (auto& w : m->ws) {
+    cudaFree(w.xq);
+    cudaFree(w.gq);
+    cudaFree(w.G);
+    cudaFree(w.Erow);
+    cudaFree(w.R);
+    cudaFree(w.E);
+    cudaFree(w.F);
+    cudaFree(w.Qg);
+    cudaFree(w.qq);
+    w = sgdml_b200_model::WS();
+  }
 }
 
-int ensure_ws(sgdml_b200_model* m, int64_t n_geo) {
-  if (n_geo <= m->ws_geo) return 0;
-  free_ws(m);
-  SG_CUDA(cudaMalloc(&m->ws_xq, sizeof(double) * n_geo * m->D));
-  SG_CUDA(cudaMalloc(&m->ws_gq, sizeof(double) * n_geo * m->D * 3));
-  SG_CUDA(cudaMalloc(&m->ws_G, sizeof(double) * n_geo * m->S * m->DP));
-  SG_CUDA(cudaMalloc(&m->ws_Erow, sizeof(double) * n_geo * m->S));
-  SG_CUDA(cudaMalloc(&m->ws_R, sizeof(double) * n_geo * 3 * m->N));
-  SG_CUDA(cudaMalloc(&m->ws_E, sizeof(double) * n_geo));
-  SG_CUDA(cudaMalloc(&m->ws_F, sizeof(double) * n_geo * 3 * m->N));
-  m->ws_geo = n_geo;
+int ensure_ws(sgdml_b200_model* m, int slot, int64_t n_geo) {
+  sgdml_b200_model::WS& w = m->ws[slot];
+  if (n_geo <= w.geo) return 0;
+  cudaFree(w.xq);
+  cudaFree(w.gq);
+  cudaFree(w.G);
+  cudaFree(w.Erow);
+  cudaFree(w.R);
+  cudaFree(w.E);
+  cudaFree(w.F);
+  cudaFree(w.Qg);
+  cudaFree(w.qq);
+  w = sgdml_b200_model::WS();
+  SG_CUDA(cudaMalloc(&w.xq, sizeof(double) * n_geo * m->D));
+  SG_CUDA(cudaMalloc(&w.gq, sizeof(double) * n_geo * m->D * 3));
+  SG_CUDA(cudaMalloc(&w.G, sizeof(double) * n_geo * m->S * m->DP));
+  SG_CUDA(cudaMalloc(&w.Erow, sizeof(double) * n_geo * m->S));
+  SG_CUDA(cudaMalloc(&w.R, sizeof(double) * n_geo * 3 * m->N));
+  SG_CUDA(cudaMalloc(&w.E, sizeof(double) * n_geo));
+  SG_CUDA(cudaMalloc(&w.F, sizeof(double) * n_geo * 3 * m->N));
+  {
+    const int64_t rows_pad = (n_geo * m->S + m->BQ - 1) / m->BQ * m->BQ;
+    SG_CUDA(cudaMalloc(&w.Qg, sizeof(double) * rows_pad * m->DS));
+    SG_CUDA(cudaMalloc(&w.qq, sizeof(double) * rows_pad));
+  }
+  w.geo = n_geo;
+  return 0;
+}
+
+int ensure_pipe(sgdml_b200_model* m) {
+  if (m->pipe_stream[0] != nullptr) return 0;
+  for (int i = 0; i < 2; ++i) SG_CUDA(cudaStreamCreateWithFlags(&m->pipe_stream[i], cudaStreamNonBlocking));
+  for (int i = 0; i < 3; ++i) SG_CUDA(cudaEventCreateWithFlags(&m->pipe_event[i], cudaEventDisableTiming));
   return 0;
 }
 
@@ -679,24 +716,33 @@ int64_t chunk_geos(const sgdml_b200_model* m) {
 }
 
 // Runs the predictor on n_geo queries whose descriptors (xq, gq) are on the device.
-int run_queries(sgdml_b200_model* m, const double* xq, const double* gq, int64_t n_geo, double std, double c,
-                double* E_dev, double* F_dev, cudaStream_t s) {
+int run_queries(sgdml_b200_model* m, int slot, const double* xq, const double* gq, int64_t n_geo, double std,
+                double c, double* E_dev, double* F_dev, cudaStream_t s) {
+  sgdml_b200_model::WS& w = m->ws[slot];
+  const int64_t n_rows = n_geo * m->S;
+  const int64_t n_rows_pad = (n_rows + m->BQ - 1) / m->BQ * m->BQ;
+  {
+    ProfScope ps(KID_PREDICT_AUX, s);
+    k_query_rows<<<(unsigned)((n_rows_pad + 7) / 8), 256, 0, s>>>(xq, m->pinv, m->mu, m->D, m->DS, m->S, n_rows,
+                                                                 n_rows_pad, w.Qg, w.qq);
+    SG_CUDA(cudaGetLastError());
+    count_launch(KID_PREDICT_AUX);
+  }
   PredictArgs a;
   a.Xc = m->Xc;
   a.JA = m->JA;
   a.mm = m->mm;
   a.xja = m->xja;
-  a.mu = m->mu;
-  a.pinv = m->pinv;
   a.D = m->D;
   a.M = m->M;
   a.S = m->S;
   a.Mpad = m->Mpad;
   a.sig = m->sig;
-  a.xq = xq;
-  a.n_rows = n_geo * m->S;
-  a.G = m->ws_G;
-  a.Erow = m->ws_Erow;
+  a.Qg = w.Qg;
+  a.qqg = w.qq;
+  a.n_rows = n_rows;
+  a.G = w.G;
+  a.Erow = w.Erow;
   {
     ProfScope ps(KID_PREDICT_MAIN, s);
     SG_TRY(launch_main(m->cfg, a, s));
@@ -704,7 +750,7 @@ int run_queries(sgdml_b200_model* m, const double* xq, const double* gq, int64_t
   }
   {
     ProfScope ps(KID_PREDICT_AUX, s);
-    k_predict_finish<<<(unsigned)n_geo, 128, sizeof(double) * m->D, s>>>(m->ws_G, m->ws_Erow, gq, m->perm, m->N, m->D,
+    k_predict_finish<<<(unsigned)n_geo, 128, sizeof(double) * m->D, s>>>(w.G, w.Erow, gq, m->perm, m->N, m->D,
                                                                           m->DP, m->S, std, c, E_dev, F_dev);
     SG_CUDA(cudaGetLastError());
     count_launch(KID_PREDICT_AUX);
@@ -830,6 +876,10 @@ int sgdml_b200_model_destroy(sgdml_b200_model* m) {
   cudaFree(m->pinv);
   cudaFree(m->R_d_desc);
   free_ws(m);
+  for (int i = 0; i < 2; ++i)
+    if (m->pipe_stream[i]) cudaStreamDestroy(m->pipe_stream[i]);
+  for (int i = 0; i < 3; ++i)
+    if (m->pipe_event[i]) cudaEventDestroy(m->pipe_event[i]);
   delete m;
   return 0;
 }
@@ -839,25 +889,47 @@ int sgdml_b200_predict(sgdml_b200_model* m, const double* R, int64_t n_geo, doub
   SG_ARG(m != nullptr && R != nullptr && F != nullptr && n_geo >= 0);
   if (n_geo == 0) return 0;
   cudaStream_t s = (cudaStream_t)stream;
-  const int64_t chunk = std::min<int64_t>(chunk_geos(m), n_geo);
-  SG_TRY(ensure_ws(m, chunk));
   const bool R_dev = is_device_ptr(R), F_dev = is_device_ptr(F), E_dev = (E != nullptr) && is_device_ptr(E);
+  const bool host_io = !R_dev || !F_dev || (E != nullptr && !E_dev);
   const int dimi = 3 * m->N;
-  for (int64_t g0 = 0; g0 < n_geo; g0 += chunk) {
+  int64_t chunk = std::min<int64_t>(chunk_geos(m), n_geo);
+  // Host buffers: split the batch into >= 4 chunks and run them on two side streams so that the
+  // H2D copy of chunk k+1 and the D2H copy of chunk k-1 overlap the kernels of chunk k.
+  const bool pipelined = host_io && n_geo >= 4096 && !profiling_enabled();
+  if (pipelined) chunk = std::min<int64_t>(chunk, std::max<int64_t>(1024, (n_geo + 3) / 4));
+  SG_TRY(ensure_ws(m, 0, chunk));
+  if (pipelined) {
+    SG_TRY(ensure_ws(m, 1, chunk));
+    SG_TRY(ensure_pipe(m));
+    SG_CUDA(cudaEventRecord(m->pipe_event[2], s));
+    SG_CUDA(cudaStreamWaitEvent(m->pipe_stream[0], m->pipe_event[2], 0));
+    SG_CUDA(cudaStreamWaitEvent(m->pipe_stream[1], m->pipe_event[2], 0));
+  }
+  int c_idx = 0;
+  for (int64_t g0 = 0; g0 < n_geo; g0 += chunk, ++c_idx) {
+    const int slot = pipelined ? (c_idx & 1) : 0;
+    cudaStream_t st = pipelined ? m->pipe_stream[slot] : s;
+    sgdml_b200_model::WS& w = m->ws[slot];
     const int64_t ng = std::min<int64_t>(chunk, n_geo - g0);
     const double* Rd = R + g0 * dimi;
     if (!R_dev) {
-      SG_CUDA(cudaMemcpyAsync(m->ws_R, Rd, sizeof(double) * ng * dimi, cudaMemcpyHostToDevice, s));
-      Rd = m->ws_R;
+      SG_CUDA(cudaMemcpyAsync(w.R, Rd, sizeof(double) * ng * dimi, cudaMemcpyHostToDevice, st));
+      Rd = w.R;
     }
-    SG_TRY(launch_desc_from_R(Rd, ng, m->N, m->ws_xq, m->ws_gq, s));
-    double* Fd = F_dev ? F + g0 * dimi : m->ws_F;
-    double* Ed = (E == nullptr) ? nullptr : (E_dev ? E + g0 : m->ws_E);
-    SG_TRY(run_queries(m, m->ws_xq, m->ws_gq, ng, m->std, m->c, Ed, Fd, s));
-    if (!F_dev) SG_CUDA(cudaMemcpyAsync(F + g0 * dimi, Fd, sizeof(double) * ng * dimi, cudaMemcpyDeviceToHost, s));
-    if (E != nullptr && !E_dev) SG_CUDA(cudaMemcpyAsync(E + g0, Ed, sizeof(double) * ng, cudaMemcpyDeviceToHost, s));
+    SG_TRY(launch_desc_from_R(Rd, ng, m->N, w.xq, w.gq, st));
+    double* Fd = F_dev ? F + g0 * dimi : w.F;
+    double* Ed = (E == nullptr) ? nullptr : (E_dev ? E + g0 : w.E);
+    SG_TRY(run_queries(m, slot, w.xq, w.gq, ng, m->std, m->c, Ed, Fd, st));
+    if (!F_dev) SG_CUDA(cudaMemcpyAsync(F + g0 * dimi, Fd, sizeof(double) * ng * dimi, cudaMemcpyDeviceToHost, st));
+    if (E != nullptr && !E_dev) SG_CUDA(cudaMemcpyAsync(E + g0, Ed, sizeof(double) * ng, cudaMemcpyDeviceToHost, st));
   }
-  if (!R_dev || !F_dev || (E != nullptr && !E_dev)) SG_CUDA(cudaStreamSynchronize(s));
+  if (pipelined) {
+    for (int i = 0; i < 2; ++i) {
+      SG_CUDA(cudaEventRecord(m->pipe_event[i], m->pipe_stream[i]));
+      SG_CUDA(cudaStreamWaitEvent(s, m->pipe_event[i], 0));
+    }
+  }
+  if (host_io) SG_CUDA(cudaStreamSynchronize(s));
   return 0;
 }
 
@@ -903,7 +975,8 @@ int sgdml_b200_predict_train(sgdml_b200_model* m, int64_t m_begin, int64_t m_end
   if (n_geo == 0) return 0;
   cudaStream_t s = (cudaStream_t)stream;
   const int64_t chunk = std::min<int64_t>(chunk_geos(m), n_geo);
-  SG_TRY(ensure_ws(m, chunk));
+  SG_TRY(ensure_ws(m, 0, chunk));
+  sgdml_b200_model::WS& w = m->ws[0];
   const bool F_dev = is_device_ptr(F), E_dev = (E != nullptr) && is_device_ptr(E);
   const int dimi = 3 * m->N;
   const double std = scaled ? m->std : 1.0, c = scaled ? m->c : 0.0;
@@ -911,9 +984,9 @@ int sgdml_b200_predict_train(sgdml_b200_model* m, int64_t m_begin, int64_t m_end
     const int64_t ng = std::min<int64_t>(chunk, n_geo - g0);
     const double* xq = m->X + (m_begin + g0) * m->D;
     const double* gq = m->R_d_desc + (m_begin + g0) * m->D * 3;
-    double* Fd = F_dev ? F + g0 * dimi : m->ws_F;
-    double* Ed = (E == nullptr) ? nullptr : (E_dev ? E + g0 : m->ws_E);
-    SG_TRY(run_queries(m, xq, gq, ng, std, c, Ed, Fd, s));
+    double* Fd = F_dev ? F + g0 * dimi : w.F;
+    double* Ed = (E == nullptr) ? nullptr : (E_dev ? E + g0 : w.E);
+    SG_TRY(run_queries(m, 0, xq, gq, ng, std, c, Ed, Fd, s));
     if (!F_dev) SG_CUDA(cudaMemcpyAsync(F + g0 * dimi, Fd, sizeof(double) * ng * dimi, cudaMemcpyDeviceToHost, s));
     if (E != nullptr && !E_dev) SG_CUDA(cudaMemcpyAsync(E + g0, Ed, sizeof(double) * ng, cudaMemcpyDeviceToHost, s));
   }

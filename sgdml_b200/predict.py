@@ -142,9 +142,11 @@ class GDMLPredict(object):
         return r.reshape(1, -1)
 
     # ------------------------------------------------------------------ prediction
-    def predict(self, R=None, return_E=True):
+    def predict(self, R=None, return_E=True, out=None):
         """predict.py:1146-1294.  R (B, 3N) [or (3N,)] float64 -> (E (B,), F (B, 3N)) or (F,).
         With R=None the cached training descriptors are evaluated (predict.py:1219-1235).
+        `out=(E, F)` (extension): preallocated outputs of the right shape/dtype on the same device as R
+        (e.g. pinned host tensors), filled in place and returned.
         NumPy in -> NumPy out; torch tensor in (CUDA, or pinned/pageable host) -> torch tensors out on the
         same device (CUDA tensors are used in place, no copies)."""
         L = _lib.lib()
@@ -172,8 +174,11 @@ class GDMLPredict(object):
                 raise ValueError('R must have 3*n_atoms columns')
             R = R.reshape(-1, dim_i)
             n = R.shape[0]
-            F = np.empty((n, dim_i))
-            E = np.empty(n) if return_E else None
+            if out is not None:
+                E, F = out
+            else:
+                F = np.empty((n, dim_i))
+                E = np.empty(n) if return_E else None
         else:
             import torch
 
@@ -181,9 +186,14 @@ class GDMLPredict(object):
                 raise ValueError('torch inputs must be float64')
             R = R.contiguous().reshape(-1, dim_i) if R.dim() != 1 else R.contiguous().reshape(1, dim_i)
             n = R.shape[0]
-            pin = (not R.is_cuda) and R.is_pinned()  # pinned host tensor in -> pinned host tensors out
-            F = torch.empty((n, dim_i), dtype=torch.float64, device=R.device, pin_memory=pin)
-            E = torch.empty((n,), dtype=torch.float64, device=R.device, pin_memory=pin) if return_E else None
+            if out is not None:
+                E, F = out
+            else:
+                pin = (not R.is_cuda) and R.is_pinned()  # pinned host tensor in -> pinned host tensors out
+                F = torch.empty((n, dim_i), dtype=torch.float64, device=R.device, pin_memory=pin)
+                E = torch.empty((n,), dtype=torch.float64, device=R.device, pin_memory=pin) if return_E else None
+        if tuple(F.shape) != (n, dim_i) or (E is not None and tuple(E.shape) != (n,)):
+            raise ValueError('out buffers have the wrong shape')
         _lib.check(
             L.sgdml_b200_predict(self._handle, _lib.ptr(R), n, _lib.ptr(E), _lib.ptr(F), _lib.current_stream()),
             'predict',
