@@ -140,6 +140,30 @@ int sgdml_b200_potrs(const double* L, int64_t n, int64_t lda, double* B, int64_t
 int sgdml_b200_solve_analytic(double* Kneg, int64_t n, int64_t lda, double lam, const double* y,
                               double* alphas, void* stream);
 
+/* ---------------------------------------------------------------- iterative solver blocks (path a)
+ * Nystroem preconditioner of solvers/iterative.py:208-351 on X = K_nm (n_rows x m, row stride ldx),
+ * the kernel columns at the inducing columns, resident in HBM (all matrix pointers below must be
+ * DEVICE pointers; vectors may be host or device). */
+
+/* K_mm = -X[row_idxs, :] (iterative.py:253); out (m x m), row stride ldo. */
+int sgdml_b200_gather_rows_neg(const double* X, int64_t ldx, int64_t m, const int64_t* row_idxs,
+                               double* out, int64_t ldo, void* stream);
+/* A[i][i] += value (the jitter escalation of _cho_factor_stable, iterative.py:414-471). */
+int sgdml_b200_add_diag(double* A, int64_t n, int64_t lda, double value, void* stream);
+/* X <- X L^-T for lower-triangular L (m x m): scipy.linalg.solve_triangular(L, X.T, trans='T').T,
+ * iterative.py:278-287 and 337-347. */
+int sgdml_b200_trsm_right_lt(const double* L, int64_t m, int64_t ldl, double* X, int64_t n_rows,
+                             int64_t ldx, void* stream);
+/* C = X^T X + lam I, lower triangle (iterative.py:293-295). */
+int sgdml_b200_gram_tn(const double* X, int64_t n_rows, int64_t m, int64_t ldx, double lam, double* C,
+                       int64_t ldc, void* stream);
+/* out[r] = |X[r, :]|^2 -- the leverage scores (iterative.py:107-109). */
+int sgdml_b200_row_sqnorms(const double* X, int64_t n_rows, int64_t m, int64_t ldx, double* out,
+                           void* stream);
+/* out = (X (X^T v) - v) / lam -- the preconditioner P v (iterative.py:136-138). */
+int sgdml_b200_nystroem_apply(const double* X, int64_t n_rows, int64_t m, int64_t ldx, double lam,
+                              const double* v, double* out, void* stream);
+
 /* C = alpha * A * B^T + beta * C on the FP64 tensor pipe (the building block of potrf's
  * trailing update; exported for tests and benchmarks).  A (m, k) lda, B (n, k) ldb,
  * C (m, n) ldc, all row-major device or host. */

@@ -17,4 +17,4 @@ inputs and freezes its outputs under ``tests/golden/*.npz``;
 ``tests/test_oracle_vs_golden.py`` checks every oracle function against them.
 """
 
-from . import desc, assemble, solve, predict, train  # noqa: F401
+from . import desc, assemble, solve, predict, train, iterative  # noqa: F401

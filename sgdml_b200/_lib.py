@@ -50,6 +50,12 @@ SIGNATURES = {
         C.c_int,
         [i64, i64, i64, C.c_double, c_void_p, i64, c_void_p, i64, C.c_double, c_void_p, i64, c_void_p],
     ),
+    'sgdml_b200_gather_rows_neg': (C.c_int, [c_void_p, i64, i64, c_void_p, c_void_p, i64, c_void_p]),
+    'sgdml_b200_add_diag': (C.c_int, [c_void_p, i64, i64, C.c_double, c_void_p]),
+    'sgdml_b200_trsm_right_lt': (C.c_int, [c_void_p, i64, i64, c_void_p, i64, i64, c_void_p]),
+    'sgdml_b200_gram_tn': (C.c_int, [c_void_p, i64, i64, i64, C.c_double, c_void_p, i64, c_void_p]),
+    'sgdml_b200_row_sqnorms': (C.c_int, [c_void_p, i64, i64, i64, c_void_p, c_void_p]),
+    'sgdml_b200_nystroem_apply': (C.c_int, [c_void_p, i64, i64, i64, C.c_double, c_void_p, c_void_p, c_void_p]),
     'sgdml_b200_set_gemm_variant': (C.c_int, [C.c_int]),
     'sgdml_b200_profile_enable': (C.c_int, [C.c_int]),
     'sgdml_b200_profile_reset': (C.c_int, []),

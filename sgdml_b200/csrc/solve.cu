@@ -17,10 +17,10 @@
 #include <cmath>
 
 #include "common.cuh"
+#include "solve.cuh"
 
 namespace sgdml {
 
-constexpr int NB = 128;  // Cholesky panel width
 
 // ====================================================================== GEMM  C (+)= A B^T
 template <int BM_, int BN_, int WM_, int WN_, int BK_, int STAGES_>
@@ -38,20 +38,6 @@ struct GCfg {
   static_assert((BM * KP) % NT == 0 && (BN * KP) % NT == 0, "loader mapping");
   static_assert(QA <= KSTEPS && QB <= KSTEPS, "one A and one B op per k-step at most");
   static_assert(BM % BN == 0, "triangular enumeration assumes BM = r BN");
-};
-
-struct GemmArgs {
-  int64_t m, n, k;
-  const double* A;
-  int64_t lda;
-  const double* B;
-  int64_t ldb;
-  double* C;
-  int64_t ldc;
-  double alpha, beta;
-  int mode;  // 0: C = alpha A B^T + beta C ; 1: C += A B^T (accumulators start from C)
-  int tri;   // 1: C square, only tiles touching the lower triangle are computed
-  const int* abort_flag;  // optional: skip all work when *abort_flag != 0
 };
 
 // shared-memory tile layout: [k/4][row][4] so that one DMMA fragment (8 rows x 4 k) is 256
@@ -374,20 +360,20 @@ __global__ void __launch_bounds__(1024) k_potf2_tile(double* __restrict__ A, int
 // Writes X over P and -X into W (row stride NB) for the trailing update.
 constexpr int RS = 64;   // rows per strip
 constexpr int SB = 32;   // substitution block
-__global__ void __launch_bounds__(256) k_trsm_strip(double* __restrict__ A, int64_t lda, int64_t k0, int kb,
-                                                    int64_t n, double* __restrict__ W, int64_t ldw, int wcol,
+__global__ void __launch_bounds__(256) k_trsm_strip(const double* __restrict__ L11, int64_t lda, int kb,
+                                                    double* __restrict__ Pbase, int64_t ldp, int64_t n_rows,
+                                                    double* __restrict__ W, int64_t ldw,
                                                     const int* __restrict__ info) {
   extern __shared__ __align__(16) double tsm[];
   constexpr int LD = NB + 4;  // == 4 mod 16: conflict-free DMMA fragment loads
   double* L = tsm;            // NB x LD
   double* X = L + NB * LD;    // RS x LD
-  if (*info != 0) return;
+  if (info != nullptr && *info != 0) return;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int lr = lane >> 2, lc = lane & 3;
-  const int64_t r0 = k0 + kb + (int64_t)blockIdx.x * RS;
-  const int rows = (int)min((int64_t)RS, n - r0);
-  const double* L11 = A + k0 * lda + k0;
-  double* P = A + r0 * lda + k0;
+  const int64_t r0 = (int64_t)blockIdx.x * RS;
+  const int rows = (int)min((int64_t)RS, n_rows - r0);
+  double* P = Pbase + r0 * ldp;
 
   for (int idx = tid; idx < NB * NB; idx += 256) {
     const int i = idx / NB, j = idx - i * NB;
@@ -395,7 +381,7 @@ __global__ void __launch_bounds__(256) k_trsm_strip(double* __restrict__ A, int6
   }
   for (int idx = tid; idx < RS * NB; idx += 256) {
     const int i = idx / NB, j = idx - i * NB;
-    X[i * LD + j] = (i < rows && j < kb) ? P[(int64_t)i * lda + j] : 0.0;
+    X[i * LD + j] = (i < rows && j < kb) ? P[(int64_t)i * ldp + j] : 0.0;
   }
   __syncthreads();
 
@@ -444,8 +430,8 @@ __global__ void __launch_bounds__(256) k_trsm_strip(double* __restrict__ A, int6
     const int i = idx / NB, j = idx - i * NB;
     if (i < rows && j < kb) {
       const double v = X[i * LD + j];
-      P[(int64_t)i * lda + j] = v;
-      W[(r0 + i) * ldw + wcol + j] = -v;
+      P[(int64_t)i * ldp + j] = v;
+      W[(r0 + i) * ldw + j] = -v;
     }
   }
 }
@@ -635,8 +621,9 @@ int potrf_device(double* A, int64_t n, int64_t lda, int* info_host, cudaStream_t
         if (rem <= 0) break;
         {
           ProfScope ps(KID_TRSM, s);
-          k_trsm_strip<<<(unsigned)((rem + RS - 1) / RS), 256, trsm_smem, s>>>(A, lda, k0, kb, n, W, NBO,
-                                                                              (int)(k0 - K0), d_info);
+          k_trsm_strip<<<(unsigned)((rem + RS - 1) / RS), 256, trsm_smem, s>>>(
+              A + k0 * lda + k0, lda, kb, A + (k0 + kb) * lda + k0, lda, rem, W + (k0 + kb) * NBO + (k0 - K0), NBO,
+              d_info);
           SG_CUDA(cudaGetLastError());
           count_launch(KID_TRSM);
         }
@@ -727,6 +714,52 @@ int potrs_device(const double* L, int64_t n, int64_t lda, double* B, int64_t nrh
     }
   }
   return 0;
+}
+
+// X <- X L^-T for a lower-triangular L (m x m) and X (n_rows x m), right-looking over 128-column
+// blocks: substitution strips for the diagonal block, DMMA GEMM for the remaining columns.
+int trsm_right_lt_device(const double* L, int64_t m, int64_t ldl, double* X, int64_t n_rows, int64_t ldx,
+                         cudaStream_t s) {
+  double* Wn = nullptr;
+  SG_CUDA(cudaMalloc(&Wn, sizeof(double) * (size_t)n_rows * NB));
+  auto body = [&]() -> int {
+    const size_t trsm_smem = sizeof(double) * (NB + RS) * (NB + 4);
+    SG_CUDA(cudaFuncSetAttribute(k_trsm_strip, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)trsm_smem));
+    for (int64_t k0 = 0; k0 < m; k0 += NB) {
+      const int kb = (int)std::min<int64_t>(NB, m - k0);
+      {
+        ProfScope ps(KID_TRSM, s);
+        k_trsm_strip<<<(unsigned)((n_rows + RS - 1) / RS), 256, trsm_smem, s>>>(L + k0 * ldl + k0, ldl, kb, X + k0, ldx,
+                                                                               n_rows, Wn, NB, nullptr);
+        SG_CUDA(cudaGetLastError());
+        count_launch(KID_TRSM);
+      }
+      const int64_t rest = m - k0 - kb;
+      if (rest > 0) {
+        GemmArgs g;
+        g.m = n_rows;
+        g.n = rest;
+        g.k = kb;
+        g.A = Wn;  // -X_blk
+        g.lda = NB;
+        g.B = L + (k0 + kb) * ldl + k0;
+        g.ldb = ldl;
+        g.C = X + (k0 + kb);
+        g.ldc = ldx;
+        g.alpha = 1.0;
+        g.beta = 1.0;
+        g.mode = 1;
+        g.tri = 0;
+        g.abort_flag = nullptr;
+        SG_TRY(launch_gemm(g, s));
+      }
+    }
+    SG_CUDA(cudaStreamSynchronize(s));
+    return 0;
+  };
+  int rc = body();
+  cudaFree(Wn);
+  return rc;
 }
 
 }  // namespace sgdml

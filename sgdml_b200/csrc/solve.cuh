@@ -1,0 +1,30 @@
+// Internal interface of the dense-solve kernels (solve.cu), shared with nystroem.cu.
+#pragma once
+#include "common.cuh"
+
+namespace sgdml {
+
+constexpr int NB = 128;  // Cholesky panel width / TRSM block
+
+struct GemmArgs {
+  int64_t m, n, k;
+  const double* A;
+  int64_t lda;
+  const double* B;
+  int64_t ldb;
+  double* C;
+  int64_t ldc;
+  double alpha, beta;
+  int mode;  // 0: C = alpha A B^T + beta C ; 1: C += A B^T (accumulators start from C)
+  int tri;   // 1: C square, only tiles touching the lower triangle are computed
+  const int* abort_flag;  // optional: skip all work when *abort_flag != 0
+};
+
+// device pointers only
+int launch_gemm(const GemmArgs& a, cudaStream_t s);
+int potrf_device(double* A, int64_t n, int64_t lda, int* info_host, cudaStream_t s);
+int potrs_device(const double* L, int64_t n, int64_t lda, double* B, int64_t nrhs, int64_t ldb, cudaStream_t s);
+int trsm_right_lt_device(const double* L, int64_t m, int64_t ldl, double* X, int64_t n_rows, int64_t ldx,
+                         cudaStream_t s);
+
+}  // namespace sgdml

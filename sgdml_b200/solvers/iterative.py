@@ -1,0 +1,319 @@
+"""``Iterative`` -- Nystroem-preconditioned CG (reference sgdml/solvers/iterative.py:60-866) on
+the B200 engine.
+
+Same algorithm and knobs as the reference: leverage-score sampling of inducing columns
+(iterative.py:353-411), the Nystroem factor B = L_inv_K_mn (iterative.py:208-351), the
+preconditioner P v = (B^T B v - v)/lam (iterative.py:136-138), the matrix-free operator
+K v = predict_train(alphas = v) - lam v (iterative.py:183-204), restarts with 1.2x more inducing
+points when CG stalls (iterative.py:726-801) and periodic checkpoints through
+`save_progr_callback` (iterative.py:675-724).
+
+What is different: the (n x m) block K_nm never leaves HBM -- it is assembled there
+(`sgdml_b200_assemble` with a column list), factorised with the engine's FP64 Cholesky / TRSM /
+Gram kernels (`csrc/nystroem.cu`, `csrc/solve.cu`), and applied with two GEMV kernels per
+iteration; K v is one launch sequence of the fused predictor on the cached training descriptors.
+The O(n) vector updates of CG stay on the host (NumPy), like SciPy's `cg` in the reference.
+"""
+
+import collections
+import logging
+import timeit
+from functools import partial
+
+import numpy as np
+
+from .. import _lib
+
+CG_STEPS_HIST_LEN = 100  # moving average window of the solver-effectiveness estimate (iterative.py:48-50)
+EFF_RESTART_THRESH = 0  # restart with a stronger preconditioner below this effectiveness [%] (iterative.py:51)
+MAX_NUM_RESTARTS = 6  # iterative.py:53
+
+DONE = 1
+NOT_DONE = 0
+
+
+class Iterative(object):
+    def __init__(self, gdml_train, desc, max_memory, max_processes, use_torch, callback=None):
+        self.log = logging.getLogger(__name__)
+        self.gdml_train = gdml_train
+        self.gdml_predict = None
+        self.desc = desc
+        self.callback = callback
+        self._max_memory = max_memory
+        self._max_processes = max_processes
+        self._use_torch = use_torch
+        self.timings = {}
+
+    # ------------------------------------------------------------------ preconditioner
+    def _cho_factor_stable(self, M, pre_reg=False, eps_mag_max=1):
+        """iterative.py:414-471: factorises the (m x m) CUDA tensor M in place, adding more and more
+        jitter to the diagonal until it is positive definite.  Returns True, or False if even
+        10**eps_mag_max did not help (callers with eps_mag_max < 1 fall back, iterative.py:312-322)."""
+        import torch
+
+        L = _lib.lib()
+        m = M.shape[0]
+        eps = np.finfo(float).eps
+        eps_mag = int(np.floor(np.log10(eps)))
+        stream = _lib.current_stream()
+        if pre_reg:
+            _lib.check(L.sgdml_b200_add_diag(M.data_ptr(), m, M.shape[1], float(eps), stream), 'add_diag')
+            eps_mag += 1
+        backup = M.clone()  # potrf overwrites its input; the reference retries from the same matrix
+        for reg in 10.0 ** np.arange(eps_mag, eps_mag_max + 1):
+            rc = L.sgdml_b200_potrf(M.data_ptr(), m, M.shape[1], stream)
+            if rc == 0:
+                return True
+            if rc < 0:
+                _lib.check(rc, 'potrf')
+            self.log.debug('Cholesky solver needs more aggressive regularization (adding {} to diagonal)'.format(reg))
+            _lib.check(L.sgdml_b200_add_diag(backup.data_ptr(), m, backup.shape[1], float(reg), stream), 'add_diag')
+            M.copy_(backup)
+        return False
+
+    def _nystroem_cholesky_factor(self, R_desc, R_d_desc, tril_perms_lin, sig, lam, use_E_cstr, col_idxs, callback=None):
+        """iterative.py:208-351.  Returns X = B^T as a CUDA tensor (n, ldx) whose first m columns are
+        meaningful (B = L_inv_K_mn is X[:, :m].T), and m."""
+        import torch
+
+        if use_E_cstr:
+            raise NotImplementedError('use_E_cstr is out of scope (SURVEY.md section 2 row 22)')
+        L = _lib.lib()
+        stream = _lib.current_stream()
+        cols = np.ascontiguousarray(col_idxs, dtype=np.int64)
+        X, m = self.gdml_train._assemble_kernel_mat_device(R_desc, R_d_desc, tril_perms_lin, sig, col_idxs=cols)
+        n, ldx = X.shape
+
+        K_mm = torch.empty((m, (m + 1) // 2 * 2), dtype=torch.float64, device='cuda')
+        _lib.check(
+            L.sgdml_b200_gather_rows_neg(X.data_ptr(), ldx, m, _lib.ptr(cols), K_mm.data_ptr(), K_mm.shape[1], stream),
+            'gather_rows_neg',
+        )  # iterative.py:253
+        if not self._cho_factor_stable(K_mm, pre_reg=True):  # iterative.py:267
+            raise np.linalg.LinAlgError('Failed to factorize K_mm despite strong regularization')
+        _lib.check(L.sgdml_b200_trsm_right_lt(K_mm.data_ptr(), m, K_mm.shape[1], X.data_ptr(), n, ldx, stream), 'trsm')
+
+        inner = K_mm  # reuse the buffer (iterative.py:293-295)
+        _lib.check(L.sgdml_b200_gram_tn(X.data_ptr(), n, m, ldx, float(lam), inner.data_ptr(), inner.shape[1], stream), 'gram')
+        if not self._cho_factor_stable(inner, eps_mag_max=-14):  # do not regularize more than 1e-14
+            raise np.linalg.LinAlgError(
+                'inner Nystroem matrix not positive definite within 1e-14 jitter (the reference falls back to QR here, '
+                'iterative.py:312-322); try fewer inducing points or a larger sigma'
+            )
+        _lib.check(L.sgdml_b200_trsm_right_lt(inner.data_ptr(), m, inner.shape[1], X.data_ptr(), n, ldx, stream), 'trsm')
+        del K_mm
+        return X, m
+
+    def _init_precon_operator(self, task, R_desc, R_d_desc, tril_perms_lin, inducing_pts_idxs, callback=None):
+        """iterative.py:83-142 -> (P_vec, lev_scores)."""
+        lam = float(task['lam'])
+        X, m = self._nystroem_cholesky_factor(
+            R_desc, R_d_desc, tril_perms_lin, task['sig'], lam, task['use_E_cstr'], inducing_pts_idxs, callback=callback
+        )
+        n, ldx = X.shape
+        L = _lib.lib()
+        lev_scores = np.empty(n)
+        _lib.check(L.sgdml_b200_row_sqnorms(X.data_ptr(), n, m, ldx, _lib.ptr(lev_scores), _lib.current_stream()), 'row_sqnorms')
+
+        def _P_vec(v):
+            v = np.ascontiguousarray(v, dtype=np.float64)
+            out = np.empty(n)
+            _lib.check(
+                L.sgdml_b200_nystroem_apply(X.data_ptr(), n, m, ldx, lam, _lib.ptr(v), _lib.ptr(out), _lib.current_stream()),
+                'nystroem_apply',
+            )
+            return out
+
+        _P_vec.keepalive = X
+        return _P_vec, lev_scores
+
+    def _init_kernel_operator(self, task, R_desc, R_d_desc, tril_perms_lin, lam, n, callback=None):
+        """iterative.py:144-206: K v = predict_train(alphas = v, std = 1) - lam v."""
+        from ..predict import GDMLPredict
+
+        v_F = np.zeros(n)
+        model = self.gdml_train.create_model(task, 'cg', R_desc, R_d_desc, tril_perms_lin, 1.0, v_F)
+        self.gdml_predict = GDMLPredict(model, max_memory=self._max_memory, max_processes=self._max_processes)
+        self.gdml_predict.set_R_desc(R_desc)
+        self.gdml_predict.set_R_d_desc(R_d_desc)
+
+        def _K_vec(v):
+            v = np.ascontiguousarray(v, dtype=np.float64)
+            self.gdml_predict.set_alphas(v)
+            pred = self.gdml_predict.kmatvec_train().ravel()
+            pred -= lam * v
+            return pred
+
+        return _K_vec
+
+    def _lev_scores(self, R_desc, R_d_desc, tril_perms_lin, sig, lam, use_E_cstr, n_inducing_pts, callback=None):
+        """iterative.py:353-399: leverage scores from a random subset of <= 10 points' worth of columns."""
+        n_train, dim_d = R_d_desc.shape[:2]
+        dim_i = 3 * int((1 + np.sqrt(8 * dim_d + 1)) / 2)
+        dim_m = dim_i * min(n_inducing_pts, 10)
+        lev_approx_idxs = np.sort(np.random.choice(n_train * dim_i, dim_m, replace=False))
+        X, m = self._nystroem_cholesky_factor(R_desc, R_d_desc, tril_perms_lin, sig, lam, use_E_cstr, lev_approx_idxs)
+        lev = np.empty(X.shape[0])
+        _lib.check(
+            _lib.lib().sgdml_b200_row_sqnorms(X.data_ptr(), X.shape[0], m, X.shape[1], _lib.ptr(lev), _lib.current_stream()),
+            'row_sqnorms',
+        )
+        return lev
+
+    def inducing_pts_from_lev_scores(self, lev_scores, N):
+        """iterative.py:401-411."""
+        idxs = np.random.choice(np.arange(lev_scores.size), N, replace=False, p=lev_scores / lev_scores.sum())
+        return np.sort(idxs)
+
+    # ------------------------------------------------------------------ solve
+    def solve(self, task, R_desc, R_d_desc, tril_perms_lin, y, y_std, tol=1e-4, save_progr_callback=None):
+        """iterative.py:473-825 -> (alphas, tol, num_iters, resid, train_rmse, inducing_pts_idxs, is_conv)."""
+        n_train, n_atoms = task['R_train'].shape[:2]
+        dim_i = 3 * n_atoms
+        sig, lam = task['sig'], float(task['lam'])
+
+        alphas0_F = task['alphas0_F'] if 'alphas0_F' in task else None
+        num_iters0 = int(task['solver_iters']) if 'solver_iters' in task else 0
+
+        max_memory_bytes = self._max_memory * 1024**3
+        n_inducing_pts = min(n_train, Iterative.max_n_inducing_pts(n_train, n_atoms, max_memory_bytes))
+        n_inducing_pts = max(n_inducing_pts, 1)
+        n_inducing_pts_init = len(task['inducing_pts_idxs']) // dim_i if 'inducing_pts_idxs' in task else None
+
+        t_start = timeit.default_timer()
+        lev_scores = None
+        if n_inducing_pts_init is not None and n_inducing_pts_init == n_inducing_pts:
+            inducing_pts_idxs = np.asarray(task['inducing_pts_idxs'])  # reuse old inducing points
+        else:
+            lev_scores = self._lev_scores(R_desc, R_d_desc, tril_perms_lin, sig, lam, task['use_E_cstr'], n_inducing_pts)
+            inducing_pts_idxs = self.inducing_pts_from_lev_scores(lev_scores, n_inducing_pts * dim_i)
+
+        P_vec, lev_scores = self._init_precon_operator(task, R_desc, R_d_desc, tril_perms_lin, inducing_pts_idxs)
+        self.timings['precon_s'] = timeit.default_timer() - t_start
+
+        n = lev_scores.size
+        K_vec = self._init_kernel_operator(task, R_desc, R_d_desc, tril_perms_lin, lam, n)
+
+        def A_vec(v):  # -K_op: the SPD operator (-K + lam I), iterative.py:740-741
+            return -K_vec(v)
+
+        y = np.ascontiguousarray(y, dtype=np.float64)
+        norm_y = np.linalg.norm(y)
+        x = np.zeros(n) if alphas0_F is None else -np.asarray(alphas0_F, dtype=np.float64).copy()
+        maxiter = 3 * n_atoms * n_train * 10  # iterative.py:746-749
+
+        num_iters = num_iters0
+        num_restarts = 0
+        steps_hist = collections.deque(maxlen=CG_STEPS_HIST_LEN)
+        is_conv = False
+        t_cg = timeit.default_timer()
+        last_ckpt = t_cg
+
+        while True:  # restart loop (iterative.py:737-801)
+            r = y - A_vec(x) if np.any(x) else y.copy()
+            resid = np.linalg.norm(r)
+            z = P_vec(r)
+            p = z.copy()
+            rz = r.dot(z)
+            restart = False
+            it_this = 0
+            while resid > tol * norm_y and it_this < maxiter:
+                Ap = A_vec(p)
+                alpha = rz / p.dot(Ap)
+                x += alpha * p
+                r -= alpha * Ap
+                old_resid, resid = resid, np.linalg.norm(r)
+                num_iters += 1
+                it_this += 1
+
+                # solver effectiveness (iterative.py:640-653)
+                steps_hist.append(resid - old_resid)
+                arr = np.array(steps_hist)
+                tot = np.abs(arr).sum()
+                ratio = (-arr.clip(max=0).sum() / tot) if tot > 0 else 1
+                eff = (int(100 * ratio) - 50) * 2
+
+                if self.callback is not None:
+                    self.callback(
+                        NOT_DONE,
+                        disp_str='Training error (RMSE): forces {:.4f}'.format(resid / np.sqrt(len(y))),
+                        sec_disp_str='{:d} iter, k={:d}'.format(num_iters, n_inducing_pts),
+                    )
+                now = timeit.default_timer()
+                if save_progr_callback is not None and now - last_ckpt > 120.0:  # iterative.py:675-724
+                    last_ckpt = now
+                    save_progr_callback(
+                        self._checkpoint_model(task, R_desc, R_d_desc, tril_perms_lin, y_std, x, tol, num_iters, resid, norm_y, inducing_pts_idxs)
+                    )
+
+                if len(steps_hist) == CG_STEPS_HIST_LEN and eff <= EFF_RESTART_THRESH and n_inducing_pts < n_train:
+                    restart = True  # iterative.py:726-735
+                    break
+                if resid <= tol * norm_y:
+                    break
+                z = P_vec(r)
+                rz_new = r.dot(z)
+                p = z + (rz_new / rz) * p
+                rz = rz_new
+
+            if not restart:
+                is_conv = resid <= tol * norm_y
+                break
+            num_restarts += 1
+            steps_hist.clear()
+            if num_restarts == MAX_NUM_RESTARTS:
+                is_conv = False
+                break
+            n_inducing_pts = min(int(np.ceil(1.2 * n_inducing_pts)), n_train)
+            inducing_pts_idxs = self.inducing_pts_from_lev_scores(lev_scores, n_inducing_pts * dim_i)
+            del P_vec
+            P_vec, lev_scores = self._init_precon_operator(task, R_desc, R_d_desc, tril_perms_lin, inducing_pts_idxs)
+
+        self.timings['cg_s'] = timeit.default_timer() - t_cg
+        self.timings['iters'] = num_iters - num_iters0
+        alphas = -x
+        train_rmse = resid / np.sqrt(len(y))
+        if self.callback is not None:
+            self.callback(
+                DONE,
+                disp_str='Training on {:,} points'.format(n_train) + ('' if is_conv else ' (NOT CONVERGED)'),
+                sec_disp_str='{:d} iterations'.format(num_iters),
+            )
+        return alphas, tol, num_iters, resid, train_rmse, inducing_pts_idxs, is_conv
+
+    def _checkpoint_model(self, task, R_desc, R_d_desc, tril_perms_lin, y_std, xk, tol, num_iters, resid, norm_y, idxs):
+        model = self.gdml_train.create_model(task, 'cg', R_desc, R_d_desc, tril_perms_lin, y_std, -xk)
+        model.update(
+            {
+                'solver_tol': tol,
+                'solver_iters': num_iters,
+                'solver_resid': resid,
+                'norm_y_train': norm_y,
+                'inducing_pts_idxs': idxs,
+            }
+        )
+        model['c'] = 0
+        if 'E_train' in task:
+            self.gdml_predict.set_alphas(-xk)
+            E_pred = self.gdml_predict.predict()[0]  # std = 1, c = 0 model
+            model['c'] = np.mean(np.squeeze(task['E_train']) - E_pred * y_std)
+        return model
+
+    # ------------------------------------------------------------------ memory heuristics
+    @staticmethod
+    def max_n_inducing_pts(n_train, n_atoms, max_memory_bytes):
+        """iterative.py:826-843 (same formula, device memory instead of host memory)."""
+        SQUARE_FACT, LINEAR_FACT = 5, 4
+        to_dof = (3 * n_atoms) ** 2 * 8
+        sq_factor = LINEAR_FACT * n_train * to_dof
+        ny_factor = SQUARE_FACT * to_dof
+        n_inducing_pts = (np.sqrt(sq_factor**2 + 4.0 * ny_factor * max_memory_bytes) - sq_factor) / (2 * ny_factor)
+        return min(int(n_inducing_pts), n_train)
+
+    @staticmethod
+    def est_memory_requirement(n_train, n_inducing_pts, n_atoms):
+        """iterative.py:845-866."""
+        SQUARE_FACT, LINEAR_FACT = 5, 4
+        est_bytes = LINEAR_FACT * n_train * n_inducing_pts * (3 * n_atoms) ** 2 * 8
+        est_bytes += SQUARE_FACT * n_inducing_pts * n_inducing_pts * (3 * n_atoms) ** 2 * 8
+        return est_bytes

@@ -20,6 +20,7 @@ from . import _lib
 from .desc import Desc, tril_perms_lin as _tril_perms_lin
 from .predict import GDMLPredict
 from .solvers.analytic import Analytic
+from .solvers.iterative import Iterative
 
 __version__ = '0.1.0'
 
@@ -109,22 +110,39 @@ class GDMLTrain(object):
         y_std = np.std(y)
         y /= y_std
 
+        # solver choice by memory, like train.py:949-975 -- but against DEVICE memory
         est_bytes_analytic = Analytic.est_memory_requirement(n_train, n_atoms)
         free_bytes, _total = _torch().cuda.mem_get_info()
         max_bytes = free_bytes if self._max_memory is None else min(free_bytes, self._max_memory * 1024**3)
-        if est_bytes_analytic > max_bytes:
-            raise NotImplementedError(
-                'K needs {:.1f} GB but only {:.1f} GB of HBM are available: the iterative solver '
-                '(solvers/iterative.py:473-825) is not part of this round'.format(
-                    est_bytes_analytic / 2**30, max_bytes / 2**30
-                )
+        use_analytic_solver = est_bytes_analytic < max_bytes
+
+        solver_keys = {}
+        if use_analytic_solver:
+            analytic = Analytic(self, desc, callback=callback)
+            alphas = analytic.solve(task, R_desc, R_d_desc, tril_perms_lin, y)
+            self.timings = dict(analytic.timings)
+        else:
+            iterative = Iterative(
+                self, desc, max_bytes / 1024**3, self._max_processes, self._use_torch, callback=callback
             )
+            (
+                alphas,
+                solver_keys['solver_tol'],
+                solver_keys['solver_iters'],
+                solver_keys['solver_resid'],
+                train_rmse,
+                solver_keys['inducing_pts_idxs'],
+                is_conv,
+            ) = iterative.solve(task, R_desc, R_d_desc, tril_perms_lin, y, y_std, save_progr_callback=save_progr_callback)
+            solver_keys['norm_y_train'] = np.linalg.norm(y)  # train.py:1030
+            self.timings = dict(iterative.timings)
+            if not is_conv:
+                self.log.warning('Iterative solver did not converge! (train.py:1032-1052)')
 
-        analytic = Analytic(self, desc, callback=callback)
-        alphas = analytic.solve(task, R_desc, R_d_desc, tril_perms_lin, y)
-        self.timings = dict(analytic.timings)
-
-        model = self.create_model(task, 'analytic', R_desc, R_d_desc, tril_perms_lin, y_std, alphas)
+        model = self.create_model(
+            task, 'analytic' if use_analytic_solver else 'cg', R_desc, R_d_desc, tril_perms_lin, y_std, alphas
+        )
+        model.update(solver_keys)
 
         if model['use_E']:  # train.py:1074-1086
             model['c'] = self._recov_int_const(model, task, R_desc=R_desc, R_d_desc=R_d_desc)

@@ -106,5 +106,69 @@ def main():
         print(name, 'K', K.shape, 'size %.0f KB' % (os.path.getsize(out) / 1024))
 
 
+def main_iterative():
+    """Nystroem-preconditioned CG (solvers/iterative.py) with the reference, forced by a tiny memory
+    limit; np.random is seeded so that the leverage-score sampling is reproducible, and the sampled
+    inducing columns are stored (the engine and the oracle then solve with the same columns)."""
+    from sgdml.solvers.iterative import Iterative
+
+    N, M, sig = 9, 40, 20
+    perms = synth.rotor_swap_group(N, 1, 1)
+    task = synth.make_task(N, M, perms, sig)
+    max_memory = 0.004  # GB -> a handful of inducing points (iterative.py:826-843)
+    gdml_train = GDMLTrain(max_memory=max_memory, max_processes=1, use_torch=False)
+    np.random.seed(1234)
+    model = gdml_train.train(task)
+    assert model['solver_name'] == 'cg'
+    desc = Desc(N, max_processes=1)
+    R = task['R_train'].reshape(M, -1)
+    R_desc, R_d_desc = desc.from_R(R, max_processes=1)
+
+    # the preconditioner the reference builds for these inducing columns, applied to a fixed vector
+    it = Iterative(gdml_train, desc, max_memory, 1, False)
+    P_op, lev_scores = it._init_precon_operator(task, R_desc, R_d_desc, model['tril_perms_lin'], model['inducing_pts_idxs'])
+    rng = np.random.default_rng(7)
+    v = rng.standard_normal(3 * N * M)
+    P_op @ v  # first call only "primes" the operator (iterative.py:122-125)
+    Pv = P_op @ v
+
+    predictor = GDMLPredict(model, max_processes=1, use_torch=False)
+    R_query = synth.geometries(N, 10, 1).reshape(10, -1)
+    E_q, F_q = predictor.predict(R_query)
+    y = task['F_train'].ravel() / model['std']
+    out = os.path.join(HERE, 'cg_n9_m40.npz')
+    np.savez_compressed(
+        out,
+        reference_version=sgdml.__version__,
+        n_atoms=N,
+        n_train=M,
+        perms=perms,
+        sig=sig,
+        lam=task['lam'],
+        max_memory_gb=max_memory,
+        inducing_pts_idxs=model['inducing_pts_idxs'],
+        alphas_F=model['alphas_F'],
+        solver_iters=model['solver_iters'],
+        solver_resid=model['solver_resid'],
+        solver_tol=model['solver_tol'],
+        norm_y_train=model['norm_y_train'],
+        std=model['std'],
+        c=model['c'],
+        lev_scores=lev_scores,
+        v=v,
+        Pv=Pv,
+        R_query=R_query,
+        E_query=E_q,
+        F_query=F_q,
+        y=y,
+    )
+    print('cg_n9_m40: %d inducing columns, %d iterations, resid %.3e (tol*|y| = %.3e), size %.0f KB'
+          % (len(model['inducing_pts_idxs']), model['solver_iters'], model['solver_resid'],
+             model['solver_tol'] * model['norm_y_train'], os.path.getsize(out) / 1024))
+
+
 if __name__ == '__main__':
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == 'iterative':
+        main_iterative()   # separate process: the reference allows one GDMLTrain instance (train.py:336-342)
+    else:
+        main()

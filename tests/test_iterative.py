@@ -1,0 +1,119 @@
+"""Nystroem-preconditioned CG (SURVEY.md section 8 row a-S2): oracle and engine against the
+reference's own iterative solve frozen in tests/golden/cg_n9_m40.npz (fixed inducing columns)."""
+
+import numpy as np
+import pytest
+
+from conftest import load_golden, rel_err
+
+from oracle import desc as odesc
+from oracle import iterative as oiter
+from oracle import predict as opredict
+
+
+def _setup():
+    from sgdml_b200 import synth
+
+    g = load_golden('cg_n9_m40')
+    N, M = int(g['n_atoms']), int(g['n_train'])
+    task = synth.make_task(N, M, g['perms'], int(g['sig']), lam=float(g['lam']))
+    R = task['R_train'].reshape(M, -1)
+    return g, task, N, M, R
+
+
+def _model_like(g, task, R_desc, alphas):
+    N = int(g['n_atoms'])
+    R = task['R_train'].reshape(R_desc.shape[0], -1)
+    _, gd = odesc.from_R(R)
+    return {
+        'type': 'm',
+        'z': task['z'],
+        'R_desc': R_desc.T,
+        'R_d_desc_alpha': odesc.d_desc_dot_vec(gd, alphas.reshape(-1, 3 * N)),
+        'alphas_F': alphas,
+        'c': float(g['c']),
+        'std': float(g['std']),
+        'sig': int(g['sig']),
+        'lam': float(g['lam']),
+        'perms': g['perms'],
+        'tril_perms_lin': odesc.tril_perms_lin(g['perms']),
+        'use_E': True,
+    }
+
+
+def test_oracle_preconditioner_and_solve():
+    g, task, N, M, R = _setup()
+    x, gd = odesc.from_R(R)
+    lin = odesc.tril_perms_lin(g['perms'])
+    B = oiter.nystroem_factor(x, gd, lin, int(g['sig']), float(g['lam']), g['inducing_pts_idxs'])
+    assert rel_err(np.einsum('ij,ij->j', B, B), g['lev_scores']) < 1e-6
+    assert rel_err(oiter.precon(B, float(g['lam']))(g['v']), g['Pv']) < 1e-5
+    alphas, info, iters, _ = oiter.solve(
+        _model_like(g, task, x, np.zeros(3 * N * M)), x, gd, lin, int(g['sig']), float(g['lam']), g['y'], g['inducing_pts_idxs']
+    )
+    assert info == 0
+    assert abs(iters - int(g['solver_iters'])) <= max(5, 0.2 * int(g['solver_iters']))
+    E, F = opredict.Predictor(_model_like(g, task, x, alphas)).predict(g['R_query'])
+    assert rel_err(F, g['F_query']) < 2e-3  # both are converged to rtol 1e-4 only
+
+
+@pytest.mark.gpu
+def test_engine_preconditioner_matches_reference():
+    import sgdml_b200
+    from sgdml_b200.desc import Desc
+    from sgdml_b200.solvers.iterative import Iterative
+
+    g, task, N, M, R = _setup()
+    t = sgdml_b200.GDMLTrain(max_memory=float(g['max_memory_gb']))
+    d = Desc(N)
+    x, gd = d.from_R(R)
+    lin = odesc.tril_perms_lin(g['perms'])
+    it = Iterative(t, d, float(g['max_memory_gb']), None, False)
+    P, lev = it._init_precon_operator(task, x, gd, lin, g['inducing_pts_idxs'])
+    assert rel_err(lev, g['lev_scores']) < 1e-6
+    assert rel_err(P(g['v']), g['Pv']) < 1e-5
+    K = it._init_kernel_operator(task, x, gd, lin, float(g['lam']), 3 * N * M)
+    Kref = oiter.kernel_op(_model_like(g, task, x, np.zeros(3 * N * M)), x, gd, float(g['lam']))
+    assert rel_err(K(g['v']), Kref(g['v'])) < 1e-10
+
+
+@pytest.mark.gpu
+def test_engine_cg_train_matches_reference():
+    """GDMLTrain.train with a memory cap that forces the iterative solver, same inducing columns as the
+    reference run: converges to the same tolerance in a similar number of iterations and predicts
+    the same forces to solver accuracy."""
+    import sgdml_b200
+
+    g, task, N, M, R = _setup()
+    task['inducing_pts_idxs'] = g['inducing_pts_idxs']
+    model = sgdml_b200.GDMLTrain(max_memory=float(g['max_memory_gb'])).train(task)
+    assert model['solver_name'] == 'cg'
+    assert np.array_equal(model['inducing_pts_idxs'], g['inducing_pts_idxs'])
+    assert model['solver_resid'] <= float(g['solver_tol']) * float(g['norm_y_train'])
+    assert abs(int(model['solver_iters']) - int(g['solver_iters'])) <= max(5, 0.2 * int(g['solver_iters']))
+    E, F = sgdml_b200.GDMLPredict(model).predict(g['R_query'])
+    assert rel_err(F, g['F_query']) < 2e-3
+    assert rel_err(E, g['E_query']) < 2e-3
+    # against the analytic solution of the same task the CG model is within solver accuracy too
+    exact = sgdml_b200.GDMLTrain().train({k: v for k, v in task.items() if k != 'inducing_pts_idxs'})
+    _, F_exact = sgdml_b200.GDMLPredict(exact).predict(g['R_query'])
+    assert rel_err(F, F_exact) < 5e-3
+
+
+@pytest.mark.gpu
+def test_engine_cg_own_sampling_converges():
+    """Leverage-score sampling path (random inducing columns, iterative.py:353-411)."""
+    import sgdml_b200
+    from sgdml_b200 import synth
+
+    N, M = 9, 60
+    perms = synth.rotor_swap_group(N, 1, 1)
+    task = synth.make_task(N, M, perms, 20)
+    np.random.seed(3)
+    model = sgdml_b200.GDMLTrain(max_memory=0.01).train(task)
+    assert model['solver_name'] == 'cg' and len(model['inducing_pts_idxs']) % (3 * N) == 0
+    exact = sgdml_b200.GDMLTrain().train(task)
+    Rq = synth.geometries(N, 20, 1).reshape(20, -1)
+    _, F = sgdml_b200.GDMLPredict(model).predict(Rq)
+    _, Fx = sgdml_b200.GDMLPredict(exact).predict(Rq)
+    assert rel_err(F, Fx) < 5e-3
