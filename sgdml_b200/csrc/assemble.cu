@@ -114,7 +114,7 @@ __global__ void __launch_bounds__(256, 2) k_assemble(const AsmArgs p) {
   double acc[ASM_NI][9];
 #pragma unroll
   for (int q = 0; q < ASM_NI; ++q) {
-    const int it = tid + q * nt;
+    const int it = (int)blockIdx.z * ASM_NI * nt + tid + q * nt;  // grid.z splits the sub-blocks of large molecules
     const bool ok = it < tj * NN;
     const int t = ok ? fastdiv(it, p.mNN) : 0;
     const int ab = ok ? it - t * NN : 0;
@@ -394,15 +394,21 @@ extern "C" int sgdml_b200_assemble(const double* R_desc, const double* R_d_desc,
 
   // ---- tile size: at most ASM_NI 3x3 sub-blocks per thread, and shared memory small enough for
   //      two co-resident CTAs per SM
-  int TJ = 0;
+  int TJ = 0, n_chunks = 1;
   for (int t = 8; t >= 1; --t)
     if ((int64_t)t * N * N <= (int64_t)ASM_NI * 256 && asm_smem_bytes(N, D, S, t) <= 110 * 1024) {
       TJ = t;
       break;
     }
   if (TJ == 0) {
-    set_last_error("sgdml_b200_assemble: this kernel supports N <= 32 atoms (N*N <= 1024 sub-blocks per CTA)");
-    return SGDML_B200_ERR_UNSUPPORTED;
+    // large molecule: one column point per CTA, its N*N sub-blocks split over grid.z (the
+    // per-permutation vectors are then recomputed by every chunk)
+    TJ = 1;
+    n_chunks = (int)(((int64_t)N * N + ASM_NI * 256 - 1) / (ASM_NI * 256));
+    if (asm_smem_bytes(N, D, S, 1) > 220 * 1024) {
+      set_last_error("sgdml_b200_assemble: atom tables of this molecule do not fit in shared memory (N <= ~50 supported)");
+      return SGDML_B200_ERR_UNSUPPORTED;
+    }
   }
   TJ = std::min(TJ, nJ);
   const size_t smem = asm_smem_bytes(N, D, S, TJ);
@@ -458,7 +464,7 @@ extern "C" int sgdml_b200_assemble(const double* R_desc, const double* R_d_desc,
     a.ldk = ldk;
     // rows on grid.y (<= 65535), column tiles on grid.x
     SG_ARG(M <= 65535);
-    dim3 grid((unsigned)ceil_div(nJ, TJ), (unsigned)M);
+    dim3 grid((unsigned)ceil_div(nJ, TJ), (unsigned)M, (unsigned)n_chunks);
     {
       ProfScope ps(KID_ASSEMBLE, s);
       k_assemble<<<grid, 256, smem, s>>>(a);

@@ -25,6 +25,7 @@
 
 #include "common.cuh"
 #include "desc.cuh"
+#include "solve.cuh"
 
 namespace sgdml {
 
@@ -474,6 +475,71 @@ __global__ void __launch_bounds__(256) k_query_rows(const double* __restrict__ x
   if (lane == 0) qqg[row] = s;
 }
 
+// ============================================================== large descriptors (D > 256)
+// The accumulator tile G (BQ x DP) of the fused kernel no longer fits the register file, so the
+// same four contractions run as plain DMMA GEMMs (csrc/solve.cu) around two element-wise kernels:
+//   S1 = Q Xc^T, S2 = Q JA^T (GEMM, k = D) -> k_transform_rows (in place: S1 -> C1, S2 -> C2)
+//   acc = C1 XcT^T + C2 JAT^T (GEMM, k = M)  -> k_combine_rows: G = (sum_m c1) Q - acc
+// Per (row, m) pair this adds 64 B of HBM traffic to >= 9 * 256 flop: far above the FP64 ridge.
+__global__ void __launch_bounds__(256) k_transform_rows(double* __restrict__ S1, double* __restrict__ S2, int64_t ldS,
+                                                        const double* __restrict__ qq, const double* __restrict__ mm,
+                                                        const double* __restrict__ xja, int M, int Mpad,
+                                                        int64_t n_rows, MaternK mk, double* __restrict__ csum,
+                                                        double* __restrict__ Erow) {
+  const int lane = threadIdx.x & 31;
+  const int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (r >= n_rows) return;
+  double* s1 = S1 + r * ldS;
+  double* s2 = S2 + r * ldS;
+  const double q5 = 5.0 * qq[r];
+  double cs = 0.0, es = 0.0;
+  for (int m = lane; m < Mpad; m += 32) {
+    double c1 = 0.0, c2 = 0.0;
+    if (m < M) {
+      const double a = s2[m] - xja[m];
+      matern52(fma(-10.0, s1[m], q5 + 5.0 * mm[m]), a, mk, c1, c2);
+      cs += c1;
+      es = fma(a, c2, es);
+    }
+    s1[m] = c1;
+    s2[m] = c2;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    cs += __shfl_xor_sync(0xffffffffu, cs, o);
+    es += __shfl_xor_sync(0xffffffffu, es, o);
+  }
+  if (lane == 0) {
+    csum[r] = cs;
+    Erow[r] = es;
+  }
+}
+
+__global__ void k_combine_rows(const double* __restrict__ Qg, int64_t ldq, const double* __restrict__ csum,
+                               double* __restrict__ G, int DP, int64_t n_rows) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n_rows * DP) return;
+  const int64_t r = idx / DP;
+  const int d = (int)(idx - r * DP);
+  G[idx] = csum[r] * Qg[r * ldq + d] - G[idx];
+}
+
+// src (rows x cols, lds) -> dst (cols x rows), ldd >= rows
+__global__ void k_transpose_pad(const double* __restrict__ src, int64_t rows, int64_t cols, int64_t lds,
+                                double* __restrict__ dst, int64_t ldd) {
+  __shared__ double tile[32][33];
+  const int64_t r0 = (int64_t)blockIdx.y * 32, c0 = (int64_t)blockIdx.x * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int64_t r = r0 + i, c = c0 + threadIdx.x;
+    tile[i][threadIdx.x] = (r < rows && c < cols) ? src[r * lds + c] : 0.0;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int64_t c = c0 + i, r = r0 + threadIdx.x;
+    if (c < cols && r < rows) dst[c * ldd + r] = tile[threadIdx.x][i];
+  }
+}
+
 // ============================================================== finishing kernel
 // F_desc[d] = sum_p G[b*S+p][perm_p[d]];  F = J_x^T F_desc (predict.py:240-243);
 // E = sum_p Erow;  outputs scaled by std, E += c (predict.py:1286-1288).
@@ -595,6 +661,8 @@ struct sgdml_b200_model {
   int N = 0, D = 0, M = 0, S = 0;
   int DP = 0, DS = 0, BM = 0, BQ = 0, Mpad = 0, cfg = -1;
   int device = 0;
+  bool large = false;                    // D > 256: GEMM-composed path
+  double *XcT = nullptr, *JAT = nullptr;  // (DP, Mpad) transposed copies for the second contraction
   double sig = 0, std = 1, c = 0;
   double *X = nullptr;    // (M, D) raw descriptors (training-point queries)
   double *Xc = nullptr, *JA = nullptr, *mm = nullptr, *xja = nullptr, *mu = nullptr;
@@ -604,7 +672,7 @@ struct sgdml_b200_model {
   struct WS {
     int64_t geo = 0;
     double *xq = nullptr, *gq = nullptr, *G = nullptr, *Erow = nullptr, *R = nullptr, *E = nullptr, *F = nullptr,
-           *Qg = nullptr, *qq = nullptr;
+           *Qg = nullptr, *qq = nullptr, *S1 = nullptr, *S2 = nullptr, *csum = nullptr;
   } ws[2];
   cudaStream_t pipe_stream[2] = {nullptr, nullptr};
   cudaEvent_t pipe_event[3] = {nullptr, nullptr, nullptr};
@@ -666,6 +734,9 @@ void free_ws(sgdml_b200_model* m) {
     cudaFree(w.F);
     cudaFree(w.Qg);
     cudaFree(w.qq);
+    cudaFree(w.S1);
+    cudaFree(w.S2);
+    cudaFree(w.csum);
     w = sgdml_b200_model::WS();
   }
 }
@@ -682,6 +753,9 @@ int ensure_ws(sgdml_b200_model* m, int slot, int64_t n_geo) {
   cudaFree(w.F);
   cudaFree(w.Qg);
   cudaFree(w.qq);
+  cudaFree(w.S1);
+  cudaFree(w.S2);
+  cudaFree(w.csum);
   w = sgdml_b200_model::WS();
   SG_CUDA(cudaMalloc(&w.xq, sizeof(double) * n_geo * m->D));
   SG_CUDA(cudaMalloc(&w.gq, sizeof(double) * n_geo * m->D * 3));
@@ -694,6 +768,11 @@ int ensure_ws(sgdml_b200_model* m, int slot, int64_t n_geo) {
     const int64_t rows_pad = (n_geo * m->S + m->BQ - 1) / m->BQ * m->BQ;
     SG_CUDA(cudaMalloc(&w.Qg, sizeof(double) * rows_pad * m->DS));
     SG_CUDA(cudaMalloc(&w.qq, sizeof(double) * rows_pad));
+    if (m->large) {
+      SG_CUDA(cudaMalloc(&w.S1, sizeof(double) * rows_pad * m->Mpad));
+      SG_CUDA(cudaMalloc(&w.S2, sizeof(double) * rows_pad * m->Mpad));
+      SG_CUDA(cudaMalloc(&w.csum, sizeof(double) * rows_pad));
+    }
   }
   w.geo = n_geo;
   return 0;
@@ -709,6 +788,7 @@ int ensure_pipe(sgdml_b200_model* m) {
 // queries per chunk: bounds the G workspace (rows * DP * 8 bytes) to ~256 MB
 int64_t chunk_geos(const sgdml_b200_model* m) {
   int64_t rows = (int64_t)(256ll << 20) / ((int64_t)m->DP * 8);
+  if (m->large) rows = std::min<int64_t>((int64_t)(2048ll << 20) / ((int64_t)m->DP * 8), (int64_t)(2048ll << 20) / ((int64_t)m->Mpad * 8));
   int64_t g = rows / m->S;
   if (g < 1) g = 1;
   if (g > 65536) g = 65536;
@@ -728,22 +808,69 @@ int run_queries(sgdml_b200_model* m, int slot, const double* xq, const double* g
     SG_CUDA(cudaGetLastError());
     count_launch(KID_PREDICT_AUX);
   }
-  PredictArgs a;
-  a.Xc = m->Xc;
-  a.JA = m->JA;
-  a.mm = m->mm;
-  a.xja = m->xja;
-  a.D = m->D;
-  a.M = m->M;
-  a.S = m->S;
-  a.Mpad = m->Mpad;
-  a.sig = m->sig;
-  a.Qg = w.Qg;
-  a.qqg = w.qq;
-  a.n_rows = n_rows;
-  a.G = w.G;
-  a.Erow = w.Erow;
-  {
+  if (m->large) {
+    ProfScope ps(KID_PREDICT_MAIN, s);
+    MaternK mk;
+    mk.sig = m->sig;
+    mk.sig_inv = 1.0 / m->sig;
+    mk.k_base = 5.0 / (3.0 * m->sig * m->sig * m->sig);
+    mk.k_c1 = mk.k_base * 5.0 / m->sig;
+    GemmArgs g;
+    g.alpha = 1.0;
+    g.beta = 0.0;
+    g.mode = 0;
+    g.tri = 0;
+    g.abort_flag = nullptr;
+    // S1 = Q Xc^T, S2 = Q JA^T   (rows x Mpad, contraction over the padded descriptor)
+    g.m = n_rows;
+    g.n = m->Mpad;
+    g.k = m->DS;
+    g.A = w.Qg;
+    g.lda = m->DS;
+    g.ldb = m->DS;
+    g.ldc = m->Mpad;
+    g.B = m->Xc;
+    g.C = w.S1;
+    SG_TRY(launch_gemm(g, s));
+    g.B = m->JA;
+    g.C = w.S2;
+    SG_TRY(launch_gemm(g, s));
+    k_transform_rows<<<(unsigned)((n_rows + 7) / 8), 256, 0, s>>>(w.S1, w.S2, m->Mpad, w.qq, m->mm, m->xja, m->M,
+                                                                   m->Mpad, n_rows, mk, w.csum, w.Erow);
+    SG_CUDA(cudaGetLastError());
+    // acc = C1 XcT^T + C2 JAT^T   (rows x DP, contraction over the training points)
+    g.n = m->DP;
+    g.k = m->Mpad;
+    g.lda = m->Mpad;
+    g.ldb = m->Mpad;
+    g.ldc = m->DP;
+    g.A = w.S1;
+    g.B = m->XcT;
+    g.C = w.G;
+    SG_TRY(launch_gemm(g, s));
+    g.mode = 1;
+    g.A = w.S2;
+    g.B = m->JAT;
+    SG_TRY(launch_gemm(g, s));
+    k_combine_rows<<<(unsigned)((n_rows * m->DP + 255) / 256), 256, 0, s>>>(w.Qg, m->DS, w.csum, w.G, m->DP, n_rows);
+    SG_CUDA(cudaGetLastError());
+    count_launch(KID_PREDICT_MAIN, 2);
+  } else {
+    PredictArgs a;
+    a.Xc = m->Xc;
+    a.JA = m->JA;
+    a.mm = m->mm;
+    a.xja = m->xja;
+    a.D = m->D;
+    a.M = m->M;
+    a.S = m->S;
+    a.Mpad = m->Mpad;
+    a.sig = m->sig;
+    a.Qg = w.Qg;
+    a.qqg = w.qq;
+    a.n_rows = n_rows;
+    a.G = w.G;
+    a.Erow = w.Erow;
     ProfScope ps(KID_PREDICT_MAIN, s);
     SG_TRY(launch_main(m->cfg, a, s));
     count_launch(KID_PREDICT_MAIN);
@@ -755,6 +882,15 @@ int run_queries(sgdml_b200_model* m, int slot, const double* xq, const double* g
     SG_CUDA(cudaGetLastError());
     count_launch(KID_PREDICT_AUX);
   }
+  return 0;
+}
+
+int refresh_transposes(sgdml_b200_model* m, bool with_x, cudaStream_t s) {
+  dim3 grid((unsigned)((m->DP + 31) / 32), (unsigned)((m->Mpad + 31) / 32));
+  if (with_x) k_transpose_pad<<<grid, dim3(32, 8), 0, s>>>(m->Xc, m->Mpad, m->DP, m->DS, m->XcT, m->Mpad);
+  k_transpose_pad<<<grid, dim3(32, 8), 0, s>>>(m->JA, m->Mpad, m->DP, m->DS, m->JAT, m->Mpad);
+  SG_CUDA(cudaGetLastError());
+  count_launch(KID_PREDICT_AUX, with_x ? 2 : 1);
   return 0;
 }
 
@@ -782,21 +918,24 @@ int sgdml_b200_model_create(sgdml_b200_model** out, int64_t n_atoms, int64_t n_t
       cfg = i;
       break;
     }
-  if (cfg < 0) {
-    set_last_error("sgdml_b200_model_create: descriptor size D > 256 (N > 23 atoms) is not supported by the fused "
-                   "predictor yet");
-    return SGDML_B200_ERR_UNSUPPORTED;
-  }
   sgdml_b200_model* m = new sgdml_b200_model();
   m->N = (int)n_atoms;
   m->D = (int)D;
   m->M = (int)n_train;
   m->S = (int)n_perms;
   m->cfg = cfg;
-  m->DP = kCfgs[cfg].DP;
+  if (cfg >= 0) {
+    m->DP = kCfgs[cfg].DP;
+    m->BQ = kCfgs[cfg].BQ;
+    m->BM = kCfgs[cfg].BM;
+  } else {
+    // D > 256 (N > 23 atoms): GEMM-composed path, any descriptor size
+    m->large = true;
+    m->DP = (int)((D + 7) / 8 * 8);
+    m->BQ = 8;
+    m->BM = 8;
+  }
   m->DS = m->DP + 4;
-  m->BQ = kCfgs[cfg].BQ;
-  m->BM = kCfgs[cfg].BM;
   m->Mpad = (int)((n_train + m->BM - 1) / m->BM * m->BM);
   m->sig = sig;
   m->std = std;
@@ -852,6 +991,11 @@ int sgdml_b200_model_create(sgdml_b200_model** out, int64_t n_atoms, int64_t n_t
                                                   m->JA);
     SG_CUDA(cudaGetLastError());
     SG_TRY(refresh_row_dots(m, true, s));
+    if (m->large) {
+      SG_CUDA(cudaMalloc(&m->XcT, sizeof(double) * (size_t)m->DP * m->Mpad));
+      SG_CUDA(cudaMalloc(&m->JAT, sizeof(double) * (size_t)m->DP * m->Mpad));
+      SG_TRY(refresh_transposes(m, true, s));
+    }
     SG_CUDA(cudaStreamSynchronize(s));
     return 0;
   };
@@ -875,6 +1019,8 @@ int sgdml_b200_model_destroy(sgdml_b200_model* m) {
   cudaFree(m->perm);
   cudaFree(m->pinv);
   cudaFree(m->R_d_desc);
+  cudaFree(m->XcT);
+  cudaFree(m->JAT);
   free_ws(m);
   for (int i = 0; i < 2; ++i)
     if (m->pipe_stream[i]) cudaStreamDestroy(m->pipe_stream[i]);
@@ -958,6 +1104,7 @@ int sgdml_b200_model_set_alphas(sgdml_b200_model* m, const double* alphas_F, voi
   SG_CUDA(cudaGetLastError());
   count_launch(KID_PREDICT_AUX);
   SG_TRY(refresh_row_dots(m, false, s));
+  if (m->large) SG_TRY(refresh_transposes(m, false, s));
   if (sA.staged()) SG_CUDA(cudaStreamSynchronize(s));
   return 0;
 }

@@ -112,6 +112,8 @@ def test_predict_golden(eng, golden):
         (18, 21, 1, 1, 40),  # D = 153 -> DP 160
         (21, 50, 1, 1, 20),  # BASELINE config 2 descriptor, D = 210 -> DP 224
         (23, 19, 0, 1, 20),  # D = 253 -> DP 256
+        (24, 30, 1, 1, 30),  # D = 276 > 256 -> GEMM-composed large-descriptor path
+        (42, 25, 2, 0, 50),  # BASELINE config 3 descriptor (D = 861), S = 9
     ],
 )
 def test_predict_vs_oracle_shapes(eng, N, M, rot, swap, sig):
@@ -243,7 +245,7 @@ def test_assemble_col_subsets(eng, golden):
     assert rel_err(K[:n], golden['K'][:, cols]) < 1e-12
 
 
-@pytest.mark.parametrize('N,M,rot,swap,sig', [(3, 4, 1, 0, 5), (7, 9, 1, 1, 15), (10, 5, 2, 1, 20)])
+@pytest.mark.parametrize('N,M,rot,swap,sig', [(3, 4, 1, 0, 5), (7, 9, 1, 1, 15), (10, 5, 2, 1, 20), (34, 3, 1, 1, 40), (42, 2, 2, 0, 50)])
 def test_assemble_vs_oracle(eng, N, M, rot, swap, sig):
     from sgdml_b200 import synth
     from sgdml_b200.desc import Desc
@@ -382,3 +384,23 @@ def test_model_npz_roundtrip(eng, golden, tmp_path):
     E0, F0 = eng.GDMLPredict(model).predict(golden['R_query'])
     E1, F1 = eng.GDMLPredict(loaded).predict(golden['R_query'])
     assert np.array_equal(F0, F1) and np.array_equal(E0, E1)
+
+
+def test_large_descriptor_kv_and_set_alphas(eng):
+    """D > 256 (GEMM-composed predictor): K @ v through set_alphas / kmatvec_train, N = 24."""
+    from sgdml_b200 import synth
+
+    N, M = 24, 6
+    perms = synth.rotor_swap_group(N, 1, 1)
+    model, x, g = _oracle_model(N, M, perms, 30, seed=5)
+    K_ref = oassemble.assemble(x, g, model['tril_perms_lin'], 30)
+    v = np.random.default_rng(2).standard_normal(M * 3 * N)
+    p = eng.GDMLPredict(model)
+    p.set_R_desc(x)
+    p.set_R_d_desc(g)
+    p.set_alphas(v)
+    assert rel_err(p.kmatvec_train().ravel(), K_ref @ v) < 1e-10
+    p.set_alphas(model['alphas_F'])
+    E, F = p.predict()
+    E_ref, F_ref = opredict.Predictor(model).predict(synth.geometries(N, M, 5).reshape(M, -1))
+    assert rel_err(F, F_ref) < 1e-10 and rel_err(E, E_ref) < 1e-10
