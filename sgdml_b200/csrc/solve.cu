@@ -15,6 +15,7 @@
 // FP64 throughout: TF32/BF16 factorisations cannot deliver 1e-6 forces at cond ~4e11.
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 
 #include "common.cuh"
 #include "solve.cuh"
@@ -592,22 +593,54 @@ __global__ void __launch_bounds__(256) k_dmma_peak(double* out, int iters, doubl
 // more math.
 constexpr int NBO_MAX = 1024;
 
+// Look-ahead: the lazy update of outer block `ob` is split into (a) the next outer block's columns,
+// issued on the caller's stream, and (b) everything to the right of them, issued on a lower-priority
+// side stream.  The latency-bound panel work of block ob+1 (potf2 tiles, substitution strips, small
+// GEMMs) then runs concurrently with (b) instead of leaving the GPU to one CTA at a time.
+// Dependencies: inner(ob+1) needs a(ob); a(ob+1) and b(ob+1) need b(ob) (same tiles, += updates);
+// b(ob) reads the -X workspace of block ob, so the workspace is double buffered.
 int potrf_device(double* A, int64_t n, int64_t lda, int* info_host, cudaStream_t s) {
   int* d_info = nullptr;
-  double* W = nullptr;
-  SG_CUDA(cudaMalloc(&d_info, sizeof(int)));
+  double* W[2] = {nullptr, nullptr};
+  cudaStream_t s2 = nullptr;
+  cudaEvent_t evI[2] = {nullptr, nullptr}, evB[2] = {nullptr, nullptr};
   // outer block: wide for large matrices (fewer passes over C), narrower when n is small
   const int NBO = (n >= 16384) ? NBO_MAX : ((n >= 4096) ? 512 : 256);
-  cudaError_t e = cudaMalloc(&W, sizeof(double) * (size_t)n * NBO);
-  if (e != cudaSuccess) {
+  // Measured on B200 (n = 32768): 0.423 s with look-ahead vs 0.413 s without -- the 1-CTA-per-SM GEMM leaves
+  // no room for the panel kernels to co-run, so the split only costs GEMM efficiency.  Kept behind an
+  // environment switch (SGDML_B200_LOOKAHEAD=1) until the trailing GEMM is made persistent on a subset of SMs.
+  const char* la = getenv("SGDML_B200_LOOKAHEAD");
+  const bool lookahead = (la && la[0] == '1') && (n > 2 * (int64_t)NBO) && !profiling_enabled();
+  auto cleanup = [&]() {
     cudaFree(d_info);
-    return fail_cuda(e, "cudaMalloc(panel workspace)", __FILE__, __LINE__);
-  }
+    cudaFree(W[0]);
+    cudaFree(W[1]);
+    if (s2) cudaStreamDestroy(s2);
+    for (int i = 0; i < 2; ++i) {
+      if (evI[i]) cudaEventDestroy(evI[i]);
+      if (evB[i]) cudaEventDestroy(evB[i]);
+    }
+  };
   auto body = [&]() -> int {
+    SG_CUDA(cudaMalloc(&d_info, sizeof(int)));
+    SG_CUDA(cudaMalloc(&W[0], sizeof(double) * (size_t)n * NBO));
+    if (lookahead) {
+      SG_CUDA(cudaMalloc(&W[1], sizeof(double) * (size_t)n * NBO));
+      int lo = 0, hi = 0;
+      SG_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));  // lo = least priority
+      SG_CUDA(cudaStreamCreateWithPriority(&s2, cudaStreamNonBlocking, lo));
+      for (int i = 0; i < 2; ++i) {
+        SG_CUDA(cudaEventCreateWithFlags(&evI[i], cudaEventDisableTiming));
+        SG_CUDA(cudaEventCreateWithFlags(&evB[i], cudaEventDisableTiming));
+      }
+    }
     SG_CUDA(cudaMemsetAsync(d_info, 0, sizeof(int), s));
     const size_t trsm_smem = sizeof(double) * (NB + RS) * (NB + 4);
     SG_CUDA(cudaFuncSetAttribute(k_trsm_strip, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)trsm_smem));
-    for (int64_t K0 = 0; K0 < n; K0 += NBO) {
+    int ob = 0;
+    int last_b = -1;
+    for (int64_t K0 = 0; K0 < n; K0 += NBO, ++ob) {
+      double* Wc = W[lookahead ? (ob & 1) : 0];
       const int64_t K1 = std::min<int64_t>(K0 + NBO, n);  // end of the outer block
       for (int64_t k0 = K0; k0 < K1; k0 += NB) {
         const int kb = (int)std::min<int64_t>(NB, n - k0);
@@ -622,7 +655,7 @@ int potrf_device(double* A, int64_t n, int64_t lda, int* info_host, cudaStream_t
         {
           ProfScope ps(KID_TRSM, s);
           k_trsm_strip<<<(unsigned)((rem + RS - 1) / RS), 256, trsm_smem, s>>>(
-              A + k0 * lda + k0, lda, kb, A + (k0 + kb) * lda + k0, lda, rem, W + (k0 + kb) * NBO + (k0 - K0), NBO,
+              A + k0 * lda + k0, lda, kb, A + (k0 + kb) * lda + k0, lda, rem, Wc + (k0 + kb) * NBO + (k0 - K0), NBO,
               d_info);
           SG_CUDA(cudaGetLastError());
           count_launch(KID_TRSM);
@@ -633,7 +666,7 @@ int potrf_device(double* A, int64_t n, int64_t lda, int* info_host, cudaStream_t
           g.m = rem;
           g.n = cols_in;
           g.k = kb;
-          g.A = W + (k0 + kb) * NBO + (k0 - K0);  // -X
+          g.A = Wc + (k0 + kb) * NBO + (k0 - K0);  // -X
           g.lda = NBO;
           g.B = A + (k0 + kb) * lda + k0;  // X rows of the outer block
           g.ldb = lda;
@@ -648,32 +681,60 @@ int potrf_device(double* A, int64_t n, int64_t lda, int* info_host, cudaStream_t
         }
       }
       const int64_t rem = n - K1;
-      if (rem > 0) {
-        GemmArgs g;
+      if (rem <= 0) break;
+      GemmArgs g;
+      g.k = K1 - K0;
+      g.lda = NBO;
+      g.ldb = lda;
+      g.ldc = lda;
+      g.alpha = 1.0;
+      g.beta = 1.0;
+      g.mode = 1;
+      g.abort_flag = d_info;
+      if (!lookahead) {
         g.m = rem;
         g.n = rem;
-        g.k = K1 - K0;
-        g.A = W + K1 * NBO;  // -X, all panels of the outer block
-        g.lda = NBO;
+        g.A = Wc + K1 * NBO;  // -X, all panels of the outer block
         g.B = A + K1 * lda + K0;
-        g.ldb = lda;
         g.C = A + K1 * lda + K1;
-        g.ldc = lda;
-        g.alpha = 1.0;
-        g.beta = 1.0;
-        g.mode = 1;
         g.tri = 1;
-        g.abort_flag = d_info;
         SG_TRY(launch_gemm(g, s));
+        continue;
+      }
+      const int64_t K2 = std::min<int64_t>(K1 + NBO, n);
+      SG_CUDA(cudaEventRecord(evI[ob & 1], s));  // panels of this block are final
+      if (last_b >= 0) SG_CUDA(cudaStreamWaitEvent(s, evB[last_b & 1], 0));
+      // (a) columns of the next outer block, all rows below
+      g.m = rem;
+      g.n = K2 - K1;
+      g.A = Wc + K1 * NBO;
+      g.B = A + K1 * lda + K0;
+      g.C = A + K1 * lda + K1;
+      g.tri = 0;
+      SG_TRY(launch_gemm(g, s));
+      // (b) the rest of the trailing matrix, lower triangle, on the side stream
+      const int64_t rem2 = n - K2;
+      if (rem2 > 0) {
+        SG_CUDA(cudaStreamWaitEvent(s2, evI[ob & 1], 0));
+        g.m = rem2;
+        g.n = rem2;
+        g.A = Wc + K2 * NBO;
+        g.B = A + K2 * lda + K0;
+        g.C = A + K2 * lda + K2;
+        g.tri = 1;
+        SG_TRY(launch_gemm(g, s2));
+        SG_CUDA(cudaEventRecord(evB[ob & 1], s2));
+        last_b = ob;
       }
     }
+    if (lookahead && last_b >= 0) SG_CUDA(cudaStreamWaitEvent(s, evB[last_b & 1], 0));
     SG_CUDA(cudaMemcpyAsync(info_host, d_info, sizeof(int), cudaMemcpyDeviceToHost, s));
     SG_CUDA(cudaStreamSynchronize(s));
+    if (s2) SG_CUDA(cudaStreamSynchronize(s2));
     return 0;
   };
   int rc = body();
-  cudaFree(d_info);
-  cudaFree(W);
+  cleanup();
   return rc;
 }
 
