@@ -93,8 +93,8 @@ __global__ void __launch_bounds__(256, 2) k_assemble(const AsmArgs p) {
   double* v = u + TJ * N3;         // TJ*N3
   double* Dg = v + TJ * N3;        // TJ*3*N3
   double* cc = Dg + TJ * 3 * N3;   // S*TJ*2
-  double* n2s = cc + S * TJ * 2;   // S*TJ  sum of squared deltas (each pair twice)
-  int* sP = reinterpret_cast<int*>(n2s + S * TJ);  // S*N
+  double* n2p = cc + S * TJ * 2;   // TJ*8  per-warp partial sums of squared deltas (each pair twice)
+  int* sP = reinterpret_cast<int*>(n2p + TJ * 8);  // S*N
   int* sPi = sP + S * N;                                // S*N
 
   load_pair_tables(p.R_d_desc + (int64_t)i * p.D * 3, p.R_desc + (int64_t)i * p.D, N, Gi, Xi, warp, lane, nw);
@@ -107,7 +107,6 @@ __global__ void __launch_bounds__(256, 2) k_assemble(const AsmArgs p) {
     sP[idx] = p.aperm[idx];
     sPi[idx] = p.apinv[idx];
   }
-  for (int idx = tid; idx < S * TJ; idx += nt) n2s[idx] = 0.0;
 
   // this thread's output items: (t, a, b) = column point, row atom, column atom
   int it_t[ASM_NI], it_a[ASM_NI], it_b[ASM_NI];
@@ -147,7 +146,7 @@ __global__ void __launch_bounds__(256, 2) k_assemble(const AsmArgs p) {
       }
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) s2 += __shfl_xor_sync(0xffffffffu, s2, o);
-      if (lane == 0 && s2 != 0.0) atomicAdd(&n2s[pp * TJ + t], s2);
+      if (lane == 0) n2p[t * 8 + warp] = s2;  // fixed-order reduction below: bit-reproducible K
     }
     __syncthreads();
 
@@ -157,7 +156,9 @@ __global__ void __launch_bounds__(256, 2) k_assemble(const AsmArgs p) {
       // Matern factors of this permutation (one thread per column point, from the tail of the CTA)
       if (tid >= nt - tj) {
         const int t = nt - 1 - tid;
-        const double nrm = sqrt(5.0) * sqrt(0.5 * n2s[pp * TJ + t]);  // every pair twice; train.py:201
+        double n2 = 0.0;
+        for (int w = 0; w < nw; ++w) n2 += n2p[t * 8 + w];
+        const double nrm = sqrt(5.0) * sqrt(0.5 * n2);  // every pair twice; train.py:201
         const double base = exp(-nrm / sig) * inv_div * 5.0;          // train.py:202
         cc[(pp * TJ + t) * 2 + 0] = base * 5.0;                       // c1 (train.py:211)
         cc[(pp * TJ + t) * 2 + 1] = (sig2 + sig * nrm) * base;        // c2 (train.py:219)
@@ -279,7 +280,7 @@ __global__ void __launch_bounds__(256, 2) k_assemble(const AsmArgs p) {
 static size_t asm_smem_bytes(int N, int D, int S, int TJ) {
   (void)D;
   const size_t N3 = 3 * (size_t)N, NN = (size_t)N * N;
-  size_t dbl = NN * 3 + NN + (size_t)TJ * (NN * 3 + NN + NN + 2 * N3 + 3 * N3) + (size_t)S * TJ * 3;
+  size_t dbl = NN * 3 + NN + (size_t)TJ * (NN * 3 + NN + NN + 2 * N3 + 3 * N3) + (size_t)S * TJ * 2 + (size_t)TJ * 8;
   return dbl * 8 + 2 * (size_t)S * N * 4;
 }
 

@@ -65,16 +65,27 @@ __global__ void k_row_sqnorms(const double* __restrict__ X, int64_t n_rows, int6
   if (lane == 0) out[r] = s;
 }
 
-// t[j] += sum_{r in chunk} X[r][j] v[r] ; grid.y = row chunks, threads over columns
+// part[chunk][j] = sum_{r in chunk} X[r][j] v[r] ; grid.y = row chunks, threads over columns.
+// Deterministic two-pass reduction (no atomics): with several ranks every rank must compute
+// bit-identical CG scalars, otherwise their iteration counts (and collectives) diverge.
 __global__ void __launch_bounds__(256) k_xt_v(const double* __restrict__ X, int64_t n_rows, int64_t m, int64_t ldx,
-                                             const double* __restrict__ v, double* __restrict__ t, int rows_per_cta) {
+                                             const double* __restrict__ v, double* __restrict__ part,
+                                             int rows_per_cta) {
   const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t r0 = (int64_t)blockIdx.y * rows_per_cta;
   const int64_t r1 = min(r0 + rows_per_cta, n_rows);
   if (j >= m) return;
   double s = 0.0;
   for (int64_t r = r0; r < r1; ++r) s = fma(X[r * ldx + j], v[r], s);
-  atomicAdd(&t[j], s);
+  part[(int64_t)blockIdx.y * m + j] = s;
+}
+
+__global__ void k_reduce_chunks(const double* __restrict__ part, int64_t n_chunks, int64_t m, double* __restrict__ t) {
+  const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= m) return;
+  double s = 0.0;
+  for (int64_t c = 0; c < n_chunks; ++c) s += part[c * m + j];
+  t[j] = s;
 }
 
 // out[r] = (X[r, :] . t - v[r]) / lam ; one warp per row
@@ -197,19 +208,22 @@ int sgdml_b200_nystroem_apply(const double* X, int64_t n_rows, int64_t m, int64_
   Staged sV, sO;
   SG_TRY(sV.init(v, sizeof(double) * (size_t)n_rows, true, s));
   SG_TRY(sO.init(out, sizeof(double) * (size_t)n_rows, false, s));
+  const int rows_per_cta = 256;
+  const int64_t n_chunks = (n_rows + rows_per_cta - 1) / rows_per_cta;
   double* t = nullptr;
-  SG_CUDA(cudaMalloc(&t, sizeof(double) * (size_t)m));
+  SG_CUDA(cudaMalloc(&t, sizeof(double) * (size_t)m * (n_chunks + 1)));  // t, then the per-chunk partials
+  double* part = t + m;
   auto body = [&]() -> int {
-    SG_CUDA(cudaMemsetAsync(t, 0, sizeof(double) * (size_t)m, s));
-    const int rows_per_cta = 256;
-    dim3 grid((unsigned)((m + 255) / 256), (unsigned)((n_rows + rows_per_cta - 1) / rows_per_cta));
+    dim3 grid((unsigned)((m + 255) / 256), (unsigned)n_chunks);
     SG_ARG(grid.y <= 65535);
-    k_xt_v<<<grid, 256, 0, s>>>(X, n_rows, m, ldx, (const double*)sV.dev(), t, rows_per_cta);
+    k_xt_v<<<grid, 256, 0, s>>>(X, n_rows, m, ldx, (const double*)sV.dev(), part, rows_per_cta);
+    SG_CUDA(cudaGetLastError());
+    k_reduce_chunks<<<ceil_div(m, 256), 256, 0, s>>>(part, n_chunks, m, t);
     SG_CUDA(cudaGetLastError());
     k_x_t_minus_v<<<ceil_div(n_rows, 8), 256, 0, s>>>(X, n_rows, m, ldx, t, (const double*)sV.dev(), 1.0 / lam,
                                                       (double*)sO.dev());
     SG_CUDA(cudaGetLastError());
-    count_launch(KID_MISC, 2);
+    count_launch(KID_MISC, 3);
     SG_TRY(sO.finish(s));
     SG_CUDA(cudaStreamSynchronize(s));
     return 0;

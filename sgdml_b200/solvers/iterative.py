@@ -137,10 +137,20 @@ class Iterative(object):
         self.gdml_predict.set_R_desc(R_desc)
         self.gdml_predict.set_R_d_desc(R_d_desc)
 
+        from .. import dist as sdist
+
+        rank, world = sdist.world_info()
+        n_train = R_desc.shape[0]
+
         def _K_vec(v):
             v = np.ascontiguousarray(v, dtype=np.float64)
             self.gdml_predict.set_alphas(v)
-            pred = self.gdml_predict.kmatvec_train().ravel()
+            if world > 1:
+                # output rows (training points) sharded over the ranks, alphas replicated, one
+                # all-gather of 3N*M/G doubles per application; every rank runs the same CG on replicated vectors
+                pred = sdist.kmatvec_sharded(lambda lo, hi: self.gdml_predict.kmatvec_train(lo, hi), n_train).ravel()
+            else:
+                pred = self.gdml_predict.kmatvec_train().ravel()
             pred -= lam * v
             return pred
 
@@ -188,6 +198,7 @@ class Iterative(object):
             lev_scores = self._lev_scores(R_desc, R_d_desc, tril_perms_lin, sig, lam, task['use_E_cstr'], n_inducing_pts)
             inducing_pts_idxs = self.inducing_pts_from_lev_scores(lev_scores, n_inducing_pts * dim_i)
 
+        inducing_pts_idxs = self._bcast_idxs(inducing_pts_idxs)
         P_vec, lev_scores = self._init_precon_operator(task, R_desc, R_d_desc, tril_perms_lin, inducing_pts_idxs)
         self.timings['precon_s'] = timeit.default_timer() - t_start
 
@@ -265,7 +276,7 @@ class Iterative(object):
                 is_conv = False
                 break
             n_inducing_pts = min(int(np.ceil(1.2 * n_inducing_pts)), n_train)
-            inducing_pts_idxs = self.inducing_pts_from_lev_scores(lev_scores, n_inducing_pts * dim_i)
+            inducing_pts_idxs = self._bcast_idxs(self.inducing_pts_from_lev_scores(lev_scores, n_inducing_pts * dim_i))
             del P_vec
             P_vec, lev_scores = self._init_precon_operator(task, R_desc, R_d_desc, tril_perms_lin, inducing_pts_idxs)
 
@@ -280,6 +291,23 @@ class Iterative(object):
                 sec_disp_str='{:d} iterations'.format(num_iters),
             )
         return alphas, tol, num_iters, resid, train_rmse, inducing_pts_idxs, is_conv
+
+    @staticmethod
+    def _bcast_idxs(idxs):
+        """The leverage-score sampling is random (iterative.py:404-409): with several ranks, rank 0's draw is
+        broadcast so that every rank builds the same preconditioner."""
+        from .. import dist as sdist
+
+        rank, world = sdist.world_info()
+        if world == 1:
+            return idxs
+        import torch
+        import torch.distributed as dist
+
+        dev = sdist._device_for_backend()
+        t = torch.from_numpy(np.ascontiguousarray(idxs, dtype=np.int64)).to(dev)
+        dist.broadcast(t, src=0)
+        return t.cpu().numpy()
 
     def _checkpoint_model(self, task, R_desc, R_d_desc, tril_perms_lin, y_std, xk, tol, num_iters, resid, norm_y, idxs):
         model = self.gdml_train.create_model(task, 'cg', R_desc, R_d_desc, tril_perms_lin, y_std, -xk)

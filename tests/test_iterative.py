@@ -117,3 +117,61 @@ def test_engine_cg_own_sampling_converges():
     _, F = sgdml_b200.GDMLPredict(model).predict(Rq)
     _, Fx = sgdml_b200.GDMLPredict(exact).predict(Rq)
     assert rel_err(F, Fx) < 5e-3
+
+
+def _cg_rank(rank, world, port, out_dir):
+    import os
+    import sys
+
+    import torch
+    import torch.distributed as dist
+
+    from conftest import ROOT
+
+    sys.path.insert(0, ROOT)
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group('nccl', rank=rank, world_size=world, device_id=torch.device('cuda', rank))
+    import sgdml_b200
+    from sgdml_b200 import synth
+
+    N, M = 9, 60
+    perms = synth.rotor_swap_group(N, 1, 1)
+    task = synth.make_task(N, M, perms, 20)
+    np.random.seed(3 + rank)  # different draws per rank: rank 0's inducing columns must win
+    model = sgdml_b200.GDMLTrain(max_memory=0.01).train(task)
+    np.savez(os.path.join(out_dir, 'cg_r%d.npz' % rank), alphas=model['alphas_F'], idxs=model['inducing_pts_idxs'], iters=model['solver_iters'])
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.gpu
+def test_engine_cg_two_ranks_sharded_kv(tmp_path):
+    """Two ranks (NCCL): K.v rows sharded + all-gather, inducing columns broadcast; both ranks end with the
+    same model, equal to the single-rank result with the same columns."""
+    import socket
+
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip('needs 2 GPUs')
+    import torch.multiprocessing as mp
+
+    s = socket.socket()
+    s.bind(('127.0.0.1', 0))
+    port = s.getsockname()[1]
+    s.close()
+    mp.spawn(_cg_rank, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    r0 = np.load(tmp_path / 'cg_r0.npz')
+    r1 = np.load(tmp_path / 'cg_r1.npz')
+    assert np.array_equal(r0['idxs'], r1['idxs']) and int(r0['iters']) == int(r1['iters'])
+    assert rel_err(r1['alphas'], r0['alphas']) < 1e-12
+    import sgdml_b200
+    from sgdml_b200 import synth
+
+    N, M = 9, 60
+    task = synth.make_task(N, M, synth.rotor_swap_group(N, 1, 1), 20)
+    task['inducing_pts_idxs'] = r0['idxs']
+    single = sgdml_b200.GDMLTrain(max_memory=0.01).train(task)
+    assert rel_err(single['alphas_F'], r0['alphas']) < 1e-9
