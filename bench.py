@@ -449,7 +449,7 @@ def run_engine(args):
             'kernel_ms_per_step': t_step * 1e3,
             'launches_per_step': main_launches / reps,
             'kernel_share_of_step': main_ms / max(main_ms + aux_ms, 1e-9),
-            'traffic': None,
+            'traffic': ncu_traffic(args.workload, B / max(main_launches / reps, 1)),
         }
         log('roofline probe done')
         if world == 1 and not args.no_cpu_baseline:
@@ -514,6 +514,16 @@ def run_engine(args):
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def ncu_traffic(workload, queries_per_launch):
+    """DRAM bytes per launch of k_predict_main from the committed ncu capture (profiles/r01_traffic.json),
+    scaled to this run's launch size; None if no capture exists for the workload."""
+    try:
+        with open(os.path.join(ROOT, 'profiles', 'r01_traffic.json')) as f:
+            return float(json.load(f)[workload]['bytes_per_query']) * queries_per_launch
+    except Exception:
+        return None
 
 
 def measured_peak(key, fallback):
