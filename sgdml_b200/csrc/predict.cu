@@ -83,6 +83,8 @@ struct PredictArgs {
   const double* Qg;     // (rows padded to BQ, DS)  q_{b,p}[e] = x_b[pinv_p[e]] - mu[e], zero padded
   const double* qqg;    // (rows padded to BQ)      |q_{b,p}|^2
   int64_t n_rows;       // B*S virtual rows
+  int64_t n_rows_pad;   // rows rounded up to BQ (stride between the per-split output planes)
+  int tiles_per_split;  // blockIdx.y handles training tiles [y*tps, (y+1)*tps): small batches split the sweep over M
   // outputs
   double* G;            // (n_rows, DP)
   double* Erow;         // (n_rows)
@@ -150,7 +152,8 @@ __global__ void __launch_bounds__(256, C::MINB) k_predict_main(const PredictArgs
   const int warp = tid >> 5, lane = tid & 31;
   const int lr = lane >> 2, lc = lane & 3;  // fragment row / k (or col pair) index
   const int64_t r0 = (int64_t)blockIdx.x * C::BQ;
-  const int n_tiles = p.Mpad / C::BM;
+  const int t_begin = (int)blockIdx.y * p.tiles_per_split;
+  const int n_tiles = min(p.Mpad / C::BM, t_begin + p.tiles_per_split);  // exclusive end of this CTA's range
   constexpr uint32_t STAGE_BYTES = (uint32_t)((2 * C::BM * C::DS + 2 * C::BM) * 8);
 
   if (tid == 0) {
@@ -162,7 +165,7 @@ __global__ void __launch_bounds__(256, C::MINB) k_predict_main(const PredictArgs
   __syncthreads();
 
   auto issue_tile = [&](int t) {
-    const int s = t & 1;
+    const int s = (t - t_begin) & 1;
     const int64_t m0 = (int64_t)t * C::BM;
     mbar_arrive_expect_tx(&bars[s], STAGE_BYTES);
     bulk_g2s(Xs + s * C::BM * C::DS, p.Xc + m0 * C::DS, C::BM * C::DS * 8, &bars[s]);
@@ -175,8 +178,8 @@ __global__ void __launch_bounds__(256, C::MINB) k_predict_main(const PredictArgs
     mbar_arrive_expect_tx(&bars[2], (uint32_t)((C::BQ * C::DS + C::BQ) * 8));
     bulk_g2s(Qs, p.Qg + r0 * C::DS, C::BQ * C::DS * 8, &bars[2]);
     bulk_g2s(qq, p.qqg + r0, C::BQ * 8, &bars[2]);
-    issue_tile(0);
-    if (n_tiles > 1) issue_tile(1);
+    issue_tile(t_begin);
+    if (t_begin + 1 < n_tiles) issue_tile(t_begin + 1);
   }
   if (tid < C::BQ) {
     csum_s[tid] = 0.0;
@@ -221,13 +224,13 @@ __global__ void __launch_bounds__(256, C::MINB) k_predict_main(const PredictArgs
   double* C1s = Ps;
   double* C2s = Ps + C::BQ * C::CS;
 
-  for (int t = 0; t < n_tiles; ++t) {
-    const int s = t & 1;
+  for (int t = t_begin; t < n_tiles; ++t) {
+    const int s = (t - t_begin) & 1;
     const double* Xt = Xs + s * C::BM * C::DS;
     const double* JAt = JAs + s * C::BM * C::DS;
     const double* mmt = mms + s * C::BM;
     const double* xjat = xjas + s * C::BM;
-    mbar_wait(&bars[s], (uint32_t)((t >> 1) & 1));
+    mbar_wait(&bars[s], (uint32_t)(((t - t_begin) >> 1) & 1));
     // real training points in this tile: the zero-padded tail of the last tile is skipped
     // (whole 8-point fragment columns in GEMM1, whole 4-point k-steps in GEMM2)
     const int mvalid = min(C::BM, p.M - t * C::BM);
@@ -437,12 +440,13 @@ __global__ void __launch_bounds__(256, C::MINB) k_predict_main(const PredictArgs
             g0 -= o.x;
             g1 -= o.y;
           }
-          *reinterpret_cast<double2*>(p.G + row * C::DP + col) = make_double2(g0, g1);
+          *reinterpret_cast<double2*>(p.G + ((int64_t)blockIdx.y * p.n_rows_pad + row) * C::DP + col) =
+              make_double2(g0, g1);
         }
       }
     }
   }
-  if (tid < C::BQ && r0 + tid < p.n_rows) p.Erow[r0 + tid] = E_s[tid];
+  if (tid < C::BQ && r0 + tid < p.n_rows) p.Erow[(int64_t)blockIdx.y * p.n_rows_pad + r0 + tid] = E_s[tid];
 }
 
 // ============================================================== query rows
@@ -546,13 +550,27 @@ __global__ void k_transpose_pad(const double* __restrict__ src, int64_t rows, in
 __global__ void __launch_bounds__(128) k_predict_finish(const double* __restrict__ G, const double* __restrict__ Erow,
                                                         const double* __restrict__ gq, const int* __restrict__ perm,
                                                         int n_atoms, int D, int DP, int S, double std, double c,
+                                                        int n_splits, int64_t plane_rows,
                                                         double* __restrict__ E, double* __restrict__ F) {
   extern __shared__ double fd[];  // D
   const int64_t b = blockIdx.x;
+  // fixed summation order (split-major, then permutation) with four independent accumulators so
+  // that the L2 round trips of the gathered loads overlap (n_splits * S terms per descriptor entry)
   for (int d = threadIdx.x; d < D; d += blockDim.x) {
-    double s = 0.0;
-    for (int pp = 0; pp < S; ++pp) s += G[(b * S + pp) * DP + perm[pp * D + d]];
-    fd[d] = s;
+    double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0, acc3 = 0.0;
+    for (int pp = 0; pp < S; ++pp) {
+      const double* gp = G + (b * S + pp) * DP + perm[pp * D + d];
+      const int64_t stride = plane_rows * DP;
+      int sp = 0;
+      for (; sp + 4 <= n_splits; sp += 4) {
+        acc0 += gp[(int64_t)sp * stride];
+        acc1 += gp[(int64_t)(sp + 1) * stride];
+        acc2 += gp[(int64_t)(sp + 2) * stride];
+        acc3 += gp[(int64_t)(sp + 3) * stride];
+      }
+      for (; sp < n_splits; ++sp) acc0 += gp[(int64_t)sp * stride];
+    }
+    fd[d] = (acc0 + acc1) + (acc2 + acc3);
   }
   __syncthreads();
   const double* g = gq + b * (int64_t)D * 3;
@@ -573,7 +591,8 @@ __global__ void __launch_bounds__(128) k_predict_finish(const double* __restrict
   }
   if (E != nullptr && threadIdx.x == 0) {
     double s = 0.0;
-    for (int pp = 0; pp < S; ++pp) s += Erow[b * S + pp];
+    for (int sp = 0; sp < n_splits; ++sp)
+      for (int pp = 0; pp < S; ++pp) s += Erow[(int64_t)sp * plane_rows + b * S + pp];
     E[b] = s * std + c;
   }
 }
@@ -697,7 +716,7 @@ const CfgInfo kCfgs[] = {{40, 64, 32}, {72, 64, 32}, {112, 64, 16}, {160, 32, 16
 const int kNumCfgs = 6;
 
 template <class C>
-int launch_main_t(const PredictArgs& a, cudaStream_t s) {
+int launch_main_t(const PredictArgs& a, int n_splits, cudaStream_t s) {
   static bool configured[64] = {false};
   int dev = 0;
   SG_CUDA(cudaGetDevice(&dev));
@@ -706,22 +725,24 @@ int launch_main_t(const PredictArgs& a, cudaStream_t s) {
     configured[dev] = true;
   }
   const int64_t grid = (a.n_rows + C::BQ - 1) / C::BQ;
-  k_predict_main<C><<<(unsigned)grid, C::NT, C::SMEM_BYTES, s>>>(a);
+  k_predict_main<C><<<dim3((unsigned)grid, (unsigned)n_splits), C::NT, C::SMEM_BYTES, s>>>(a);
   SG_CUDA(cudaGetLastError());
   return 0;
 }
 
-int launch_main(int cfg, const PredictArgs& a, cudaStream_t s) {
+int launch_main(int cfg, const PredictArgs& a, int n_splits, cudaStream_t s) {
   switch (cfg) {
-    case 0: return launch_main_t<Cfg40>(a, s);
-    case 1: return launch_main_t<Cfg72>(a, s);
-    case 2: return launch_main_t<Cfg112>(a, s);
-    case 3: return launch_main_t<Cfg160>(a, s);
-    case 4: return launch_main_t<Cfg224>(a, s);
-    case 5: return launch_main_t<Cfg256>(a, s);
+    case 0: return launch_main_t<Cfg40>(a, n_splits, s);
+    case 1: return launch_main_t<Cfg72>(a, n_splits, s);
+    case 2: return launch_main_t<Cfg112>(a, n_splits, s);
+    case 3: return launch_main_t<Cfg160>(a, n_splits, s);
+    case 4: return launch_main_t<Cfg224>(a, n_splits, s);
+    case 5: return launch_main_t<Cfg256>(a, n_splits, s);
   }
   return fail_arg("no predictor tile configuration for this descriptor size");
 }
+
+int64_t chunk_geos(const sgdml_b200_model* m);
 
 void free_ws(sgdml_b200_model* m) {
   for (auto& w : m->ws) {
@@ -743,6 +764,10 @@ void free_ws(sgdml_b200_model* m) {
 
 int ensure_ws(sgdml_b200_model* m, int slot, int64_t n_geo) {
   sgdml_b200_model::WS& w = m->ws[slot];
+  if (!m->large) {  // room for the per-split output planes of small batches (<= ~300 CTAs x BQ rows)
+    const int64_t min_geo = (int64_t)(2 * 148 + 8) * m->BQ / m->S + 1;
+    n_geo = std::max<int64_t>(n_geo, std::min<int64_t>(min_geo, chunk_geos(m)));
+  }
   if (n_geo <= w.geo) return 0;
   cudaFree(w.xq);
   cudaFree(w.gq);
@@ -759,8 +784,12 @@ int ensure_ws(sgdml_b200_model* m, int slot, int64_t n_geo) {
   w = sgdml_b200_model::WS();
   SG_CUDA(cudaMalloc(&w.xq, sizeof(double) * n_geo * m->D));
   SG_CUDA(cudaMalloc(&w.gq, sizeof(double) * n_geo * m->D * 3));
-  SG_CUDA(cudaMalloc(&w.G, sizeof(double) * n_geo * m->S * m->DP));
-  SG_CUDA(cudaMalloc(&w.Erow, sizeof(double) * n_geo * m->S));
+  {
+    // padded to whole row tiles: the per-split output planes of small batches are laid out with that stride
+    const int64_t rows_cap = (n_geo * m->S + m->BQ - 1) / m->BQ * m->BQ;
+    SG_CUDA(cudaMalloc(&w.G, sizeof(double) * rows_cap * m->DP));
+    SG_CUDA(cudaMalloc(&w.Erow, sizeof(double) * rows_cap));
+  }
   SG_CUDA(cudaMalloc(&w.R, sizeof(double) * n_geo * 3 * m->N));
   SG_CUDA(cudaMalloc(&w.E, sizeof(double) * n_geo));
   SG_CUDA(cudaMalloc(&w.F, sizeof(double) * n_geo * 3 * m->N));
@@ -801,6 +830,7 @@ int run_queries(sgdml_b200_model* m, int slot, const double* xq, const double* g
   sgdml_b200_model::WS& w = m->ws[slot];
   const int64_t n_rows = n_geo * m->S;
   const int64_t n_rows_pad = (n_rows + m->BQ - 1) / m->BQ * m->BQ;
+  int n_splits = 1;
   {
     ProfScope ps(KID_PREDICT_AUX, s);
     k_query_rows<<<(unsigned)((n_rows_pad + 7) / 8), 256, 0, s>>>(xq, m->pinv, m->mu, m->D, m->DS, m->S, n_rows,
@@ -869,16 +899,31 @@ int run_queries(sgdml_b200_model* m, int slot, const double* xq, const double* g
     a.Qg = w.Qg;
     a.qqg = w.qq;
     a.n_rows = n_rows;
+    a.n_rows_pad = n_rows_pad;
     a.G = w.G;
     a.Erow = w.Erow;
+    // small batches: split the sweep over the training points across CTAs so that the grid fills the
+    // GPU (partial G / E planes are summed by the finishing kernel); bounded by the workspace capacity
+    {
+      const int n_tiles = m->Mpad / m->BM;
+      const int64_t q_tiles = n_rows_pad / m->BQ;
+      const int64_t target = 2 * (int64_t)num_sms();
+      int64_t sp = (target + q_tiles - 1) / q_tiles;
+      const int64_t cap_rows = (w.geo * m->S + m->BQ - 1) / m->BQ * m->BQ;
+      sp = std::min<int64_t>(sp, cap_rows / n_rows_pad);
+      sp = std::max<int64_t>(1, std::min<int64_t>(sp, n_tiles));
+      a.tiles_per_split = (int)((n_tiles + sp - 1) / sp);
+      n_splits = (n_tiles + a.tiles_per_split - 1) / a.tiles_per_split;
+    }
     ProfScope ps(KID_PREDICT_MAIN, s);
-    SG_TRY(launch_main(m->cfg, a, s));
+    SG_TRY(launch_main(m->cfg, a, n_splits, s));
     count_launch(KID_PREDICT_MAIN);
   }
   {
     ProfScope ps(KID_PREDICT_AUX, s);
     k_predict_finish<<<(unsigned)n_geo, 128, sizeof(double) * m->D, s>>>(w.G, w.Erow, gq, m->perm, m->N, m->D,
-                                                                          m->DP, m->S, std, c, E_dev, F_dev);
+                                                                          m->DP, m->S, std, c, n_splits, n_rows_pad,
+                                                                          E_dev, F_dev);
     SG_CUDA(cudaGetLastError());
     count_launch(KID_PREDICT_AUX);
   }

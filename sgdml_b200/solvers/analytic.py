@@ -46,7 +46,10 @@ class Analytic(object):
         # BASELINE config 2) is kept out of the assembly timing
         n = n_train * 3 * self.desc.n_atoms
         ldk = (n + 1) // 2 * 2
+        t_alloc = timeit.default_timer()
         K = torch.empty((n, ldk), dtype=torch.float64, device='cuda')
+        torch.cuda.synchronize()
+        t_alloc = timeit.default_timer() - t_alloc
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
         ev[0].record()
         K, n = self.gdml_train._assemble_kernel_mat_device(
@@ -83,8 +86,12 @@ class Analytic(object):
         self.timings = {
             'assemble_s': ev[0].elapsed_time(ev[1]) * 1e-3,
             'solve_s': ev[1].elapsed_time(ev[2]) * 1e-3,
+            'alloc_s': t_alloc,
         }
+        t_free = timeit.default_timer()
         del K
+        torch.cuda.synchronize()
+        self.timings['free_s'] = timeit.default_timer() - t_free
 
         if self.callback is not None:
             dur_s = timeit.default_timer() - start

@@ -90,6 +90,7 @@ class GDMLTrain(object):
     # ------------------------------------------------------------------ training
     def train(self, task, save_progr_callback=None, callback=None):
         """train.py:836-1088.  Returns the model dict."""
+        t_all = timeit.default_timer()
         task = dict(task)
         if task.get('use_E_cstr', False):
             raise NotImplementedError('use_E_cstr is out of scope (SURVEY.md section 2 row 22)')
@@ -110,6 +111,7 @@ class GDMLTrain(object):
         y_std = np.std(y)
         y /= y_std
 
+        t_desc = timeit.default_timer() - t_all
         # solver choice by memory, like train.py:949-975 -- but against DEVICE memory
         est_bytes_analytic = Analytic.est_memory_requirement(n_train, n_atoms)
         free_bytes, _total = _torch().cuda.mem_get_info()
@@ -139,13 +141,16 @@ class GDMLTrain(object):
             if not is_conv:
                 self.log.warning('Iterative solver did not converge! (train.py:1032-1052)')
 
+        t0 = timeit.default_timer()
         model = self.create_model(
             task, 'analytic' if use_analytic_solver else 'cg', R_desc, R_d_desc, tril_perms_lin, y_std, alphas
         )
         model.update(solver_keys)
-
+        t1 = timeit.default_timer()
         if model['use_E']:  # train.py:1074-1086
             model['c'] = self._recov_int_const(model, task, R_desc=R_desc, R_d_desc=R_d_desc)
+        t2 = timeit.default_timer()
+        self.timings.update({'desc_s': t_desc, 'model_s': t1 - t0, 'int_const_s': t2 - t1, 'total_s': t2 - t_all})
         return model
 
     def _recov_int_const(self, model, task, R_desc=None, R_d_desc=None):

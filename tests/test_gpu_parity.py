@@ -404,3 +404,25 @@ def test_large_descriptor_kv_and_set_alphas(eng):
     E, F = p.predict()
     E_ref, F_ref = opredict.Predictor(model).predict(synth.geometries(N, M, 5).reshape(M, -1))
     assert rel_err(F, F_ref) < 1e-10 and rel_err(E, E_ref) < 1e-10
+
+
+@pytest.mark.parametrize('B', [1, 2, 7, 100, 700])
+def test_predict_small_batches_split_over_training_points(eng, B):
+    """Small batches split the sweep over M across CTAs (per-split partial planes summed by the finishing
+    kernel): same answer as the oracle for any batch size, including the single-geometry MD case."""
+    from sgdml_b200 import synth
+
+    N, M = 9, 200
+    perms = synth.rotor_swap_group(N, 1, 1)
+    model, _, _ = _oracle_model(N, M, perms, 20, seed=11)
+    Rq = synth.geometries(N, B, 1).reshape(B, -1)
+    E_ref, F_ref = opredict.Predictor(model).predict(Rq)
+    E, F = eng.GDMLPredict(model).predict(Rq)
+    assert rel_err(F, F_ref) < 1e-10 and rel_err(E, E_ref) < 1e-10
+    N2, M2 = 21, 130
+    perms2 = synth.rotor_swap_group(N2, 1, 1)
+    model2, _, _ = _oracle_model(N2, M2, perms2, 20, seed=12)
+    Rq2 = synth.geometries(N2, min(B, 40), 1).reshape(min(B, 40), -1)
+    E_ref, F_ref = opredict.Predictor(model2).predict(Rq2)
+    E, F = eng.GDMLPredict(model2).predict(Rq2)
+    assert rel_err(F, F_ref) < 1e-10 and rel_err(E, E_ref) < 1e-10
