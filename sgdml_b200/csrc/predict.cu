@@ -547,6 +547,7 @@ __global__ void k_transpose_pad(const double* __restrict__ src, int64_t rows, in
 // ============================================================== finishing kernel
 // F_desc[d] = sum_p G[b*S+p][perm_p[d]];  F = J_x^T F_desc (predict.py:240-243);
 // E = sum_p Erow;  outputs scaled by std, E += c (predict.py:1286-1288).
+// One CTA per query: threads over descriptor entries, then over force components.
 __global__ void __launch_bounds__(128) k_predict_finish(const double* __restrict__ G, const double* __restrict__ Erow,
                                                         const double* __restrict__ gq, const int* __restrict__ perm,
                                                         int n_atoms, int D, int DP, int S, double std, double c,
@@ -554,13 +555,13 @@ __global__ void __launch_bounds__(128) k_predict_finish(const double* __restrict
                                                         double* __restrict__ E, double* __restrict__ F) {
   extern __shared__ double fd[];  // D
   const int64_t b = blockIdx.x;
-  // fixed summation order (split-major, then permutation) with four independent accumulators so
+  // fixed summation order (permutation-major, then split) with four independent accumulators so
   // that the L2 round trips of the gathered loads overlap (n_splits * S terms per descriptor entry)
+  const int64_t stride = plane_rows * DP;
   for (int d = threadIdx.x; d < D; d += blockDim.x) {
     double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0, acc3 = 0.0;
     for (int pp = 0; pp < S; ++pp) {
       const double* gp = G + (b * S + pp) * DP + perm[pp * D + d];
-      const int64_t stride = plane_rows * DP;
       int sp = 0;
       for (; sp + 4 <= n_splits; sp += 4) {
         acc0 += gp[(int64_t)sp * stride];
@@ -589,11 +590,15 @@ __global__ void __launch_bounds__(128) k_predict_finish(const double* __restrict
     }
     F[b * 3 * n_atoms + idx] = s * std;
   }
-  if (E != nullptr && threadIdx.x == 0) {
+  if (E != nullptr && threadIdx.x < 32) {
     double s = 0.0;
-    for (int sp = 0; sp < n_splits; ++sp)
-      for (int pp = 0; pp < S; ++pp) s += Erow[(int64_t)sp * plane_rows + b * S + pp];
-    E[b] = s * std + c;
+    for (int t = threadIdx.x; t < n_splits * S; t += 32) {
+      const int sp = t / S, pp = t - sp * S;
+      s += Erow[(int64_t)sp * plane_rows + b * S + pp];
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (threadIdx.x == 0) E[b] = s * std + c;
   }
 }
 
@@ -911,6 +916,7 @@ int run_queries(sgdml_b200_model* m, int slot, const double* xq, const double* g
       int64_t sp = (target + q_tiles - 1) / q_tiles;
       const int64_t cap_rows = (w.geo * m->S + m->BQ - 1) / m->BQ * m->BQ;
       sp = std::min<int64_t>(sp, cap_rows / n_rows_pad);
+      sp = std::min<int64_t>(sp, 2 * (int64_t)std::ceil(std::sqrt(2.0 * n_tiles)));  // finishing cost grows with splits
       sp = std::max<int64_t>(1, std::min<int64_t>(sp, n_tiles));
       a.tiles_per_split = (int)((n_tiles + sp - 1) / sp);
       n_splits = (n_tiles + a.tiles_per_split - 1) / a.tiles_per_split;
@@ -921,9 +927,9 @@ int run_queries(sgdml_b200_model* m, int slot, const double* xq, const double* g
   }
   {
     ProfScope ps(KID_PREDICT_AUX, s);
-    k_predict_finish<<<(unsigned)n_geo, 128, sizeof(double) * m->D, s>>>(w.G, w.Erow, gq, m->perm, m->N, m->D,
-                                                                          m->DP, m->S, std, c, n_splits, n_rows_pad,
-                                                                          E_dev, F_dev);
+    k_predict_finish<<<(unsigned)n_geo, 128, sizeof(double) * m->D, s>>>(w.G, w.Erow, gq, m->perm, m->N, m->D, m->DP,
+                                                                          m->S, std, c, n_splits, n_rows_pad, E_dev,
+                                                                          F_dev);
     SG_CUDA(cudaGetLastError());
     count_launch(KID_PREDICT_AUX);
   }
