@@ -34,6 +34,7 @@ struct AsmArgs {
   const int64_t* dest;     // (nJ, 3N) destination column in K or -1
   int N, D, M, S, nJ, TJ;
   unsigned mN, mNN, mPer;  // ceil(2^32 / d) for d = N, N*N, 5N
+  int sym;                 // full square matrix: compute blocks j >= i only and mirror them (K_ji = K_ij^T)
   double sig, scale;
   double* K;
   int64_t ldk;
@@ -83,6 +84,7 @@ __global__ void __launch_bounds__(256, 2) k_assemble(const AsmArgs p) {
   const int i = blockIdx.y;
   const int jt0 = blockIdx.x * TJ;
   const int tj = min(TJ, p.nJ - jt0);
+  if (p.sym && jt0 + tj - 1 < i) return;  // (sym: jpts is the identity) every column point of the tile is < i
 
   double* Gi = sm;                 // NN3
   double* Xi = Gi + NN3;           // NN
@@ -114,8 +116,9 @@ __global__ void __launch_bounds__(256, 2) k_assemble(const AsmArgs p) {
 #pragma unroll
   for (int q = 0; q < ASM_NI; ++q) {
     const int it = (int)blockIdx.z * ASM_NI * nt + tid + q * nt;  // grid.z splits the sub-blocks of large molecules
-    const bool ok = it < tj * NN;
+    bool ok = it < tj * NN;
     const int t = ok ? fastdiv(it, p.mNN) : 0;
+    if (p.sym && jt0 + t < i) ok = false;  // mirrored from block (j, i) instead
     const int ab = ok ? it - t * NN : 0;
     it_t[q] = ok ? t : -1;
     it_a[q] = fastdiv(ab, p.mN);
@@ -258,7 +261,7 @@ __global__ void __launch_bounds__(256, 2) k_assemble(const AsmArgs p) {
     // (no barrier here: the next S1 only writes Dl / cc[pp+1]; u, v, Dg are rewritten after it)
   }
 
-  // ---- single store of the finished 3x3 sub-blocks
+  // ---- single store of the finished 3x3 sub-blocks (+ the mirrored block in symmetric mode)
 #pragma unroll
   for (int q = 0; q < ASM_NI; ++q) {
     const int t = it_t[q];
@@ -272,6 +275,15 @@ __global__ void __launch_bounds__(256, 2) k_assemble(const AsmArgs p) {
       for (int c2i = 0; c2i < 3; ++c2i) {
         const int64_t col = dst[c2i];
         if (col >= 0) Krow[col] = p.scale * acc[q][c * 3 + c2i];
+      }
+    }
+    if (p.sym && jt0 + t > i) {
+      const int j = jt0 + t;
+#pragma unroll
+      for (int c2i = 0; c2i < 3; ++c2i) {
+        double* Krow = p.K + ((int64_t)j * N3 + 3 * b + c2i) * p.ldk + (int64_t)i * N3 + 3 * a;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) Krow[c] = p.scale * acc[q][c * 3 + c2i];
       }
     }
   }
@@ -456,6 +468,7 @@ extern "C" int sgdml_b200_assemble(const double* R_desc, const double* R_d_desc,
     a.S = S;
     a.nJ = nJ;
     a.TJ = TJ;
+    a.sym = (col_idxs == nullptr) ? 1 : 0;
     a.mN = (unsigned)((0x100000000ull + N - 1) / N);
     a.mNN = (unsigned)((0x100000000ull + (uint64_t)N * N - 1) / ((uint64_t)N * N));
     a.mPer = (unsigned)((0x100000000ull + 5 * N - 1) / (5 * N));
