@@ -192,7 +192,8 @@ int sgdml_b200_fp64_peak_tflops(double* tflops);
 int sgdml_b200_fp64_peak_tflops_sustained(double seconds, double* tflops);
 
 /* Test / tuning hook: selects the GEMM kernel used by dgemm_nt and potrf's trailing update.
- * 0 = 128x128 DMMA tiles (default), 1 = 128x64 DMMA tiles, 2 = scalar FMA reference kernel. */
+ * 0 = 128x128 DMMA tiles fed by cp.async, 1 = 128x64 DMMA tiles, 2 = scalar FMA reference kernel,
+ * 3 = 128x128 DMMA tiles fed by TMA tensor maps (cp.async.bulk.tensor + mbarrier ring; default). */
 int sgdml_b200_set_gemm_variant(int variant);
 
 #ifdef __cplusplus

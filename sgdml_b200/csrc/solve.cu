@@ -13,6 +13,8 @@
 //                     m8n8k4.f64 -> SASS DMMA; tcgen05 has no f64 kind), lower tiles only,
 //                     4-stage cp.async pipeline, fragment-major shared-memory tiles.
 // FP64 throughout: TF32/BF16 factorisations cannot deliver 1e-6 forces at cond ~4e11.
+#include <cuda.h>  // CUtensorMap types only: cuTensorMapEncodeTiled is resolved at run time (no libcuda link)
+
 #include <algorithm>
 #include <cmath>
 #include <cstdlib>
@@ -219,10 +221,255 @@ __global__ void k_gemm_nt_naive(const GemmArgs p) {
   }
 }
 
+
+// ====================================================================== TMA variant of the GEMM
+// Same tiles and DMMA inner loop as k_gemm_nt, but the operand pipeline is Blackwell/Hopper style:
+// one elected thread issues cp.async.bulk.tensor (2-D tensor maps, 128-byte swizzle, SASS UTMALDG)
+// into a 3-stage ring, completion is signalled on mbarriers (full: transaction bytes; empty: one
+// arrival per consumer warp) -- no per-thread address arithmetic, no LDGSTS, and no CTA-wide barrier
+// in the main loop.  Each stage holds two 128-row x 16-double boxes per operand (a box row is exactly
+// the 128-byte swizzle span); a fragment element (row, k) lives at
+//   box + row*128 + ((chunk ^ (row & 7)) << 4) + (k & 1)*8,   chunk = (k & 15) >> 1.
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* tm, int c0, int c1, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+          smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(tm)), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+constexpr int TG_BM = 128, TG_BN = 128, TG_BK = 32, TG_STAGES = 3;
+constexpr int TG_BOX_BYTES = 128 * 128;                     // 128 rows x 16 doubles
+constexpr int TG_STAGE_BYTES = 4 * TG_BOX_BYTES;            // A: 2 boxes, B: 2 boxes
+constexpr size_t TG_SMEM_BYTES = (size_t)TG_STAGES * TG_STAGE_BYTES + 64;
+
+__global__ void __launch_bounds__(256) k_gemm_nt_tma(const __grid_constant__ CUtensorMap tmA,
+                                                     const __grid_constant__ CUtensorMap tmB, const GemmArgs p) {
+  extern __shared__ __align__(1024) unsigned char tsm2[];
+  if (p.abort_flag != nullptr && *p.abort_flag != 0) return;
+  uint64_t* full = reinterpret_cast<uint64_t*>(tsm2 + (size_t)TG_STAGES * TG_STAGE_BYTES);
+  uint64_t* empty = full + TG_STAGES;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int lr = lane >> 2, lc = lane & 3;
+  constexpr int WM = 2, WN = 4, TR = TG_BM / (8 * WM), TC = TG_BN / (8 * WN);
+
+  int64_t ti, tj;
+  if (p.tri) {
+    constexpr int GS = 8;
+    constexpr int PER = GS * GS;
+    const int64_t sb = blockIdx.x / PER;
+    const int local = (int)(blockIdx.x - sb * PER);
+    int64_t t = (int64_t)((sqrt(8.0 * (double)sb + 1.0) - 1.0) * 0.5);
+    while ((t + 1) * (t + 2) / 2 <= sb) ++t;
+    while (t * (t + 1) / 2 > sb) --t;
+    const int64_t sj = sb - t * (t + 1) / 2;
+    ti = t * GS + local / GS;
+    tj = sj * GS + local % GS;
+    if (tj * TG_BN >= (ti + 1) * TG_BM) return;
+  } else {
+    const int64_t ntn = (p.n + TG_BN - 1) / TG_BN;
+    ti = blockIdx.x / ntn;
+    tj = blockIdx.x - ti * ntn;
+  }
+  const int64_t m0 = ti * TG_BM, n0 = tj * TG_BN;
+  if (m0 >= p.m || n0 >= p.n) return;
+
+  if (tid == 0) {
+#pragma unroll
+    for (int st = 0; st < TG_STAGES; ++st) {
+      mbar_init(&full[st], 1);
+      mbar_init(&empty[st], 8);
+    }
+    fence_mbar_init();
+  }
+  __syncthreads();
+
+  const int KT = (int)((p.k + TG_BK - 1) / TG_BK);
+  auto issue = [&](int kt) {
+    const int st = kt % TG_STAGES;
+    unsigned char* base = tsm2 + (size_t)st * TG_STAGE_BYTES;
+    const int k0 = kt * TG_BK;
+    mbar_arrive_expect_tx(&full[st], (uint32_t)TG_STAGE_BYTES);
+    tma_load_2d(base, &tmA, k0, (int)m0, &full[st]);
+    tma_load_2d(base + TG_BOX_BYTES, &tmA, k0 + 16, (int)m0, &full[st]);
+    tma_load_2d(base + 2 * TG_BOX_BYTES, &tmB, k0, (int)n0, &full[st]);
+    tma_load_2d(base + 3 * TG_BOX_BYTES, &tmB, k0 + 16, (int)n0, &full[st]);
+  };
+  if (tid == 0) {
+    issue(0);
+    if (KT > 1) issue(1);
+  }
+
+  const int wm = warp / WN, wn = warp % WN;
+  const int row0 = wm * TR * 8, col0 = wn * TC * 8;
+  double acc[TR][TC][2];
+  if (p.mode == 1) {
+#pragma unroll
+    for (int i = 0; i < TR; ++i) {
+      const int64_t r = m0 + row0 + i * 8 + lr;
+#pragma unroll
+      for (int j = 0; j < TC; ++j) {
+        const int64_t c = n0 + col0 + j * 8 + 2 * lc;
+        double2 v = make_double2(0.0, 0.0);
+        if (r < p.m && c + 1 < p.n)
+          v = *reinterpret_cast<const double2*>(p.C + r * p.ldc + c);
+        else if (r < p.m && c < p.n)
+          v.x = p.C[r * p.ldc + c];
+        acc[i][j][0] = v.x;
+        acc[i][j][1] = v.y;
+      }
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < TR; ++i)
+#pragma unroll
+      for (int j = 0; j < TC; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+  }
+
+  // per-lane constants of the swizzled fragment addresses
+  const int a_row_off = (row0 + lr) * 128 + ((lc & 1) << 3);
+  const int b_row_off = (col0 + lr) * 128 + ((lc & 1) << 3);
+  const int half = lc >> 1;
+
+  for (int kt = 0; kt < KT; ++kt) {
+    if (tid == 0 && kt + 2 < KT) {
+      // stage (kt+2)%3 was last read for tile kt-1: wait until all 8 consumer warps released it
+      if (kt >= 1) mbar_wait(&empty[(kt + 2) % TG_STAGES], (uint32_t)(((kt - 1) / TG_STAGES) & 1));
+      issue(kt + 2);
+    }
+    const int st = kt % TG_STAGES;
+    mbar_wait(&full[st], (uint32_t)((kt / TG_STAGES) & 1));
+    const unsigned char* As = tsm2 + (size_t)st * TG_STAGE_BYTES;
+    const unsigned char* Bs = As + 2 * TG_BOX_BYTES;
+#pragma unroll
+    for (int ks = 0; ks < TG_BK / 4; ++ks) {
+      const int box = ks >> 2;
+      const int sw = (((2 * (ks & 3) + half) ^ lr) << 4);
+      double fa[TR], fb[TC];
+#pragma unroll
+      for (int i = 0; i < TR; ++i)
+        fa[i] = *reinterpret_cast<const double*>(As + box * TG_BOX_BYTES + a_row_off + i * 8 * 128 + sw);
+#pragma unroll
+      for (int j = 0; j < TC; ++j)
+        fb[j] = *reinterpret_cast<const double*>(Bs + box * TG_BOX_BYTES + b_row_off + j * 8 * 128 + sw);
+#pragma unroll
+      for (int i = 0; i < TR; ++i)
+#pragma unroll
+        for (int j = 0; j < TC; ++j) dmma884(acc[i][j][0], acc[i][j][1], fa[i], fb[j]);
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty[st]);
+  }
+
+#pragma unroll
+  for (int i = 0; i < TR; ++i) {
+    const int64_t r = m0 + row0 + i * 8 + lr;
+    if (r >= p.m) continue;
+    double old0[TC], old1[TC];
+    if (p.mode == 0 && p.beta != 0.0) {
+#pragma unroll
+      for (int j = 0; j < TC; ++j) {
+        const int64_t c = n0 + col0 + j * 8 + 2 * lc;
+        const double* src = p.C + r * p.ldc + c;
+        old0[j] = (c < p.n) ? src[0] : 0.0;
+        old1[j] = (c + 1 < p.n) ? src[1] : 0.0;
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < TC; ++j) {
+      const int64_t c = n0 + col0 + j * 8 + 2 * lc;
+      if (c >= p.n) continue;
+      double* dst = p.C + r * p.ldc + c;
+      double v0 = acc[i][j][0], v1 = acc[i][j][1];
+      if (p.mode == 0) {
+        v0 *= p.alpha;
+        v1 *= p.alpha;
+        if (p.beta != 0.0) {
+          v0 += p.beta * old0[j];
+          v1 += p.beta * old1[j];
+        }
+      }
+      if (c + 1 < p.n)
+        *reinterpret_cast<double2*>(dst) = make_double2(v0, v1);
+      else
+        dst[0] = v0;
+    }
+  }
+}
+
+typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                        const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                        CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_tmapEncodeTiled tmap_encoder() {
+  static PFN_tmapEncodeTiled fn = nullptr;
+  if (fn == nullptr) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_tmapEncodeTiled>(ptr);
+  }
+  return fn;
+}
+
+// row-major (rows x cols) FP64 matrix with row stride ld -> 2-D map with 16 x 128 boxes, 128 B swizzle
+static int make_operand_map(CUtensorMap* tm, const double* base, int64_t rows, int64_t cols, int64_t ld) {
+  PFN_tmapEncodeTiled enc = tmap_encoder();
+  if (enc == nullptr) {
+    set_last_error("cuTensorMapEncodeTiled is not available from this driver");
+    return SGDML_B200_ERR_UNSUPPORTED;
+  }
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 8};
+  cuuint32_t box[2] = {16, 128};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    char buf[128];
+    snprintf(buf, sizeof(buf), "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+    set_last_error(buf);
+    return SGDML_B200_ERR_ARG;
+  }
+  return 0;
+}
+
+static int launch_gemm_tma(const GemmArgs& a, cudaStream_t s) {
+  static bool configured[64] = {false};
+  int dev = 0;
+  SG_CUDA(cudaGetDevice(&dev));
+  if (dev >= 0 && dev < 64 && !configured[dev]) {
+    SG_CUDA(cudaFuncSetAttribute(k_gemm_nt_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TG_SMEM_BYTES));
+    configured[dev] = true;
+  }
+  CUtensorMap tmA, tmB;
+  SG_TRY(make_operand_map(&tmA, a.A, a.m, a.k, a.lda));
+  SG_TRY(make_operand_map(&tmB, a.B, a.n, a.k, a.ldb));
+  const int64_t ntm = (a.m + TG_BM - 1) / TG_BM, ntn = (a.n + TG_BN - 1) / TG_BN;
+  int64_t blocks;
+  if (a.tri) {
+    const int64_t sr = (ntm + 7) / 8;
+    blocks = sr * (sr + 1) / 2 * 64;
+  } else {
+    blocks = ntm * ntn;
+  }
+  if (blocks == 0) return 0;
+  ProfScope ps(KID_GEMM, s);
+  k_gemm_nt_tma<<<(unsigned)blocks, 256, TG_SMEM_BYTES, s>>>(tmA, tmB, a);
+  SG_CUDA(cudaGetLastError());
+  count_launch(KID_GEMM);
+  return 0;
+}
+
 using GBig = GCfg<128, 128, 2, 4, 32, 3>;   // 196 KB smem, 1 CTA/SM
 using GTall = GCfg<128, 64, 4, 2, 16, 4>;   // 98 KB smem, 2 CTAs/SM
 
-static int g_gemm_variant = 0;  // 0: 128x128 tiles (1 CTA/SM), 1: 128x64 tiles (2 CTAs/SM)
+static int g_gemm_variant = 3;  // 0: 128x128 cp.async, 1: 128x64 cp.async (2 CTAs/SM), 2: scalar, 3: 128x128 TMA (default)
 
 template <class G>
 static int launch_gemm_t(const GemmArgs& a, cudaStream_t s) {
@@ -265,6 +512,7 @@ int launch_gemm(const GemmArgs& a, cudaStream_t s) {
     return 0;
   }
   if (g_gemm_variant == 1) return launch_gemm_t<GTall>(a, s);
+  if (g_gemm_variant == 3 && tmap_encoder() != nullptr) return launch_gemm_tma(a, s);  // else: cp.async tiles
   return launch_gemm_t<GBig>(a, s);
 }
 

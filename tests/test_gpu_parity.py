@@ -260,7 +260,7 @@ def test_assemble_vs_oracle(eng, N, M, rot, swap, sig):
 
 
 # --------------------------------------------------------------------------- dense solve
-@pytest.mark.parametrize('variant', [0, 1, 2])
+@pytest.mark.parametrize('variant', [0, 1, 2, 3])
 @pytest.mark.parametrize('m,n,k', [(128, 128, 128), (300, 200, 64), (257, 129, 130), (64, 1000, 16), (33, 17, 7)])
 def test_dgemm_nt(eng, variant, m, n, k):
     from sgdml_b200 import _lib
@@ -275,11 +275,11 @@ def test_dgemm_nt(eng, variant, m, n, k):
     try:
         _lib.check(L.sgdml_b200_dgemm_nt(m, n, k, 0.75, _lib.ptr(A), k, _lib.ptr(B), k, -1.25, _lib.ptr(C), n, None), 'dgemm')
     finally:
-        L.sgdml_b200_set_gemm_variant(0)
+        L.sgdml_b200_set_gemm_variant(3)
     assert rel_err(C, ref) < 1e-13
 
 
-@pytest.mark.parametrize('variant', [0, 1])
+@pytest.mark.parametrize('variant', [0, 1, 3])
 @pytest.mark.parametrize('n', [64, 128, 200, 513, 1400])
 def test_potrf_potrs(eng, variant, n):
     import scipy.linalg
@@ -295,7 +295,7 @@ def test_potrf_potrs(eng, variant, n):
     try:
         _lib.check(L.sgdml_b200_potrf(_lib.ptr(Af), n, n, None), 'potrf')
     finally:
-        L.sgdml_b200_set_gemm_variant(0)
+        L.sgdml_b200_set_gemm_variant(3)
     Lg = np.tril(Af)
     Lr = scipy.linalg.cholesky(A, lower=True)
     assert rel_err(Lg, Lr) < 1e-10
