@@ -1,6 +1,6 @@
 #!/bin/bash
 # ncu capture of the big (k = NBO = 1024) trailing-update GEMM inside potrf, aspirin M=500 (n = 31500).
-# Step 1 lists the k_gemm_nt launches; step 2 captures the first one with a grid larger than 20000 CTAs.
+# Step 1 lists the GEMM launches; step 2 captures the first one with a grid larger than 20000 CTAs.
 NCU="ncu --clock-control none"
 $NCU --metrics gpu__time_duration.sum --csv -k regex:k_gemm_nt -c 120 --log-file gpurun_out/gemm_list.csv \
   python tools/train_probe.py aspirin 500 > /dev/null 2>&1
@@ -16,6 +16,6 @@ for n,r in enumerate(rows[start:]):
         print(n); break
 PY
 )
-echo "first big trailing GEMM is k_gemm_nt launch #$IDX"
+echo "first big trailing GEMM is k_gemm_nt* launch #$IDX"
 $NCU --set full --import-source on -k regex:k_gemm_nt -s $IDX -c 1 -f -o gpurun_out/r01f_gemm_trailing \
   python tools/train_probe.py aspirin 500 > /dev/null 2>&1
