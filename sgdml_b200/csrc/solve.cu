@@ -561,8 +561,9 @@ __global__ void __launch_bounds__(1024) k_potf2_tile(double* __restrict__ A, int
         failed = true;
         break;
       }
-      const double d = sqrt(ajj);
-      const double dinv = 1.0 / d;
+      // one rsqrt instead of sqrt + division (two ~400-cycle dependent sequences per column)
+      const double dinv = rsqrt(ajj);
+      const double d = ajj * dinv;
       double ci[4], cl[4];
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
@@ -617,6 +618,7 @@ __global__ void __launch_bounds__(256) k_trsm_strip(const double* __restrict__ L
   constexpr int LD = NB + 4;  // == 4 mod 16: conflict-free DMMA fragment loads
   double* L = tsm;            // NB x LD
   double* X = L + NB * LD;    // RS x LD
+  __shared__ double rdiag[NB];  // 1 / L[c][c]: the substitution multiplies instead of dividing
   if (info != nullptr && *info != 0) return;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int lr = lane >> 2, lc = lane & 3;
@@ -632,6 +634,7 @@ __global__ void __launch_bounds__(256) k_trsm_strip(const double* __restrict__ L
     const int i = idx / NB, j = idx - i * NB;
     X[i * LD + j] = (i < rows && j < kb) ? P[(int64_t)i * ldp + j] : 0.0;
   }
+  if (tid < NB) rdiag[tid] = (tid < kb) ? 1.0 / L11[(int64_t)tid * lda + tid] : 1.0;
   __syncthreads();
 
   for (int jb = 0; jb < NB / SB; ++jb) {
@@ -664,7 +667,7 @@ __global__ void __launch_bounds__(256) k_trsm_strip(const double* __restrict__ L
       for (int c = 0; c < SB; ++c) x[c] = X[tid * LD + c0 + c];
 #pragma unroll
       for (int c = 0; c < SB; ++c) {
-        const double xc = x[c] / L[(c0 + c) * LD + c0 + c];
+        const double xc = x[c] * rdiag[c0 + c];
         x[c] = xc;
 #pragma unroll
         for (int l = c + 1; l < SB; ++l) x[l] = fma(-xc, L[(c0 + l) * LD + c0 + c], x[l]);
@@ -730,6 +733,8 @@ __global__ void __launch_bounds__(256) k_trsv_diag1(const double* __restrict__ A
     const int i = idx / NB, j = idx - i * NB;
     Ls[i * LD + j] = (i < nb && j <= i) ? Lkk[(int64_t)i * lda + j] : ((i == j) ? 1.0 : 0.0);
   }
+  double* rd = Ls + NB * LD;  // NB reciprocals of the diagonal
+  if (tid < NB) rd[tid] = (tid < nb) ? 1.0 / Lkk[(int64_t)tid * lda + tid] : 1.0;
   __syncthreads();
   if (tid >= 32) return;
   const int lane = tid;
@@ -744,7 +749,7 @@ __global__ void __launch_bounds__(256) k_trsv_diag1(const double* __restrict__ A
     for (int qj = 0; qj < 4; ++qj) {
       for (int jj = 0; jj < 32; ++jj) {
         const int j = qj * 32 + jj;
-        const double xj = __shfl_sync(0xffffffffu, x[qj], jj) / Ls[j * LD + j];
+        const double xj = __shfl_sync(0xffffffffu, x[qj], jj) * rd[j];
         if (lane == jj) x[qj] = xj;
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
@@ -758,7 +763,7 @@ __global__ void __launch_bounds__(256) k_trsv_diag1(const double* __restrict__ A
     for (int qj = 3; qj >= 0; --qj) {
       for (int jj = 31; jj >= 0; --jj) {
         const int j = qj * 32 + jj;
-        const double xj = __shfl_sync(0xffffffffu, x[qj], jj) / Ls[j * LD + j];
+        const double xj = __shfl_sync(0xffffffffu, x[qj], jj) * rd[j];
         if (lane == jj) x[qj] = xj;
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
