@@ -120,6 +120,21 @@ int sgdml_b200_assemble(const double* R_desc, const double* R_d_desc, const int6
                         const int64_t* col_idxs, int64_t n_cols, double scale, double* K,
                         int64_t ldk, void* stream);
 
+/* Row-sharded form of sgdml_b200_assemble (SURVEY.md section 8e "explicit K assembly": blocks are
+ * independent, each GPU assembles the block rows of its own training points).  Only the row
+ * points [m_begin, m_end) are produced: K is ((m_end - m_begin)*3N, n_cols) and
+ *   K[(i - m_begin)*3N + r, c] = scale * K_ref[i*3N + r, col_idxs[c]].
+ * This is the loop `for i in range(n_train)` of train.py:193-194 cut into ranges. */
+int sgdml_b200_assemble_rows(const double* R_desc, const double* R_d_desc,
+                             const int64_t* tril_perms_lin, int64_t n_atoms, int64_t n_train,
+                             int64_t n_perms, double sig, const int64_t* col_idxs, int64_t n_cols,
+                             double scale, int64_t m_begin, int64_t m_end, double* K, int64_t ldk,
+                             void* stream);
+
+/* Tuning / test hook: 0 = kernel chosen by molecule size (default), 1 = always the large-molecule
+ * kernel (tables in global memory), which molecules above ~50 atoms need. */
+int sgdml_b200_set_assemble_variant(int variant);
+
 /* ---------------------------------------------------------------- dense solve (path a) */
 
 /* scipy.linalg.cho_factor (LAPACK dpotrf) as used by analytic.py:94-96 and
@@ -163,6 +178,16 @@ int sgdml_b200_row_sqnorms(const double* X, int64_t n_rows, int64_t m, int64_t l
 /* out = (X (X^T v) - v) / lam -- the preconditioner P v (iterative.py:136-138). */
 int sgdml_b200_nystroem_apply(const double* X, int64_t n_rows, int64_t m, int64_t ldx, double lam,
                               const double* v, double* out, void* stream);
+
+/* The two halves of sgdml_b200_nystroem_apply for a ROW-SHARDED factor (SURVEY.md section 8e
+ * "Nystroem factor (m,n): shard n"): each GPU holds the rows X_loc of its own training points,
+ *   t_loc = X_loc^T v_loc            (project; the caller all-reduces t over the GPUs)
+ *   out_loc = (X_loc t - v_loc)/lam  (expand;  the caller all-gathers out)
+ * which together are iterative.py:136-138 on the full factor. */
+int sgdml_b200_nystroem_project(const double* X, int64_t n_rows, int64_t m, int64_t ldx,
+                                const double* v, double* t, void* stream);
+int sgdml_b200_nystroem_expand(const double* X, int64_t n_rows, int64_t m, int64_t ldx, double lam,
+                               const double* t, const double* v, double* out, void* stream);
 
 /* C = alpha * A * B^T + beta * C on the FP64 tensor pipe (the building block of potrf's
  * trailing update; exported for tests and benchmarks).  A (m, k) lda, B (n, k) ldb,

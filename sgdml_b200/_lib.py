@@ -43,6 +43,12 @@ SIGNATURES = {
         C.c_int,
         [c_void_p, c_void_p, c_void_p, i64, i64, i64, C.c_double, c_void_p, i64, C.c_double, c_void_p, i64, c_void_p],
     ),
+    'sgdml_b200_assemble_rows': (
+        C.c_int,
+        [c_void_p, c_void_p, c_void_p, i64, i64, i64, C.c_double, c_void_p, i64, C.c_double, i64, i64, c_void_p, i64,
+         c_void_p],
+    ),
+    'sgdml_b200_set_assemble_variant': (C.c_int, [C.c_int]),
     'sgdml_b200_potrf': (C.c_int, [c_void_p, i64, i64, c_void_p]),
     'sgdml_b200_potrs': (C.c_int, [c_void_p, i64, i64, c_void_p, i64, i64, c_void_p]),
     'sgdml_b200_solve_analytic': (C.c_int, [c_void_p, i64, i64, C.c_double, c_void_p, c_void_p, c_void_p]),
@@ -56,6 +62,11 @@ SIGNATURES = {
     'sgdml_b200_gram_tn': (C.c_int, [c_void_p, i64, i64, i64, C.c_double, c_void_p, i64, c_void_p]),
     'sgdml_b200_row_sqnorms': (C.c_int, [c_void_p, i64, i64, i64, c_void_p, c_void_p]),
     'sgdml_b200_nystroem_apply': (C.c_int, [c_void_p, i64, i64, i64, C.c_double, c_void_p, c_void_p, c_void_p]),
+    'sgdml_b200_nystroem_project': (C.c_int, [c_void_p, i64, i64, i64, c_void_p, c_void_p, c_void_p]),
+    'sgdml_b200_nystroem_expand': (
+        C.c_int,
+        [c_void_p, i64, i64, i64, C.c_double, c_void_p, c_void_p, c_void_p, c_void_p],
+    ),
     'sgdml_b200_set_gemm_variant': (C.c_int, [C.c_int]),
     'sgdml_b200_profile_enable': (C.c_int, [C.c_int]),
     'sgdml_b200_profile_reset': (C.c_int, []),

@@ -33,6 +33,7 @@ struct AsmArgs {
   const int* jpts;         // (nJ) training point of each block-column
   const int64_t* dest;     // (nJ, 3N) destination column in K or -1
   int N, D, M, S, nJ, TJ;
+  int i0;                  // first row point of this call (row-sharded assembly): K row block = i - i0
   unsigned mN, mNN, mPer;  // ceil(2^32 / d) for d = N, N*N, 5N
   int sym;                 // full square matrix: compute blocks j >= i only and mirror them (K_ji = K_ij^T)
   double sig, scale;
@@ -81,7 +82,7 @@ __global__ void __launch_bounds__(256, 2) k_assemble(const AsmArgs p) {
   const int tid = threadIdx.x, nt = blockDim.x;
   const int warp = tid >> 5, lane = tid & 31, nw = nt >> 5;
 
-  const int i = blockIdx.y;
+  const int i = p.i0 + blockIdx.y;
   const int jt0 = blockIdx.x * TJ;
   const int tj = min(TJ, p.nJ - jt0);
   if (p.sym && jt0 + tj - 1 < i) return;  // (sym: jpts is the identity) every column point of the tile is < i
@@ -270,14 +271,14 @@ __global__ void __launch_bounds__(256, 2) k_assemble(const AsmArgs p) {
     const int64_t* dst = p.dest + (int64_t)(jt0 + t) * N3 + 3 * b;
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
-      double* Krow = p.K + ((int64_t)i * N3 + 3 * a + c) * p.ldk;
+      double* Krow = p.K + ((int64_t)(i - p.i0) * N3 + 3 * a + c) * p.ldk;
 #pragma unroll
       for (int c2i = 0; c2i < 3; ++c2i) {
         const int64_t col = dst[c2i];
         if (col >= 0) Krow[col] = p.scale * acc[q][c * 3 + c2i];
       }
     }
-    if (p.sym && jt0 + t > i) {
+    if (p.sym && jt0 + t > i) {  // (sym implies i0 == 0)
       const int j = jt0 + t;
 #pragma unroll
       for (int c2i = 0; c2i < 3; ++c2i) {
@@ -287,6 +288,209 @@ __global__ void __launch_bounds__(256, 2) k_assemble(const AsmArgs p) {
       }
     }
   }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Large molecules (N > ~50: the atom tables of one block no longer fit in shared memory; BASELINE
+// configs 4 and 5).  Same mathematics and the same summation order as k_assemble, but the tables
+// live in a private slab of global memory per CTA (L1/L2 resident), the CTAs are persistent
+// (2 per SM, each walking a contiguous range of (row point, column point) blocks so the row tables
+// are rebuilt only when i changes), and the per-permutation vectors u, v, Dg of ALL permutations
+// are kept so that the 3x3 sub-blocks can be accumulated in register-sized passes without
+// recomputing them.  Only the delta table (N*N doubles) stays in shared memory when it fits.
+__global__ void __launch_bounds__(256, 2)
+    k_assemble_large(const AsmArgs p, double* slabs, int64_t slab_stride, int64_t n_work, int dl_in_smem) {
+  extern __shared__ __align__(16) double sm[];
+  __shared__ double n2p[8];
+  const int N = p.N, S = p.S;
+  const int N3 = 3 * N, NN = N * N, NN3 = NN * 3;
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const int warp = tid >> 5, lane = tid & 31, nw = nt >> 5;
+
+  double* sl = slabs + (int64_t)blockIdx.x * slab_stride;
+  double* Gi = sl;                    // NN3
+  double* Xi = Gi + NN3;              // NN
+  double* Gj = Xi + NN;               // NN3
+  double* Xj = Gj + NN3;              // NN
+  double* uS = Xj + NN;               // S*N3
+  double* vS = uS + (int64_t)S * N3;  // S*N3
+  double* DgS = vS + (int64_t)S * N3;        // S*3*N3
+  double* cc = DgS + (int64_t)S * 3 * N3;    // S*2
+  double* Dl = dl_in_smem ? sm : cc + 2 * S;  // NN
+
+  const double sig = p.sig;
+  const double sig2 = sig * sig;
+  const double inv_div = 1.0 / (3.0 * sig2 * sig2);
+
+  const int64_t w0 = n_work * (int64_t)blockIdx.x / gridDim.x;
+  const int64_t w1 = n_work * ((int64_t)blockIdx.x + 1) / gridDim.x;
+  int cur_i = -1;
+  for (int64_t w = w0; w < w1; ++w) {
+    const int i = p.i0 + (int)(w / p.nJ);
+    const int jt = (int)(w % p.nJ);
+    const int j = p.jpts[jt];
+    __syncthreads();  // the previous block's accumulation passes have finished reading the slab
+    if (i != cur_i) {
+      load_pair_tables(p.R_d_desc + (int64_t)i * p.D * 3, p.R_desc + (int64_t)i * p.D, N, Gi, Xi, warp, lane, nw);
+      cur_i = i;
+    }
+    load_pair_tables(p.R_d_desc + (int64_t)j * p.D * 3, p.R_desc + (int64_t)j * p.D, N, Gj, Xj, warp, lane, nw);
+    __syncthreads();
+
+    // ---- phase A: per-permutation vectors (S1 + S2 of k_assemble), kept for all permutations
+    for (int pp = 0; pp < S; ++pp) {
+      const int* P = p.aperm + pp * N;
+      const int* Pi = p.apinv + pp * N;
+      double s2 = 0.0;
+      for (int e = tid; e < NN; e += nt) {
+        const int b = fastdiv(e, p.mN);
+        const int g = e - b * N;
+        const double dl = Xi[Pi[b] * N + Pi[g]] - Xj[e];
+        Dl[e] = dl;
+        s2 = fma(dl, dl, s2);
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+      if (lane == 0) n2p[warp] = s2;
+      __syncthreads();
+      if (tid == nt - 1) {
+        double n2 = 0.0;
+        for (int w8 = 0; w8 < nw; ++w8) n2 += n2p[w8];
+        const double nrm = sqrt(5.0) * sqrt(0.5 * n2);
+        const double base = exp(-nrm / sig) * inv_div * 5.0;
+        cc[pp * 2 + 0] = base * 5.0;
+        cc[pp * 2 + 1] = (sig2 + sig * nrm) * base;
+      }
+      double* u = uS + (int64_t)pp * N3;
+      double* v = vS + (int64_t)pp * N3;
+      double* Dg = DgS + (int64_t)pp * 3 * N3;
+      for (int r = tid; r < 5 * N; r += nt) {
+        if (r < N) {
+          const int a = r, pa = P[a];
+          const double* gi = Gi + a * N3;
+          const double* dl = Dl + pa * N;
+          double s0 = 0.0, s1 = 0.0, s2b = 0.0;
+          for (int g = 0; g < N; ++g) {
+            const double d = dl[P[g]];
+            s0 = fma(gi[g * 3 + 0], d, s0);
+            s1 = fma(gi[g * 3 + 1], d, s1);
+            s2b = fma(gi[g * 3 + 2], d, s2b);
+          }
+          u[3 * a + 0] = -s0;
+          u[3 * a + 1] = -s1;
+          u[3 * a + 2] = -s2b;
+        } else if (r < 2 * N) {
+          const int b = r - N;
+          const double* gj = Gj + b * N3;
+          const double* dl = Dl + b * N;
+          double s0 = 0.0, s1 = 0.0, s2b = 0.0;
+          for (int g = 0; g < N; ++g) {
+            const double d = dl[g];
+            s0 = fma(gj[g * 3 + 0], d, s0);
+            s1 = fma(gj[g * 3 + 1], d, s1);
+            s2b = fma(gj[g * 3 + 2], d, s2b);
+          }
+          v[3 * b + 0] = -s0;
+          v[3 * b + 1] = -s1;
+          v[3 * b + 2] = -s2b;
+        } else {
+          const int ac = r - 2 * N;
+          const int a = (int)__umulhi((unsigned)ac, 0x55555556u), c = ac - 3 * a;
+          const double* gi = Gi + a * N3 + c;
+          const double* gj = Gj + P[a] * N3;
+          double s0 = 0.0, s1 = 0.0, s2b = 0.0;
+          for (int g = 0; g < N; ++g) {
+            const double x = gi[g * 3];
+            const double* y = gj + P[g] * 3;
+            s0 = fma(x, y[0], s0);
+            s1 = fma(x, y[1], s1);
+            s2b = fma(x, y[2], s2b);
+          }
+          Dg[ac * 3 + 0] = s0;
+          Dg[ac * 3 + 1] = s1;
+          Dg[ac * 3 + 2] = s2b;
+        }
+      }
+      __syncthreads();  // Dl and n2p are rewritten by the next permutation
+    }
+
+    // ---- phase B: passes of ASM_NI sub-blocks per thread over the N*N atom pairs (S3 of k_assemble)
+    for (int base0 = 0; base0 < NN; base0 += ASM_NI * nt) {
+      int it_a[ASM_NI], it_b[ASM_NI];
+      double acc[ASM_NI][9];
+#pragma unroll
+      for (int q = 0; q < ASM_NI; ++q) {
+        const int it = base0 + tid + q * nt;
+        const bool ok = it < NN;
+        it_a[q] = ok ? fastdiv(it, p.mN) : -1;
+        it_b[q] = ok ? it - it_a[q] * N : 0;
+#pragma unroll
+        for (int e = 0; e < 9; ++e) acc[q][e] = 0.0;
+      }
+      for (int pp = 0; pp < S; ++pp) {
+        const int* P = p.aperm + pp * N;
+        const int* Pi = p.apinv + pp * N;
+        const double c1 = cc[pp * 2 + 0], c2 = cc[pp * 2 + 1];
+        const double* u = uS + (int64_t)pp * N3;
+        const double* v = vS + (int64_t)pp * N3;
+        const double* Dg = DgS + (int64_t)pp * 3 * N3;
+#pragma unroll
+        for (int q = 0; q < ASM_NI; ++q) {
+          const int a = it_a[q], b = it_b[q];
+          if (a < 0) continue;
+          const double* ua = u + 3 * a;
+          const double* vb = v + 3 * b;
+          const int pa = P[a];
+          if (b != pa) {
+            const double* gi = Gi + (a * N + Pi[b]) * 3;
+            const double* gj = Gj + (pa * N + b) * 3;
+            double t0[3], t1[3];
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+              t0[c] = c2 * gi[c];
+              t1[c] = gj[c];
+            }
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+              const double cu = c1 * ua[c];
+#pragma unroll
+              for (int c2i = 0; c2i < 3; ++c2i)
+                acc[q][c * 3 + c2i] = fma(t0[c], t1[c2i], fma(cu, vb[c2i], acc[q][c * 3 + c2i]));
+            }
+          } else {
+            const double* dg = Dg + 9 * a;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+              const double cu = c1 * ua[c];
+#pragma unroll
+              for (int c2i = 0; c2i < 3; ++c2i)
+                acc[q][c * 3 + c2i] = fma(-c2, dg[c * 3 + c2i], fma(cu, vb[c2i], acc[q][c * 3 + c2i]));
+            }
+          }
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < ASM_NI; ++q) {
+        const int a = it_a[q], b = it_b[q];
+        if (a < 0) continue;
+        const int64_t* dst = p.dest + (int64_t)jt * N3 + 3 * b;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          double* Krow = p.K + ((int64_t)(i - p.i0) * N3 + 3 * a + c) * p.ldk;
+#pragma unroll
+          for (int c2i = 0; c2i < 3; ++c2i) {
+            const int64_t col = dst[c2i];
+            if (col >= 0) Krow[col] = p.scale * acc[q][c * 3 + c2i];
+          }
+        }
+      }
+    }
+  }
+}
+
+static size_t asm_large_slab_doubles(int N, int S) {
+  const size_t N3 = 3 * (size_t)N, NN = (size_t)N * N;
+  return 2 * (NN * 3 + NN) + (size_t)S * (2 * N3 + 3 * N3 + 2) + NN;
 }
 
 static size_t asm_smem_bytes(int N, int D, int S, int TJ) {
@@ -344,16 +548,27 @@ static bool atom_perm_from_desc_perm(const int* dperm, int N, int* P) {
   return true;
 }
 
-extern "C" int sgdml_b200_assemble(const double* R_desc, const double* R_d_desc, const int64_t* tril_perms_lin,
-                                   int64_t n_atoms, int64_t n_train, int64_t n_perms, double sig,
-                                   const int64_t* col_idxs, int64_t n_cols, double scale, double* K, int64_t ldk,
-                                   void* stream) {
+static int g_asm_variant = 0;  // 0: by size; 1: always the large-molecule kernel (tests)
+
+extern "C" int sgdml_b200_set_assemble_variant(int variant) {
+  SG_ARG(variant == 0 || variant == 1);
+  g_asm_variant = variant;
+  return 0;
+}
+
+extern "C" int sgdml_b200_assemble_rows(const double* R_desc, const double* R_d_desc, const int64_t* tril_perms_lin,
+                                        int64_t n_atoms, int64_t n_train, int64_t n_perms, double sig,
+                                        const int64_t* col_idxs, int64_t n_cols, double scale, int64_t m_begin,
+                                        int64_t m_end, double* K, int64_t ldk, void* stream) {
   SG_TRY(require_device());
   SG_ARG(R_desc != nullptr && R_d_desc != nullptr && tril_perms_lin != nullptr && K != nullptr);
   SG_ARG(n_atoms >= 2 && n_train >= 1 && n_perms >= 1 && sig > 0);
+  SG_ARG(m_begin >= 0 && m_begin < m_end && m_end <= n_train);
   const int N = (int)n_atoms, M = (int)n_train, S = (int)n_perms;
   const int D = N * (N - 1) / 2, N3 = 3 * N;
   const int64_t n = (int64_t)M * N3;
+  const int n_rowpts = (int)(m_end - m_begin);
+  const int64_t n_rows = (int64_t)n_rowpts * N3;
   if (col_idxs == nullptr) SG_ARG(n_cols == n);
   SG_ARG(n_cols >= 1 && n_cols <= n && ldk >= n_cols);
   cudaStream_t s = (cudaStream_t)stream;
@@ -408,39 +623,41 @@ extern "C" int sgdml_b200_assemble(const double* R_desc, const double* R_d_desc,
   // ---- tile size: at most ASM_NI 3x3 sub-blocks per thread, and shared memory small enough for
   //      two co-resident CTAs per SM
   int TJ = 0, n_chunks = 1;
-  for (int t = 8; t >= 1; --t)
+  bool large = g_asm_variant == 1;
+  for (int t = 8; t >= 1 && !large; --t)
     if ((int64_t)t * N * N <= (int64_t)ASM_NI * 256 && asm_smem_bytes(N, D, S, t) <= 110 * 1024) {
       TJ = t;
       break;
     }
-  if (TJ == 0) {
-    // large molecule: one column point per CTA, its N*N sub-blocks split over grid.z (the
+  if (TJ == 0 && !large) {
+    // mid-sized molecule: one column point per CTA, its N*N sub-blocks split over grid.z (the
     // per-permutation vectors are then recomputed by every chunk)
     TJ = 1;
     n_chunks = (int)(((int64_t)N * N + ASM_NI * 256 - 1) / (ASM_NI * 256));
-    if (asm_smem_bytes(N, D, S, 1) > 220 * 1024) {
-      set_last_error("sgdml_b200_assemble: atom tables of this molecule do not fit in shared memory (N <= ~50 supported)");
-      return SGDML_B200_ERR_UNSUPPORTED;
-    }
+    if (asm_smem_bytes(N, D, S, 1) > 220 * 1024) large = true;  // tables beyond shared memory: k_assemble_large
   }
+  if (large) TJ = 1;
   TJ = std::min(TJ, nJ);
   const size_t smem = asm_smem_bytes(N, D, S, TJ);
+  SG_ARG((int64_t)N * N < (1 << 20) && N < 4096);  // fastdiv range
 
   Staged sX, sG, sK;
   SG_TRY(sX.init(R_desc, sizeof(double) * (size_t)M * D, true, s));
   SG_TRY(sG.init(R_d_desc, sizeof(double) * (size_t)M * D * 3, true, s));
   const bool K_host = !is_device_ptr(K);
-  SG_TRY(sK.init(K, sizeof(double) * (size_t)n * ldk, false, s));
-  if (K_host && ldk != n_cols) SG_CUDA(cudaMemsetAsync(sK.dev(), 0, sizeof(double) * (size_t)n * ldk, s));
+  SG_TRY(sK.init(K, sizeof(double) * (size_t)n_rows * ldk, false, s));
+  if (K_host && ldk != n_cols) SG_CUDA(cudaMemsetAsync(sK.dev(), 0, sizeof(double) * (size_t)n_rows * ldk, s));
 
   int *d_dperm = nullptr, *d_aperm = nullptr, *d_apinv = nullptr, *d_jpts = nullptr;
   int64_t* d_dest = nullptr;
+  double* d_slabs = nullptr;
   auto cleanup = [&]() {
     cudaFree(d_dperm);
     cudaFree(d_aperm);
     cudaFree(d_apinv);
     cudaFree(d_jpts);
     cudaFree(d_dest);
+    cudaFree(d_slabs);
   };
   auto body = [&]() -> int {
     SG_CUDA(cudaMalloc(&d_dperm, sizeof(int) * dperm.size()));
@@ -453,7 +670,6 @@ extern "C" int sgdml_b200_assemble(const double* R_desc, const double* R_d_desc,
     SG_CUDA(cudaMemcpyAsync(d_apinv, apinv.data(), sizeof(int) * apinv.size(), cudaMemcpyHostToDevice, s));
     SG_CUDA(cudaMemcpyAsync(d_jpts, jpts.data(), sizeof(int) * jpts.size(), cudaMemcpyHostToDevice, s));
     SG_CUDA(cudaMemcpyAsync(d_dest, dest.data(), sizeof(int64_t) * dest.size(), cudaMemcpyHostToDevice, s));
-    SG_CUDA(cudaFuncSetAttribute(k_assemble, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     AsmArgs a;
     a.R_desc = (const double*)sX.dev();
     a.R_d_desc = (const double*)sG.dev();
@@ -468,7 +684,9 @@ extern "C" int sgdml_b200_assemble(const double* R_desc, const double* R_d_desc,
     a.S = S;
     a.nJ = nJ;
     a.TJ = TJ;
-    a.sym = (col_idxs == nullptr) ? 1 : 0;
+    a.i0 = (int)m_begin;
+    // symmetric mode (upper block triangle computed, lower mirrored) needs every row point in this call
+    a.sym = (col_idxs == nullptr && n_rowpts == M && !large) ? 1 : 0;
     a.mN = (unsigned)((0x100000000ull + N - 1) / N);
     a.mNN = (unsigned)((0x100000000ull + (uint64_t)N * N - 1) / ((uint64_t)N * N));
     a.mPer = (unsigned)((0x100000000ull + 5 * N - 1) / (5 * N));
@@ -476,12 +694,29 @@ extern "C" int sgdml_b200_assemble(const double* R_desc, const double* R_d_desc,
     a.scale = scale;
     a.K = (double*)sK.dev();
     a.ldk = ldk;
-    // rows on grid.y (<= 65535), column tiles on grid.x
-    SG_ARG(M <= 65535);
-    dim3 grid((unsigned)ceil_div(nJ, TJ), (unsigned)M, (unsigned)n_chunks);
-    {
+    if (!large) {
+      // rows on grid.y (<= 65535), column tiles on grid.x
+      SG_ARG(n_rowpts <= 65535);
+      SG_CUDA(cudaFuncSetAttribute(k_assemble, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      dim3 grid((unsigned)ceil_div(nJ, TJ), (unsigned)n_rowpts, (unsigned)n_chunks);
       ProfScope ps(KID_ASSEMBLE, s);
       k_assemble<<<grid, 256, smem, s>>>(a);
+      SG_CUDA(cudaGetLastError());
+      count_launch(KID_ASSEMBLE);
+    } else {
+      int dev = 0, n_sm = 0;
+      SG_CUDA(cudaGetDevice(&dev));
+      SG_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+      const int64_t n_work = (int64_t)n_rowpts * nJ;
+      const int n_cta = (int)std::min<int64_t>(n_work, 2 * (int64_t)n_sm);  // persistent, 2 per SM
+      const size_t dl_bytes = sizeof(double) * (size_t)N * N;
+      const int dl_in_smem = dl_bytes <= 100 * 1024 ? 1 : 0;  // two CTAs per SM keep their delta tables on chip
+      const size_t slab = (asm_large_slab_doubles(N, S) + 1) / 2 * 2;
+      SG_CUDA(cudaMalloc(&d_slabs, sizeof(double) * slab * (size_t)n_cta));
+      if (dl_in_smem)
+        SG_CUDA(cudaFuncSetAttribute(k_assemble_large, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dl_bytes));
+      ProfScope ps(KID_ASSEMBLE, s);
+      k_assemble_large<<<n_cta, 256, dl_in_smem ? dl_bytes : 0, s>>>(a, d_slabs, (int64_t)slab, n_work, dl_in_smem);
       SG_CUDA(cudaGetLastError());
       count_launch(KID_ASSEMBLE);
     }
@@ -493,4 +728,12 @@ extern "C" int sgdml_b200_assemble(const double* R_desc, const double* R_d_desc,
   int rc = body();
   cleanup();
   return rc;
+}
+
+extern "C" int sgdml_b200_assemble(const double* R_desc, const double* R_d_desc, const int64_t* tril_perms_lin,
+                                   int64_t n_atoms, int64_t n_train, int64_t n_perms, double sig,
+                                   const int64_t* col_idxs, int64_t n_cols, double scale, double* K, int64_t ldk,
+                                   void* stream) {
+  return sgdml_b200_assemble_rows(R_desc, R_d_desc, tril_perms_lin, n_atoms, n_train, n_perms, sig, col_idxs, n_cols,
+                                  scale, 0, n_train, K, ldk, stream);
 }

@@ -199,6 +199,29 @@ int sgdml_b200_row_sqnorms(const double* X, int64_t n_rows, int64_t m, int64_t l
   return 0;
 }
 
+// t = X^T v (m doubles, device), deterministic two-pass reduction
+static int xt_v_device(const double* X, int64_t n_rows, int64_t m, int64_t ldx, const double* v_dev, double* t_dev,
+                       cudaStream_t s) {
+  const int rows_per_cta = 256;
+  const int64_t n_chunks = (n_rows + rows_per_cta - 1) / rows_per_cta;
+  double* part = nullptr;
+  SG_CUDA(cudaMalloc(&part, sizeof(double) * (size_t)m * n_chunks));
+  auto body = [&]() -> int {
+    dim3 grid((unsigned)((m + 255) / 256), (unsigned)n_chunks);
+    SG_ARG(grid.y <= 65535);
+    k_xt_v<<<grid, 256, 0, s>>>(X, n_rows, m, ldx, v_dev, part, rows_per_cta);
+    SG_CUDA(cudaGetLastError());
+    k_reduce_chunks<<<ceil_div(m, 256), 256, 0, s>>>(part, n_chunks, m, t_dev);
+    SG_CUDA(cudaGetLastError());
+    count_launch(KID_MISC, 2);
+    SG_CUDA(cudaStreamSynchronize(s));  // `part` is freed below
+    return 0;
+  };
+  int rc = body();
+  cudaFree(part);
+  return rc;
+}
+
 int sgdml_b200_nystroem_apply(const double* X, int64_t n_rows, int64_t m, int64_t ldx, double lam, const double* v,
                               double* out, void* stream) {
   SG_TRY(require_device());
@@ -208,22 +231,14 @@ int sgdml_b200_nystroem_apply(const double* X, int64_t n_rows, int64_t m, int64_
   Staged sV, sO;
   SG_TRY(sV.init(v, sizeof(double) * (size_t)n_rows, true, s));
   SG_TRY(sO.init(out, sizeof(double) * (size_t)n_rows, false, s));
-  const int rows_per_cta = 256;
-  const int64_t n_chunks = (n_rows + rows_per_cta - 1) / rows_per_cta;
   double* t = nullptr;
-  SG_CUDA(cudaMalloc(&t, sizeof(double) * (size_t)m * (n_chunks + 1)));  // t, then the per-chunk partials
-  double* part = t + m;
+  SG_CUDA(cudaMalloc(&t, sizeof(double) * (size_t)m));
   auto body = [&]() -> int {
-    dim3 grid((unsigned)((m + 255) / 256), (unsigned)n_chunks);
-    SG_ARG(grid.y <= 65535);
-    k_xt_v<<<grid, 256, 0, s>>>(X, n_rows, m, ldx, (const double*)sV.dev(), part, rows_per_cta);
-    SG_CUDA(cudaGetLastError());
-    k_reduce_chunks<<<ceil_div(m, 256), 256, 0, s>>>(part, n_chunks, m, t);
-    SG_CUDA(cudaGetLastError());
+    SG_TRY(xt_v_device(X, n_rows, m, ldx, (const double*)sV.dev(), t, s));
     k_x_t_minus_v<<<ceil_div(n_rows, 8), 256, 0, s>>>(X, n_rows, m, ldx, t, (const double*)sV.dev(), 1.0 / lam,
                                                       (double*)sO.dev());
     SG_CUDA(cudaGetLastError());
-    count_launch(KID_MISC, 3);
+    count_launch(KID_MISC);
     SG_TRY(sO.finish(s));
     SG_CUDA(cudaStreamSynchronize(s));
     return 0;
@@ -231,6 +246,39 @@ int sgdml_b200_nystroem_apply(const double* X, int64_t n_rows, int64_t m, int64_
   int rc = body();
   cudaFree(t);
   return rc;
+}
+
+int sgdml_b200_nystroem_project(const double* X, int64_t n_rows, int64_t m, int64_t ldx, const double* v, double* t,
+                                void* stream) {
+  SG_TRY(require_device());
+  SG_ARG(X != nullptr && v != nullptr && t != nullptr && n_rows >= 1 && m >= 1 && ldx >= m && is_device_ptr(X));
+  cudaStream_t s = (cudaStream_t)stream;
+  Staged sV, sT;
+  SG_TRY(sV.init(v, sizeof(double) * (size_t)n_rows, true, s));
+  SG_TRY(sT.init(t, sizeof(double) * (size_t)m, false, s));
+  SG_TRY(xt_v_device(X, n_rows, m, ldx, (const double*)sV.dev(), (double*)sT.dev(), s));
+  SG_TRY(sT.finish(s));
+  SG_CUDA(cudaStreamSynchronize(s));
+  return 0;
+}
+
+int sgdml_b200_nystroem_expand(const double* X, int64_t n_rows, int64_t m, int64_t ldx, double lam, const double* t,
+                               const double* v, double* out, void* stream) {
+  SG_TRY(require_device());
+  SG_ARG(X != nullptr && t != nullptr && v != nullptr && out != nullptr && n_rows >= 1 && m >= 1 && ldx >= m && lam > 0.0);
+  SG_ARG(is_device_ptr(X));
+  cudaStream_t s = (cudaStream_t)stream;
+  Staged sT, sV, sO;
+  SG_TRY(sT.init(t, sizeof(double) * (size_t)m, true, s));
+  SG_TRY(sV.init(v, sizeof(double) * (size_t)n_rows, true, s));
+  SG_TRY(sO.init(out, sizeof(double) * (size_t)n_rows, false, s));
+  k_x_t_minus_v<<<ceil_div(n_rows, 8), 256, 0, s>>>(X, n_rows, m, ldx, (const double*)sT.dev(), (const double*)sV.dev(),
+                                                    1.0 / lam, (double*)sO.dev());
+  SG_CUDA(cudaGetLastError());
+  count_launch(KID_MISC);
+  SG_TRY(sO.finish(s));
+  SG_CUDA(cudaStreamSynchronize(s));
+  return 0;
 }
 
 }  // extern "C"

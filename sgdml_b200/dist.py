@@ -109,3 +109,175 @@ def broadcast_coefficients(alphas_F, c, std, src=0, group=None):
     dist.broadcast(buf, src=src, group=group)
     host = buf.cpu().numpy()
     return host[: a.size].copy(), float(host[a.size]), float(host[a.size + 1])
+
+
+# --------------------------------------------------------------------------- row-sharded Nystroem factor
+# SURVEY.md section 8e, rows "explicit K assembly" and "Nystroem factor (m, n): shard n": each rank
+# assembles and keeps only the block rows of K_nm that belong to its own training points.  The two
+# small (m x m) matrices are summed over the ranks (this is the all-reduce BASELINE config 4 names),
+# factorised redundantly (bit-identical on every rank), and applied to the local rows.  The
+# algorithms are written as generators that yield at every exchange:
+#   ('sum', tensor)      -> the tensor is summed over the ranks in place
+#   ('gather', rows)     -> the row-sharded NumPy array is gathered; the full array is sent back
+# `run_steps` drives one generator with torch.distributed; `run_steps_virtual` drives the generators
+# of several virtual ranks in lockstep inside ONE process (single-GPU tests of the sharded path).
+# `ops` supplies the compute (the CUDA engine in solvers/iterative.py; NumPy stand-ins in the CPU tests).
+
+
+def all_reduce_sum_(t, group=None):
+    """In-place sum over the ranks of a torch tensor living on the backend's device."""
+    dist = _dist()
+    if world_info(group)[1] > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+    return t
+
+
+def nystroem_factor_steps(ops, rank, world, n_train, dim_i, cols, lam):
+    """Row-sharded iterative.py:208-351.  Returns (X_loc, lo, hi): the rows [lo*dim_i, hi*dim_i) of
+    the factor B^T = K_nm L^-T L_inner^-T (first len(cols) columns of X_loc)."""
+    lo, hi = shard_bounds(n_train, world, rank)
+    cols = np.ascontiguousarray(cols, dtype=np.int64)
+    m = len(cols)
+    X = ops.assemble_rows(lo, hi, cols)  # local rows of K_nm (iterative.py:237-247)
+    own = np.nonzero((cols >= lo * dim_i) & (cols < hi * dim_i))[0]
+    A = ops.new_square(m)
+    ops.put_neg_rows(A, own, X, cols[own] - lo * dim_i, m)  # rows of K_mm = -K_nm[cols] owned here (iterative.py:253)
+    yield 'sum', A
+    if not ops.cho_factor_stable(A, pre_reg=True):  # iterative.py:267
+        raise np.linalg.LinAlgError('Failed to factorize K_mm despite strong regularization')
+    ops.trsm_right_lt(A, X, m)  # iterative.py:278-287 on the local rows
+    ops.gram(X, m, A)  # local part of K_nm^T K_nm (iterative.py:293-295)
+    yield 'sum', A
+    ops.add_diag(A, m, lam)
+    if not ops.cho_factor_stable(A, eps_mag_max=-14):
+        raise np.linalg.LinAlgError(
+            'inner Nystroem matrix not positive definite within 1e-14 jitter (the reference falls back to QR here, '
+            'iterative.py:312-322); try fewer inducing points or a larger sigma'
+        )
+    ops.trsm_right_lt(A, X, m)  # iterative.py:337-347
+    return X, lo, hi
+
+
+def lev_scores_steps(ops, X, m, dim_i):
+    """Leverage scores (iterative.py:107-109) of a row-sharded factor, gathered on every rank."""
+    full = yield 'gather', ops.row_sqnorms(X, m).reshape(-1, dim_i)
+    return full.ravel()
+
+
+def precon_apply_steps(ops, X, m, lam, v, lo, hi, dim_i):
+    """P v = (B^T (B v) - v)/lam (iterative.py:136-138) with B^T row-sharded: one m-vector
+    all-reduce and one all-gather of the n-vector per application."""
+    v_loc = np.ascontiguousarray(v[lo * dim_i : hi * dim_i], dtype=np.float64)
+    t = ops.project(X, m, v_loc)
+    yield 'sum', t
+    out_loc = ops.expand(X, m, lam, t, v_loc)
+    full = yield 'gather', out_loc.reshape(-1, dim_i)
+    return full.ravel()
+
+
+def run_steps(gen, n_train, group=None):
+    """Drives one rank's generator with torch.distributed collectives."""
+    try:
+        op, payload = next(gen)
+        while True:
+            if op == 'sum':
+                all_reduce_sum_(payload, group)
+                res = None
+            elif op == 'gather':
+                res = all_gather_rows(payload, n_train, group)
+            else:
+                raise ValueError(op)
+            op, payload = gen.send(res)
+    except StopIteration as e:
+        return e.value
+
+
+def run_steps_virtual(gens):
+    """Drives the generators of len(gens) virtual ranks in lockstep in this process; returns their
+    return values.  Same exchanges as run_steps, done by hand."""
+    world = len(gens)
+    results = [None] * world
+    msgs = [next(g) for g in gens]
+    while True:
+        ops_ = {op for op, _ in msgs}
+        assert len(ops_) == 1, 'virtual ranks diverged'
+        op = ops_.pop()
+        if op == 'sum':
+            total = msgs[0][1].clone()
+            for _, t in msgs[1:]:
+                total += t
+            for _, t in msgs:
+                t.copy_(total)
+            sends = [None] * world
+        elif op == 'gather':
+            full = np.concatenate([np.asarray(p) for _, p in msgs], axis=0)
+            sends = [full] * world
+        else:
+            raise ValueError(op)
+        nxt, done = [], 0
+        for r, g in enumerate(gens):
+            try:
+                nxt.append(g.send(sends[r]))
+            except StopIteration as e:
+                results[r] = e.value
+                done += 1
+        if done == world:
+            return results
+        assert done == 0, 'virtual ranks diverged'
+        msgs = nxt
+
+
+# --------------------------------------------------------------------------- prediction sharded over training points
+def model_shard(model, lo, hi):
+    """The part of a model dict that belongs to training points [lo, hi), as a raw-sum model
+    (std = 1, c = 0): predictions of the shards add up to the unscaled prediction of `model`."""
+    n_train = model['R_desc'].shape[1]
+    sub = dict(model)
+    sub['R_desc'] = np.ascontiguousarray(np.asarray(model['R_desc'])[:, lo:hi])  # stored (D, M), train.py:807
+    sub['R_d_desc_alpha'] = np.ascontiguousarray(np.asarray(model['R_d_desc_alpha'])[lo:hi])
+    sub['alphas_F'] = np.asarray(model['alphas_F']).reshape(n_train, -1)[lo:hi].ravel()
+    if 'idxs_train' in model:
+        sub['idxs_train'] = np.asarray(model['idxs_train'])[lo:hi]
+    sub['std'] = 1.0
+    sub['c'] = 0.0
+    return sub
+
+
+class TrainPointShardedPredictor(object):
+    """SURVEY.md section 8e "predict, small B / huge M*S": the sum over training points is split
+    across the ranks (M/G points each, predict.py:1280-1284 already sums partial results), every
+    rank evaluates the WHOLE query batch against its shard, then ONE all-reduce of B*(3N+1) doubles
+    (the back-projection J^T is linear, so the partial forces are summed after it).
+
+    predictor_cls(model) must offer .predict(R) -> (E, F): sgdml_b200.GDMLPredict on the GPU box,
+    the oracle predictor in the CPU tests."""
+
+    def __init__(self, model, predictor_cls, group=None):
+        self.group = group
+        rank, world = world_info(group)
+        n_train = model['R_desc'].shape[1]
+        self.lo, self.hi = shard_bounds(n_train, world, rank)
+        self.std = float(model['std']) if 'std' in model else 1.0
+        self.c = float(model['c'])
+        self.dim_i = 3 * int(np.asarray(model['z']).shape[0])
+        self.part = predictor_cls(model_shard(model, self.lo, self.hi)) if self.hi > self.lo else None
+
+    def predict(self, R, return_E=True):
+        import torch
+
+        R = np.asarray(R, dtype=np.float64)
+        if R.ndim == 1:
+            R = R[None, :]  # predict.py:1183-1184
+        B = R.shape[0]
+        buf = np.zeros((B, self.dim_i + 1))
+        if self.part is not None:
+            E, F = self.part.predict(R)
+            buf[:, 0], buf[:, 1:] = E, F.reshape(B, -1)
+        if world_info(self.group)[1] > 1:
+            t = torch.from_numpy(buf).to(_device_for_backend(self.group))
+            all_reduce_sum_(t, self.group)
+            buf = t.cpu().numpy()
+        F = buf[:, 1:] * self.std  # predict.py:1286-1288
+        if not return_E:
+            return (F,)
+        return buf[:, 0] * self.std + self.c, F

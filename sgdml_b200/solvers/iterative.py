@@ -32,6 +32,76 @@ DONE = 1
 NOT_DONE = 0
 
 
+class _EngineNystroemOps(object):
+    """Compute side of the row-sharded Nystroem factor (dist.nystroem_factor_steps and friends) on
+    the CUDA engine: every method is one C-ABI call on this rank's rows; matrices are CUDA tensors."""
+
+    def __init__(self, solver, R_desc, R_d_desc, tril_perms_lin, sig):
+        self.solver = solver
+        self.args = (R_desc, R_d_desc, tril_perms_lin, sig)
+
+    def assemble_rows(self, lo, hi, cols):
+        X, _ = self.solver.gdml_train._assemble_kernel_mat_device(*self.args, col_idxs=cols, rows=(lo, hi))
+        return X
+
+    def new_square(self, m):
+        import torch
+
+        return torch.zeros((m, (m + 1) // 2 * 2), dtype=torch.float64, device='cuda')
+
+    def put_neg_rows(self, A, pos, X, local_rows, m):
+        import torch
+
+        if len(pos):
+            A[torch.as_tensor(pos, device=A.device), :m] = -X[torch.as_tensor(local_rows, device=A.device), :m]
+
+    def cho_factor_stable(self, A, **kw):
+        return self.solver._cho_factor_stable(A, **kw)
+
+    def trsm_right_lt(self, A, X, m):
+        _lib.check(
+            _lib.lib().sgdml_b200_trsm_right_lt(A.data_ptr(), m, A.shape[1], X.data_ptr(), X.shape[0], X.shape[1], _lib.current_stream()),
+            'trsm',
+        )
+
+    def gram(self, X, m, A):
+        _lib.check(
+            _lib.lib().sgdml_b200_gram_tn(X.data_ptr(), X.shape[0], m, X.shape[1], 0.0, A.data_ptr(), A.shape[1], _lib.current_stream()),
+            'gram',
+        )
+
+    def add_diag(self, A, m, value):
+        _lib.check(_lib.lib().sgdml_b200_add_diag(A.data_ptr(), m, A.shape[1], float(value), _lib.current_stream()), 'add_diag')
+
+    def row_sqnorms(self, X, m):
+        out = np.empty(X.shape[0])
+        _lib.check(
+            _lib.lib().sgdml_b200_row_sqnorms(X.data_ptr(), X.shape[0], m, X.shape[1], _lib.ptr(out), _lib.current_stream()),
+            'row_sqnorms',
+        )
+        return out
+
+    def project(self, X, m, v_loc):
+        import torch
+
+        t = torch.empty(m, dtype=torch.float64, device='cuda')
+        _lib.check(
+            _lib.lib().sgdml_b200_nystroem_project(X.data_ptr(), X.shape[0], m, X.shape[1], _lib.ptr(v_loc), t.data_ptr(), _lib.current_stream()),
+            'nystroem_project',
+        )
+        return t
+
+    def expand(self, X, m, lam, t, v_loc):
+        out = np.empty(X.shape[0])
+        _lib.check(
+            _lib.lib().sgdml_b200_nystroem_expand(
+                X.data_ptr(), X.shape[0], m, X.shape[1], float(lam), t.data_ptr(), _lib.ptr(v_loc), _lib.ptr(out), _lib.current_stream()
+            ),
+            'nystroem_expand',
+        )
+        return out
+
+
 class Iterative(object):
     def __init__(self, gdml_train, desc, max_memory, max_processes, use_torch, callback=None):
         self.log = logging.getLogger(__name__)
@@ -104,8 +174,42 @@ class Iterative(object):
         del K_mm
         return X, m
 
+    @staticmethod
+    def _shard_precon(n_train):
+        """Row-shard the Nystroem factor over the ranks whenever there are
+        several ranks and every rank gets at least one training point."""
+        from .. import dist as sdist
+
+        rank, world = sdist.world_info()
+        return world > 1 and n_train >= world
+
+    def _init_precon_operator_sharded(self, task, R_desc, R_d_desc, tril_perms_lin, inducing_pts_idxs):
+        """Row-sharded form of _init_precon_operator: every rank assembles, factorises and applies only
+        the rows of its own training points; (m x m) all-reduces during the set-up, one m-vector
+        all-reduce and one n-vector all-gather per application."""
+        from .. import dist as sdist
+
+        rank, world = sdist.world_info()
+        lam = float(task['lam'])
+        n_train = R_desc.shape[0]
+        dim_i = 3 * task['R_train'].shape[1]
+        m = len(inducing_pts_idxs)
+        ops = _EngineNystroemOps(self, R_desc, R_d_desc, tril_perms_lin, task['sig'])
+        X, lo, hi = sdist.run_steps(
+            sdist.nystroem_factor_steps(ops, rank, world, n_train, dim_i, inducing_pts_idxs, lam), n_train
+        )
+        lev_scores = sdist.run_steps(sdist.lev_scores_steps(ops, X, m, dim_i), n_train)
+
+        def _P_vec(v):
+            return sdist.run_steps(sdist.precon_apply_steps(ops, X, m, lam, v, lo, hi, dim_i), n_train)
+
+        _P_vec.keepalive = X
+        return _P_vec, lev_scores
+
     def _init_precon_operator(self, task, R_desc, R_d_desc, tril_perms_lin, inducing_pts_idxs, callback=None):
         """iterative.py:83-142 -> (P_vec, lev_scores)."""
+        if self._shard_precon(R_desc.shape[0]):
+            return self._init_precon_operator_sharded(task, R_desc, R_d_desc, tril_perms_lin, inducing_pts_idxs)
         lam = float(task['lam'])
         X, m = self._nystroem_cholesky_factor(
             R_desc, R_d_desc, tril_perms_lin, task['sig'], lam, task['use_E_cstr'], inducing_pts_idxs, callback=callback
@@ -162,6 +266,18 @@ class Iterative(object):
         dim_i = 3 * int((1 + np.sqrt(8 * dim_d + 1)) / 2)
         dim_m = dim_i * min(n_inducing_pts, 10)
         lev_approx_idxs = np.sort(np.random.choice(n_train * dim_i, dim_m, replace=False))
+        if self._shard_precon(n_train):
+            from .. import dist as sdist
+
+            if use_E_cstr:
+                raise NotImplementedError('use_E_cstr is out of scope (SURVEY.md section 2 row 22)')
+            rank, world = sdist.world_info()
+            lev_approx_idxs = self._bcast_idxs(lev_approx_idxs)  # one draw (rank 0's) for the shared factor
+            ops = _EngineNystroemOps(self, R_desc, R_d_desc, tril_perms_lin, sig)
+            X, lo, hi = sdist.run_steps(
+                sdist.nystroem_factor_steps(ops, rank, world, n_train, dim_i, lev_approx_idxs, lam), n_train
+            )
+            return sdist.run_steps(sdist.lev_scores_steps(ops, X, len(lev_approx_idxs), dim_i), n_train)
         X, m = self._nystroem_cholesky_factor(R_desc, R_d_desc, tril_perms_lin, sig, lam, use_E_cstr, lev_approx_idxs)
         lev = np.empty(X.shape[0])
         _lib.check(

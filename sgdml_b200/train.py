@@ -179,10 +179,12 @@ class GDMLTrain(object):
 
     # ------------------------------------------------------------------ kernel matrix
     def _assemble_kernel_mat_device(
-        self, R_desc, R_d_desc, tril_perms_lin, sig, col_idxs=None, scale=1.0, ldk=None, out=None
+        self, R_desc, R_d_desc, tril_perms_lin, sig, col_idxs=None, scale=1.0, ldk=None, out=None, rows=None
     ):
         """K (or scale*K) assembled into a new CUDA tensor of shape (3NM, ldk); only the first
-        n_cols columns are meaningful.  col_idxs: None | sorted unique int array."""
+        n_cols columns are meaningful.  col_idxs: None | sorted unique int array.
+        rows=(m_begin, m_end): only the block rows of these training points (row-sharded
+        assembly); the tensor then has (m_end - m_begin)*3N rows."""
         torch = _torch()
         R_desc = np.ascontiguousarray(R_desc, dtype=np.float64)
         R_d_desc = np.ascontiguousarray(R_d_desc, dtype=np.float64)
@@ -198,13 +200,15 @@ class GDMLTrain(object):
             n_cols = len(cols)
         if ldk is None:
             ldk = (n_cols + 1) // 2 * 2  # even row stride keeps the DMMA GEMM on its aligned path
+        m_begin, m_end = (0, n_train) if rows is None else (int(rows[0]), int(rows[1]))
+        n_rows = (m_end - m_begin) * 3 * n_atoms
         if out is not None:
             K, ldk = out, out.shape[1]
-            assert K.shape[0] == n and ldk >= n_cols and K.is_cuda and K.dtype == torch.float64
+            assert K.shape[0] == n_rows and ldk >= n_cols and K.is_cuda and K.dtype == torch.float64
         else:
-            K = torch.empty((n, ldk), dtype=torch.float64, device='cuda')
+            K = torch.empty((n_rows, ldk), dtype=torch.float64, device='cuda')
         _lib.check(
-            _lib.lib().sgdml_b200_assemble(
+            _lib.lib().sgdml_b200_assemble_rows(
                 _lib.ptr(R_desc),
                 _lib.ptr(R_d_desc),
                 _lib.ptr(tril_perms_lin),
@@ -215,6 +219,8 @@ class GDMLTrain(object):
                 _lib.ptr(cols),
                 n_cols,
                 float(scale),
+                m_begin,
+                m_end,
                 K.data_ptr(),
                 ldk,
                 _lib.current_stream(),

@@ -259,6 +259,75 @@ def test_assemble_vs_oracle(eng, N, M, rot, swap, sig):
     assert rel_err(K, K_ref) < 1e-12
 
 
+def test_assemble_large_kernel_matches_small(eng, golden):
+    """The large-molecule kernel (tables in global memory) keeps the summation order of the
+    shared-memory kernel: bit-identical blocks on the golden cases."""
+    from sgdml_b200 import _lib
+    from sgdml_b200.desc import Desc
+
+    N = int(golden['n_atoms'])
+    n = golden['K'].shape[0]
+    t = eng.GDMLTrain()
+    args = (golden['R_desc'], golden['R_d_desc'], golden['tril_perms_lin'], int(golden['sig']), Desc(N))
+    cols = np.unique(np.random.default_rng(1).integers(0, n, size=31))
+    K_small_full = t._assemble_kernel_mat(*args)
+    K_small_cols = t._assemble_kernel_mat(*args, col_idxs=cols)
+    _lib.lib().sgdml_b200_set_assemble_variant(1)
+    try:
+        K_full = t._assemble_kernel_mat(*args)
+        K_cols = t._assemble_kernel_mat(*args, col_idxs=cols)
+    finally:
+        _lib.lib().sgdml_b200_set_assemble_variant(0)
+    assert np.array_equal(K_cols, K_small_cols)
+    assert rel_err(K_full, golden['K']) < 1e-12
+    iu = np.triu_indices(n)  # the symmetric kernel computes the upper block triangle and mirrors it
+    blk = (iu[0] // (3 * N)) <= (iu[1] // (3 * N))
+    assert np.array_equal(K_full[iu][blk], K_small_full[iu][blk])
+
+
+@pytest.mark.parametrize('N,M,rot,swap,sig', [(60, 3, 1, 1, 50), (100, 2, 2, 0, 50), (53, 2, 0, 1, 30)])
+def test_assemble_large_molecules_vs_oracle(eng, N, M, rot, swap, sig):
+    """BASELINE configs 4-5 sizes (60 and 100 atoms): tables beyond shared memory."""
+    from sgdml_b200 import synth
+    from sgdml_b200.desc import Desc
+
+    perms = synth.rotor_swap_group(N, rot, swap)
+    R = synth.geometries(N, M, 2).reshape(M, -1)
+    x, g = odesc.from_R(R)
+    lin = odesc.tril_perms_lin(perms)
+    K_ref = oassemble.assemble(x, g, lin, sig)
+    t = eng.GDMLTrain()
+    K = t._assemble_kernel_mat(x, g, lin, sig, Desc(N))
+    assert rel_err(K, K_ref) < 1e-12
+    cols = np.unique(np.random.default_rng(2).integers(0, K_ref.shape[0], size=40))
+    K = t._assemble_kernel_mat(x, g, lin, sig, Desc(N), col_idxs=cols)
+    assert rel_err(K, K_ref[:, cols]) < 1e-12
+
+
+@pytest.mark.parametrize('large', [0, 1])
+def test_assemble_row_ranges(eng, golden, large):
+    """Row-sharded assembly (sgdml_b200_assemble_rows): the block rows of any range of training
+    points equal the corresponding rows of the full matrix."""
+    from sgdml_b200 import _lib
+
+    N, M = int(golden['n_atoms']), golden['R_desc'].shape[0]
+    n = golden['K'].shape[0]
+    t = eng.GDMLTrain()
+    args = (golden['R_desc'], golden['R_d_desc'], golden['tril_perms_lin'], int(golden['sig']))
+    cols = np.unique(np.random.default_rng(3).integers(0, n, size=29))
+    _lib.lib().sgdml_b200_set_assemble_variant(large)
+    try:
+        K_cols, _ = t._assemble_kernel_mat_device(*args, col_idxs=cols)
+        for lo, hi in [(0, 1), (1, M), (M // 3, 2 * M // 3 + 1)]:
+            Kr, nc = t._assemble_kernel_mat_device(*args, col_idxs=cols, rows=(lo, hi))
+            assert Kr.shape[0] == (hi - lo) * 3 * N
+            assert np.array_equal(Kr[:, :nc].cpu().numpy(), K_cols[lo * 3 * N : hi * 3 * N, :nc].cpu().numpy())
+            Kr, nc = t._assemble_kernel_mat_device(*args, rows=(lo, hi))  # all columns, part of the rows
+            assert rel_err(Kr[:, :nc].cpu().numpy(), golden['K'][lo * 3 * N : hi * 3 * N]) < 1e-12
+    finally:
+        _lib.lib().sgdml_b200_set_assemble_variant(0)
+
+
 # --------------------------------------------------------------------------- dense solve
 @pytest.mark.parametrize('variant', [0, 1, 2, 3])
 @pytest.mark.parametrize('m,n,k', [(128, 128, 128), (300, 200, 64), (257, 129, 130), (64, 1000, 16), (33, 17, 7)])

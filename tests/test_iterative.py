@@ -78,6 +78,37 @@ def test_engine_preconditioner_matches_reference():
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize('world', [2, 3])
+def test_engine_sharded_preconditioner_virtual_ranks(world):
+    """Row-sharded Nystroem factor on the engine (sgdml_b200_assemble_rows, local TRSM / Gram,
+    nystroem_project / nystroem_expand), driven for `world` virtual ranks on one GPU: same leverage
+    scores and P.v as the reference's unsharded factor."""
+    import sgdml_b200
+    from sgdml_b200 import dist as sdist
+    from sgdml_b200.desc import Desc
+    from sgdml_b200.solvers.iterative import Iterative, _EngineNystroemOps
+
+    g, task, N, M, R = _setup()
+    t = sgdml_b200.GDMLTrain(max_memory=float(g['max_memory_gb']))
+    d = Desc(N)
+    x, gd = d.from_R(R)
+    lin = odesc.tril_perms_lin(g['perms'])
+    it = Iterative(t, d, float(g['max_memory_gb']), None, False)
+    cols, lam, dim_i = g['inducing_pts_idxs'], float(g['lam']), 3 * N
+    ops = [_EngineNystroemOps(it, x, gd, lin, task['sig']) for _ in range(world)]
+    facs = sdist.run_steps_virtual([sdist.nystroem_factor_steps(ops[r], r, world, M, dim_i, cols, lam) for r in range(world)])
+    assert sum(f[0].shape[0] for f in facs) == M * dim_i  # every rank holds only its own rows
+    levs = sdist.run_steps_virtual([sdist.lev_scores_steps(ops[r], facs[r][0], len(cols), dim_i) for r in range(world)])
+    Pvs = sdist.run_steps_virtual(
+        [sdist.precon_apply_steps(ops[r], facs[r][0], len(cols), lam, g['v'], facs[r][1], facs[r][2], dim_i) for r in range(world)]
+    )
+    for r in range(world):
+        assert rel_err(levs[r], g['lev_scores']) < 1e-6
+        assert rel_err(Pvs[r], g['Pv']) < 1e-5
+        assert np.array_equal(Pvs[r], Pvs[0])
+
+
+@pytest.mark.gpu
 def test_engine_cg_train_matches_reference():
     """GDMLTrain.train with a memory cap that forces the iterative solver, same inducing columns as the
     reference run: converges to the same tolerance in a similar number of iterations and predicts
@@ -141,15 +172,31 @@ def _cg_rank(rank, world, port, out_dir):
     task = synth.make_task(N, M, perms, 20)
     np.random.seed(3 + rank)  # different draws per rank: rank 0's inducing columns must win
     model = sgdml_b200.GDMLTrain(max_memory=0.01).train(task)
-    np.savez(os.path.join(out_dir, 'cg_r%d.npz' % rank), alphas=model['alphas_F'], idxs=model['inducing_pts_idxs'], iters=model['solver_iters'])
+    # prediction with the sum over training points sharded across the ranks + one all-reduce
+    from conftest import golden_model
+
+    from sgdml_b200 import dist as sdist
+
+    gq = load_golden('n9_m16_s6')
+    E_tp, F_tp = sdist.TrainPointShardedPredictor(golden_model(gq), sgdml_b200.GDMLPredict).predict(gq['R_query'])
+    np.savez(
+        os.path.join(out_dir, 'cg_r%d.npz' % rank),
+        alphas=model['alphas_F'],
+        idxs=model['inducing_pts_idxs'],
+        iters=model['solver_iters'],
+        E_tp=E_tp,
+        F_tp=F_tp,
+    )
     dist.barrier()
     dist.destroy_process_group()
 
 
 @pytest.mark.gpu
 def test_engine_cg_two_ranks_sharded_kv(tmp_path):
-    """Two ranks (NCCL): K.v rows sharded + all-gather, inducing columns broadcast; both ranks end with the
-    same model, equal to the single-rank result with the same columns."""
+    """Two ranks (NCCL): K.v rows sharded + all-gather, Nystroem factor row-sharded (all-reduces of the
+    (m x m) matrices and of B v), inducing columns broadcast; both ranks end with the same model, equal
+    to the single-rank result with the same columns up to solver accuracy.  Also the prediction
+    with training points sharded across the ranks (one all-reduce)."""
     import socket
 
     import torch
@@ -174,4 +221,24 @@ def test_engine_cg_two_ranks_sharded_kv(tmp_path):
     task = synth.make_task(N, M, synth.rotor_swap_group(N, 1, 1), 20)
     task['inducing_pts_idxs'] = r0['idxs']
     single = sgdml_b200.GDMLTrain(max_memory=0.01).train(task)
-    assert rel_err(single['alphas_F'], r0['alphas']) < 1e-9
+    assert rel_err(single['alphas_F'], r0['alphas']) < 1e-6  # the sharded Gram sums in a different order
+    gq = load_golden('n9_m16_s6')
+    for r in (r0, r1):
+        assert rel_err(r['F_tp'], gq['F_query']) < 1e-9
+        assert rel_err(r['E_tp'], gq['E_query']) < 1e-9
+
+
+@pytest.mark.gpu
+def test_train_point_sharded_predictor_single_rank():
+    import sgdml_b200
+    from conftest import golden_model
+    from sgdml_b200 import dist as sdist
+
+    gq = load_golden('n9_m16_s6')
+    model = golden_model(gq)
+    E, F = sdist.TrainPointShardedPredictor(model, sgdml_b200.GDMLPredict).predict(gq['R_query'])
+    assert rel_err(F, gq['F_query']) < 1e-9 and rel_err(E, gq['E_query']) < 1e-9
+    M = model['R_desc'].shape[1]
+    parts = [sgdml_b200.GDMLPredict(sdist.model_shard(model, lo, hi)).predict(gq['R_query']) for lo, hi in [(0, 7), (7, M)]]
+    F_sum = (parts[0][1] + parts[1][1]) * float(model['std'])
+    assert rel_err(F_sum, gq['F_query']) < 1e-9
