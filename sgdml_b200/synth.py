@@ -86,6 +86,68 @@ def rotor_swap_group(n_atoms, n_rotors=1, n_swaps=1):
     return close_group(gens, n_atoms)
 
 
+def c60_geometry(radius=3.55):
+    """Ideal truncated icosahedron (buckyball C60): the 60 vertices are the even (cyclic)
+    permutations of (0, +-1, +-3phi), (+-1, +-(2+phi), +-2phi), (+-phi, +-2, +-(2phi+1)),
+    scaled to the given radius [A]."""
+    phi = (1.0 + np.sqrt(5.0)) / 2.0
+    base = []
+    for a, b, c in [(0.0, 1.0, 3 * phi), (1.0, 2 + phi, 2 * phi), (phi, 2.0, 2 * phi + 1)]:
+        for sa in ((1,) if a == 0 else (1, -1)):
+            for sb in (1, -1):
+                for sc in (1, -1):
+                    base.append((sa * a, sb * b, sc * c))
+    pts = []
+    for v in base:
+        for k in range(3):  # cyclic coordinate permutations
+            pts.append((v[(0 + k) % 3], v[(1 + k) % 3], v[(2 + k) % 3]))
+    r0 = np.array(sorted(set(pts)), dtype=np.float64)
+    assert r0.shape == (60, 3)
+    return r0 * (radius / np.linalg.norm(r0[0]))
+
+
+def icosahedral_group(r0=None):
+    """The 120 atom permutations of the full icosahedral point group I_h acting on the C60
+    vertices: the group is generated from a 2-fold, a 3-fold and a 5-fold rotation plus the
+    inversion, closed under multiplication, and every 3x3 matrix is turned into a permutation by
+    nearest-atom matching.  Identity first."""
+    if r0 is None:
+        r0 = c60_geometry()
+    phi = (1.0 + np.sqrt(5.0)) / 2.0
+    c2 = np.diag([-1.0, -1.0, 1.0])
+    c3 = np.array([[0.0, 0.0, 1.0], [1.0, 0.0, 0.0], [0.0, 1.0, 0.0]])  # x -> y -> z -> x
+    ax = np.array([0.0, 1.0, phi]) / np.sqrt(1 + phi * phi)  # a 5-fold axis (icosahedron vertex)
+    th = 2 * np.pi / 5
+    Kx = np.array([[0, -ax[2], ax[1]], [ax[2], 0, -ax[0]], [-ax[1], ax[0], 0]])
+    c5 = np.eye(3) + np.sin(th) * Kx + (1 - np.cos(th)) * (Kx @ Kx)
+    gens = [c2, c3, c5, -np.eye(3)]
+    mats = [np.eye(3)]
+    keys = {tuple(np.round(np.eye(3), 6).ravel())}
+    frontier = [np.eye(3)]
+    while frontier:
+        nxt = []
+        for A in frontier:
+            for G in gens:
+                B = G @ A
+                k = tuple(np.round(B, 6).ravel() + 0.0)
+                if k not in keys:
+                    keys.add(k)
+                    mats.append(B)
+                    nxt.append(B)
+        frontier = nxt
+        if len(mats) > 120:
+            raise ValueError('generators do not close into I_h')
+    assert len(mats) == 120
+    perms = []
+    for A in mats:
+        moved = r0 @ A.T
+        d = np.linalg.norm(moved[:, None, :] - r0[None, :, :], axis=-1)
+        p = np.argmin(d, axis=1)
+        assert np.all(d[np.arange(60), p] < 1e-6) and len(set(p.tolist())) == 60
+        perms.append(p)
+    return np.array(perms, dtype=np.int64)
+
+
 # name -> (n_atoms, n_train, n_rotors, n_swaps, sig): BASELINE.json configs with the
 # synthetic defaults fixed in SURVEY.md section 8d.
 CONFIGS = {
@@ -93,12 +155,22 @@ CONFIGS = {
     'aspirin': dict(n_atoms=21, n_train=1000, n_rotors=1, n_swaps=1, sig=20),  # cfg 2, S=6
     'ac-ala3-nhme': dict(n_atoms=42, n_train=2000, n_rotors=5, n_swaps=0, sig=50),  # cfg 3, S=243
     'synthetic100': dict(n_atoms=100, n_train=5000, n_rotors=1, n_swaps=2, sig=50),  # cfg 4, S=12
+    'c60': dict(n_atoms=60, n_train=3000, group='ih', sig=50),  # cfg 5, S=120 (I_h on the ideal buckyball)
 }
 
 
-def make_task(n_atoms, n_train, perms, sig, lam=1e-10, seed=0, use_E=True):
+def config_perms_and_r0(name):
+    """(perms, base geometry or None) of a named config."""
+    cfg = CONFIGS[name]
+    if cfg.get('group') == 'ih':
+        r0 = c60_geometry()
+        return icosahedral_group(r0), r0
+    return rotor_swap_group(cfg['n_atoms'], cfg['n_rotors'], cfg['n_swaps']), None
+
+
+def make_task(n_atoms, n_train, perms, sig, lam=1e-10, seed=0, use_E=True, r0=None):
     """A task dict with the keys GDMLTrain.train reads (reference sgdml/train.py:507-524)."""
-    R = geometries(n_atoms, n_train, seed)
+    R = geometries(n_atoms, n_train, seed, r0=r0)
     E, F = toy_pes(R)
     return {
         'type': 't',
@@ -126,17 +198,17 @@ def make_config_task(name, n_train=None, seed=0):
     cfg = dict(CONFIGS[name])
     if n_train is not None:
         cfg['n_train'] = n_train
-    perms = rotor_swap_group(cfg['n_atoms'], cfg['n_rotors'], cfg['n_swaps'])
-    return make_task(cfg['n_atoms'], cfg['n_train'], perms, cfg['sig'], seed=seed)
+    perms, r0 = config_perms_and_r0(name)
+    return make_task(cfg['n_atoms'], cfg['n_train'], perms, cfg['sig'], seed=seed, r0=r0)
 
 
-def random_model(n_atoms, n_train, perms, sig, seed=0, alpha_scale=1.0):
+def random_model(n_atoms, n_train, perms, sig, seed=0, alpha_scale=1.0, r0=None):
     """A model dict with random (not trained) coefficients -- for predictor benchmarks
     at sizes where training would be the dominant cost.  Same key layout as
     GDMLTrain.create_model (reference sgdml/train.py:793-830)."""
     from .desc import Desc, tril_perms_lin
 
-    R = geometries(n_atoms, n_train, seed).reshape(n_train, -1)
+    R = geometries(n_atoms, n_train, seed, r0=r0).reshape(n_train, -1)
     rng = np.random.default_rng(seed + 99)
     alphas = alpha_scale * rng.standard_normal(n_train * 3 * n_atoms)
     desc = Desc(n_atoms)

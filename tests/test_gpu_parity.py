@@ -328,6 +328,29 @@ def test_assemble_row_ranges(eng, golden, large):
         _lib.lib().sgdml_b200_set_assemble_variant(0)
 
 
+def test_c60_icosahedral_config(eng):
+    """BASELINE config 5 shape: buckyball, 60 atoms, the 120 permutations of I_h (reduced M)."""
+    from sgdml_b200 import synth
+    from sgdml_b200.desc import Desc
+
+    perms, r0 = synth.config_perms_and_r0('c60')
+    assert perms.shape == (120, 60)
+    M = 3
+    R = synth.geometries(60, M, 0, r0=r0).reshape(M, -1)
+    x, g = odesc.from_R(R)
+    lin = odesc.tril_perms_lin(perms)
+    assert np.array_equal(eng.desc.tril_perms_lin(perms), lin)
+    cols = np.arange(180, 360)  # the block column of training point 1
+    K_ref = oassemble.assemble(x, g, lin, 50, col_idxs=cols)
+    K = eng.GDMLTrain()._assemble_kernel_mat(x, g, lin, 50, Desc(60), col_idxs=cols)
+    assert rel_err(K, K_ref) < 1e-12
+    model = synth.random_model(60, 5, perms, 50, seed=4, r0=r0)
+    Rq = synth.geometries(60, 7, 1, r0=r0).reshape(7, -1)
+    E_ref, F_ref = opredict.Predictor(model).predict(Rq)
+    E, F = eng.GDMLPredict(model).predict(Rq)
+    assert rel_err(F, F_ref) < 1e-9 and rel_err(E, E_ref) < 1e-9
+
+
 # --------------------------------------------------------------------------- dense solve
 @pytest.mark.parametrize('variant', [0, 1, 2, 3])
 @pytest.mark.parametrize('m,n,k', [(128, 128, 128), (300, 200, 64), (257, 129, 130), (64, 1000, 16), (33, 17, 7)])

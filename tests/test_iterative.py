@@ -179,6 +179,7 @@ def _cg_rank(rank, world, port, out_dir):
 
     gq = load_golden('n9_m16_s6')
     E_tp, F_tp = sdist.TrainPointShardedPredictor(golden_model(gq), sgdml_b200.GDMLPredict).predict(gq['R_query'])
+    F_q = sgdml_b200.GDMLPredict(model).predict(synth.geometries(N, 20, 1).reshape(20, -1))[1]
     np.savez(
         os.path.join(out_dir, 'cg_r%d.npz' % rank),
         alphas=model['alphas_F'],
@@ -186,6 +187,9 @@ def _cg_rank(rank, world, port, out_dir):
         iters=model['solver_iters'],
         E_tp=E_tp,
         F_tp=F_tp,
+        F_q=F_q,
+        resid=model['solver_resid'],
+        norm_y=model['norm_y_train'],
     )
     dist.barrier()
     dist.destroy_process_group()
@@ -221,7 +225,13 @@ def test_engine_cg_two_ranks_sharded_kv(tmp_path):
     task = synth.make_task(N, M, synth.rotor_swap_group(N, 1, 1), 20)
     task['inducing_pts_idxs'] = r0['idxs']
     single = sgdml_b200.GDMLTrain(max_memory=0.01).train(task)
-    assert rel_err(single['alphas_F'], r0['alphas']) < 1e-6  # the sharded Gram sums in a different order
+    # the sharded Gram matrix is summed in a different order, so the two CG runs agree to solver accuracy
+    # (tol 1e-4 on the residual), not to rounding
+    assert float(r0['resid']) <= 1e-4 * float(r0['norm_y'])
+    assert abs(int(single['solver_iters']) - int(r0['iters'])) <= max(5, 0.2 * int(r0['iters']))
+    assert rel_err(single['alphas_F'], r0['alphas']) < 2e-2
+    F_single = sgdml_b200.GDMLPredict(single).predict(synth.geometries(N, 20, 1).reshape(20, -1))[1]
+    assert rel_err(F_single, r0['F_q']) < 2e-3
     gq = load_golden('n9_m16_s6')
     for r in (r0, r1):
         assert rel_err(r['F_tp'], gq['F_query']) < 1e-9
