@@ -35,7 +35,10 @@ WORKLOADS = {
     'ethanol': ('ethanol', 'configs[0]: ethanol 9 atoms, 200 train, 6 perms (synthetic, SURVEY 8d)'),
     # prediction only (random coefficients): training at this size needs the iterative solver
     'ac-ala3-nhme': ('ac-ala3-nhme', 'configs[2]: Ac-Ala3-NHMe 42 atoms, 2000 train, 243 perms, predict at batch 4096 (synthetic, SURVEY 8d)'),
+    'synthetic100': ('synthetic100', 'configs[3]: synthetic 100-atom molecule, 5000 train, 12 perms, predict at batch 512 (synthetic, SURVEY 8d)'),
+    'c60': ('c60', 'configs[4]: buckyball C60, 3000 train, 120 perms (I_h), predict at batch 256 (synthetic, SURVEY 8d)'),
 }
+PREDICT_ONLY = {'ac-ala3-nhme': 4096, 'synthetic100': 512, 'c60': 256}  # workload -> default batch
 
 
 T0 = time.perf_counter()
@@ -139,6 +142,7 @@ def workload_cfg(args):
     cfg = dict(synth.CONFIGS[WORKLOADS[args.workload][0]])
     if args.n_train is not None:
         cfg['n_train'] = args.n_train
+    cfg['name'] = WORKLOADS[args.workload][0]
     return cfg
 
 
@@ -156,7 +160,7 @@ def oracle_random_model(cfg, perms):
     from sgdml_b200 import synth
 
     N, M = cfg['n_atoms'], cfg['n_train']
-    R = synth.geometries(N, M, 0).reshape(M, -1)
+    R = synth.geometries(N, M, 0, r0=synth.config_perms_and_r0(cfg['name'])[1]).reshape(M, -1)
     rng = np.random.default_rng(99)
     alphas = rng.standard_normal(M * 3 * N)
     x, g = odesc.from_R(R)
@@ -176,6 +180,15 @@ def oracle_random_model(cfg, perms):
     }
 
 
+def cpu_workers(cfg, n_perms):
+    """Worker processes of the CPU arm: all host threads, unless the per-worker permuted caches
+    (2 * M*S*D doubles, predict.py:426-441) would not fit in ~128 GB of host memory together."""
+    cores = os.cpu_count() or 1
+    D = cfg['n_atoms'] * (cfg['n_atoms'] - 1) // 2
+    cache = 2.0 * cfg['n_train'] * n_perms * D * 8
+    return int(max(1, min(cores, 128e9 // cache)))
+
+
 class CpuPredictor(object):
     """The CPU arm: oracle port of predict.py:84-245 on a persistent pool over the host threads."""
 
@@ -188,7 +201,8 @@ class CpuPredictor(object):
     def rate(self, n_queries, seed=1):
         from sgdml_b200 import synth
 
-        Rq = synth.geometries(self.cfg['n_atoms'], n_queries, seed).reshape(n_queries, -1)
+        r0 = synth.config_perms_and_r0(self.cfg['name'])[1]
+        Rq = synth.geometries(self.cfg['n_atoms'], n_queries, seed, r0=r0).reshape(n_queries, -1)
         t0 = time.perf_counter()
         self.pp.predict(Rq)
         return n_queries / (time.perf_counter() - t0)
@@ -207,9 +221,9 @@ def run_reference(args):
     from sgdml_b200 import synth
 
     cfg = workload_cfg(args)
-    perms = synth.rotor_swap_group(cfg['n_atoms'], cfg['n_rotors'], cfg['n_swaps'])
+    perms, _ = synth.config_perms_and_r0(cfg['name'])
     model = oracle_random_model(cfg, perms)
-    cores = os.cpu_count() or 1
+    cores = cpu_workers(cfg, len(perms))
     cpu = CpuPredictor(model, cfg, cores)
     # calibrate the per-step sample (~4 s per step) so that warmup + steps stay within a few minutes
     cpu.rate(cores, seed=3)  # spin the pool up
@@ -280,7 +294,7 @@ def run_engine(args):
     cfg = workload_cfg(args)
     N, M = cfg['n_atoms'], cfg['n_train']
     D = N * (N - 1) // 2
-    perms = synth.rotor_swap_group(N, cfg['n_rotors'], cfg['n_swaps'])
+    perms, r0 = synth.config_perms_and_r0(cfg['name'])
     S = len(perms)
     n = 3 * N * M
 
@@ -294,7 +308,7 @@ def run_engine(args):
     task = synth.make_task(N, M, perms, cfg['sig'])
     trainer = sgdml_b200.GDMLTrain()
     if args.no_train:
-        model = synth.random_model(N, M, perms, cfg['sig'])
+        model = synth.random_model(N, M, perms, cfg['sig'], r0=r0)
     else:
         alphas_t = torch.empty(n + 2, dtype=torch.float64, device='cuda')
         if rank == 0:
@@ -367,7 +381,7 @@ def run_engine(args):
 
     # ---------------- prediction steps, inputs resident in HBM
     B = args.batch
-    Rq_host = synth.geometries(N, B, 1 + rank).reshape(B, -1)
+    Rq_host = synth.geometries(N, B, 1 + rank, r0=r0).reshape(B, -1)
     Rq_dev = torch.from_numpy(Rq_host).cuda()
     # the clock sampler (an nvidia-smi child process) is started BEFORE the warm-up so that its
     # start-up (fork, NVML initialisation) cannot disturb the timed region
@@ -436,14 +450,24 @@ def run_engine(args):
         t_step = main_ms * 1e-3 / reps
         fp64_peak = fp64_peak_tflops(L)
         achieved = flops_step / t_step * 1e-12
+        # flops the kernels actually issue on the DMMA pipe: the GEMM form needs 8 per (row, m, d)
+        # (2 GEMMs in, 2 GEMMs out) instead of the 9 of the reference's elementwise form,
+        # on descriptors padded to the tile width
+        fused = D <= 256
+        DP = next(p for p in (40, 72, 112, 160, 224, 256) if p >= D) if fused else (D + 3) // 4 * 4
+        executed = 8.0 * M * S * DP * B / t_step * 1e-12
         roofline = {
             'bound': 'tensor',
             'pipe': 'fp64 tensor pipe (mma.sync.m8n8k4.f64 -> DMMA); tcgen05 has no f64 kind',
-            'kernel': 'k_predict_main',
+            'kernel': 'k_predict_main' if fused else 'GEMM-composed predictor: 4 x k_gemm_nt_tma + k_transform_rows + k_combine_rows',
             'achieved': achieved,
             'peak': fp64_peak,
             'unit': 'TFLOP/s',
             'frac': achieved / fp64_peak,
+            'executed_tflops': executed,
+            'frac_executed': executed / fp64_peak,
+            'note': 'achieved counts the algorithmic 9*M*S*D flops per query of SURVEY 8d; the kernels issue 8*M*S*DP '
+            '(GEMM form, padded D), so frac can exceed frac_executed (= DMMA-pipe utilisation) by up to 9/8',
             'peak_source': 'live DMMA m8n8k4 probe (sgdml_b200_fp64_peak_tflops), burst; MEASURED_PEAKS.json carries only HBM and bf16 peaks',
             'algorithmic_flops_per_step': flops_step,
             'kernel_ms_per_step': t_step * 1e3,
@@ -453,7 +477,7 @@ def run_engine(args):
         }
         log('roofline probe done')
         if world == 1 and not args.no_cpu_baseline:
-            cores = os.cpu_count() or 1
+            cores = cpu_workers(cfg, S)
             cmodel = oracle_random_model(cfg, perms)
             cpu = CpuPredictor(cmodel, cfg, cores)
             cpu.rate(cores, seed=3)  # spin the pool up
@@ -547,10 +571,10 @@ def fp64_peak_tflops(L):
 
 def main():
     args = parse_args()
-    if args.workload == 'ac-ala3-nhme':
+    if args.workload in PREDICT_ONLY:
         args.no_train = True
         if args.batch == 65536:
-            args.batch = 4096
+            args.batch = PREDICT_ONLY[args.workload]
     if args.impl == 'reference':
         run_reference(args)
     else:

@@ -30,8 +30,9 @@ def cho_factor_stable(M, pre_reg=False, eps_mag_max=1):
     return None
 
 
-def nystroem_factor(R_desc, R_d_desc, tril_perms_lin, sig, lam, col_idxs):
-    """B = L_inv_K_mn (m, n), iterative.py:208-351."""
+def nystroem_factor(R_desc, R_d_desc, tril_perms_lin, sig, lam, col_idxs, force_qr=False):
+    """B = L_inv_K_mn (m, n), iterative.py:208-351.  force_qr: take the QR branch of
+    iterative.py:312-322 even if the inner Cholesky factorisation would succeed (tests)."""
     col_idxs = np.asarray(col_idxs)
     K_nm = oassemble.assemble(R_desc, R_d_desc, tril_perms_lin, sig, col_idxs=col_idxs)  # iterative.py:237-247
     K_mm = -K_nm[col_idxs, :]  # iterative.py:253
@@ -39,7 +40,13 @@ def nystroem_factor(R_desc, R_d_desc, tril_perms_lin, sig, lam, col_idxs):
     K_nm = sp.linalg.solve_triangular(L_mm, K_nm.T, lower=lower, trans='T', check_finite=False).T  # :278-287
     inner = K_nm.T.dot(K_nm)  # iterative.py:293
     inner[np.diag_indices_from(inner)] += lam
-    L, lower = cho_factor_stable(inner, eps_mag_max=-14)  # iterative.py:305
+    res = None if force_qr else cho_factor_stable(inner, eps_mag_max=-14)  # iterative.py:305
+    if res is not None:
+        L, lower = res
+    else:  # iterative.py:312-322: R factor of the stacked ((n + m) x m) matrix [K_nm; sqrt(lam) I]
+        m = K_nm.shape[1]
+        L = np.linalg.qr(np.vstack([K_nm, np.sqrt(lam) * np.eye(m)]), mode='r')
+        lower = False
     K_nm = sp.linalg.solve_triangular(L, K_nm.T, lower=lower, trans='T', check_finite=False).T  # :337-347
     return K_nm.T
 

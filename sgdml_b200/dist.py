@@ -149,12 +149,27 @@ def nystroem_factor_steps(ops, rank, world, n_train, dim_i, cols, lam):
     ops.gram(X, m, A)  # local part of K_nm^T K_nm (iterative.py:293-295)
     yield 'sum', A
     ops.add_diag(A, m, lam)
-    if not ops.cho_factor_stable(A, eps_mag_max=-14):
-        raise np.linalg.LinAlgError(
-            'inner Nystroem matrix not positive definite within 1e-14 jitter (the reference falls back to QR here, '
-            'iterative.py:312-322); try fewer inducing points or a larger sigma'
-        )
-    ops.trsm_right_lt(A, X, m)  # iterative.py:337-347
+    if ops.cho_factor_stable(A, eps_mag_max=-14):  # do not regularize more than 1e-14 (iterative.py:305-307)
+        ops.trsm_right_lt(A, X, m)  # iterative.py:337-347
+    else:
+        # iterative.py:312-322: the reference takes the R factor of a Householder QR of the stacked
+        # ((n + m) x m) matrix [K_nm; sqrt(lam) I] and solves with it.  R^T R is the same inner matrix,
+        # so X R^-1 is the top block of the thin Q factor; it is formed here by shifted CholeskyQR3
+        # (three Gram + Cholesky + triangular-solve passes, the first one shifted), which is
+        # backward stable for condition numbers up to ~1/eps and needs only the (m x m) all-reduce.
+        n_rows = n_train * dim_i
+        Y = ops.scaled_identity(m, np.sqrt(lam))  # the bottom block, replicated on every rank
+        for it in range(3):
+            ops.gram(X, m, A)
+            yield 'sum', A
+            ops.add_gram(Y, m, A)
+            if it == 0:
+                eps = np.finfo(float).eps
+                ops.add_diag(A, m, 11.0 * (m * (n_rows + m) + m * (m + 1)) * eps * ops.trace(A, m))
+            if not ops.potrf(A):
+                raise np.linalg.LinAlgError('QR fallback of the Nystroem factor failed (matrix not positive definite)')
+            ops.trsm_right_lt(A, X, m)
+            ops.trsm_right_lt(A, Y, m)
     return X, lo, hi
 
 

@@ -52,8 +52,37 @@ class _EngineNystroemOps(object):
     def put_neg_rows(self, A, pos, X, local_rows, m):
         import torch
 
-        if len(pos):
+        if len(pos) == m:  # every inducing row lives here (single rank): one gather kernel
+            rows = np.ascontiguousarray(local_rows, dtype=np.int64)
+            _lib.check(
+                _lib.lib().sgdml_b200_gather_rows_neg(X.data_ptr(), X.shape[1], m, _lib.ptr(rows), A.data_ptr(), A.shape[1], _lib.current_stream()),
+                'gather_rows_neg',
+            )
+        elif len(pos):
             A[torch.as_tensor(pos, device=A.device), :m] = -X[torch.as_tensor(local_rows, device=A.device), :m]
+
+    def scaled_identity(self, m, value):
+        import torch
+
+        Y = torch.zeros((m, (m + 1) // 2 * 2), dtype=torch.float64, device='cuda')
+        Y[:, :m].fill_diagonal_(float(value))
+        return Y
+
+    def add_gram(self, Y, m, A):
+        G = self.new_square(m)
+        self.gram(Y, m, G)
+        A += G  # (only the lower triangles are meaningful)
+
+    def trace(self, A, m):
+        import torch
+
+        return float(torch.diagonal(A[:, :m]).sum())
+
+    def potrf(self, A):
+        rc = _lib.lib().sgdml_b200_potrf(A.data_ptr(), A.shape[0], A.shape[1], _lib.current_stream())
+        if rc < 0:
+            _lib.check(rc, 'potrf')
+        return rc == 0
 
     def cho_factor_stable(self, A, **kw):
         return self.solver._cho_factor_stable(A, **kw)
@@ -143,36 +172,18 @@ class Iterative(object):
 
     def _nystroem_cholesky_factor(self, R_desc, R_d_desc, tril_perms_lin, sig, lam, use_E_cstr, col_idxs, callback=None):
         """iterative.py:208-351.  Returns X = B^T as a CUDA tensor (n, ldx) whose first m columns are
-        meaningful (B = L_inv_K_mn is X[:, :m].T), and m."""
-        import torch
+        meaningful (B = L_inv_K_mn is X[:, :m].T), and m.  Single-rank form of
+        dist.nystroem_factor_steps (the same steps, no exchange)."""
+        from .. import dist as sdist
 
         if use_E_cstr:
             raise NotImplementedError('use_E_cstr is out of scope (SURVEY.md section 2 row 22)')
-        L = _lib.lib()
-        stream = _lib.current_stream()
+        n_train, dim_d = R_d_desc.shape[:2]
+        dim_i = 3 * int((1 + np.sqrt(8 * dim_d + 1)) / 2)
         cols = np.ascontiguousarray(col_idxs, dtype=np.int64)
-        X, m = self.gdml_train._assemble_kernel_mat_device(R_desc, R_d_desc, tril_perms_lin, sig, col_idxs=cols)
-        n, ldx = X.shape
-
-        K_mm = torch.empty((m, (m + 1) // 2 * 2), dtype=torch.float64, device='cuda')
-        _lib.check(
-            L.sgdml_b200_gather_rows_neg(X.data_ptr(), ldx, m, _lib.ptr(cols), K_mm.data_ptr(), K_mm.shape[1], stream),
-            'gather_rows_neg',
-        )  # iterative.py:253
-        if not self._cho_factor_stable(K_mm, pre_reg=True):  # iterative.py:267
-            raise np.linalg.LinAlgError('Failed to factorize K_mm despite strong regularization')
-        _lib.check(L.sgdml_b200_trsm_right_lt(K_mm.data_ptr(), m, K_mm.shape[1], X.data_ptr(), n, ldx, stream), 'trsm')
-
-        inner = K_mm  # reuse the buffer (iterative.py:293-295)
-        _lib.check(L.sgdml_b200_gram_tn(X.data_ptr(), n, m, ldx, float(lam), inner.data_ptr(), inner.shape[1], stream), 'gram')
-        if not self._cho_factor_stable(inner, eps_mag_max=-14):  # do not regularize more than 1e-14
-            raise np.linalg.LinAlgError(
-                'inner Nystroem matrix not positive definite within 1e-14 jitter (the reference falls back to QR here, '
-                'iterative.py:312-322); try fewer inducing points or a larger sigma'
-            )
-        _lib.check(L.sgdml_b200_trsm_right_lt(inner.data_ptr(), m, inner.shape[1], X.data_ptr(), n, ldx, stream), 'trsm')
-        del K_mm
-        return X, m
+        ops = _EngineNystroemOps(self, R_desc, R_d_desc, tril_perms_lin, sig)
+        X, _, _ = sdist.run_steps_virtual([sdist.nystroem_factor_steps(ops, 0, 1, n_train, dim_i, cols, lam)])[0]
+        return X, len(cols)
 
     @staticmethod
     def _shard_precon(n_train):

@@ -43,9 +43,13 @@ class NumpyNystroemOps(object):
     def put_neg_rows(self, A, pos, X, local_rows, m):
         A.numpy()[pos, :m] = -X.numpy()[local_rows, :m]
 
+    force_qr = False  # tests: pretend the inner Cholesky failed (iterative.py:312-322)
+
     def cho_factor_stable(self, A, **kw):
         from oracle import iterative as oiter
 
+        if self.force_qr and 'eps_mag_max' in kw:
+            return False
         res = oiter.cho_factor_stable(A.numpy(), **kw)
         if res is None:
             return False
@@ -62,6 +66,24 @@ class NumpyNystroemOps(object):
 
     def add_diag(self, A, m, value):
         A.numpy()[np.diag_indices(m)] += value
+
+    def scaled_identity(self, m, value):
+        import torch
+
+        return torch.from_numpy(np.eye(m) * value)
+
+    def add_gram(self, Y, m, A):
+        A.numpy()[:] += Y.numpy().T @ Y.numpy()
+
+    def trace(self, A, m):
+        return float(np.trace(A.numpy()))
+
+    def potrf(self, A):
+        try:
+            A.numpy()[:] = np.linalg.cholesky(A.numpy())
+        except np.linalg.LinAlgError:
+            return False
+        return True
 
     def row_sqnorms(self, X, m):
         return np.einsum('ij,ij->i', X.numpy()[:, :m], X.numpy()[:, :m])
@@ -197,6 +219,34 @@ def test_virtual_ranks_match_unsharded():
         for r in range(world):
             assert np.max(np.abs(levs[r] - lev_ref)) < 1e-6 * np.max(np.abs(lev_ref))
             assert np.max(np.abs(Pvs[r] - Pv_ref)) < 1e-6 * np.max(np.abs(Pv_ref))
+
+
+def test_qr_fallback_matches_cholesky_path():
+    """iterative.py:312-322 (inner matrix not positive definite): the oracle follows the reference (R of a
+    Householder QR of [K_nm; sqrt(lam) I]); the engine's steps use shifted CholeskyQR3.  Forced on a
+    well-conditioned case, both must reproduce the Cholesky path's preconditioner."""
+    from oracle import iterative as oiter
+    from sgdml_b200 import dist as sdist
+
+    g = load_golden('n9_m16_s6')
+    n_train, dim_i, lam = g['R_desc'].shape[0], 3 * int(g['n_atoms']), float(g['lam'])
+    cols = golden_inducing_cols(g)
+    lev_ref, Pv_ref = _nystroem_reference(g)
+    B = oiter.nystroem_factor(g['R_desc'], g['R_d_desc'], g['tril_perms_lin'], int(g['sig']), lam, cols, force_qr=True)
+    assert np.max(np.abs(oiter.precon(B, lam)(g['v']) - Pv_ref)) < 1e-6 * np.max(np.abs(Pv_ref))
+    for world in (1, 2):
+        ops = [NumpyNystroemOps(g) for _ in range(world)]
+        for o in ops:
+            o.force_qr = True
+        facs = sdist.run_steps_virtual(
+            [sdist.nystroem_factor_steps(ops[r], r, world, n_train, dim_i, cols, lam) for r in range(world)]
+        )
+        Pvs = sdist.run_steps_virtual(
+            [sdist.precon_apply_steps(ops[r], facs[r][0], len(cols), lam, g['v'], facs[r][1], facs[r][2], dim_i) for r in range(world)]
+        )
+        levs = sdist.run_steps_virtual([sdist.lev_scores_steps(ops[r], facs[r][0], len(cols), dim_i) for r in range(world)])
+        assert np.max(np.abs(Pvs[0] - Pv_ref)) < 1e-6 * np.max(np.abs(Pv_ref))
+        assert np.max(np.abs(levs[0] - lev_ref)) < 1e-6 * np.max(np.abs(lev_ref))
 
 
 def test_model_shards_add_up():

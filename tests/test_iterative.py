@@ -109,6 +109,36 @@ def test_engine_sharded_preconditioner_virtual_ranks(world):
 
 
 @pytest.mark.gpu
+def test_engine_qr_fallback(monkeypatch):
+    """iterative.py:312-322 on the engine (shifted CholeskyQR3 on [K_nm; sqrt(lam) I]), forced by making
+    the inner Cholesky report failure: same leverage scores and P.v as the reference's factor."""
+    import sgdml_b200
+    from sgdml_b200.desc import Desc
+    from sgdml_b200.solvers.iterative import Iterative
+
+    g, task, N, M, R = _setup()
+    t = sgdml_b200.GDMLTrain(max_memory=float(g['max_memory_gb']))
+    d = Desc(N)
+    x, gd = d.from_R(R)
+    lin = odesc.tril_perms_lin(g['perms'])
+    it = Iterative(t, d, float(g['max_memory_gb']), None, False)
+    real = it._cho_factor_stable
+    calls = []
+
+    def fake(A, pre_reg=False, eps_mag_max=1):
+        if eps_mag_max == -14:
+            calls.append(1)
+            return False
+        return real(A, pre_reg=pre_reg, eps_mag_max=eps_mag_max)
+
+    monkeypatch.setattr(it, '_cho_factor_stable', fake)
+    P, lev = it._init_precon_operator(task, x, gd, lin, g['inducing_pts_idxs'])
+    assert calls
+    assert rel_err(lev, g['lev_scores']) < 1e-6
+    assert rel_err(P(g['v']), g['Pv']) < 1e-5
+
+
+@pytest.mark.gpu
 def test_engine_cg_train_matches_reference():
     """GDMLTrain.train with a memory cap that forces the iterative solver, same inducing columns as the
     reference run: converges to the same tolerance in a similar number of iterations and predicts
