@@ -75,9 +75,17 @@ __global__ void __launch_bounds__(256) k_xt_v(const double* __restrict__ X, int6
   const int64_t r0 = (int64_t)blockIdx.y * rows_per_cta;
   const int64_t r1 = min(r0 + rows_per_cta, n_rows);
   if (j >= m) return;
-  double s = 0.0;
-  for (int64_t r = r0; r < r1; ++r) s = fma(X[r * ldx + j], v[r], s);
-  part[(int64_t)blockIdx.y * m + j] = s;
+  // four independent accumulators: four loads in flight per thread (fixed order -> deterministic)
+  double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+  int64_t r = r0;
+  for (; r + 3 < r1; r += 4) {
+    s0 = fma(X[r * ldx + j], v[r], s0);
+    s1 = fma(X[(r + 1) * ldx + j], v[r + 1], s1);
+    s2 = fma(X[(r + 2) * ldx + j], v[r + 2], s2);
+    s3 = fma(X[(r + 3) * ldx + j], v[r + 3], s3);
+  }
+  for (; r < r1; ++r) s0 = fma(X[r * ldx + j], v[r], s0);
+  part[(int64_t)blockIdx.y * m + j] = (s0 + s1) + (s2 + s3);
 }
 
 __global__ void k_reduce_chunks(const double* __restrict__ part, int64_t n_chunks, int64_t m, double* __restrict__ t) {
@@ -95,8 +103,17 @@ __global__ void k_x_t_minus_v(const double* __restrict__ X, int64_t n_rows, int6
   const int lane = threadIdx.x & 31;
   const int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (r >= n_rows) return;
-  double s = 0.0;
-  for (int64_t j = lane; j < m; j += 32) s = fma(X[r * ldx + j], t[j], s);
+  const double* __restrict__ x = X + r * ldx;
+  double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+  int64_t j = lane;
+  for (; j + 96 < m; j += 128) {
+    s0 = fma(x[j], t[j], s0);
+    s1 = fma(x[j + 32], t[j + 32], s1);
+    s2 = fma(x[j + 64], t[j + 64], s2);
+    s3 = fma(x[j + 96], t[j + 96], s3);
+  }
+  for (; j < m; j += 32) s0 = fma(x[j], t[j], s0);
+  double s = (s0 + s1) + (s2 + s3);
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
   if (lane == 0) out[r] = (s - v[r]) * lam_inv;
@@ -199,27 +216,59 @@ int sgdml_b200_row_sqnorms(const double* X, int64_t n_rows, int64_t m, int64_t l
   return 0;
 }
 
-// t = X^T v (m doubles, device), deterministic two-pass reduction
+// Scratch buffer of the preconditioner application: P v runs once per CG iteration, so its
+// temporaries (staged vectors, per-chunk partial sums) are kept between calls instead of being
+// cudaMalloc'ed and cudaFree'd (which synchronises the device) every time.  One per host thread
+// and device; grown on demand.
+struct Scratch {
+  double* p = nullptr;
+  size_t cap = 0;  // doubles
+  int dev = -1;
+  ~Scratch() {}  // freed with the context at process exit
+};
+static thread_local Scratch g_scratch;
+
+static int scratch_get(size_t n_doubles, double** out) {
+  int dev = 0;
+  SG_CUDA(cudaGetDevice(&dev));
+  if (g_scratch.dev != dev || g_scratch.cap < n_doubles) {
+    if (g_scratch.p != nullptr && g_scratch.dev == dev) cudaFree(g_scratch.p);
+    g_scratch.p = nullptr;
+    g_scratch.cap = 0;
+    SG_CUDA(cudaMalloc(&g_scratch.p, sizeof(double) * n_doubles));
+    g_scratch.cap = n_doubles;
+    g_scratch.dev = dev;
+  }
+  *out = g_scratch.p;
+  return 0;
+}
+
+static const int XTV_ROWS_PER_CTA = 256;
+static int64_t xtv_chunks(int64_t n_rows) { return (n_rows + XTV_ROWS_PER_CTA - 1) / XTV_ROWS_PER_CTA; }
+
+// t = X^T v (m doubles, device), deterministic two-pass reduction; part: m * xtv_chunks(n_rows) doubles
 static int xt_v_device(const double* X, int64_t n_rows, int64_t m, int64_t ldx, const double* v_dev, double* t_dev,
-                       cudaStream_t s) {
-  const int rows_per_cta = 256;
-  const int64_t n_chunks = (n_rows + rows_per_cta - 1) / rows_per_cta;
-  double* part = nullptr;
-  SG_CUDA(cudaMalloc(&part, sizeof(double) * (size_t)m * n_chunks));
-  auto body = [&]() -> int {
-    dim3 grid((unsigned)((m + 255) / 256), (unsigned)n_chunks);
-    SG_ARG(grid.y <= 65535);
-    k_xt_v<<<grid, 256, 0, s>>>(X, n_rows, m, ldx, v_dev, part, rows_per_cta);
-    SG_CUDA(cudaGetLastError());
-    k_reduce_chunks<<<ceil_div(m, 256), 256, 0, s>>>(part, n_chunks, m, t_dev);
-    SG_CUDA(cudaGetLastError());
-    count_launch(KID_MISC, 2);
-    SG_CUDA(cudaStreamSynchronize(s));  // `part` is freed below
+                       double* part, cudaStream_t s) {
+  const int64_t n_chunks = xtv_chunks(n_rows);
+  dim3 grid((unsigned)((m + 255) / 256), (unsigned)n_chunks);
+  SG_ARG(grid.y <= 65535);
+  k_xt_v<<<grid, 256, 0, s>>>(X, n_rows, m, ldx, v_dev, part, XTV_ROWS_PER_CTA);
+  SG_CUDA(cudaGetLastError());
+  k_reduce_chunks<<<ceil_div(m, 256), 256, 0, s>>>(part, n_chunks, m, t_dev);
+  SG_CUDA(cudaGetLastError());
+  count_launch(KID_MISC, 2);
+  return 0;
+}
+
+// device view of a possibly-host input vector: host data is copied into `slot` (scratch memory)
+static int stage_in(const double* user, size_t n, double* slot, cudaStream_t s, const double** dev) {
+  if (is_device_ptr(user)) {
+    *dev = user;
     return 0;
-  };
-  int rc = body();
-  cudaFree(part);
-  return rc;
+  }
+  SG_CUDA(cudaMemcpyAsync(slot, user, sizeof(double) * n, cudaMemcpyHostToDevice, s));
+  *dev = slot;
+  return 0;
 }
 
 int sgdml_b200_nystroem_apply(const double* X, int64_t n_rows, int64_t m, int64_t ldx, double lam, const double* v,
@@ -228,24 +277,21 @@ int sgdml_b200_nystroem_apply(const double* X, int64_t n_rows, int64_t m, int64_
   SG_ARG(X != nullptr && v != nullptr && out != nullptr && n_rows >= 1 && m >= 1 && ldx >= m && lam > 0.0);
   SG_ARG(is_device_ptr(X));
   cudaStream_t s = (cudaStream_t)stream;
-  Staged sV, sO;
-  SG_TRY(sV.init(v, sizeof(double) * (size_t)n_rows, true, s));
-  SG_TRY(sO.init(out, sizeof(double) * (size_t)n_rows, false, s));
-  double* t = nullptr;
-  SG_CUDA(cudaMalloc(&t, sizeof(double) * (size_t)m));
-  auto body = [&]() -> int {
-    SG_TRY(xt_v_device(X, n_rows, m, ldx, (const double*)sV.dev(), t, s));
-    k_x_t_minus_v<<<ceil_div(n_rows, 8), 256, 0, s>>>(X, n_rows, m, ldx, t, (const double*)sV.dev(), 1.0 / lam,
-                                                      (double*)sO.dev());
-    SG_CUDA(cudaGetLastError());
-    count_launch(KID_MISC);
-    SG_TRY(sO.finish(s));
-    SG_CUDA(cudaStreamSynchronize(s));
-    return 0;
-  };
-  int rc = body();
-  cudaFree(t);
-  return rc;
+  const size_t n = (size_t)n_rows, mm = (size_t)m;
+  double* sc = nullptr;
+  SG_TRY(scratch_get(mm + mm * (size_t)xtv_chunks(n_rows) + 2 * n, &sc));
+  double *t = sc, *part = sc + mm, *v_slot = part + mm * (size_t)xtv_chunks(n_rows), *out_slot = v_slot + n;
+  const double* v_dev = nullptr;
+  SG_TRY(stage_in(v, n, v_slot, s, &v_dev));
+  const bool out_host = !is_device_ptr(out);
+  double* out_dev = out_host ? out_slot : out;
+  SG_TRY(xt_v_device(X, n_rows, m, ldx, v_dev, t, part, s));
+  k_x_t_minus_v<<<ceil_div(n_rows, 8), 256, 0, s>>>(X, n_rows, m, ldx, t, v_dev, 1.0 / lam, out_dev);
+  SG_CUDA(cudaGetLastError());
+  count_launch(KID_MISC);
+  if (out_host) SG_CUDA(cudaMemcpyAsync(out, out_dev, sizeof(double) * n, cudaMemcpyDeviceToHost, s));
+  SG_CUDA(cudaStreamSynchronize(s));  // the scratch buffer is reused by the next call
+  return 0;
 }
 
 int sgdml_b200_nystroem_project(const double* X, int64_t n_rows, int64_t m, int64_t ldx, const double* v, double* t,
@@ -253,11 +299,16 @@ int sgdml_b200_nystroem_project(const double* X, int64_t n_rows, int64_t m, int6
   SG_TRY(require_device());
   SG_ARG(X != nullptr && v != nullptr && t != nullptr && n_rows >= 1 && m >= 1 && ldx >= m && is_device_ptr(X));
   cudaStream_t s = (cudaStream_t)stream;
-  Staged sV, sT;
-  SG_TRY(sV.init(v, sizeof(double) * (size_t)n_rows, true, s));
-  SG_TRY(sT.init(t, sizeof(double) * (size_t)m, false, s));
-  SG_TRY(xt_v_device(X, n_rows, m, ldx, (const double*)sV.dev(), (double*)sT.dev(), s));
-  SG_TRY(sT.finish(s));
+  const size_t n = (size_t)n_rows, mm = (size_t)m;
+  double* sc = nullptr;
+  SG_TRY(scratch_get(mm + mm * (size_t)xtv_chunks(n_rows) + n, &sc));
+  double *t_slot = sc, *part = sc + mm, *v_slot = part + mm * (size_t)xtv_chunks(n_rows);
+  const double* v_dev = nullptr;
+  SG_TRY(stage_in(v, n, v_slot, s, &v_dev));
+  const bool t_host = !is_device_ptr(t);
+  double* t_dev = t_host ? t_slot : t;
+  SG_TRY(xt_v_device(X, n_rows, m, ldx, v_dev, t_dev, part, s));
+  if (t_host) SG_CUDA(cudaMemcpyAsync(t, t_dev, sizeof(double) * mm, cudaMemcpyDeviceToHost, s));
   SG_CUDA(cudaStreamSynchronize(s));
   return 0;
 }
@@ -268,15 +319,19 @@ int sgdml_b200_nystroem_expand(const double* X, int64_t n_rows, int64_t m, int64
   SG_ARG(X != nullptr && t != nullptr && v != nullptr && out != nullptr && n_rows >= 1 && m >= 1 && ldx >= m && lam > 0.0);
   SG_ARG(is_device_ptr(X));
   cudaStream_t s = (cudaStream_t)stream;
-  Staged sT, sV, sO;
-  SG_TRY(sT.init(t, sizeof(double) * (size_t)m, true, s));
-  SG_TRY(sV.init(v, sizeof(double) * (size_t)n_rows, true, s));
-  SG_TRY(sO.init(out, sizeof(double) * (size_t)n_rows, false, s));
-  k_x_t_minus_v<<<ceil_div(n_rows, 8), 256, 0, s>>>(X, n_rows, m, ldx, (const double*)sT.dev(), (const double*)sV.dev(),
-                                                    1.0 / lam, (double*)sO.dev());
+  const size_t n = (size_t)n_rows, mm = (size_t)m;
+  double* sc = nullptr;
+  SG_TRY(scratch_get(mm + 2 * n, &sc));
+  double *t_slot = sc, *v_slot = sc + mm, *out_slot = v_slot + n;
+  const double *t_dev = nullptr, *v_dev = nullptr;
+  SG_TRY(stage_in(t, mm, t_slot, s, &t_dev));
+  SG_TRY(stage_in(v, n, v_slot, s, &v_dev));
+  const bool out_host = !is_device_ptr(out);
+  double* out_dev = out_host ? out_slot : out;
+  k_x_t_minus_v<<<ceil_div(n_rows, 8), 256, 0, s>>>(X, n_rows, m, ldx, t_dev, v_dev, 1.0 / lam, out_dev);
   SG_CUDA(cudaGetLastError());
   count_launch(KID_MISC);
-  SG_TRY(sO.finish(s));
+  if (out_host) SG_CUDA(cudaMemcpyAsync(out, out_dev, sizeof(double) * n, cudaMemcpyDeviceToHost, s));
   SG_CUDA(cudaStreamSynchronize(s));
   return 0;
 }

@@ -324,6 +324,7 @@ class Iterative(object):
         else:
             lev_scores = self._lev_scores(R_desc, R_d_desc, tril_perms_lin, sig, lam, task['use_E_cstr'], n_inducing_pts)
             inducing_pts_idxs = self.inducing_pts_from_lev_scores(lev_scores, n_inducing_pts * dim_i)
+            self.timings['lev_scores_s'] = timeit.default_timer() - t_start
 
         inducing_pts_idxs = self._bcast_idxs(inducing_pts_idxs)
         P_vec, lev_scores = self._init_precon_operator(task, R_desc, R_d_desc, tril_perms_lin, inducing_pts_idxs)
@@ -332,8 +333,24 @@ class Iterative(object):
         n = lev_scores.size
         K_vec = self._init_kernel_operator(task, R_desc, R_d_desc, tril_perms_lin, lam, n)
 
+        self.timings.update({'kvec_s': 0.0, 'pvec_s': 0.0})
+
         def A_vec(v):  # -K_op: the SPD operator (-K + lam I), iterative.py:740-741
-            return -K_vec(v)
+            t_op = timeit.default_timer()
+            out = -K_vec(v)
+            self.timings['kvec_s'] += timeit.default_timer() - t_op
+            return out
+
+        def _timed_precon(fn):
+            def P(v):
+                t_op = timeit.default_timer()
+                out = fn(v)
+                self.timings['pvec_s'] += timeit.default_timer() - t_op
+                return out
+
+            return P
+
+        P_vec = _timed_precon(P_vec)
 
         y = np.ascontiguousarray(y, dtype=np.float64)
         norm_y = np.linalg.norm(y)
@@ -406,6 +423,7 @@ class Iterative(object):
             inducing_pts_idxs = self._bcast_idxs(self.inducing_pts_from_lev_scores(lev_scores, n_inducing_pts * dim_i))
             del P_vec
             P_vec, lev_scores = self._init_precon_operator(task, R_desc, R_d_desc, tril_perms_lin, inducing_pts_idxs)
+            P_vec = _timed_precon(P_vec)
 
         self.timings['cg_s'] = timeit.default_timer() - t_cg
         self.timings['iters'] = num_iters - num_iters0
