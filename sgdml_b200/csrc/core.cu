@@ -44,13 +44,67 @@ bool is_device_ptr(const void* p) {
   return attr.type == cudaMemoryTypeDevice || attr.type == cudaMemoryTypeManaged;
 }
 
+// ---- staging-buffer pool (see the comment on class Staged)
+namespace {
+struct PoolBuf {
+  void* p;
+  size_t cap;
+  int dev;
+};
+struct StagePool {
+  std::vector<PoolBuf> free_;
+  size_t bytes = 0;
+};
+thread_local StagePool g_pool;
+constexpr size_t POOL_MAX_BUF = (size_t)256 << 20;     // larger staging buffers are not kept
+constexpr size_t POOL_MAX_TOTAL = (size_t)1024 << 20;  // per host thread
+constexpr size_t POOL_MAX_COUNT = 32;
+
+cudaError_t pool_get(size_t bytes, int dev, void** out, size_t* cap) {
+  int best = -1;
+  for (int i = 0; i < (int)g_pool.free_.size(); ++i) {
+    const PoolBuf& b = g_pool.free_[(size_t)i];
+    if (b.dev == dev && b.cap >= bytes && b.cap <= 2 * bytes + 4096 &&
+        (best < 0 || b.cap < g_pool.free_[(size_t)best].cap))
+      best = i;
+  }
+  if (best >= 0) {
+    *out = g_pool.free_[(size_t)best].p;
+    *cap = g_pool.free_[(size_t)best].cap;
+    g_pool.bytes -= *cap;
+    g_pool.free_.erase(g_pool.free_.begin() + best);
+    return cudaSuccess;
+  }
+  *cap = bytes;
+  return cudaMalloc(out, bytes);
+}
+
+void pool_put(void* p, size_t cap, int dev) {
+  if (cap > POOL_MAX_BUF) {
+    cudaFree(p);
+    return;
+  }
+  while (!g_pool.free_.empty() && (g_pool.bytes + cap > POOL_MAX_TOTAL || g_pool.free_.size() >= POOL_MAX_COUNT)) {
+    cudaFree(g_pool.free_.front().p);  // oldest first
+    g_pool.bytes -= g_pool.free_.front().cap;
+    g_pool.free_.erase(g_pool.free_.begin());
+  }
+  g_pool.free_.push_back(PoolBuf{p, cap, dev});
+  g_pool.bytes += cap;
+}
+}  // namespace
+
 Staged::~Staged() {
-  if (owns_ && dev_) cudaFree(dev_);
+  if (owns_ && dev_) {
+    cudaStreamSynchronize(stream_);  // nothing queued on the buffer's stream may still touch it
+    pool_put(dev_, cap_, dev_id_);
+  }
 }
 
 int Staged::init(const void* user, size_t bytes, bool copy_in, cudaStream_t s) {
   user_ = const_cast<void*>(user);
   bytes_ = bytes;
+  stream_ = s;
   if (user == nullptr || bytes == 0) {
     dev_ = nullptr;
     owns_ = false;
@@ -61,7 +115,8 @@ int Staged::init(const void* user, size_t bytes, bool copy_in, cudaStream_t s) {
     owns_ = false;
     return 0;
   }
-  SG_CUDA(cudaMalloc(&dev_, bytes));
+  SG_CUDA(cudaGetDevice(&dev_id_));
+  SG_CUDA(pool_get(bytes, dev_id_, &dev_, &cap_));
   owns_ = true;
   if (copy_in) SG_CUDA(cudaMemcpyAsync(dev_, user, bytes, cudaMemcpyHostToDevice, s));
   return 0;

@@ -32,6 +32,16 @@ DONE = 1
 NOT_DONE = 0
 
 
+def _dot(a, b):
+    """Inner product of two CG vectors without the BLAS thread pool: on the 128-thread host waking the
+    pool up between two GPU calls cost ~10-20 ms per call (more than the K.v product itself)."""
+    return float(np.einsum('i,i->', a, b))
+
+
+def _norm(a):
+    return float(np.sqrt(np.einsum('i,i->', a, a)))
+
+
 class _EngineNystroemOps(object):
     """Compute side of the row-sharded Nystroem factor (dist.nystroem_factor_steps and friends) on
     the CUDA engine: every method is one C-ABI call on this rank's rows; matrices are CUDA tensors."""
@@ -353,7 +363,7 @@ class Iterative(object):
         P_vec = _timed_precon(P_vec)
 
         y = np.ascontiguousarray(y, dtype=np.float64)
-        norm_y = np.linalg.norm(y)
+        norm_y = _norm(y)
         x = np.zeros(n) if alphas0_F is None else -np.asarray(alphas0_F, dtype=np.float64).copy()
         maxiter = 3 * n_atoms * n_train * 10  # iterative.py:746-749
 
@@ -366,18 +376,18 @@ class Iterative(object):
 
         while True:  # restart loop (iterative.py:737-801)
             r = y - A_vec(x) if np.any(x) else y.copy()
-            resid = np.linalg.norm(r)
+            resid = _norm(r)
             z = P_vec(r)
             p = z.copy()
-            rz = r.dot(z)
+            rz = _dot(r, z)
             restart = False
             it_this = 0
             while resid > tol * norm_y and it_this < maxiter:
                 Ap = A_vec(p)
-                alpha = rz / p.dot(Ap)
+                alpha = rz / _dot(p, Ap)
                 x += alpha * p
                 r -= alpha * Ap
-                old_resid, resid = resid, np.linalg.norm(r)
+                old_resid, resid = resid, _norm(r)
                 num_iters += 1
                 it_this += 1
 
@@ -407,7 +417,7 @@ class Iterative(object):
                 if resid <= tol * norm_y:
                     break
                 z = P_vec(r)
-                rz_new = r.dot(z)
+                rz_new = _dot(r, z)
                 p = z + (rz_new / rz) * p
                 rz = rz_new
 
