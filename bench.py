@@ -62,6 +62,8 @@ def parse_args():
     ap.add_argument('--cpu-seconds', type=float, default=15.0, help='target duration of the cpu_baseline sample')
     ap.add_argument('--no-cpu-baseline', action='store_true', help='skip the cpu_baseline leg (profiling runs)')
     ap.add_argument('--ref-batch', type=int, default=None, help='queries per step of the reference arm')
+    ap.add_argument('--ref-worker', default=None, help=argparse.SUPPRESS)  # internal: JSON spec of a reference-arm subprocess
+    ap.add_argument('--ref-train-worker', default=None, help=argparse.SUPPRESS)  # internal: reference training sample
     return ap.parse_args()
 
 
@@ -211,10 +213,202 @@ class CpuPredictor(object):
         self.pp.close()
 
 
+# The UNMODIFIED reference (stefanch/sGDML v1.0.3) lives in baseline/_ref when it was installed in the
+# build container (git-ignored, but it travels to the GPU box with the snapshot).  It is run in a fresh
+# interpreter: its worker pool forks (predict.py:36), which must not happen in a process that has
+# initialised CUDA or torch's thread pools.
+REF_DIR = os.path.join(ROOT, 'baseline', '_ref')
+
+
+def reference_available():
+    if os.environ.get('SGDML_B200_NO_REFERENCE'):  # tests: force the oracle-port fallback
+        return False
+    return os.path.isfile(os.path.join(REF_DIR, 'sgdml', 'predict.py'))
+
+
+def ref_worker_main(spec):
+    """Runs inside the subprocess: GDMLPredict(model, use_torch=False) of the reference, its own process
+    pool over the host threads in bulk mode (predict.py:1236-1256); prints one JSON line."""
+    import logging
+
+    sys.path.insert(0, REF_DIR)
+    from sgdml.predict import GDMLPredict  # the reference, not this repo
+
+    from sgdml_b200 import synth
+
+    cfg = spec['cfg']
+    perms, r0 = synth.config_perms_and_r0(cfg['name'])
+    model = oracle_random_model(cfg, perms)
+    N = cfg['n_atoms']
+    cores = int(spec['cores'])
+    pred = GDMLPredict(model, max_processes=cores, use_torch=False, log_level=logging.CRITICAL)
+
+    def rate(n_queries, seed):
+        Rq = synth.geometries(N, n_queries, seed, r0=r0).reshape(n_queries, -1)
+        t0 = time.perf_counter()
+        pred.predict(Rq)
+        return n_queries / (time.perf_counter() - t0)
+
+    # The reference tunes (bulk mode, workers, chunk size) with prepare_parallel (predict.py:776-1044), whose
+    # run time is unbounded on a many-core host; the same three knobs are set here through the same setters
+    # from a short list, keeping the fastest.
+    pred._set_bulk_mp(True)
+    pred._set_num_workers(max(cores - 1, 1))
+    best = (0.0, None)
+    n_probe = max(2 * cores, 64)
+    rate(n_probe, 3)  # spin the pool up
+    for chunk in [None, 256, 64, 16]:
+        if chunk is not None and chunk >= cfg['n_train']:
+            continue
+        pred._set_chunk_size(chunk)
+        r = rate(n_probe, 5)
+        if r > best[0]:
+            best = (r, chunk)
+    pred._set_chunk_size(best[1])
+    per_step = int(spec['per_step'] or max(cores, min(200000, best[0] * float(spec['seconds_per_step']))))
+    for _ in range(int(spec['warmup'])):
+        rate(per_step, 7)
+    t0 = time.perf_counter()
+    for k in range(int(spec['steps'])):
+        rate(per_step, 11 + k)
+    dt = time.perf_counter() - t0
+    # parity of the arm itself: the reference against this repo's oracle on a few queries
+    from oracle import predict as opredict
+
+    Rq = synth.geometries(N, 4, 1, r0=r0).reshape(4, -1)
+    _, F_ref = pred.predict(Rq)
+    _, F_orc = opredict.Predictor(model).predict(Rq)
+    dev = float(np.max(np.abs(F_ref - F_orc)) / np.max(np.abs(F_orc)))
+    print(json.dumps({'per_step': per_step, 'steps': int(spec['steps']), 'seconds': dt, 'chunk_size': best[1],
+                      'workers': int(pred.num_workers), 'oracle_vs_reference_rel': dev}))
+    sys.stdout.flush()
+    os._exit(0)  # the reference's pool has no clean shutdown path (predict.py:462-470)
+
+
+def ref_train_worker_main(spec):
+    """Runs inside a subprocess: the reference's training path on a BOUNDED sample.
+    part 'assemble': GDMLTrain._assemble_kernel_mat (train.py:1260-1535) for the first k block-columns, its
+    own process pool over the host threads; part 'cholesky': scipy.linalg.cho_factor + cho_solve
+    (analytic.py:94-99) at a reduced n.  The caller scales by M/k and (n/n_s)^3."""
+    sys.path.insert(0, REF_DIR)
+    from sgdml_b200 import synth
+
+    cfg = spec['cfg']
+    N, M = cfg['n_atoms'], cfg['n_train']
+    if spec['part'] == 'assemble':
+        from sgdml.train import GDMLTrain
+        from sgdml.utils.desc import Desc
+
+        cores = int(spec['cores'])
+        perms, r0 = synth.config_perms_and_r0(cfg['name'])
+        R = synth.geometries(N, M, 0, r0=r0).reshape(M, -1)
+        desc = Desc(N, max_processes=cores)
+        t0 = time.perf_counter()
+        R_desc, R_d_desc = desc.from_R(R, max_processes=cores)
+        t_desc = time.perf_counter() - t0
+        tril_perms = np.array([Desc.perm(p) for p in perms])
+        tril_perms_lin = (tril_perms + np.arange(len(perms))[:, None] * desc.dim).flatten('F')
+        gdml = GDMLTrain(max_processes=cores, use_torch=False)
+        k, t = 1, 0.0
+        while True:  # grow the sample until it takes a few seconds
+            t0 = time.perf_counter()
+            gdml._assemble_kernel_mat(R_desc, R_d_desc, tril_perms_lin, cfg['sig'], desc, col_idxs=np.s_[: k * 3 * N])
+            t = time.perf_counter() - t0
+            if t >= float(spec['seconds']) or k >= M:
+                break
+            k = min(M, max(k + 1, int(k * min(8.0, 1.3 * float(spec['seconds']) / max(t, 1e-3)))))
+        print(json.dumps({'col_points': k, 'seconds': t, 'desc_seconds': t_desc, 'workers': cores}))
+    else:
+        import scipy.linalg
+
+        n_s = int(spec['n_sample'])
+        rng = np.random.default_rng(0)
+        A = rng.standard_normal((n_s, n_s))
+        A = A @ A.T + n_s * np.eye(n_s)
+        y = rng.standard_normal(n_s)
+        t0 = time.perf_counter()
+        L, lower = scipy.linalg.cho_factor(A, overwrite_a=True, check_finite=False)  # analytic.py:94-96
+        scipy.linalg.cho_solve((L, lower), y, overwrite_b=True, check_finite=False)  # analytic.py:97-99
+        print(json.dumps({'n_sample': n_s, 'seconds': time.perf_counter() - t0}))
+    sys.stdout.flush()
+    os._exit(0)
+
+
+def reference_train_estimate(cfg, cores, seconds=6.0):
+    """CPU time of the reference's K assembly + Cholesky solve for this workload, EXTRAPOLATED from bounded
+    samples run with the unmodified reference (None if it is not installed)."""
+    if not reference_available():
+        return None
+    N, M = cfg['n_atoms'], cfg['n_train']
+    n = 3 * N * M
+    out = {}
+    for part, threads in (('assemble', '1'), ('cholesky', None)):
+        spec = {'cfg': cfg, 'cores': cores, 'part': part, 'seconds': seconds, 'n_sample': min(n, 12000)}
+        env = dict(os.environ)
+        for k in ('OMP_NUM_THREADS', 'OPENBLAS_NUM_THREADS', 'MKL_NUM_THREADS'):
+            if threads is None:
+                env.pop(k, None)  # LAPACK on all the threads it wants
+            else:
+                env[k] = threads  # pool of single-threaded workers
+        env['CUDA_VISIBLE_DEVICES'] = ''
+        for k in ('RANK', 'WORLD_SIZE', 'LOCAL_RANK'):
+            env.pop(k, None)
+        try:
+            res = subprocess.run([sys.executable, os.path.abspath(__file__), '--ref-train-worker', json.dumps(spec)],
+                                 env=env, capture_output=True, text=True, timeout=90 + 10 * seconds)
+            out[part] = json.loads(res.stdout.strip().splitlines()[-1])
+        except Exception as e:  # noqa: BLE001 -- a reported baseline must never take the benchmark down
+            log('reference training sample (%s) failed: %r' % (part, e))
+            return None
+    a, c = out['assemble'], out['cholesky']
+    assemble_s = a['seconds'] * M / a['col_points']
+    solve_s = c['seconds'] * (n / c['n_sample']) ** 3
+    return {
+        'kind': 'reference',
+        'extrapolated': True,
+        'cores': cores,
+        'assemble_s': assemble_s,
+        'solve_s': solve_s,
+        'total_s': assemble_s + solve_s,
+        'sample': 'unmodified reference: GDMLTrain._assemble_kernel_mat on the first %d of %d block-columns (%.1f s, %d worker '
+        'processes) scaled by M/k; scipy cho_factor + cho_solve at n = %d (%.2f s, LAPACK threads unrestricted) scaled by (n/n_s)^3'
+        % (a['col_points'], M, a['seconds'], a['workers'], c['n_sample'], c['seconds']),
+    }
+
+
+def run_reference_subprocess(cfg, cores, warmup, steps, per_step, seconds_per_step, timeout_s):
+    """-> dict (see ref_worker_main) or None if the reference is not installed / failed / timed out."""
+    if not reference_available():
+        return None
+    spec = {'cfg': cfg, 'cores': cores, 'warmup': warmup, 'steps': steps, 'per_step': per_step,
+            'seconds_per_step': seconds_per_step}
+    env = dict(os.environ)
+    for k in ('OMP_NUM_THREADS', 'OPENBLAS_NUM_THREADS', 'MKL_NUM_THREADS'):
+        env[k] = '1'  # one BLAS thread per worker process: the pool already uses every host thread
+    env['CUDA_VISIBLE_DEVICES'] = ''
+    for k in ('RANK', 'WORLD_SIZE', 'LOCAL_RANK'):
+        env.pop(k, None)
+    try:
+        out = subprocess.run([sys.executable, os.path.abspath(__file__), '--ref-worker', json.dumps(spec)],
+                             env=env, capture_output=True, text=True, timeout=timeout_s)
+    except subprocess.TimeoutExpired:
+        log('reference subprocess timed out after %.0f s' % timeout_s)
+        return None
+    if out.returncode != 0:
+        log('reference subprocess failed: %s' % out.stderr.strip()[-400:])
+        return None
+    for ln in reversed(out.stdout.strip().splitlines()):
+        try:
+            return json.loads(ln)
+        except ValueError:
+            continue
+    return None
+
+
 def run_reference(args):
-    """`--impl reference`: the reference's own CPU algorithm for the prediction path (the
-    oracle port of predict.py:84-245, one geometry per worker task like its bulk_mp mode) on all
-    host threads.  Under torchrun only rank 0 works."""
+    """`--impl reference`: the reference's own CPU implementation of the prediction path on all host
+    threads -- the unmodified reference from baseline/_ref when it is installed (kind "reference"),
+    otherwise the oracle port of predict.py:84-245 (kind "port").  Under torchrun only rank 0 works."""
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
@@ -222,22 +416,34 @@ def run_reference(args):
 
     cfg = workload_cfg(args)
     perms, _ = synth.config_perms_and_r0(cfg['name'])
-    model = oracle_random_model(cfg, perms)
-    cores = cpu_workers(cfg, len(perms))
-    cpu = CpuPredictor(model, cfg, cores)
-    # calibrate the per-step sample (~4 s per step) so that warmup + steps stay within a few minutes
-    cpu.rate(cores, seed=3)  # spin the pool up
-    rate_probe = cpu.rate(4 * cores, seed=5)
-    per_step = args.ref_batch or int(max(cores, min(200000, rate_probe * 4.0)))
-    for _ in range(args.warmup):
-        cpu.rate(per_step, seed=7)
-    t0 = time.perf_counter()
-    for k in range(args.steps):
-        cpu.rate(per_step, seed=11 + k)
-    dt = time.perf_counter() - t0
-    cpu.close()
-    value = per_step * args.steps / dt
     S = len(perms)
+    cores = os.cpu_count() or 1
+    # each step a bounded sample (~4 s) so that warmup + steps stay within a few minutes
+    res = run_reference_subprocess(cfg, cores, args.warmup, args.steps, args.ref_batch, 4.0,
+                                   timeout_s=120 + 30.0 * (args.warmup + args.steps))
+    if res is not None:
+        kind = 'reference'
+        per_step, dt = res['per_step'], res['seconds']
+        sample = ('%d steps x %d query geometries, unmodified reference GDMLPredict(use_torch=False).predict, bulk mode, '
+                  '%d worker processes (1 BLAS thread each), chunk_size %s; oracle vs reference on 4 queries: %.1e rel'
+                  % (args.steps, per_step, res['workers'], res['chunk_size'], res['oracle_vs_reference_rel']))
+    else:
+        kind = 'port'
+        model = oracle_random_model(cfg, perms)
+        cores = cpu_workers(cfg, S)
+        cpu = CpuPredictor(model, cfg, cores)
+        cpu.rate(cores, seed=3)  # spin the pool up
+        rate_probe = cpu.rate(4 * cores, seed=5)
+        per_step = args.ref_batch or int(max(cores, min(200000, rate_probe * 4.0)))
+        for _ in range(args.warmup):
+            cpu.rate(per_step, seed=7)
+        t0 = time.perf_counter()
+        for k in range(args.steps):
+            cpu.rate(per_step, seed=11 + k)
+        dt = time.perf_counter() - t0
+        cpu.close()
+        sample = '%d steps x %d query geometries, NumPy oracle port, process pool over all host threads (1 BLAS thread each)' % (args.steps, per_step)
+    value = per_step * args.steps / dt
     line = {
         'impl': 'reference',
         'metric': 'force_predictions_per_s',
@@ -264,8 +470,8 @@ def run_reference(args):
             'value': value,
             'unit': 'predictions/s',
             'cores': cores,
-            'kind': 'port',
-            'sample': '%d steps x %d query geometries, NumPy oracle port, process pool over all host threads (1 BLAS thread each)' % (args.steps, per_step),
+            'kind': kind,
+            'sample': sample,
         },
         'e2e': {'value': value, 'unit': 'predictions/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
@@ -477,24 +683,47 @@ def run_engine(args):
         }
         log('roofline probe done')
         if world == 1 and not args.no_cpu_baseline:
-            cores = cpu_workers(cfg, S)
-            cmodel = oracle_random_model(cfg, perms)
-            cpu = CpuPredictor(cmodel, cfg, cores)
-            cpu.rate(cores, seed=3)  # spin the pool up
-            rate_probe = cpu.rate(4 * cores, seed=5)
-            nq = int(max(cores, min(400000, rate_probe * args.cpu_seconds)))
-            log('cpu baseline: %d queries on %d threads (probe rate %.1f/s)' % (nq, cores, rate_probe))
-            rate = cpu.rate(nq)
-            cpu.close()
-            log('cpu baseline done: %.1f predictions/s' % rate)
-            cpu_baseline = {
-                'value': rate,
-                'unit': 'predictions/s',
-                'cores': cores,
-                'kind': 'port',
-                'sample': '%d query geometries of the same workload, NumPy oracle port of predict.py:84-245, process pool over all host threads (1 BLAS thread each)'
-                % nq,
-            }
+            cfg_named = dict(cfg)
+            all_cores = os.cpu_count() or 1
+            # the unmodified reference on all host threads when baseline/_ref is installed (one step of
+            # ~cpu_seconds), otherwise the oracle port
+            res = run_reference_subprocess(cfg_named, all_cores, 0, 1, None, args.cpu_seconds, timeout_s=120 + 4 * args.cpu_seconds)
+            if res is not None:
+                rate = res['per_step'] * res['steps'] / res['seconds']
+                log('cpu baseline (reference): %.1f predictions/s' % rate)
+                cpu_baseline = {
+                    'value': rate,
+                    'unit': 'predictions/s',
+                    'cores': all_cores,
+                    'kind': 'reference',
+                    'sample': '%d query geometries of the same workload, unmodified reference GDMLPredict(use_torch=False).predict in bulk mode, '
+                    '%d worker processes (1 BLAS thread each), chunk_size %s; oracle vs reference on 4 queries: %.1e rel'
+                    % (res['per_step'], res['workers'], res['chunk_size'], res['oracle_vs_reference_rel']),
+                }
+            else:
+                cores = cpu_workers(cfg, S)
+                cmodel = oracle_random_model(cfg, perms)
+                cpu = CpuPredictor(cmodel, cfg, cores)
+                cpu.rate(cores, seed=3)  # spin the pool up
+                rate_probe = cpu.rate(4 * cores, seed=5)
+                nq = int(max(cores, min(400000, rate_probe * args.cpu_seconds)))
+                log('cpu baseline: %d queries on %d threads (probe rate %.1f/s)' % (nq, cores, rate_probe))
+                rate = cpu.rate(nq)
+                cpu.close()
+                log('cpu baseline done: %.1f predictions/s' % rate)
+                cpu_baseline = {
+                    'value': rate,
+                    'unit': 'predictions/s',
+                    'cores': cores,
+                    'kind': 'port',
+                    'sample': '%d query geometries of the same workload, NumPy oracle port of predict.py:84-245, process pool over all host threads (1 BLAS thread each)'
+                    % nq,
+                }
+
+    if rank == 0 and world == 1 and train_info is not None and not args.no_cpu_baseline:
+        # the reference's own CPU training path beside it (bounded samples, extrapolated: SURVEY.md section 8d)
+        train_info['cpu_reference'] = reference_train_estimate(dict(cfg), os.cpu_count() or 1)
+        log('reference training estimate: %s' % (train_info['cpu_reference'],))
 
     if rank == 0:
         line = {
@@ -571,6 +800,12 @@ def fp64_peak_tflops(L):
 
 def main():
     args = parse_args()
+    if args.ref_worker is not None:
+        ref_worker_main(json.loads(args.ref_worker))
+        return
+    if args.ref_train_worker is not None:
+        ref_train_worker_main(json.loads(args.ref_train_worker))
+        return
     if args.workload in PREDICT_ONLY:
         args.no_train = True
         if args.batch == 65536:

@@ -85,18 +85,26 @@ def test_synth_generators_are_deterministic():
     assert abs(-(Ep[0] - E[0]) / h - F[0, 2, 1]) < 1e-4
 
 
-def test_bench_reference_arm_runs_on_cpu():
-    """`bench.py --impl reference` prints one JSON line with the contract's keys (tiny sample)."""
+@pytest.mark.parametrize('force_port', [False, True])
+def test_bench_reference_arm_runs_on_cpu(force_port):
+    """`bench.py --impl reference` prints one JSON line with the contract's keys (tiny sample): the
+    unmodified reference from baseline/_ref when it is installed, the oracle port otherwise."""
     import json
     import subprocess
     import sys
 
+    env = dict(os.environ)
+    if force_port:
+        env['SGDML_B200_NO_REFERENCE'] = '1'
     out = subprocess.check_output(
         [sys.executable, os.path.join(ROOT, 'bench.py'), '--impl', 'reference', '--workload', 'ethanol', '--n-train', '20',
          '--steps', '1', '--warmup', '0', '--ref-batch', '8'],
         text=True,
+        env=env,
     )
     line = json.loads(out.strip().splitlines()[-1])
     assert line['impl'] == 'reference' and line['value'] > 0
     for k in ('metric', 'unit', 'cpu_baseline', 'e2e', 'config', 'higher_is_better'):
         assert k in line
+    have_ref = os.path.isfile(os.path.join(ROOT, 'baseline', '_ref', 'sgdml', 'predict.py'))
+    assert line['cpu_baseline']['kind'] == ('reference' if have_ref and not force_port else 'port')
