@@ -310,13 +310,14 @@ def ref_train_worker_main(spec):
         tril_perms_lin = (tril_perms + np.arange(len(perms))[:, None] * desc.dim).flatten('F')
         gdml = GDMLTrain(max_processes=cores, use_torch=False)
         k, t = 1, 0.0
+        k_max = max(1, min(M, int(4e9 / (8.0 * 3 * N * M * 3 * N))))  # the host copy of the sampled columns stays below 4 GB
         while True:  # grow the sample until it takes a few seconds
             t0 = time.perf_counter()
             gdml._assemble_kernel_mat(R_desc, R_d_desc, tril_perms_lin, cfg['sig'], desc, col_idxs=np.s_[: k * 3 * N])
             t = time.perf_counter() - t0
-            if t >= float(spec['seconds']) or k >= M:
+            if t >= float(spec['seconds']) or k >= k_max:
                 break
-            k = min(M, max(k + 1, int(k * min(8.0, 1.3 * float(spec['seconds']) / max(t, 1e-3)))))
+            k = min(k_max, max(k + 1, int(k * min(8.0, 1.3 * float(spec['seconds']) / max(t, 1e-3)))))
         print(json.dumps({'col_points': k, 'seconds': t, 'desc_seconds': t_desc, 'workers': cores}))
     else:
         import scipy.linalg

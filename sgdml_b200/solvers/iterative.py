@@ -18,7 +18,6 @@ The O(n) vector updates of CG stay on the host (NumPy), like SciPy's `cg` in the
 import collections
 import logging
 import timeit
-from functools import partial
 
 import numpy as np
 
