@@ -7,6 +7,8 @@ GPU box):
 
     cp -r /root/reference/sgdml baseline/_ref/          # writable copy (predict.py:1046-1074)
     PYTHONPATH=baseline/_ref:. python tests/golden/make_golden.py
+    PYTHONPATH=baseline/_ref:. python tests/golden/make_golden.py iterative
+    PYTHONPATH=baseline/_ref:. python tests/golden/make_golden.py c60
 
 Each fixture holds the inputs (geometries, labels, perms, sig, lam, query geometries) and
 the reference outputs of every hot-path stage: tril_perms_lin (Desc.perm / train.py:897-904),
@@ -167,8 +169,60 @@ def main_iterative():
              model['solver_tol'] * model['norm_y_train'], os.path.getsize(out) / 1024))
 
 
+def main_c60():
+    """BASELINE config 5 shape at reduced M: buckyball C60 (60 atoms, D = 1770) with the 120 permutations of
+    I_h.  One block column of K and predictions of a model with random (not trained: K is numerically
+    singular at this symmetry) coefficients -- pins the large-molecule assembly and the large-descriptor
+    predictor to the reference."""
+    N, M, sig = 60, 2, 50
+    r0 = synth.c60_geometry()
+    perms = synth.icosahedral_group(r0)
+    task = synth.make_task(N, M, perms, sig, r0=r0)
+    desc = Desc(N, max_processes=1)
+    tril_perms = np.array([Desc.perm(p) for p in perms])
+    tril_perms_lin = (tril_perms + np.arange(len(perms))[:, None] * desc.dim).flatten('F')
+    R = task['R_train'].reshape(M, -1)
+    R_desc, R_d_desc = desc.from_R(R, max_processes=1)
+    gdml_train = GDMLTrain(max_processes=1, use_torch=False)
+    K_cols = gdml_train._assemble_kernel_mat(R_desc, R_d_desc, tril_perms_lin, sig, desc, col_idxs=np.arange(3 * N, 6 * N))  # index-list mode (train.py:1376-1407)
+    rng = np.random.default_rng(11)
+    alphas_F = rng.standard_normal(M * 3 * N)
+    model = gdml_train.create_model(task, 'analytic', R_desc, R_d_desc, tril_perms_lin, 1.7, alphas_F)
+    model['c'] = -3.25
+    predictor = GDMLPredict(model, max_processes=1, use_torch=False)
+    R_query = synth.geometries(N, 3, 1, r0=r0).reshape(3, -1)
+    E_q, F_q = predictor.predict(R_query)
+    out = os.path.join(HERE, 'big_c60_m2_s120.npz')
+    np.savez_compressed(
+        out,
+        reference_version=sgdml.__version__,
+        n_atoms=N,
+        perms=perms,
+        sig=sig,
+        lam=task['lam'],
+        z=task['z'],
+        R_train=task['R_train'],
+        tril_perms_lin=tril_perms_lin.astype(np.int64),
+        R_desc=R_desc,
+        R_d_desc=R_d_desc,
+        K_cols=K_cols,
+        col_start=3 * N,
+        alphas_F=alphas_F,
+        R_d_desc_alpha=model['R_d_desc_alpha'],
+        model_R_desc=model['R_desc'],
+        std=model['std'],
+        c=model['c'],
+        R_query=R_query,
+        E_query=E_q,
+        F_query=F_q,
+    )
+    print('big_c60_m2_s120: K_cols', K_cols.shape, 'size %.0f KB' % (os.path.getsize(out) / 1024))
+
+
 if __name__ == '__main__':
-    if len(sys.argv) > 1 and sys.argv[1] == 'iterative':
+    if len(sys.argv) > 1 and sys.argv[1] == 'c60':
+        main_c60()
+    elif len(sys.argv) > 1 and sys.argv[1] == 'iterative':
         main_iterative()   # separate process: the reference allows one GDMLTrain instance (train.py:336-342)
     else:
         main()

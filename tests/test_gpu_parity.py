@@ -7,7 +7,7 @@ import pytest
 
 pytestmark = pytest.mark.gpu
 
-from conftest import golden_model, golden_task, rel_err  # noqa: E402
+from conftest import golden_model, golden_task, load_golden, rel_err  # noqa: E402
 
 import oracle  # noqa: E402,F401
 from oracle import assemble as oassemble  # noqa: E402
@@ -349,6 +349,24 @@ def test_c60_icosahedral_config(eng):
     E_ref, F_ref = opredict.Predictor(model).predict(Rq)
     E, F = eng.GDMLPredict(model).predict(Rq)
     assert rel_err(F, F_ref) < 1e-9 and rel_err(E, E_ref) < 1e-9
+
+
+def test_c60_reference_fixture(eng):
+    """The engine against the reference's own C60 / I_h outputs (tests/golden/big_c60_m2_s120.npz):
+    k_assemble_large and the GEMM-composed large-descriptor predictor."""
+    from sgdml_b200.desc import Desc
+
+    g = load_golden('big_c60_m2_s120')
+    N = int(g['n_atoms'])
+    assert np.array_equal(eng.desc.tril_perms_lin(g['perms']), g['tril_perms_lin'])
+    x, gd = Desc(N).from_R(g['R_train'].reshape(len(g['R_train']), -1))
+    assert rel_err(x, g['R_desc']) < 1e-13 and rel_err(gd, g['R_d_desc']) < 1e-13
+    c0 = int(g['col_start'])
+    cols = np.arange(c0, c0 + 3 * N)
+    K = eng.GDMLTrain()._assemble_kernel_mat(g['R_desc'], g['R_d_desc'], g['tril_perms_lin'], int(g['sig']), Desc(N), col_idxs=cols)
+    assert rel_err(K, g['K_cols']) < 1e-11
+    E, F = eng.GDMLPredict(golden_model(g)).predict(g['R_query'])
+    assert rel_err(F, g['F_query']) < 1e-9 and rel_err(E, g['E_query']) < 1e-9
 
 
 # --------------------------------------------------------------------------- dense solve
