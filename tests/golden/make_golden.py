@@ -9,6 +9,7 @@ GPU box):
     PYTHONPATH=baseline/_ref:. python tests/golden/make_golden.py
     PYTHONPATH=baseline/_ref:. python tests/golden/make_golden.py iterative
     PYTHONPATH=baseline/_ref:. python tests/golden/make_golden.py c60
+    PYTHONPATH=baseline/_ref:. python tests/golden/make_golden.py n100
 
 Each fixture holds the inputs (geometries, labels, perms, sig, lam, query geometries) and
 the reference outputs of every hot-path stage: tril_perms_lin (Desc.perm / train.py:897-904),
@@ -219,8 +220,59 @@ def main_c60():
     print('big_c60_m2_s120: K_cols', K_cols.shape, 'size %.0f KB' % (os.path.getsize(out) / 1024))
 
 
+def main_n100():
+    """BASELINE config 4 shape at reduced M: synthetic 100-atom molecule (D = 4950), S = 12 (one rotor, two
+    swaps).  Every 5th column of the second block column of K (index-list mode) and predictions of a
+    random-coefficient model."""
+    N, M, sig = 100, 2, 50
+    perms = synth.rotor_swap_group(N, 1, 2)
+    task = synth.make_task(N, M, perms, sig)
+    desc = Desc(N, max_processes=1)
+    tril_perms = np.array([Desc.perm(p) for p in perms])
+    tril_perms_lin = (tril_perms + np.arange(len(perms))[:, None] * desc.dim).flatten('F')
+    R = task['R_train'].reshape(M, -1)
+    R_desc, R_d_desc = desc.from_R(R, max_processes=1)
+    gdml_train = GDMLTrain(max_processes=1, use_torch=False)
+    cols = np.arange(3 * N, 6 * N, 5)
+    K_cols = gdml_train._assemble_kernel_mat(R_desc, R_d_desc, tril_perms_lin, sig, desc, col_idxs=cols)
+    rng = np.random.default_rng(12)
+    alphas_F = rng.standard_normal(M * 3 * N)
+    model = gdml_train.create_model(task, 'analytic', R_desc, R_d_desc, tril_perms_lin, 0.6, alphas_F)
+    model['c'] = 12.5
+    predictor = GDMLPredict(model, max_processes=1, use_torch=False)
+    R_query = synth.geometries(N, 3, 1).reshape(3, -1)
+    E_q, F_q = predictor.predict(R_query)
+    out = os.path.join(HERE, 'big_n100_m2_s12.npz')
+    np.savez_compressed(
+        out,
+        reference_version=sgdml.__version__,
+        n_atoms=N,
+        perms=perms,
+        sig=sig,
+        lam=task['lam'],
+        z=task['z'],
+        R_train=task['R_train'],
+        tril_perms_lin=tril_perms_lin.astype(np.int64),
+        R_desc=R_desc,
+        R_d_desc=R_d_desc,
+        K_cols=K_cols,
+        cols=cols,
+        alphas_F=alphas_F,
+        R_d_desc_alpha=model['R_d_desc_alpha'],
+        model_R_desc=model['R_desc'],
+        std=model['std'],
+        c=model['c'],
+        R_query=R_query,
+        E_query=E_q,
+        F_query=F_q,
+    )
+    print('big_n100_m2_s12: K_cols', K_cols.shape, 'size %.0f KB' % (os.path.getsize(out) / 1024))
+
+
 if __name__ == '__main__':
-    if len(sys.argv) > 1 and sys.argv[1] == 'c60':
+    if len(sys.argv) > 1 and sys.argv[1] == 'n100':
+        main_n100()
+    elif len(sys.argv) > 1 and sys.argv[1] == 'c60':
         main_c60()
     elif len(sys.argv) > 1 and sys.argv[1] == 'iterative':
         main_iterative()   # separate process: the reference allows one GDMLTrain instance (train.py:336-342)

@@ -369,6 +369,23 @@ def test_c60_reference_fixture(eng):
     assert rel_err(F, g['F_query']) < 1e-9 and rel_err(E, g['E_query']) < 1e-9
 
 
+def test_n100_reference_fixture(eng):
+    """The engine against the reference's own outputs for a 100-atom molecule (config 4 shape,
+    tests/golden/big_n100_m2_s12.npz): k_assemble_large with an index-list column subset and the
+    GEMM-composed predictor at D = 4950."""
+    from sgdml_b200.desc import Desc
+
+    g = load_golden('big_n100_m2_s12')
+    N = int(g['n_atoms'])
+    assert np.array_equal(eng.desc.tril_perms_lin(g['perms']), g['tril_perms_lin'])
+    x, gd = Desc(N).from_R(g['R_train'].reshape(len(g['R_train']), -1))
+    assert rel_err(x, g['R_desc']) < 1e-13 and rel_err(gd, g['R_d_desc']) < 1e-13
+    K = eng.GDMLTrain()._assemble_kernel_mat(g['R_desc'], g['R_d_desc'], g['tril_perms_lin'], int(g['sig']), Desc(N), col_idxs=g['cols'])
+    assert rel_err(K, g['K_cols']) < 1e-11
+    E, F = eng.GDMLPredict(golden_model(g)).predict(g['R_query'])
+    assert rel_err(F, g['F_query']) < 1e-9 and rel_err(E, g['E_query']) < 1e-9
+
+
 # --------------------------------------------------------------------------- dense solve
 @pytest.mark.parametrize('variant', [0, 1, 2, 3])
 @pytest.mark.parametrize('m,n,k', [(128, 128, 128), (300, 200, 64), (257, 129, 130), (64, 1000, 16), (33, 17, 7)])
