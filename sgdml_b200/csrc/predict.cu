@@ -927,7 +927,15 @@ int run_queries(sgdml_b200_model* m, int slot, const double* xq, const double* g
   }
   {
     ProfScope ps(KID_PREDICT_AUX, s);
-    k_predict_finish<<<(unsigned)n_geo, 128, sizeof(double) * m->D, s>>>(w.G, w.Erow, gq, m->perm, m->N, m->D, m->DP,
+    const size_t fd_bytes = sizeof(double) * (size_t)m->D;
+    if (fd_bytes > 48 * 1024) {  // molecules above 111 atoms: opt in to more than the default dynamic shared memory
+      if (fd_bytes > 200 * 1024) {
+        set_last_error("sgdml_b200_predict: descriptor too long for the finishing kernel (n_atoms <= ~225 supported)");
+        return SGDML_B200_ERR_UNSUPPORTED;
+      }
+      SG_CUDA(cudaFuncSetAttribute(k_predict_finish, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fd_bytes));
+    }
+    k_predict_finish<<<(unsigned)n_geo, 128, fd_bytes, s>>>(w.G, w.Erow, gq, m->perm, m->N, m->D, m->DP,
                                                                           m->S, std, c, n_splits, n_rows_pad, E_dev,
                                                                           F_dev);
     SG_CUDA(cudaGetLastError());
