@@ -1,0 +1,70 @@
+"""Bring-up harness for the tcgen05 FP64-via-INT8 GEMM (csrc/ozaki.cu): against NumPy FP64 and against an
+exact NumPy model of the slicing.  GPU only."""
+
+import numpy as np
+import pytest
+
+from conftest import rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+def _run(m, n, k, S, tri=False, alpha=1.0, seed=0, scale_rows=False):
+    import torch
+
+    from sgdml_b200 import _lib
+
+    _lib.require_gpu()
+    rng = np.random.default_rng(seed)
+    A = rng.standard_normal((m, k))
+    B = A if tri else rng.standard_normal((n, k))
+    if scale_rows:  # rows of very different magnitude: the per-row exponents matter
+        A = A * np.exp2(rng.integers(-20, 20, size=(m, 1)).astype(np.float64))
+        if not tri:
+            B = B * np.exp2(rng.integers(-20, 20, size=(n, 1)).astype(np.float64))
+        else:
+            B = A
+    C0 = rng.standard_normal((m, n))
+    Ad = torch.from_numpy(A).cuda()
+    Bd = Ad if tri else torch.from_numpy(B).cuda()
+    Cd = torch.from_numpy(C0).cuda()
+    _lib.check(
+        _lib.lib().sgdml_b200_ozaki_gemm_nt(
+            m, n, k, float(alpha), Ad.data_ptr(), k, Bd.data_ptr(), k, Cd.data_ptr(), n, S, 1 if tri else 0, _lib.current_stream()
+        ),
+        'ozaki_gemm_nt',
+    )
+    torch.cuda.synchronize()
+    return A, B, C0, Cd.cpu().numpy()
+
+
+def _scale(A, B):
+    return np.abs(A) @ np.abs(B).T  # componentwise error bound of a dot product
+
+
+@pytest.mark.parametrize('m,n,k', [(128, 64, 128), (128, 64, 256), (256, 128, 128), (300, 200, 130), (129, 65, 1000), (64, 8, 40)])
+def test_ozaki_gemm_matches_fp64(m, n, k):
+    A, B, C0, C = _run(m, n, k, 7)
+    ref = C0 + A @ B.T
+    assert np.max(np.abs(C - ref) / (_scale(A, B) + 1e-300)) < 1e-12
+
+
+def test_ozaki_gemm_row_scaling_and_alpha():
+    A, B, C0, C = _run(200, 136, 384, 7, alpha=-1.0, scale_rows=True, seed=3)
+    ref = C0 - A @ B.T
+    assert np.max(np.abs(C - ref) / (_scale(A, B) + np.abs(C0) + 1e-300)) < 1e-12
+
+
+def test_ozaki_gemm_tri():
+    A, B, C0, C = _run(384, 384, 256, 7, tri=True, alpha=-1.0, seed=5)
+    ref = C0 - A @ A.T
+    il = np.tril_indices(384)
+    assert np.max(np.abs(C[il] - ref[il]) / (_scale(A, A)[il] + 1e-300)) < 1e-12
+
+
+@pytest.mark.parametrize('S', [4, 5, 6, 7])
+def test_ozaki_gemm_slice_count(S):
+    """The error falls by 2^-7 per slice (tools/ozaki_study.py: 7e-8, 1e-10, 4e-12, 2e-14 for S = 4..7)."""
+    A, B, C0, C = _run(256, 192, 512, S, seed=7)
+    err = rel_err(C - C0, A @ B.T)
+    assert err < 4.0 * 2.0 ** (-7 * S + 4)
