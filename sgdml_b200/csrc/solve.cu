@@ -864,6 +864,8 @@ int potrf_device(double* A, int64_t n, int64_t lda, int* info_host, cudaStream_t
   // environment switch (SGDML_B200_LOOKAHEAD=1) until the trailing GEMM is made persistent on a subset of SMs.
   const char* la = getenv("SGDML_B200_LOOKAHEAD");
   const bool lookahead = (la && la[0] == '1') && (n > 2 * (int64_t)NBO) && !profiling_enabled();
+  const char* oz = getenv("SGDML_B200_OZAKI_SLICES");  // 0 / unset: FP64 DMMA trailing updates (default)
+  const int oz_slices = (oz != nullptr) ? std::max(0, std::min(7, atoi(oz))) : 0;
   auto cleanup = [&]() {
     cudaFree(d_info);
     cudaFree(W[0]);
@@ -945,6 +947,13 @@ int potrf_device(double* A, int64_t n, int64_t lda, int* info_host, cudaStream_t
       g.mode = 1;
       g.abort_flag = d_info;
       if (!lookahead) {
+        if (oz_slices > 0) {
+          // EXPERIMENTAL (csrc/ozaki.cu, not validated on hardware yet): the trailing update on the tcgen05
+          // tensor cores, C -= X X^T through exact int8 slice products
+          const double* X = A + K1 * lda + K0;
+          SG_TRY(ozaki_gemm_nt_device(rem, rem, K1 - K0, -1.0, X, lda, X, lda, A + K1 * lda + K1, lda, oz_slices, 1, s));
+          continue;
+        }
         g.m = rem;
         g.n = rem;
         g.A = Wc + K1 * NBO;  // -X, all panels of the outer block

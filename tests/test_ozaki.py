@@ -68,3 +68,27 @@ def test_ozaki_gemm_slice_count(S):
     A, B, C0, C = _run(256, 192, 512, S, seed=7)
     err = rel_err(C - C0, A @ B.T)
     assert err < 4.0 * 2.0 ** (-7 * S + 4)
+
+
+def test_potrf_with_int8_trailing_updates(monkeypatch):
+    """Cholesky with the trailing updates on the tcgen05 int8 path (SGDML_B200_OZAKI_SLICES=7) against the
+    FP64 DMMA factorisation of the same matrix."""
+    import torch
+
+    from sgdml_b200 import _lib
+
+    _lib.require_gpu()
+    n = 3000
+    rng = np.random.default_rng(1)
+    G = rng.standard_normal((n, n // 4))
+    A = G @ G.T + 1e-3 * np.eye(n)  # condition ~1e6
+    outs = {}
+    for mode in ('0', '7'):
+        monkeypatch.setenv('SGDML_B200_OZAKI_SLICES', mode)
+        Ad = torch.from_numpy(A.copy()).cuda()
+        _lib.check(_lib.lib().sgdml_b200_potrf(Ad.data_ptr(), n, n, _lib.current_stream()), 'potrf')
+        torch.cuda.synchronize()
+        outs[mode] = np.tril(Ad.cpu().numpy())
+    L0, L7 = outs['0'], outs['7']
+    assert rel_err(L7 @ L7.T, A) < 1e-12
+    assert rel_err(L7, L0) < 1e-9
