@@ -126,5 +126,70 @@ def main():
               % (s, s * (s + 1) // 2, gerr, rel(al, al_ref), rel(F, F_ref), resid))
 
 
-if __name__ == '__main__':
+if __name__ == '__main__' and not (len(sys.argv) > 1 and sys.argv[1] == 'predict'):
     main()
+
+
+# ---------------------------------------------------------------------------------------------
+# Second question: how many slices does the PREDICTOR need?  (python tools/ozaki_study.py predict)
+def predict_gemm_form(model, R, gemm):
+    """GEMM form of predict.py:199-217 as the engine evaluates it (permutations applied to the query:
+    q_p[e] = x[pinv_p[e]]; descriptors centred by their column mean), with a pluggable A B^T."""
+    N = len(model['z'])
+    sig = float(model['sig'])
+    S = len(np.asarray(model['perms']))
+    D = N * (N - 1) // 2
+    lin = np.asarray(model['tril_perms_lin']).reshape(D, S)  # lin[d*S + p] = perm_p[d] + p*D
+    perm = (lin - np.arange(S)[None, :] * D).T  # (S, D): perm_p[d]
+    pinv = np.argsort(perm, axis=1)
+    X = np.asarray(model['R_desc']).T  # (M, D)
+    JA = np.asarray(model['R_d_desc_alpha'])
+    mu = X.mean(axis=0)
+    Xc = X - mu
+    xja = np.einsum('md,md->m', Xc, JA)
+    mm = np.einsum('md,md->m', Xc, Xc)
+    xq, gq = odesc.from_R(R)
+    B = len(R)
+    Q = np.stack([xq[b][pinv[p]] - mu for b in range(B) for p in range(S)])  # (B*S, D)
+    qq = np.einsum('rd,rd->r', Q, Q)
+    S1 = gemm(Q, Xc)
+    S2 = gemm(Q, JA)
+    n = np.sqrt(np.maximum(5.0 * (qq[:, None] + mm[None, :] - 2.0 * S1), 0.0))
+    a = S2 - xja[None, :]
+    e = np.exp(-n / sig)
+    c1 = 25.0 / (3 * sig**4) * e * a
+    c2 = 5.0 / (3 * sig**3) * (n + sig) * e
+    G = c1.sum(axis=1)[:, None] * Q - gemm(c1, np.ascontiguousarray(Xc.T)) - gemm(c2, np.ascontiguousarray(JA.T))
+    fd = np.zeros((B, D))
+    for b in range(B):
+        for p in range(S):
+            fd[b] += G[b * S + p][perm[p]]
+    return odesc.vec_dot_d_desc(gq, fd) * float(model['std'])
+
+
+def main_predict():
+    N, M = 21, 100
+    perms = synth.rotor_swap_group(N, 1, 1)
+    model = None
+    from sgdml_b200 import synth as _s
+
+    task = _s.make_task(N, M, perms, 20)
+    R = task['R_train'].reshape(M, -1)
+    x, g = odesc.from_R(R)
+    lin = odesc.tril_perms_lin(perms)
+    rng = np.random.default_rng(3)
+    alphas = rng.standard_normal(M * 3 * N)
+    model = {'type': 'm', 'z': task['z'], 'R_desc': x.T, 'R_d_desc_alpha': odesc.d_desc_dot_vec(g, alphas.reshape(M, -1)),
+             'alphas_F': alphas, 'c': 0.0, 'std': 1.0, 'sig': 20, 'lam': 1e-10, 'perms': perms, 'tril_perms_lin': lin,
+             'use_E': True}
+    Rq = _s.geometries(N, 6, 1).reshape(6, -1)
+    F_ref = opredict.Predictor(model).predict(Rq)[1]
+    F64 = predict_gemm_form(model, Rq, lambda A, B: A @ B.T)
+    print('GEMM form in FP64 vs direct form: %.2e' % (np.max(np.abs(F64 - F_ref)) / np.max(np.abs(F_ref))))
+    for s in (3, 4, 5, 6, 7):
+        F = predict_gemm_form(model, Rq, lambda A, B, s=s: ozaki_gemm_nt(A, B, s))
+        print('S = %d (%2d int8 GEMMs): forces vs FP64 %.2e' % (s, s * (s + 1) // 2, np.max(np.abs(F - F_ref)) / np.max(np.abs(F_ref))))
+
+
+if __name__ == '__main__' and len(sys.argv) > 1 and sys.argv[1] == 'predict':
+    main_predict()
