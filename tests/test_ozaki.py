@@ -92,3 +92,21 @@ def test_potrf_with_int8_trailing_updates(monkeypatch):
     L0, L7 = outs['0'], outs['7']
     assert rel_err(L7 @ L7.T, A) < 1e-12
     assert rel_err(L7, L0) < 1e-9
+
+
+def test_large_descriptor_predictor_on_int8_path(monkeypatch):
+    """GEMM-composed predictor (D > 256) with its four contractions on the tcgen05 int8 path, 4 and 5
+    slices: forces against the oracle (tools/ozaki_study.py predict: 8.8e-9 / 6.5e-11)."""
+    import sgdml_b200
+    from oracle import predict as opredict
+    from sgdml_b200 import synth
+
+    N, M = 30, 40
+    perms = synth.rotor_swap_group(N, 1, 1)
+    model = synth.random_model(N, M, perms, 30, seed=2)
+    Rq = synth.geometries(N, 9, 1).reshape(9, -1)
+    E_ref, F_ref = opredict.Predictor(model).predict(Rq)
+    for S, tol in ((4, 1e-6), (5, 1e-8), (7, 1e-11)):
+        monkeypatch.setenv('SGDML_B200_OZAKI_PREDICT_SLICES', str(S))
+        E, F = sgdml_b200.GDMLPredict(model).predict(Rq)
+        assert rel_err(F, F_ref) < tol and rel_err(E, E_ref) < tol
