@@ -348,69 +348,104 @@ struct OzOperand {
   int64_t rows_pad = 0, kp = 0;
 };
 
-static int oz_split(const double* X, int64_t rows, int64_t k, int64_t ldx, int S, int pad_rows_to, OzOperand* o,
-                    cudaStream_t s) {
-  o->rows_pad = (rows + pad_rows_to - 1) / pad_rows_to * pad_rows_to;
+static size_t oz_plane_bytes(int64_t rows, int64_t k, int S) {
+  const int64_t rows_pad = (rows + OZ_BM - 1) / OZ_BM * OZ_BM, kp = (k + OZ_BK - 1) / OZ_BK * OZ_BK;
+  return (size_t)S * rows_pad * kp;
+}
+
+// slices X (rows x k) into caller-provided device memory
+static int oz_split_into(const double* X, int64_t rows, int64_t k, int64_t ldx, int S, int8_t* planes, int* exps,
+                         OzOperand* o, cudaStream_t s) {
+  o->rows_pad = (rows + OZ_BM - 1) / OZ_BM * OZ_BM;
   o->kp = (k + OZ_BK - 1) / OZ_BK * OZ_BK;
-  SG_CUDA(cudaMalloc(&o->planes, (size_t)S * o->rows_pad * o->kp));
-  SG_CUDA(cudaMalloc(&o->exps, sizeof(int) * (size_t)o->rows_pad));
+  o->planes = planes;
+  o->exps = exps;
   k_ozaki_split<<<ceil_div(o->rows_pad, 8), 256, 0, s>>>(X, rows, k, ldx, S, o->rows_pad, o->kp, o->planes, o->exps);
   SG_CUDA(cudaGetLastError());
   count_launch(KID_GEMM);
   return 0;
 }
 
+static int oz_launch(const OzOperand& oa, const OzOperand& ob, int64_t m, int64_t n, double alpha, double* C,
+                     int64_t ldc, int S, int tri, cudaStream_t s) {
+  CUtensorMap tmA, tmB;
+  SG_TRY(oz_make_map(&tmA, oa.planes, S, oa.rows_pad, oa.kp, OZ_BM));
+  SG_TRY(oz_make_map(&tmB, ob.planes, S, ob.rows_pad, ob.kp, OZ_BN));
+  static bool configured[64] = {false};
+  int dev = 0;
+  SG_CUDA(cudaGetDevice(&dev));
+  if (dev >= 0 && dev < 64 && !configured[dev]) {
+    SG_CUDA(cudaFuncSetAttribute(k_ozaki_gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)OZ_SMEM_BYTES));
+    configured[dev] = true;
+  }
+  OzArgs a;
+  a.m = m;
+  a.n = n;
+  a.kp = oa.kp;
+  a.S = S;
+  a.tri = tri;
+  a.alpha = alpha;
+  a.ea = oa.exps;
+  a.eb = ob.exps;
+  a.C = C;
+  a.ldc = ldc;
+  dim3 grid((unsigned)ceil_div(n, OZ_BN), (unsigned)ceil_div(m, OZ_BM));
+  SG_ARG(grid.y <= 65535);
+  ProfScope ps(KID_GEMM, s);
+  k_ozaki_gemm<<<grid, 192, OZ_SMEM_BYTES, s>>>(tmA, tmB, a);
+  SG_CUDA(cudaGetLastError());
+  count_launch(KID_GEMM);
+  return 0;
+}
+
+// Workspace of the symmetric update used by potrf: allocated once per factorisation (a cudaMalloc /
+// cudaFree pair costs ~20 ms in a process that holds tens of GB -- see csrc/core.cu), reused by every
+// outer step, no host synchronisation in between.
+int ozaki_syrk_workspace_bytes(int64_t max_rows, int64_t max_k, int S, size_t* plane_bytes, size_t* exp_bytes) {
+  *plane_bytes = oz_plane_bytes(max_rows, max_k, S);
+  *exp_bytes = sizeof(int) * (size_t)((max_rows + OZ_BM - 1) / OZ_BM * OZ_BM);
+  return 0;
+}
+
+// C (n x n, lower-triangle tiles) += alpha X X^T with X (n x k): stream-ordered, no allocation
+int ozaki_syrk_device(int64_t n, int64_t k, double alpha, const double* X, int64_t ldx, double* C, int64_t ldc, int S,
+                      int8_t* planes, int* exps, cudaStream_t s) {
+  SG_ARG(S >= 2 && S <= OZ_MAX_S && n >= 1 && k >= 1 && k <= (1 << 14));
+  OzOperand o;
+  SG_TRY(oz_split_into(X, n, k, ldx, S, planes, exps, &o, s));
+  return oz_launch(o, o, n, n, alpha, C, ldc, S, 1, s);
+}
+
 // C (m x n, ldc) += alpha * A (m x k, lda) * B (n x k, ldb)^T through S int8 slices per operand.
 // tri != 0: m == n and only tiles touching the lower triangle are updated.  All pointers on the device.
+// Self-contained form (allocates and frees its slice planes, synchronises the stream): tests and the
+// predictor experiment; the Cholesky uses ozaki_syrk_device.
 int ozaki_gemm_nt_device(int64_t m, int64_t n, int64_t k, double alpha, const double* A, int64_t lda, const double* B,
                          int64_t ldb, double* C, int64_t ldc, int S, int tri, cudaStream_t s) {
   SG_ARG(S >= 2 && S <= OZ_MAX_S && m >= 1 && n >= 1 && k >= 1);
   SG_ARG(k <= (1 << 14));  // int32 accumulation stays exact: 64^2 * k * S < 2^31
-  OzOperand oa, ob;
   const bool same = (A == B && m == n && lda == ldb);
+  int8_t *pa = nullptr, *pb = nullptr;
+  int *xa = nullptr, *xb = nullptr;
   auto cleanup = [&]() {
-    cudaFree(oa.planes);
-    cudaFree(oa.exps);
-    if (!same) {
-      cudaFree(ob.planes);
-      cudaFree(ob.exps);
-    }
+    cudaFree(pa);
+    cudaFree(xa);
+    cudaFree(pb);
+    cudaFree(xb);
   };
   auto body = [&]() -> int {
-    SG_TRY(oz_split(A, m, k, lda, S, OZ_BM, &oa, s));
-    if (same)
+    OzOperand oa, ob;
+    SG_CUDA(cudaMalloc(&pa, oz_plane_bytes(m, k, S)));
+    SG_CUDA(cudaMalloc(&xa, sizeof(int) * (size_t)((m + OZ_BM - 1) / OZ_BM * OZ_BM)));
+    SG_TRY(oz_split_into(A, m, k, lda, S, pa, xa, &oa, s));
+    if (same) {
       ob = oa;
-    else
-      SG_TRY(oz_split(B, n, k, ldb, S, OZ_BM, &ob, s));
-    CUtensorMap tmA, tmB;
-    SG_TRY(oz_make_map(&tmA, oa.planes, S, oa.rows_pad, oa.kp, OZ_BM));
-    SG_TRY(oz_make_map(&tmB, ob.planes, S, ob.rows_pad, ob.kp, OZ_BN));
-    static bool configured[64] = {false};
-    int dev = 0;
-    SG_CUDA(cudaGetDevice(&dev));
-    if (dev >= 0 && dev < 64 && !configured[dev]) {
-      SG_CUDA(cudaFuncSetAttribute(k_ozaki_gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)OZ_SMEM_BYTES));
-      configured[dev] = true;
+    } else {
+      SG_CUDA(cudaMalloc(&pb, oz_plane_bytes(n, k, S)));
+      SG_CUDA(cudaMalloc(&xb, sizeof(int) * (size_t)((n + OZ_BM - 1) / OZ_BM * OZ_BM)));
+      SG_TRY(oz_split_into(B, n, k, ldb, S, pb, xb, &ob, s));
     }
-    OzArgs a;
-    a.m = m;
-    a.n = n;
-    a.kp = oa.kp;
-    a.S = S;
-    a.tri = tri;
-    a.alpha = alpha;
-    a.ea = oa.exps;
-    a.eb = ob.exps;
-    a.C = C;
-    a.ldc = ldc;
-    dim3 grid((unsigned)ceil_div(n, OZ_BN), (unsigned)ceil_div(m, OZ_BM));
-    SG_ARG(grid.y <= 65535);
-    {
-      ProfScope ps(KID_GEMM, s);
-      k_ozaki_gemm<<<grid, 192, OZ_SMEM_BYTES, s>>>(tmA, tmB, a);
-      SG_CUDA(cudaGetLastError());
-      count_launch(KID_GEMM);
-    }
+    SG_TRY(oz_launch(oa, ob, m, n, alpha, C, ldc, S, tri, s));
     SG_CUDA(cudaStreamSynchronize(s));  // the planes are freed below
     return 0;
   };
