@@ -13,9 +13,10 @@
 // forces agree with the FP64 factorisation to 2e-11 at cond(K) = 2e10; S = 8 is FP64-equivalent.
 //
 // Kernel structure (one CTA per 128 x 64 tile of C, 192 threads, warp-specialised):
-//   warp 0   TMA producer: 3-D tensor maps over the slice planes [S][rows][k] (int8, K-major, 128-byte
-//            swizzle); a pipeline UNIT is one slice p of one 128-wide k-block: A^(p) 128x128 B (16 KB)
-//            + B^(p) 64x128 B (8 KB); units travel through a ring of S + 2 slots with full/empty mbarriers
+//   warp 0   TMA producer: 3-D tensor maps over the slice planes [S][rows][k] (int8, K-major, swizzled);
+//            a pipeline UNIT is one slice p of one BK-wide k-block (BK = 64: A^(p) 128x64 B = 8 KB +
+//            B^(p) 64x64 B = 4 KB); units travel through a ring of up to 18 slots (216 KB, more than two
+//            k-blocks of all 7 slices) with full/empty mbarriers
 //   warp 1   MMA issuer (one elected lane): per k-block the pairs are issued in groups r = 1, 2, ...
 //            (all pairs with min(p, q) = r), after which slices r and S + 1 - r are dead and their
 //            slots are handed back with tcgen05.commit -- the same order the producer refills them in
@@ -34,13 +35,25 @@ namespace sgdml {
 
 constexpr int OZ_BITS = 7;
 constexpr int OZ_MAX_S = 7;
-constexpr int OZ_BM = 128, OZ_BN = 64, OZ_BK = 128;       // BK in int8 elements = bytes = one swizzle row
-constexpr int OZ_A_BYTES = OZ_BM * OZ_BK;                  // 16 KB
-constexpr int OZ_B_BYTES = OZ_BN * OZ_BK;                  //  8 KB
-constexpr int OZ_UNIT_BYTES = OZ_A_BYTES + OZ_B_BYTES;     // 24 KB (both parts 1024-byte aligned)
-constexpr int OZ_MAX_RING = OZ_MAX_S + 2;
+constexpr int OZ_BM = 128, OZ_BN = 64;
+constexpr int OZ_KPAD = 128;                               // the contraction length is padded to a multiple of this
+// BK = bytes (= int8 elements) of k per pipeline unit = width of one swizzle row.  64 (64-byte swizzle) is the
+// default: a unit is 12 KB, the ring holds 18 of them = two and a half k-blocks of all 7 slices, so the
+// loads of the next k-block never wait for the current one to retire.  128 (128-byte swizzle, the layout every
+// library GEMM uses) halves the ring depth to 9 units and is kept selectable for bring-up.
+constexpr int OZ_RING_BYTES = 216 * 1024;
+constexpr int OZ_MAX_RING = 18;
 constexpr int OZ_UMMA_K = 32;                              // k per tcgen05.mma for 8-bit operands
 constexpr int OZ_TMEM_COLS = 512;                          // S * 64 <= 448, allocation must be a power of two
+template <int BK>
+struct OzCfg {
+  static_assert(BK == 64 || BK == 128, "unit width = swizzle span");
+  static constexpr int A_BYTES = OZ_BM * BK;
+  static constexpr int B_BYTES = OZ_BN * BK;
+  static constexpr int UNIT_BYTES = A_BYTES + B_BYTES;      // 12 KB / 24 KB; both parts 1024-byte aligned
+  static constexpr int MAX_SLOTS = OZ_RING_BYTES / UNIT_BYTES;  // 18 / 9
+};
+__host__ __device__ inline int oz_ring_slots(int S, int max_slots) { return (2 * S + 4 < max_slots) ? 2 * S + 4 : max_slots; }
 
 // ---------------------------------------------------------------- splitting kernel
 // One warp per row: exponent from the row maximum, then S rounds of (scale by 2^7, round to nearest,
@@ -112,13 +125,15 @@ __device__ __forceinline__ void tc_mma_i8(uint32_t tmem_d, uint64_t desc_a, uint
 //   [0,14) start address >> 4 | [16,30) leading byte offset >> 4 (1 for swizzled K-major) |
 //   [32,46) stride byte offset >> 4 (1024 B between 8-row groups) | [46,48) version = 1 (Blackwell) |
 //   [49,52) base offset = 0 (tiles are 1024-byte aligned) | [61,64) layout type = 2 (SWIZZLE_128B)
-__device__ __forceinline__ uint64_t umma_desc_k128(uint32_t smem_addr) {
+// (64-byte swizzle: rows 64 bytes apart, atom 512 bytes, layout type 4)
+template <int BK>
+__device__ __forceinline__ uint64_t umma_desc_kmajor(uint32_t smem_addr) {
   uint64_t d = 0;
   d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
   d |= (uint64_t)1 << 16;
-  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)((8 * BK) >> 4) << 32;
   d |= (uint64_t)1 << 46;
-  d |= (uint64_t)2 << 61;
+  d |= (uint64_t)(BK == 128 ? 2 : 4) << 61;
   return d;
 }
 // Instruction descriptor (cute::UMMA::InstrDescriptor): [4,6) D format = 2 (S32) | [7,10) A format = 1
@@ -144,7 +159,7 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, int (&v)[32]) {
 
 struct OzArgs {
   int64_t m, n;      // C is m x n (rows of A, rows of B)
-  int64_t kp;        // padded contraction length (multiple of OZ_BK)
+  int64_t kp;        // padded contraction length (multiple of OZ_KPAD)
   int S;             // slices per operand
   int tri;           // 1: only tiles that touch the lower triangle (m == n, A and B the same row set)
   double alpha;      // +1 or -1 (any finite value works)
@@ -162,20 +177,23 @@ struct OzSmemTail {
   double col_scale[OZ_BN];
 };
 
-constexpr size_t OZ_SMEM_BYTES = (size_t)OZ_MAX_RING * OZ_UNIT_BYTES + sizeof(OzSmemTail) + 1024;
+constexpr size_t OZ_SMEM_BYTES = (size_t)OZ_RING_BYTES + sizeof(OzSmemTail) + 1024;
 
 // slice visited at position idx of a k-block: 1, S, 2, S-1, ...  (1-based slice numbers)
 __device__ __forceinline__ int oz_order(int idx, int S) { return (idx & 1) ? S - (idx >> 1) : 1 + (idx >> 1); }
 // position of slice p in that order
 __device__ __forceinline__ int oz_pos(int p, int S) { return (2 * p <= S + 1) ? 2 * (p - 1) : 2 * (S - p) + 1; }
 
+template <int BK>
 __global__ void __launch_bounds__(192, 1) k_ozaki_gemm(const __grid_constant__ CUtensorMap tmA,
                                                       const __grid_constant__ CUtensorMap tmB, const OzArgs p) {
+  using Cfg = OzCfg<BK>;
+  constexpr int OZ_A_BYTES = Cfg::A_BYTES, OZ_UNIT_BYTES = Cfg::UNIT_BYTES, OZ_BK = BK;
   extern __shared__ unsigned char oz_raw[];
   // 1024-byte alignment for the swizzled tiles
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(oz_raw) + 1023) & ~(uintptr_t)1023);
-  const int S = p.S, R = S + 2;
-  OzSmemTail* tail = reinterpret_cast<OzSmemTail*>(smem + (size_t)OZ_MAX_RING * OZ_UNIT_BYTES);
+  const int S = p.S, R = oz_ring_slots(S, Cfg::MAX_SLOTS);
+  OzSmemTail* tail = reinterpret_cast<OzSmemTail*>(smem + (size_t)OZ_RING_BYTES);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
   const int64_t m0 = (int64_t)blockIdx.y * OZ_BM, n0 = (int64_t)blockIdx.x * OZ_BN;
@@ -249,9 +267,9 @@ __global__ void __launch_bounds__(192, 1) k_ozaki_gemm(const __grid_constant__ C
               const uint32_t d_addr = tmem + (uint32_t)(level - 2) * OZ_BN;
 #pragma unroll
               for (int ks = 0; ks < OZ_BK / OZ_UMMA_K; ++ks) {
-                // advancing along K inside the 128-byte swizzle row: +32 bytes on the start address
-                const uint64_t da = umma_desc_k128(a_addr + ks * OZ_UMMA_K);
-                const uint64_t db = umma_desc_k128(b_addr + ks * OZ_UMMA_K);
+                // advancing along K inside the swizzle row: +32 bytes on the start address
+                const uint64_t da = umma_desc_kmajor<BK>(a_addr + ks * OZ_UMMA_K);
+                const uint64_t db = umma_desc_kmajor<BK>(b_addr + ks * OZ_UMMA_K);
                 tc_mma_i8(d_addr, da, db, IDESC, (level_started >> level) & 1u);
                 level_started |= 1u << level;
               }
@@ -320,7 +338,7 @@ static PFN_tmapEncodeTiled oz_tmap_encoder() {
 }
 
 // planes [S][rows_pad][kp] int8 -> 3-D map, box = 128 bytes of k x box_rows rows x 1 slice, 128-byte swizzle
-static int oz_make_map(CUtensorMap* tm, const int8_t* planes, int S, int64_t rows_pad, int64_t kp, int box_rows) {
+static int oz_make_map(CUtensorMap* tm, const int8_t* planes, int S, int64_t rows_pad, int64_t kp, int box_rows, int bk) {
   PFN_tmapEncodeTiled enc = oz_tmap_encoder();
   if (enc == nullptr) {
     set_last_error("cuTensorMapEncodeTiled is not available from this driver");
@@ -328,10 +346,11 @@ static int oz_make_map(CUtensorMap* tm, const int8_t* planes, int S, int64_t row
   }
   cuuint64_t dims[3] = {(cuuint64_t)kp, (cuuint64_t)rows_pad, (cuuint64_t)S};
   cuuint64_t strides[2] = {(cuuint64_t)kp, (cuuint64_t)(rows_pad * kp)};
-  cuuint32_t box[3] = {(cuuint32_t)OZ_BK, (cuuint32_t)box_rows, 1};
+  cuuint32_t box[3] = {(cuuint32_t)bk, (cuuint32_t)box_rows, 1};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<int8_t*>(planes), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, bk == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     char buf[128];
@@ -349,7 +368,7 @@ struct OzOperand {
 };
 
 static size_t oz_plane_bytes(int64_t rows, int64_t k, int S) {
-  const int64_t rows_pad = (rows + OZ_BM - 1) / OZ_BM * OZ_BM, kp = (k + OZ_BK - 1) / OZ_BK * OZ_BK;
+  const int64_t rows_pad = (rows + OZ_BM - 1) / OZ_BM * OZ_BM, kp = (k + OZ_KPAD - 1) / OZ_KPAD * OZ_KPAD;
   return (size_t)S * rows_pad * kp;
 }
 
@@ -357,7 +376,7 @@ static size_t oz_plane_bytes(int64_t rows, int64_t k, int S) {
 static int oz_split_into(const double* X, int64_t rows, int64_t k, int64_t ldx, int S, int8_t* planes, int* exps,
                          OzOperand* o, cudaStream_t s) {
   o->rows_pad = (rows + OZ_BM - 1) / OZ_BM * OZ_BM;
-  o->kp = (k + OZ_BK - 1) / OZ_BK * OZ_BK;
+  o->kp = (k + OZ_KPAD - 1) / OZ_KPAD * OZ_KPAD;
   o->planes = planes;
   o->exps = exps;
   k_ozaki_split<<<ceil_div(o->rows_pad, 8), 256, 0, s>>>(X, rows, k, ldx, S, o->rows_pad, o->kp, o->planes, o->exps);
@@ -368,14 +387,18 @@ static int oz_split_into(const double* X, int64_t rows, int64_t k, int64_t ldx, 
 
 static int oz_launch(const OzOperand& oa, const OzOperand& ob, int64_t m, int64_t n, double alpha, double* C,
                      int64_t ldc, int S, int tri, cudaStream_t s) {
+  // unit width: 64 bytes (default, deep ring) or 128 bytes (SGDML_B200_OZAKI_BK=128, the plain 128-byte swizzle)
+  const char* bke = getenv("SGDML_B200_OZAKI_BK");
+  const int bk = (bke != nullptr && atoi(bke) == 128) ? 128 : 64;
   CUtensorMap tmA, tmB;
-  SG_TRY(oz_make_map(&tmA, oa.planes, S, oa.rows_pad, oa.kp, OZ_BM));
-  SG_TRY(oz_make_map(&tmB, ob.planes, S, ob.rows_pad, ob.kp, OZ_BN));
+  SG_TRY(oz_make_map(&tmA, oa.planes, S, oa.rows_pad, oa.kp, OZ_BM, bk));
+  SG_TRY(oz_make_map(&tmB, ob.planes, S, ob.rows_pad, ob.kp, OZ_BN, bk));
   static bool configured[64] = {false};
   int dev = 0;
   SG_CUDA(cudaGetDevice(&dev));
   if (dev >= 0 && dev < 64 && !configured[dev]) {
-    SG_CUDA(cudaFuncSetAttribute(k_ozaki_gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)OZ_SMEM_BYTES));
+    SG_CUDA(cudaFuncSetAttribute(k_ozaki_gemm<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)OZ_SMEM_BYTES));
+    SG_CUDA(cudaFuncSetAttribute(k_ozaki_gemm<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)OZ_SMEM_BYTES));
     configured[dev] = true;
   }
   OzArgs a;
@@ -392,7 +415,10 @@ static int oz_launch(const OzOperand& oa, const OzOperand& ob, int64_t m, int64_
   dim3 grid((unsigned)ceil_div(n, OZ_BN), (unsigned)ceil_div(m, OZ_BM));
   SG_ARG(grid.y <= 65535);
   ProfScope ps(KID_GEMM, s);
-  k_ozaki_gemm<<<grid, 192, OZ_SMEM_BYTES, s>>>(tmA, tmB, a);
+  if (bk == 128)
+    k_ozaki_gemm<128><<<grid, 192, OZ_SMEM_BYTES, s>>>(tmA, tmB, a);
+  else
+    k_ozaki_gemm<64><<<grid, 192, OZ_SMEM_BYTES, s>>>(tmA, tmB, a);
   SG_CUDA(cudaGetLastError());
   count_launch(KID_GEMM);
   return 0;

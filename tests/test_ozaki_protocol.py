@@ -29,8 +29,12 @@ class MBar(object):
         return (self.done & 1) != parity
 
 
-def simulate(S, KB, seed):
-    R = S + 2
+def ring_slots(S, max_slots):
+    return min(2 * S + 4, max_slots)
+
+
+def simulate(S, KB, seed, max_slots=18):
+    R = ring_slots(S, max_slots)
     rng = random.Random(seed)
     full = [MBar() for _ in range(R)]
     empty = [MBar() for _ in range(R)]
@@ -121,11 +125,12 @@ def simulate(S, KB, seed):
     return pairs
 
 
+@pytest.mark.parametrize('max_slots', [18, 9])  # unit width 64 B (default) / 128 B
 @pytest.mark.parametrize('S', [2, 3, 4, 5, 6, 7])
-def test_ring_protocol(S):
-    for KB in (1, 2, 3, 8):
+def test_ring_protocol(S, max_slots):
+    for KB in (1, 2, 3, 8, 16):
         for seed in range(5):
-            pairs = simulate(S, KB, seed)
+            pairs = simulate(S, KB, seed, max_slots)
             n_pairs = sum(1 for p in range(1, S + 1) for q in range(1, S + 1) if p + q <= S + 1)
             assert pairs == KB * n_pairs
 
