@@ -9,6 +9,14 @@ from conftest import rel_err
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(params=['128', '64'], autouse=True)
+def unit_width(request, monkeypatch):
+    """Both pipeline-unit widths of the kernel: 128-byte swizzle (9-slot ring) first -- the layout every library
+    GEMM uses, so failures there point at the kernel logic rather than at the 64-byte swizzle descriptors."""
+    monkeypatch.setenv('SGDML_B200_OZAKI_BK', request.param)
+    return request.param
+
+
 def _run(m, n, k, S, tri=False, alpha=1.0, seed=0, scale_rows=False):
     import torch
 
