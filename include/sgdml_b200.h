@@ -205,6 +205,11 @@ int sgdml_b200_dgemm_nt(int64_t m, int64_t n, int64_t k, double alpha, const dou
 int sgdml_b200_ozaki_gemm_nt(int64_t m, int64_t n, int64_t k, double alpha, const double* A, int64_t lda,
                              const double* B, int64_t ldb, double* C, int64_t ldc, int n_slices, int tri,
                              void* stream);
+/* Bring-up aid for the above: also returns the int8 slice planes ([n_slices][rows padded to 128][k padded to
+ * 128]), the row exponents and the raw int32 level sums ([n_slices][m][n]); any output may be NULL. */
+int sgdml_b200_ozaki_debug(int64_t m, int64_t n, int64_t k, const double* A, int64_t lda, const double* B,
+                           int64_t ldb, double* C, int64_t ldc, int n_slices, int8_t* planes_a, int* exps_a,
+                           int8_t* planes_b, int* exps_b, int* levels, void* stream);
 
 /* ---------------------------------------------------------------- launch accounting / profiling
  * Kernel families: 0 predictor main kernel, 1 predictor auxiliary kernels, 2 K assembly,

@@ -167,6 +167,7 @@ struct OzArgs {
   const int* eb;     // row exponents of B (n_pad)
   double* C;
   int64_t ldc;
+  int* dbg_levels;   // bring-up: raw int32 level sums, [S][m][n] (NULL in production)
 };
 
 struct OzSmemTail {
@@ -301,6 +302,12 @@ __global__ void __launch_bounds__(192, 1) k_ozaki_gemm(const __grid_constant__ C
         const double w = ldexp(1.0, -OZ_BITS * level);
 #pragma unroll
         for (int j = 0; j < 32; ++j) acc[j] = fma((double)v[j], w, acc[j]);
+        if (p.dbg_levels != nullptr && gr < p.m) {
+          for (int j = 0; j < 32; ++j) {
+            const int64_t gc = n0 + half * 32 + j;
+            if (gc < p.n) p.dbg_levels[((int64_t)(level - 2) * p.m + gr) * p.n + gc] = v[j];
+          }
+        }
       }
       if (gr < p.m) {
         double* crow = p.C + gr * p.ldc + n0 + half * 32;
@@ -386,7 +393,7 @@ static int oz_split_into(const double* X, int64_t rows, int64_t k, int64_t ldx, 
 }
 
 static int oz_launch(const OzOperand& oa, const OzOperand& ob, int64_t m, int64_t n, double alpha, double* C,
-                     int64_t ldc, int S, int tri, cudaStream_t s) {
+                     int64_t ldc, int S, int tri, cudaStream_t s, int* dbg_levels = nullptr) {
   // unit width: 64 bytes (default, deep ring) or 128 bytes (SGDML_B200_OZAKI_BK=128, the plain 128-byte swizzle)
   const char* bke = getenv("SGDML_B200_OZAKI_BK");
   const int bk = (bke != nullptr && atoi(bke) == 128) ? 128 : 64;
@@ -412,6 +419,7 @@ static int oz_launch(const OzOperand& oa, const OzOperand& ob, int64_t m, int64_
   a.eb = ob.exps;
   a.C = C;
   a.ldc = ldc;
+  a.dbg_levels = dbg_levels;
   dim3 grid((unsigned)ceil_div(n, OZ_BN), (unsigned)ceil_div(m, OZ_BM));
   SG_ARG(grid.y <= 65535);
   ProfScope ps(KID_GEMM, s);
@@ -480,9 +488,56 @@ int ozaki_gemm_nt_device(int64_t m, int64_t n, int64_t k, double alpha, const do
   return rc;
 }
 
+// Bring-up aid: runs the split and the int8 products and hands back every intermediate.
+//   planes_a [S][m_pad][kp] int8, exps_a [m_pad], planes_b / exps_b likewise, levels [S][m][n] int32
+// (all device pointers; any of them may be NULL).  C receives C + A B^T as usual.
+int ozaki_debug_device(int64_t m, int64_t n, int64_t k, const double* A, int64_t lda, const double* B, int64_t ldb,
+                       double* C, int64_t ldc, int S, int8_t* planes_a, int* exps_a, int8_t* planes_b, int* exps_b,
+                       int* levels, cudaStream_t s) {
+  SG_ARG(S >= 2 && S <= OZ_MAX_S && m >= 1 && n >= 1 && k >= 1 && k <= (1 << 14));
+  int8_t *pa = nullptr, *pb = nullptr;
+  int *xa = nullptr, *xb = nullptr;
+  auto cleanup = [&]() {
+    cudaFree(pa);
+    cudaFree(xa);
+    cudaFree(pb);
+    cudaFree(xb);
+  };
+  auto body = [&]() -> int {
+    OzOperand oa, ob;
+    const size_t ba = oz_plane_bytes(m, k, S), bb = oz_plane_bytes(n, k, S);
+    const size_t ea = sizeof(int) * (size_t)((m + OZ_BM - 1) / OZ_BM * OZ_BM), eb = sizeof(int) * (size_t)((n + OZ_BM - 1) / OZ_BM * OZ_BM);
+    SG_CUDA(cudaMalloc(&pa, ba));
+    SG_CUDA(cudaMalloc(&xa, ea));
+    SG_CUDA(cudaMalloc(&pb, bb));
+    SG_CUDA(cudaMalloc(&xb, eb));
+    SG_TRY(oz_split_into(A, m, k, lda, S, pa, xa, &oa, s));
+    SG_TRY(oz_split_into(B, n, k, ldb, S, pb, xb, &ob, s));
+    if (planes_a) SG_CUDA(cudaMemcpyAsync(planes_a, pa, ba, cudaMemcpyDeviceToDevice, s));
+    if (exps_a) SG_CUDA(cudaMemcpyAsync(exps_a, xa, ea, cudaMemcpyDeviceToDevice, s));
+    if (planes_b) SG_CUDA(cudaMemcpyAsync(planes_b, pb, bb, cudaMemcpyDeviceToDevice, s));
+    if (exps_b) SG_CUDA(cudaMemcpyAsync(exps_b, xb, eb, cudaMemcpyDeviceToDevice, s));
+    if (C != nullptr) SG_TRY(oz_launch(oa, ob, m, n, 1.0, C, ldc, S, 0, s, levels));
+    SG_CUDA(cudaStreamSynchronize(s));
+    return 0;
+  };
+  int rc = body();
+  cleanup();
+  return rc;
+}
+
 }  // namespace sgdml
 
 using namespace sgdml;
+
+extern "C" int sgdml_b200_ozaki_debug(int64_t m, int64_t n, int64_t k, const double* A, int64_t lda, const double* B,
+                                      int64_t ldb, double* C, int64_t ldc, int n_slices, int8_t* planes_a, int* exps_a,
+                                      int8_t* planes_b, int* exps_b, int* levels, void* stream) {
+  SG_TRY(require_device());
+  SG_ARG(A != nullptr && B != nullptr && lda >= k && ldb >= k);
+  return ozaki_debug_device(m, n, k, A, lda, B, ldb, C, ldc, n_slices, planes_a, exps_a, planes_b, exps_b, levels,
+                            (cudaStream_t)stream);
+}
 
 extern "C" int sgdml_b200_ozaki_gemm_nt(int64_t m, int64_t n, int64_t k, double alpha, const double* A, int64_t lda,
                                         const double* B, int64_t ldb, double* C, int64_t ldc, int n_slices, int tri,

@@ -50,6 +50,80 @@ def _scale(A, B):
     return np.abs(A) @ np.abs(B).T  # componentwise error bound of a dot product
 
 
+# ------------------------------------------------------------------------------------------------
+# Staged bring-up: (1) the split kernel alone, (2) the raw int32 level sums of one tile against exact
+# NumPy integer products, (3) everything above.  Run in this order when the kernel first meets hardware:
+#   pytest tests/test_ozaki.py -x -q -k "stage1 or stage2"
+def _np_split(A, S, bits=7):
+    amax = np.max(np.abs(A), axis=1)
+    e = np.zeros(len(A), dtype=np.int64)
+    nz = amax > 0
+    e[nz] = np.frexp(amax[nz])[1] + 1
+    r = A / np.exp2(e)[:, None]
+    out = np.empty((S,) + A.shape, dtype=np.int64)
+    for p in range(S):
+        r = r * (1 << bits)
+        q = np.rint(r)
+        out[p] = q.astype(np.int64)
+        r = r - q
+    return e, out
+
+
+def _debug(m, n, k, S, seed=0, with_product=True):
+    import torch
+
+    from sgdml_b200 import _lib
+
+    _lib.require_gpu()
+    rng = np.random.default_rng(seed)
+    A = rng.standard_normal((m, k)) * np.exp2(rng.integers(-3, 3, size=(m, 1)).astype(np.float64))
+    B = rng.standard_normal((n, k))
+    mp, np_, kp = -(-m // 128) * 128, -(-n // 128) * 128, -(-k // 128) * 128
+    Ad, Bd = torch.from_numpy(A).cuda(), torch.from_numpy(B).cuda()
+    pa = torch.zeros((S, mp, kp), dtype=torch.int8, device='cuda')
+    pb = torch.zeros((S, np_, kp), dtype=torch.int8, device='cuda')
+    ea = torch.zeros(mp, dtype=torch.int32, device='cuda')
+    eb = torch.zeros(np_, dtype=torch.int32, device='cuda')
+    lv = torch.zeros((S, m, n), dtype=torch.int32, device='cuda')
+    Cd = torch.zeros((m, n), dtype=torch.float64, device='cuda')
+    _lib.check(
+        _lib.lib().sgdml_b200_ozaki_debug(
+            m, n, k, Ad.data_ptr(), k, Bd.data_ptr(), k, Cd.data_ptr() if with_product else None, n, S,
+            pa.data_ptr(), ea.data_ptr(), pb.data_ptr(), eb.data_ptr(), lv.data_ptr() if with_product else None,
+            _lib.current_stream(),
+        ),
+        'ozaki_debug',
+    )
+    torch.cuda.synchronize()
+    return A, B, pa.cpu().numpy(), ea.cpu().numpy(), pb.cpu().numpy(), eb.cpu().numpy(), lv.cpu().numpy(), Cd.cpu().numpy()
+
+
+def test_stage1_split_kernel():
+    A, B, pa, ea, pb, eb, _, _ = _debug(130, 70, 200, 7, with_product=False)
+    for X, planes, exps in ((A, pa, ea), (B, pb, eb)):
+        e, sl = _np_split(X, 7)
+        rows, k = X.shape
+        assert np.array_equal(exps[:rows], e)
+        assert np.array_equal(planes[:, :rows, :k].astype(np.int64), sl)
+        assert not planes[:, rows:, :].any() and not planes[:, :, k:].any()  # zero padding
+
+
+@pytest.mark.parametrize('m,n,k', [(128, 64, 128), (128, 64, 64), (130, 70, 200)])
+def test_stage2_raw_level_sums(m, n, k):
+    S = 7
+    A, B, pa, ea, pb, eb, lv, C = _debug(m, n, k, S)
+    sa, sb = pa[:, :m, :].astype(np.int64), pb[:, :n, :].astype(np.int64)
+    for level in range(2, S + 2):
+        want = np.zeros((m, n), dtype=np.int64)
+        for p in range(1, S + 1):
+            q = level - p
+            if 1 <= q <= S:
+                want += sa[p - 1] @ sb[q - 1].T
+        assert np.array_equal(lv[level - 2].astype(np.int64), want), 'level %d' % level
+    ref = A @ B.T
+    assert np.max(np.abs(C - ref) / (np.abs(A) @ np.abs(B).T)) < 1e-12
+
+
 @pytest.mark.parametrize('m,n,k', [(128, 64, 128), (128, 64, 256), (256, 128, 128), (300, 200, 130), (129, 65, 1000), (64, 8, 40)])
 def test_ozaki_gemm_matches_fp64(m, n, k):
     A, B, C0, C = _run(m, n, k, 7)
