@@ -196,6 +196,21 @@ int sgdml_b200_dgemm_nt(int64_t m, int64_t n, int64_t k, double alpha, const dou
                         int64_t lda, const double* B, int64_t ldb, double beta, double* C,
                         int64_t ldc, void* stream);
 
+/* EXPERIMENTAL (not yet run on hardware, see csrc/ozaki.cu): the same product through the tcgen05 tensor
+ * cores -- A and B are cut into n_slices signed 7-bit slices per row-scaled entry and every slice pair is
+ * multiplied exactly by tcgen05.mma kind::i8 (int32 accumulators in tensor memory); C += alpha * A * B^T.
+ * n_slices = 7 reproduces the FP64 Cholesky trailing update (analytic.py:94-96) to ~1e-14 relative, 8 would
+ * be FP64-equivalent (tools/ozaki_study.py).  tri != 0: m == n, only tiles touching the lower triangle.
+ * All pointers must be device pointers; k <= 16384. */
+int sgdml_b200_ozaki_gemm_nt(int64_t m, int64_t n, int64_t k, double alpha, const double* A, int64_t lda,
+                             const double* B, int64_t ldb, double* C, int64_t ldc, int n_slices, int tri,
+                             void* stream);
+/* Bring-up aid for the above: also returns the int8 slice planes ([n_slices][rows padded to 128][k padded to
+ * 128]), the row exponents and the raw int32 level sums ([n_slices][m][n]); any output may be NULL. */
+int sgdml_b200_ozaki_debug(int64_t m, int64_t n, int64_t k, const double* A, int64_t lda, const double* B,
+                           int64_t ldb, double* C, int64_t ldc, int n_slices, int8_t* planes_a, int* exps_a,
+                           int8_t* planes_b, int* exps_b, int* levels, void* stream);
+
 /* ---------------------------------------------------------------- launch accounting / profiling
  * Kernel families: 0 predictor main kernel, 1 predictor auxiliary kernels, 2 K assembly,
  * 3 DMMA GEMM (Cholesky trailing update), 4 potf2 diagonal tiles, 5 panel TRSM strips,

@@ -856,6 +856,23 @@ int run_queries(sgdml_b200_model* m, int slot, const double* xq, const double* g
     g.mode = 0;
     g.tri = 0;
     g.abort_flag = nullptr;
+    // EXPERIMENTAL (csrc/ozaki.cu, not validated on hardware yet): the four contractions on the tcgen05
+    // tensor cores through exact int8 slice products; predictions need 4 slices for the 1e-6 force
+    // tolerance (tools/ozaki_study.py predict: 8.8e-9)
+    const char* ozp = getenv("SGDML_B200_OZAKI_PREDICT_SLICES");
+    const int oz_s = (ozp != nullptr) ? std::max(0, std::min(7, atoi(ozp))) : 0;
+    if (oz_s >= 2 && m->DS <= (1 << 14) && m->Mpad <= (1 << 14)) {
+      SG_CUDA(cudaMemsetAsync(w.S1, 0, sizeof(double) * (size_t)n_rows * m->Mpad, s));
+      SG_CUDA(cudaMemsetAsync(w.S2, 0, sizeof(double) * (size_t)n_rows * m->Mpad, s));
+      SG_TRY(ozaki_gemm_nt_device(n_rows, m->Mpad, m->DS, 1.0, w.Qg, m->DS, m->Xc, m->DS, w.S1, m->Mpad, oz_s, 0, s));
+      SG_TRY(ozaki_gemm_nt_device(n_rows, m->Mpad, m->DS, 1.0, w.Qg, m->DS, m->JA, m->DS, w.S2, m->Mpad, oz_s, 0, s));
+      k_transform_rows<<<(unsigned)((n_rows + 7) / 8), 256, 0, s>>>(w.S1, w.S2, m->Mpad, w.qq, m->mm, m->xja, m->M,
+                                                                     m->Mpad, n_rows, mk, w.csum, w.Erow);
+      SG_CUDA(cudaGetLastError());
+      SG_CUDA(cudaMemsetAsync(w.G, 0, sizeof(double) * (size_t)n_rows * m->DP, s));
+      SG_TRY(ozaki_gemm_nt_device(n_rows, m->DP, m->Mpad, 1.0, w.S1, m->Mpad, m->XcT, m->Mpad, w.G, m->DP, oz_s, 0, s));
+      SG_TRY(ozaki_gemm_nt_device(n_rows, m->DP, m->Mpad, 1.0, w.S2, m->Mpad, m->JAT, m->Mpad, w.G, m->DP, oz_s, 0, s));
+    } else {
     // S1 = Q Xc^T, S2 = Q JA^T   (rows x Mpad, contraction over the padded descriptor)
     g.m = n_rows;
     g.n = m->Mpad;
@@ -887,6 +904,7 @@ int run_queries(sgdml_b200_model* m, int slot, const double* xq, const double* g
     g.A = w.S2;
     g.B = m->JAT;
     SG_TRY(launch_gemm(g, s));
+    }
     k_combine_rows<<<(unsigned)((n_rows * m->DP + 255) / 256), 256, 0, s>>>(w.Qg, m->DS, w.csum, w.G, m->DP, n_rows);
     SG_CUDA(cudaGetLastError());
     count_launch(KID_PREDICT_MAIN, 2);

@@ -864,7 +864,13 @@ int potrf_device(double* A, int64_t n, int64_t lda, int* info_host, cudaStream_t
   // environment switch (SGDML_B200_LOOKAHEAD=1) until the trailing GEMM is made persistent on a subset of SMs.
   const char* la = getenv("SGDML_B200_LOOKAHEAD");
   const bool lookahead = (la && la[0] == '1') && (n > 2 * (int64_t)NBO) && !profiling_enabled();
+  const char* oz = getenv("SGDML_B200_OZAKI_SLICES");  // 0 / unset: FP64 DMMA trailing updates (default)
+  const int oz_slices = (oz != nullptr) ? std::max(0, std::min(7, atoi(oz))) : 0;
+  int8_t* oz_planes = nullptr;  // slice planes of the current outer panel (experimental tcgen05 path)
+  int* oz_exps = nullptr;
   auto cleanup = [&]() {
+    cudaFree(oz_planes);
+    cudaFree(oz_exps);
     cudaFree(d_info);
     cudaFree(W[0]);
     cudaFree(W[1]);
@@ -877,6 +883,12 @@ int potrf_device(double* A, int64_t n, int64_t lda, int* info_host, cudaStream_t
   auto body = [&]() -> int {
     SG_CUDA(cudaMalloc(&d_info, sizeof(int)));
     SG_CUDA(cudaMalloc(&W[0], sizeof(double) * (size_t)n * NBO));
+    if (oz_slices > 0 && !lookahead) {
+      size_t pb = 0, eb = 0;
+      SG_TRY(ozaki_syrk_workspace_bytes(n, NBO, oz_slices, &pb, &eb));
+      SG_CUDA(cudaMalloc(&oz_planes, pb));
+      SG_CUDA(cudaMalloc(&oz_exps, eb));
+    }
     if (lookahead) {
       SG_CUDA(cudaMalloc(&W[1], sizeof(double) * (size_t)n * NBO));
       int lo = 0, hi = 0;
@@ -945,6 +957,13 @@ int potrf_device(double* A, int64_t n, int64_t lda, int* info_host, cudaStream_t
       g.mode = 1;
       g.abort_flag = d_info;
       if (!lookahead) {
+        if (oz_slices > 0) {
+          // EXPERIMENTAL (csrc/ozaki.cu, not validated on hardware yet): the trailing update on the tcgen05
+          // tensor cores, C -= X X^T through exact int8 slice products
+          const double* X = A + K1 * lda + K0;
+          SG_TRY(ozaki_syrk_device(rem, K1 - K0, -1.0, X, lda, A + K1 * lda + K1, lda, oz_slices, oz_planes, oz_exps, s));
+          continue;
+        }
         g.m = rem;
         g.n = rem;
         g.A = Wc + K1 * NBO;  // -X, all panels of the outer block
