@@ -121,9 +121,15 @@ __global__ void __launch_bounds__(256, 2) k_assemble(const AsmArgs p) {
     const int t = ok ? fastdiv(it, p.mNN) : 0;
     if (p.sym && jt0 + t < i) ok = false;  // mirrored from block (j, i) instead
     const int ab = ok ? it - t * NN : 0;
-    it_t[q] = ok ? t : -1;
     it_a[q] = fastdiv(ab, p.mN);
     it_b[q] = ab - it_a[q] * N;
+    if (ok && !p.sym) {
+      // column subsets (Nystroem set-up): a sub-block none of whose three columns is kept is never stored,
+      // so it is not accumulated either
+      const int64_t* dst = p.dest + (int64_t)(jt0 + t) * N3 + 3 * it_b[q];
+      if (dst[0] < 0 && dst[1] < 0 && dst[2] < 0) ok = false;
+    }
+    it_t[q] = ok ? t : -1;
 #pragma unroll
     for (int e = 0; e < 9; ++e) acc[q][e] = 0.0;
   }
@@ -421,9 +427,15 @@ __global__ void __launch_bounds__(256, 2)
 #pragma unroll
       for (int q = 0; q < ASM_NI; ++q) {
         const int it = base0 + tid + q * nt;
-        const bool ok = it < NN;
-        it_a[q] = ok ? fastdiv(it, p.mN) : -1;
-        it_b[q] = ok ? it - it_a[q] * N : 0;
+        bool ok = it < NN;
+        int a_ = ok ? fastdiv(it, p.mN) : -1;
+        const int b_ = ok ? it - a_ * N : 0;
+        if (ok) {  // sub-blocks whose three columns are all dropped are never stored: skip them
+          const int64_t* dst = p.dest + (int64_t)jt * N3 + 3 * b_;
+          if (dst[0] < 0 && dst[1] < 0 && dst[2] < 0) a_ = -1;
+        }
+        it_a[q] = a_;
+        it_b[q] = b_;
 #pragma unroll
         for (int e = 0; e < 9; ++e) acc[q][e] = 0.0;
       }
