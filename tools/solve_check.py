@@ -1,0 +1,80 @@
+#!/usr/bin/env python
+"""Independent check of a trained model: the K.v identity (iterative.py:183-204) evaluates
+(K - lam I) alphas with the PREDICTOR kernels, which share no code with the assembly and Cholesky
+kernels that produced alphas, and compares it with the labels y (analytic.py:65-99 solves exactly this
+system).  Also reports the force error on a sample of training points.
+
+    python tools/solve_check.py --workload aspirin --n-train 300        # n = 18900 (NBO = 1024 path)
+    SGDML_B200_OZAKI_SLICES=7 python tools/solve_check.py ...          # tcgen05 int8 trailing updates
+"""
+
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def residual_report(model, task, predictor=None):
+    """-> dict(residual_rel, backward_err, force_rel_max): ||(K - lam I) alphas - y|| / ||y|| with K.alphas from
+    GDMLPredict.kmatvec_train (raw sums), y = F_train / std."""
+    import sgdml_b200
+    from sgdml_b200.desc import Desc
+
+    M, N = task['R_train'].shape[:2]
+    if predictor is None:
+        predictor = sgdml_b200.GDMLPredict(model)
+        _, R_d_desc = Desc(N).from_R(np.ascontiguousarray(task['R_train'], dtype=np.float64).reshape(M, -1))
+        predictor.set_R_d_desc(R_d_desc if M > 1 else R_d_desc[None])
+    alphas = np.ascontiguousarray(model['alphas_F'], dtype=np.float64)
+    predictor.set_alphas(alphas)
+    Kv = predictor.kmatvec_train().ravel()
+    std = float(model['std'])
+    y = np.asarray(task['F_train'], dtype=np.float64).ravel() / std
+    lam = float(model['lam'])
+    r = Kv - lam * alphas - y
+    ny = float(np.linalg.norm(y))
+    F_pred = Kv.reshape(M, -1) * std  # = GDMLPredict.predict on the training points (forces)
+    F_ref = np.asarray(task['F_train'], dtype=np.float64).reshape(M, -1)
+    return {
+        'residual_rel': float(np.linalg.norm(r) / ny),
+        'residual_max_rel': float(np.max(np.abs(r)) / np.max(np.abs(y))),
+        # normwise backward error of the solve: ||r|| / (||Kv|| + lam ||alphas|| + ||y||)
+        'backward_err': float(np.linalg.norm(r) / (np.linalg.norm(Kv) + lam * np.linalg.norm(alphas) + ny)),
+        'force_rel_max_train': float(np.max(np.abs(F_pred - F_ref)) / np.max(np.abs(F_ref))),
+        'alphas_norm': float(np.linalg.norm(alphas)),
+    }
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--workload', default='aspirin')
+    ap.add_argument('--n-train', type=int, default=None)
+    args = ap.parse_args()
+    import torch
+
+    import sgdml_b200
+    from sgdml_b200 import synth
+
+    task = synth.make_config_task(args.workload, n_train=args.n_train)
+    M, N = task['R_train'].shape[:2]
+    tr = sgdml_b200.GDMLTrain()
+    tr.train(synth.make_config_task(args.workload, n_train=min(M, 40)))  # warm-up
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    model = tr.train(task)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    rep = residual_report(model, task)
+    rep.update({'workload': args.workload, 'n': 3 * N * M, 'train_s': dt, 'timings': tr.timings,
+                'ozaki_slices': os.environ.get('SGDML_B200_OZAKI_SLICES', '0')})
+    print(json.dumps(rep))
+
+
+if __name__ == '__main__':
+    main()
