@@ -103,6 +103,9 @@ int sgdml_b200_model_set_alphas(sgdml_b200_model* model, const double* alphas_F,
 int sgdml_b200_predict_train(sgdml_b200_model* model, int64_t m_begin, int64_t m_end, int scaled,
                              double* E, double* F, void* stream);
 
+/* Shape of a model: n_atoms, n_train, n_perms (any pointer may be NULL). */
+int sgdml_b200_model_dims(const sgdml_b200_model* model, int64_t* n_atoms, int64_t* n_train, int64_t* n_perms);
+
 /* Reads back R_d_desc_alpha (M, D) -- the `R_d_desc_alpha` key of the model file
  * (train.py:791, 808). */
 int sgdml_b200_model_get_R_d_desc_alpha(sgdml_b200_model* model, double* out);
@@ -132,7 +135,9 @@ int sgdml_b200_assemble_rows(const double* R_desc, const double* R_d_desc,
                              void* stream);
 
 /* Tuning / test hook: 0 = kernel chosen by molecule size (default), 1 = always the large-molecule
- * kernel (tables in global memory), which molecules above ~50 atoms need. */
+ * kernel (tables in global memory), which molecules above ~50 atoms need; 1000 + r = at most r row
+ * points per launch of the small-molecule kernel (default 65535, the grid limit; tests lower it to
+ * cover the multi-launch path that row ranges above 65535 training points take). */
 int sgdml_b200_set_assemble_variant(int variant);
 
 /* ---------------------------------------------------------------- dense solve (path a) */
@@ -188,6 +193,34 @@ int sgdml_b200_nystroem_project(const double* X, int64_t n_rows, int64_t m, int6
                                 const double* v, double* t, void* stream);
 int sgdml_b200_nystroem_expand(const double* X, int64_t n_rows, int64_t m, int64_t ldx, double lam,
                                const double* t, const double* v, double* out, void* stream);
+
+/* ---------------------------------------------------------------- device-resident PCG (path a, large systems)
+ * scipy.sparse.linalg.cg as driven by Iterative.solve, iterative.py:740-752, on the operators of
+ * iterative.py:183-206 (K v = predict_train(alphas = v), here sgdml_b200_model_set_alphas +
+ * sgdml_b200_predict_train on `model`, which must have been given its training Jacobians with
+ * sgdml_b200_model_set_R_d_desc) and iterative.py:120-142 (P v = (X (X^T v) - v)/lam with the Nystroem
+ * factor X = B^T).  Solves (-K + lam I) x = y; the caller takes alphas = -x (iterative.py:803).
+ * All CG vectors stay in HBM (`workspace`, DEVICE memory of at least
+ * sgdml_b200_pcg_workspace_doubles(n, n_rows_loc, m_ind, check_every) doubles, n = 3N * n_train); the host sees
+ * the residual norms of the last iterations every <= check_every iterations through `progress` (non-zero
+ * return = stop: the reference's restart / interrupt logic, iterative.py:726-735), nothing else.
+ *   y (n), x (n, in: start vector unless x_is_zero, out: solution): host or device.
+ *   tol_abs: stop when |r| <= tol_abs (the reference passes tol * |y|, iterative.py:744).
+ * Several GPUs: this rank evaluates the K.v rows of training points [m_begin, m_end) and holds
+ * the rows X_loc ((m_end - m_begin)*3N x m_ind, row stride ldx) of the factor; `exchange` is called, in stream
+ * order, with DEVICE buffers inside `workspace`:
+ *   op 0: sum `count` doubles at `buf` over the ranks in place   (X^T v, m_ind doubles)
+ *   op 1: all-gather: `buf` is the full vector (count = n), the rows this rank owns are in place
+ * and must enqueue the collective on `stream` (torch.distributed / NCCL on the Python host).  exchange == NULL:
+ * single rank, m_begin = 0, m_end = n_train.  m_ind = 0: no preconditioner (z = r). */
+typedef int (*sgdml_b200_exchange_fn)(void* ctx, int op, double* buf, int64_t count);
+typedef int (*sgdml_b200_pcg_progress_fn)(void* ctx, int64_t iters_done, const double* resid_hist, int64_t n_new);
+int64_t sgdml_b200_pcg_workspace_doubles(int64_t n, int64_t n_rows_loc, int64_t m_ind, int64_t check_every);
+int sgdml_b200_pcg(sgdml_b200_model* model, int64_t m_begin, int64_t m_end, const double* X_loc, int64_t m_ind,
+                   int64_t ldx, double lam, const double* y, double* x, int x_is_zero, double tol_abs,
+                   int64_t max_iters, int64_t check_every, double* workspace, int64_t workspace_doubles,
+                   sgdml_b200_exchange_fn exchange, void* exchange_ctx, sgdml_b200_pcg_progress_fn progress,
+                   void* progress_ctx, int64_t* iters_out, double* resid_out, void* stream);
 
 /* C = alpha * A * B^T + beta * C on the FP64 tensor pipe (the building block of potrf's
  * trailing update; exported for tests and benchmarks).  A (m, k) lda, B (n, k) ldb,

@@ -76,6 +76,13 @@ SIGNATURES = {
         C.c_int,
         [c_void_p, i64, i64, i64, C.c_double, c_void_p, c_void_p, c_void_p, c_void_p],
     ),
+    'sgdml_b200_model_dims': (C.c_int, [c_void_p, c_int64_p, c_int64_p, c_int64_p]),
+    'sgdml_b200_pcg_workspace_doubles': (C.c_int64, [i64, i64, i64, i64]),
+    'sgdml_b200_pcg': (
+        C.c_int,
+        [c_void_p, i64, i64, c_void_p, i64, i64, C.c_double, c_void_p, c_void_p, C.c_int, C.c_double, i64, i64,
+         c_void_p, i64, c_void_p, c_void_p, c_void_p, c_void_p, c_int64_p, c_double_p, c_void_p],
+    ),
     'sgdml_b200_set_gemm_variant': (C.c_int, [C.c_int]),
     'sgdml_b200_profile_enable': (C.c_int, [C.c_int]),
     'sgdml_b200_profile_reset': (C.c_int, []),
@@ -83,6 +90,11 @@ SIGNATURES = {
     'sgdml_b200_fp64_peak_tflops': (C.c_int, [C.POINTER(C.c_double)]),
     'sgdml_b200_fp64_peak_tflops_sustained': (C.c_int, [C.c_double, C.POINTER(C.c_double)]),
 }
+
+
+# callback types of sgdml_b200_pcg (include/sgdml_b200.h)
+EXCHANGE_FN = C.CFUNCTYPE(C.c_int, c_void_p, C.c_int, c_void_p, i64)
+PROGRESS_FN = C.CFUNCTYPE(C.c_int, c_void_p, i64, c_double_p, i64)
 
 
 class EngineError(RuntimeError):

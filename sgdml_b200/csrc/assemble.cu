@@ -561,8 +561,15 @@ static bool atom_perm_from_desc_perm(const int* dperm, int N, int* P) {
 }
 
 static int g_asm_variant = 0;  // 0: by size; 1: always the large-molecule kernel (tests)
+static int g_asm_max_rowpts = 65535;  // row points per launch of k_assemble (grid.y limit; lowered by tests)
 
 extern "C" int sgdml_b200_set_assemble_variant(int variant) {
+  // 0 / 1: kernel choice; 1000 + r (test hook): at most r row points per launch of the small-molecule kernel
+  if (variant >= 1000) {
+    SG_ARG(variant - 1000 >= 1 && variant - 1000 <= 65535);
+    g_asm_max_rowpts = variant - 1000;
+    return 0;
+  }
   SG_ARG(variant == 0 || variant == 1);
   g_asm_variant = variant;
   return 0;
@@ -707,14 +714,23 @@ extern "C" int sgdml_b200_assemble_rows(const double* R_desc, const double* R_d_
     a.K = (double*)sK.dev();
     a.ldk = ldk;
     if (!large) {
-      // rows on grid.y (<= 65535), column tiles on grid.x
-      SG_ARG(n_rowpts <= 65535);
+      // rows on grid.y, column tiles on grid.x; grid.y is limited to 65535, so longer row ranges (the
+      // iterative solver assembles K_nm over ALL training points of a rank) run as several launches,
+      // each with its own first row point and K row offset
       SG_CUDA(cudaFuncSetAttribute(k_assemble, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      dim3 grid((unsigned)ceil_div(nJ, TJ), (unsigned)n_rowpts, (unsigned)n_chunks);
+      const int max_rows_per_launch = g_asm_max_rowpts;
+      if (n_rowpts > max_rows_per_launch) a.sym = 0;  // the mirrored store addresses absolute row points
       ProfScope ps(KID_ASSEMBLE, s);
-      k_assemble<<<grid, 256, smem, s>>>(a);
-      SG_CUDA(cudaGetLastError());
-      count_launch(KID_ASSEMBLE);
+      for (int r0 = 0; r0 < n_rowpts; r0 += max_rows_per_launch) {
+        const int nr = std::min(max_rows_per_launch, n_rowpts - r0);
+        AsmArgs ac = a;
+        ac.i0 = (int)m_begin + r0;
+        ac.K = a.K + (int64_t)r0 * N3 * ldk;
+        dim3 grid((unsigned)ceil_div(nJ, TJ), (unsigned)nr, (unsigned)n_chunks);
+        k_assemble<<<grid, 256, smem, s>>>(ac);
+        SG_CUDA(cudaGetLastError());
+        count_launch(KID_ASSEMBLE);
+      }
     } else {
       int dev = 0, n_sm = 0;
       SG_CUDA(cudaGetDevice(&dev));

@@ -121,6 +121,34 @@ __global__ void k_x_t_minus_v(const double* __restrict__ X, int64_t n_rows, int6
 
 }  // namespace sgdml
 
+static const int XTV_ROWS_PER_CTA = 256;
+namespace sgdml {
+int64_t xtv_chunks(int64_t n_rows) { return (n_rows + XTV_ROWS_PER_CTA - 1) / XTV_ROWS_PER_CTA; }
+
+// out = (X t - v)/lam on device vectors, stream-ordered, no synchronisation (csrc/pcg.cu)
+int x_t_minus_v_device(const double* X, int64_t n_rows, int64_t m, int64_t ldx, double lam, const double* t_dev,
+                       const double* v_dev, double* out_dev, cudaStream_t s) {
+  k_x_t_minus_v<<<ceil_div(n_rows, 8), 256, 0, s>>>(X, n_rows, m, ldx, t_dev, v_dev, 1.0 / lam, out_dev);
+  SG_CUDA(cudaGetLastError());
+  count_launch(KID_MISC);
+  return 0;
+}
+
+// t = X^T v (m doubles, device), deterministic two-pass reduction; part: m * xtv_chunks(n_rows) doubles
+int xt_v_device(const double* X, int64_t n_rows, int64_t m, int64_t ldx, const double* v_dev, double* t_dev,
+                       double* part, cudaStream_t s) {
+  const int64_t n_chunks = xtv_chunks(n_rows);
+  dim3 grid((unsigned)((m + 255) / 256), (unsigned)n_chunks);
+  SG_ARG(grid.y <= 65535);
+  k_xt_v<<<grid, 256, 0, s>>>(X, n_rows, m, ldx, v_dev, part, XTV_ROWS_PER_CTA);
+  SG_CUDA(cudaGetLastError());
+  k_reduce_chunks<<<ceil_div(m, 256), 256, 0, s>>>(part, n_chunks, m, t_dev);
+  SG_CUDA(cudaGetLastError());
+  count_launch(KID_MISC, 2);
+  return 0;
+}
+}  // namespace sgdml
+
 using namespace sgdml;
 
 extern "C" {
@@ -240,23 +268,6 @@ static int scratch_get(size_t n_doubles, double** out) {
     g_scratch.dev = dev;
   }
   *out = g_scratch.p;
-  return 0;
-}
-
-static const int XTV_ROWS_PER_CTA = 256;
-static int64_t xtv_chunks(int64_t n_rows) { return (n_rows + XTV_ROWS_PER_CTA - 1) / XTV_ROWS_PER_CTA; }
-
-// t = X^T v (m doubles, device), deterministic two-pass reduction; part: m * xtv_chunks(n_rows) doubles
-static int xt_v_device(const double* X, int64_t n_rows, int64_t m, int64_t ldx, const double* v_dev, double* t_dev,
-                       double* part, cudaStream_t s) {
-  const int64_t n_chunks = xtv_chunks(n_rows);
-  dim3 grid((unsigned)((m + 255) / 256), (unsigned)n_chunks);
-  SG_ARG(grid.y <= 65535);
-  k_xt_v<<<grid, 256, 0, s>>>(X, n_rows, m, ldx, v_dev, part, XTV_ROWS_PER_CTA);
-  SG_CUDA(cudaGetLastError());
-  k_reduce_chunks<<<ceil_div(m, 256), 256, 0, s>>>(part, n_chunks, m, t_dev);
-  SG_CUDA(cudaGetLastError());
-  count_launch(KID_MISC, 2);
   return 0;
 }
 

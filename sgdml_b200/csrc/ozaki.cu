@@ -13,19 +13,24 @@
 // forces agree with the FP64 factorisation to 2e-11 at cond(K) = 2e10; S = 8 is FP64-equivalent.
 //
 // Kernel structure (one CTA per 128 x 64 tile of C, 192 threads, warp-specialised):
-//   warp 0   TMA producer: 3-D tensor maps over the slice planes [S][rows][k] (int8, K-major, swizzled);
-//            a pipeline UNIT is one slice p of one BK-wide k-block (BK = 64: A^(p) 128x64 B = 8 KB +
-//            B^(p) 64x64 B = 4 KB); units travel through a ring of up to 18 slots (216 KB, more than two
-//            k-blocks of all 7 slices) with full/empty mbarriers
+//   layout   the split kernel writes the slices UNIT-MAJOR and PRE-SWIZZLED: a pipeline unit -- slice p of one
+//            64-wide k-block for a tile of 128 rows -- is one contiguous 8 KB block of global memory holding
+//            exactly the bytes of the canonical K-major 64-byte-swizzle shared-memory tile, so a unit is fetched
+//            with two 1-D bulk copies (cp.async.bulk, A 8 KB + B 4 KB) that stream whole DRAM pages.  (The first
+//            version read row-major planes through 3-D tensor maps: 64-byte fragments 1 KB apart, which ran at
+//            14 GB/s per SM -- measured, profiles/r02_ozaki_bringup.md.)
+//   warp 0   producer: units travel through a ring of 18 slots (216 KB, two and a half k-blocks of all 7
+//            slices) with full/empty mbarriers
 //   warp 1   MMA issuer (one elected lane): per k-block the pairs are issued in groups r = 1, 2, ...
 //            (all pairs with min(p, q) = r), after which slices r and S + 1 - r are dead and their
 //            slots are handed back with tcgen05.commit -- the same order the producer refills them in
 //   warps 2-5 epilogue: the S level accumulators (S x 64 TMEM columns) are read with tcgen05.ld, summed
-//            smallest level first in FP64 registers, scaled by 2^(ea_i + eb_j) and added to C
+//            smallest level first in FP64 registers, scaled by 2^(ea_i + eb_j), transposed through shared
+//            memory and added to C with row-contiguous (coalesced) accesses
+//   raster   CTAs are numbered super-tile by super-tile (8 x 16 tiles = 1024 x 1024 of C, one wave of CTAs), so
+//            the slices a wave reads (2 x 1024 rows) stay L2-resident while they are reused
 //
-// STATUS: written against the PTX ISA / CuTe descriptor definitions without access to a GPU (the
-// round-1 GPU budget was spent); it compiles for sm_100a (SASS: UTCIMMA, UTMALDG.3D, LDTM) but has
-// NOT been run.  It is therefore not wired into potrf; tests/test_ozaki.py is the bring-up harness.
+// Brought up on hardware in round 2 (tests/test_ozaki.py: exact integer level sums, FP64 parity, potrf).
 #include <cuda.h>
 
 #include "common.cuh"
@@ -37,27 +42,36 @@ constexpr int OZ_BITS = 7;
 constexpr int OZ_MAX_S = 7;
 constexpr int OZ_BM = 128, OZ_BN = 64;
 constexpr int OZ_KPAD = 128;                               // the contraction length is padded to a multiple of this
-// BK = bytes (= int8 elements) of k per pipeline unit = width of one swizzle row.  64 (64-byte swizzle) is the
-// default: a unit is 12 KB, the ring holds 18 of them = two and a half k-blocks of all 7 slices, so the
-// loads of the next k-block never wait for the current one to retire.  128 (128-byte swizzle, the layout every
-// library GEMM uses) halves the ring depth to 9 units and is kept selectable for bring-up.
+// BK = bytes (= int8 elements) of k per pipeline unit = width of one swizzle row (64-byte swizzle): a unit is
+// 12 KB, the ring holds 18 of them = two and a half k-blocks of all 7 slices, so the loads of the next k-block
+// never wait for the current one to retire.
+constexpr int OZ_BK = 64;
 constexpr int OZ_RING_BYTES = 216 * 1024;
 constexpr int OZ_MAX_RING = 18;
 constexpr int OZ_UMMA_K = 32;                              // k per tcgen05.mma for 8-bit operands
 constexpr int OZ_TMEM_COLS = 512;                          // S * 64 <= 448, allocation must be a power of two
-template <int BK>
-struct OzCfg {
-  static_assert(BK == 64 || BK == 128, "unit width = swizzle span");
-  static constexpr int A_BYTES = OZ_BM * BK;
-  static constexpr int B_BYTES = OZ_BN * BK;
-  static constexpr int UNIT_BYTES = A_BYTES + B_BYTES;      // 12 KB / 24 KB; both parts 1024-byte aligned
-  static constexpr int MAX_SLOTS = OZ_RING_BYTES / UNIT_BYTES;  // 18 / 9
-};
-__host__ __device__ inline int oz_ring_slots(int S, int max_slots) { return (2 * S + 4 < max_slots) ? 2 * S + 4 : max_slots; }
+constexpr int OZ_A_BYTES = OZ_BM * OZ_BK;                  // 8 KB: one unit of a 128-row tile (global and shared)
+constexpr int OZ_B_BYTES = OZ_BN * OZ_BK;                  // 4 KB
+constexpr int OZ_UNIT_BYTES = OZ_A_BYTES + OZ_B_BYTES;     // 12 KB; both parts 1024-byte aligned
+constexpr int OZ_GSM = 8, OZ_GSN = 16;                     // super-tile: 8 x 16 tiles = 1024 x 1024 elements of C
+__host__ __device__ inline int oz_ring_slots(int S) { return (2 * S + 4 < OZ_MAX_RING) ? 2 * S + 4 : OZ_MAX_RING; }
 
-// ---------------------------------------------------------------- splitting kernel
-// One warp per row: exponent from the row maximum, then S rounds of (scale by 2^7, round to nearest,
-// subtract).  planes: [S][rows_pad][kp] int8, zero padded; exps: [rows_pad].
+// ---------------------------------------------------------------- splitting kernels
+// Row exponent + S rounds of (scale by 2^7, round to nearest, subtract): x = 2^e sum_p q_p 2^(-7p), |q_p| <= 64.
+__device__ __forceinline__ int oz_row_exponent(const double* __restrict__ x, int64_t k, int lane) {
+  double amax = 0.0;
+  for (int64_t j = lane; j < k; j += 32) amax = fmax(amax, fabs(x[j]));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) amax = fmax(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+  int e = 0;
+  if (amax > 0.0) {
+    frexp(amax, &e);  // amax = f 2^e, f in [0.5, 1)
+    e += 1;           // |x| 2^-e < 1/2
+  }
+  return e;
+}
+
+// Plain layout (bring-up aid only): planes [S][rows_pad][kp] int8, zero padded; exps [rows_pad].
 __global__ void __launch_bounds__(256) k_ozaki_split(const double* __restrict__ X, int64_t rows, int64_t k, int64_t ldx,
                                                     int S, int64_t rows_pad, int64_t kp, int8_t* __restrict__ planes,
                                                     int* __restrict__ exps) {
@@ -71,15 +85,7 @@ __global__ void __launch_bounds__(256) k_ozaki_split(const double* __restrict__ 
     return;
   }
   const double* x = X + r * ldx;
-  double amax = 0.0;
-  for (int64_t j = lane; j < k; j += 32) amax = fmax(amax, fabs(x[j]));
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) amax = fmax(amax, __shfl_xor_sync(0xffffffffu, amax, o));
-  int e = 0;
-  if (amax > 0.0) {
-    frexp(amax, &e);  // amax = f 2^e, f in [0.5, 1)
-    e += 1;           // |x| 2^-e < 1/2
-  }
+  const int e = oz_row_exponent(x, k, lane);
   if (lane == 0) exps[r] = e;
   for (int64_t j = lane; j < kp; j += 32) {
     double v = (j < k) ? ldexp(x[j], -e) : 0.0;
@@ -92,14 +98,47 @@ __global__ void __launch_bounds__(256) k_ozaki_split(const double* __restrict__ 
   }
 }
 
-// ---------------------------------------------------------------- tcgen05 / TMEM helpers
-__device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* tm, int c0, int c1, int c2, uint64_t* bar) {
-  asm volatile(
-      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
-          smem_u32(smem_dst)),
-      "l"(reinterpret_cast<uint64_t>(tm)), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar))
-      : "memory");
+// Unit-major pre-swizzled layout (what the GEMM reads): units [kb][p][row tile of 128] of 8192 bytes each; inside a
+// unit, row r (0..127) is 64 bytes at r*64 and its 16-byte chunk c is stored at chunk c ^ ((r >> 1) & 3) -- the
+// byte image of the canonical K-major SWIZZLE_64B shared-memory tile, so that a unit is fetched by ONE contiguous
+// bulk copy (a 64-row B tile is the upper or lower half of a unit: the swizzle only involves row bits 1-2).
+// One warp per row; every lane converts 4 consecutive k (one 32-bit store per slice).
+__global__ void __launch_bounds__(256) k_ozaki_split_sw(const double* __restrict__ X, int64_t rows, int64_t k,
+                                                       int64_t ldx, int S, int64_t rows_pad, int64_t kp,
+                                                       int8_t* __restrict__ units, int* __restrict__ exps) {
+  const int lane = threadIdx.x & 31;
+  const int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (r >= rows_pad) return;
+  const int64_t RT = rows_pad / OZ_BM, rt = r / OZ_BM;
+  const int rin = (int)(r - rt * OZ_BM);
+  const int sw = (rin >> 1) & 3;
+  int e = 0;
+  const double* x = X + r * ldx;
+  if (r < rows) e = oz_row_exponent(x, k, lane);
+  if (lane == 0) exps[r] = e;
+  const double sc = ldexp(1.0, -e);  // exact power of two
+  for (int64_t j0 = (int64_t)lane * 4; j0 < kp; j0 += 128) {
+    double v[4];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) v[t] = (r < rows && j0 + t < k) ? x[j0 + t] * sc : 0.0;
+    const int64_t kb = j0 / OZ_BK;
+    const int jj = (int)(j0 - kb * OZ_BK);  // byte within the 64-byte row: chunk jj/16, offset jj%16 (multiple of 4)
+    const int off = rin * OZ_BK + (((jj >> 4) ^ sw) << 4) + (jj & 15);
+    for (int p = 0; p < S; ++p) {
+      uint32_t word = 0;
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        v[t] *= (double)(1 << OZ_BITS);
+        const double q = rint(v[t]);
+        v[t] -= q;
+        word |= ((uint32_t)(int)q & 0xffu) << (8 * t);
+      }
+      *reinterpret_cast<uint32_t*>(units + (((kb * S + p) * RT + rt) * (int64_t)OZ_A_BYTES + off)) = word;
+    }
+  }
 }
+
+// ---------------------------------------------------------------- tcgen05 / TMEM helpers
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 // arrives (count 1) on an mbarrier once every tcgen05.mma issued so far by this thread has completed
@@ -119,21 +158,19 @@ __device__ __forceinline__ void tc_mma_i8(uint32_t tmem_d, uint64_t desc_a, uint
       "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
 }
-// Shared-memory matrix descriptor, K-major operand in the canonical 128-byte-swizzle layout TMA writes
-// (cute::UMMA::SmemDescriptor, cute/arch/mma_sm100_desc.hpp): rows are 128 bytes apart, an 8-row swizzle
-// atom is 1024 bytes.
+// Shared-memory matrix descriptor, K-major operand in the canonical 64-byte-swizzle layout
+// (cute::UMMA::SmemDescriptor, cute/arch/mma_sm100_desc.hpp): rows are 64 bytes apart, an 8-row swizzle atom is
+// 512 bytes, the 16-byte chunk index of a row is XORed with bits [1,3) of the row number.
 //   [0,14) start address >> 4 | [16,30) leading byte offset >> 4 (1 for swizzled K-major) |
-//   [32,46) stride byte offset >> 4 (1024 B between 8-row groups) | [46,48) version = 1 (Blackwell) |
-//   [49,52) base offset = 0 (tiles are 1024-byte aligned) | [61,64) layout type = 2 (SWIZZLE_128B)
-// (64-byte swizzle: rows 64 bytes apart, atom 512 bytes, layout type 4)
-template <int BK>
+//   [32,46) stride byte offset >> 4 (512 B between 8-row groups) | [46,48) version = 1 (Blackwell) |
+//   [49,52) base offset = 0 (tiles are 1024-byte aligned) | [61,64) layout type = 4 (SWIZZLE_64B)
 __device__ __forceinline__ uint64_t umma_desc_kmajor(uint32_t smem_addr) {
   uint64_t d = 0;
   d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
   d |= (uint64_t)1 << 16;
-  d |= (uint64_t)((8 * BK) >> 4) << 32;
+  d |= (uint64_t)((8 * OZ_BK) >> 4) << 32;
   d |= (uint64_t)1 << 46;
-  d |= (uint64_t)(BK == 128 ? 2 : 4) << 61;
+  d |= (uint64_t)4 << 61;
   return d;
 }
 // Instruction descriptor (cute::UMMA::InstrDescriptor): [4,6) D format = 2 (S32) | [7,10) A format = 1
@@ -160,14 +197,19 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, int (&v)[32]) {
 struct OzArgs {
   int64_t m, n;      // C is m x n (rows of A, rows of B)
   int64_t kp;        // padded contraction length (multiple of OZ_KPAD)
+  int64_t rt_a, rt_b;  // 128-row tiles per slice of A / B (the unit strides)
   int S;             // slices per operand
   int tri;           // 1: only tiles that touch the lower triangle (m == n, A and B the same row set)
   double alpha;      // +1 or -1 (any finite value works)
+  const int8_t* ua;  // units of A: [kb][p][rt_a][8192]
+  const int8_t* ub;  // units of B
   const int* ea;     // row exponents of A (m_pad)
   const int* eb;     // row exponents of B (n_pad)
   double* C;
   int64_t ldc;
   int* dbg_levels;   // bring-up: raw int32 level sums, [S][m][n] (NULL in production)
+  int dbg_flags;     // timing experiments (SGDML_B200_OZAKI_DBG): 1 = no global read-modify-write in the epilogue,
+                     // 2 = no tcgen05.mma issued, 4 = epilogue reads only one level
 };
 
 struct OzSmemTail {
@@ -179,27 +221,51 @@ struct OzSmemTail {
 };
 
 constexpr size_t OZ_SMEM_BYTES = (size_t)OZ_RING_BYTES + sizeof(OzSmemTail) + 1024;
+constexpr int OZ_STAGE_LD = 33;  // doubles per row of the epilogue transpose tiles (32 + 1: conflict-free both ways)
+static_assert(4 * 32 * OZ_STAGE_LD * 8 <= OZ_RING_BYTES, "the epilogue stages through the (then idle) ring");
 
 // slice visited at position idx of a k-block: 1, S, 2, S-1, ...  (1-based slice numbers)
 __device__ __forceinline__ int oz_order(int idx, int S) { return (idx & 1) ? S - (idx >> 1) : 1 + (idx >> 1); }
 // position of slice p in that order
 __device__ __forceinline__ int oz_pos(int p, int S) { return (2 * p <= S + 1) ? 2 * (p - 1) : 2 * (S - p) + 1; }
 
-template <int BK>
-__global__ void __launch_bounds__(192, 1) k_ozaki_gemm(const __grid_constant__ CUtensorMap tmA,
-                                                      const __grid_constant__ CUtensorMap tmB, const OzArgs p) {
-  using Cfg = OzCfg<BK>;
-  constexpr int OZ_A_BYTES = Cfg::A_BYTES, OZ_UNIT_BYTES = Cfg::UNIT_BYTES, OZ_BK = BK;
+// CTA number -> tile (tm, tn), super-tile by super-tile; false if the CTA has no tile
+__device__ __forceinline__ bool oz_tile_of_cta(const OzArgs& p, int64_t cta, int64_t& tm, int64_t& tn) {
+  constexpr int PER = OZ_GSM * OZ_GSN;
+  const int64_t ntm = (p.m + OZ_BM - 1) / OZ_BM, ntn = (p.n + OZ_BN - 1) / OZ_BN;
+  const int64_t sb = cta / PER;
+  const int local = (int)(cta - sb * PER);
+  int64_t si, sj;
+  if (p.tri) {  // super-tiles of the lower triangle (1024 x 1024 each): row t holds t + 1 of them
+    int64_t t = (int64_t)((sqrt(8.0 * (double)sb + 1.0) - 1.0) * 0.5);
+    while ((t + 1) * (t + 2) / 2 <= sb) ++t;
+    while (t * (t + 1) / 2 > sb) --t;
+    si = t;
+    sj = sb - t * (t + 1) / 2;
+  } else {
+    const int64_t nsn = (ntn + OZ_GSN - 1) / OZ_GSN;
+    si = sb / nsn;
+    sj = sb - si * nsn;
+  }
+  // inside a super-tile the n tiles of one m tile are adjacent: concurrently resident CTAs share the A tile
+  tm = si * OZ_GSM + local / OZ_GSN;
+  tn = sj * OZ_GSN + local % OZ_GSN;
+  if (tm >= ntm || tn >= ntn) return false;
+  if (p.tri && tn * OZ_BN > tm * OZ_BM + OZ_BM - 1) return false;  // entirely above the diagonal
+  return true;
+}
+
+__global__ void __launch_bounds__(192, 1) k_ozaki_gemm(const OzArgs p) {
   extern __shared__ unsigned char oz_raw[];
   // 1024-byte alignment for the swizzled tiles
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(oz_raw) + 1023) & ~(uintptr_t)1023);
-  const int S = p.S, R = oz_ring_slots(S, Cfg::MAX_SLOTS);
+  const int S = p.S, R = oz_ring_slots(S);
   OzSmemTail* tail = reinterpret_cast<OzSmemTail*>(smem + (size_t)OZ_RING_BYTES);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
-  const int64_t m0 = (int64_t)blockIdx.y * OZ_BM, n0 = (int64_t)blockIdx.x * OZ_BN;
-  if (m0 >= p.m || n0 >= p.n) return;
-  if (p.tri && n0 > m0 + OZ_BM - 1) return;  // the tile lies entirely above the diagonal
+  int64_t tm, tn;
+  if (!oz_tile_of_cta(p, (int64_t)blockIdx.x, tm, tn)) return;
+  const int64_t m0 = tm * OZ_BM, n0 = tn * OZ_BN;
 
   if (tid == 0) {
     for (int i = 0; i < R; ++i) {
@@ -226,8 +292,11 @@ __global__ void __launch_bounds__(192, 1) k_ozaki_gemm(const __grid_constant__ C
   const int KB = (int)(p.kp / OZ_BK);
 
   if (warp == 0) {
-    // ===================================================== TMA producer
+    // ===================================================== producer: two contiguous bulk copies per unit
     if (lane == 0) {
+      const int8_t* a_base = p.ua + tm * (int64_t)OZ_A_BYTES;
+      const int8_t* b_base = p.ub + (n0 / OZ_BM) * (int64_t)OZ_A_BYTES + (n0 % OZ_BM) * OZ_BK;
+      const int64_t a_stride = p.rt_a * (int64_t)OZ_A_BYTES, b_stride = p.rt_b * (int64_t)OZ_A_BYTES;  // per (kb, slice)
       int64_t u = 0;
       for (int kb = 0; kb < KB; ++kb) {
         for (int idx = 0; idx < S; ++idx, ++u) {
@@ -235,10 +304,10 @@ __global__ void __launch_bounds__(192, 1) k_ozaki_gemm(const __grid_constant__ C
           const uint32_t round = (uint32_t)(u / R);
           if (round > 0) mbar_wait(&tail->empty[slot], (round - 1) & 1);  // the slot's previous unit is dead
           unsigned char* base = smem + (size_t)slot * OZ_UNIT_BYTES;
-          const int sl = oz_order(idx, S) - 1;
+          const int64_t ks = (int64_t)kb * S + (oz_order(idx, S) - 1);
           mbar_arrive_expect_tx(&tail->full[slot], (uint32_t)OZ_UNIT_BYTES);
-          tma_load_3d(base, &tmA, kb * OZ_BK, (int)m0, sl, &tail->full[slot]);
-          tma_load_3d(base + OZ_A_BYTES, &tmB, kb * OZ_BK, (int)n0, sl, &tail->full[slot]);
+          bulk_g2s(base, a_base + ks * a_stride, OZ_A_BYTES, &tail->full[slot]);
+          bulk_g2s(base + OZ_A_BYTES, b_base + ks * b_stride, OZ_B_BYTES, &tail->full[slot]);
         }
       }
     }
@@ -269,9 +338,9 @@ __global__ void __launch_bounds__(192, 1) k_ozaki_gemm(const __grid_constant__ C
 #pragma unroll
               for (int ks = 0; ks < OZ_BK / OZ_UMMA_K; ++ks) {
                 // advancing along K inside the swizzle row: +32 bytes on the start address
-                const uint64_t da = umma_desc_kmajor<BK>(a_addr + ks * OZ_UMMA_K);
-                const uint64_t db = umma_desc_kmajor<BK>(b_addr + ks * OZ_UMMA_K);
-                tc_mma_i8(d_addr, da, db, IDESC, (level_started >> level) & 1u);
+                const uint64_t da = umma_desc_kmajor(a_addr + ks * OZ_UMMA_K);
+                const uint64_t db = umma_desc_kmajor(b_addr + ks * OZ_UMMA_K);
+                if (!(p.dbg_flags & 2)) tc_mma_i8(d_addr, da, db, IDESC, (level_started >> level) & 1u);
                 level_started |= 1u << level;
               }
             }
@@ -281,7 +350,7 @@ __global__ void __launch_bounds__(192, 1) k_ozaki_gemm(const __grid_constant__ C
           if (S + 1 - r != r) tc_commit(&tail->empty[(ub + oz_pos(S + 1 - r, S)) % R]);
         }
       }
-      tc_commit(&tail->acc_full);  // every accumulator is final
+      tc_commit(&tail->acc_full);  // every accumulator is final (and every unit has been consumed)
     }
   } else {
     // ===================================================== epilogue (warps 2..5 = 128 threads)
@@ -291,12 +360,13 @@ __global__ void __launch_bounds__(192, 1) k_ozaki_gemm(const __grid_constant__ C
     mbar_wait(&tail->acc_full, 0);
     tc_fence_after();
     const double row_scale = (gr < p.m) ? p.alpha * ldexp(1.0, p.ea[gr]) : 0.0;
+    double* stage = reinterpret_cast<double*>(smem) + (size_t)quad * 32 * OZ_STAGE_LD;  // this warp's 32 x 32 tile
 #pragma unroll 1
     for (int half = 0; half < OZ_BN / 32; ++half) {
       double acc[32];
 #pragma unroll
       for (int j = 0; j < 32; ++j) acc[j] = 0.0;
-      for (int level = S + 1; level >= 2; --level) {  // smallest contributions first
+      for (int level = (p.dbg_flags & 4) ? 2 : S + 1; level >= 2; --level) {  // smallest contributions first
         int v[32];
         tmem_ld_32x32(tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)((level - 2) * OZ_BN + half * 32), v);
         const double w = ldexp(1.0, -OZ_BITS * level);
@@ -309,12 +379,19 @@ __global__ void __launch_bounds__(192, 1) k_ozaki_gemm(const __grid_constant__ C
           }
         }
       }
-      if (gr < p.m) {
-        double* crow = p.C + gr * p.ldc + n0 + half * 32;
+      // transpose through shared memory: thread = row on the TMEM side, lane = column on the global side, so
+      // that every warp-wide access to C covers 256 contiguous bytes of one row
+      __syncwarp();
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const int64_t gc = n0 + half * 32 + j;
-          if (gc < p.n) crow[j] += acc[j] * row_scale * tail->col_scale[half * 32 + j];
+      for (int j = 0; j < 32; ++j) stage[lane * OZ_STAGE_LD + j] = acc[j] * row_scale * tail->col_scale[half * 32 + j];
+      __syncwarp();
+      if (!(p.dbg_flags & 1)) {
+        const int64_t gc = n0 + half * 32 + lane;
+        const int rows_here = (int)max((int64_t)0, min((int64_t)32, p.m - (m0 + quad * 32)));
+        if (gc < p.n) {
+          double* cp = p.C + (m0 + quad * 32) * p.ldc + gc;
+#pragma unroll 4
+          for (int r = 0; r < rows_here; ++r) cp[(int64_t)r * p.ldc] += stage[r * OZ_STAGE_LD + lane];
         }
       }
     }
@@ -328,48 +405,8 @@ __global__ void __launch_bounds__(192, 1) k_ozaki_gemm(const __grid_constant__ C
 }
 
 // ---------------------------------------------------------------- host side
-typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                        const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                        CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static PFN_tmapEncodeTiled oz_tmap_encoder() {
-  static PFN_tmapEncodeTiled fn = nullptr;
-  if (fn == nullptr) {
-    void* ptr = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess &&
-        q == cudaDriverEntryPointSuccess)
-      fn = reinterpret_cast<PFN_tmapEncodeTiled>(ptr);
-  }
-  return fn;
-}
-
-// planes [S][rows_pad][kp] int8 -> 3-D map, box = 128 bytes of k x box_rows rows x 1 slice, 128-byte swizzle
-static int oz_make_map(CUtensorMap* tm, const int8_t* planes, int S, int64_t rows_pad, int64_t kp, int box_rows, int bk) {
-  PFN_tmapEncodeTiled enc = oz_tmap_encoder();
-  if (enc == nullptr) {
-    set_last_error("cuTensorMapEncodeTiled is not available from this driver");
-    return SGDML_B200_ERR_UNSUPPORTED;
-  }
-  cuuint64_t dims[3] = {(cuuint64_t)kp, (cuuint64_t)rows_pad, (cuuint64_t)S};
-  cuuint64_t strides[2] = {(cuuint64_t)kp, (cuuint64_t)(rows_pad * kp)};
-  cuuint32_t box[3] = {(cuuint32_t)bk, (cuuint32_t)box_rows, 1};
-  cuuint32_t estr[3] = {1, 1, 1};
-  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<int8_t*>(planes), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, bk == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
-                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) {
-    char buf[128];
-    snprintf(buf, sizeof(buf), "cuTensorMapEncodeTiled (int8 planes) failed with CUresult %d", (int)r);
-    set_last_error(buf);
-    return SGDML_B200_ERR_ARG;
-  }
-  return 0;
-}
-
 struct OzOperand {
-  int8_t* planes = nullptr;
+  int8_t* units = nullptr;   // [kb][p][rt][8192]
   int* exps = nullptr;
   int64_t rows_pad = 0, kp = 0;
 };
@@ -379,14 +416,14 @@ static size_t oz_plane_bytes(int64_t rows, int64_t k, int S) {
   return (size_t)S * rows_pad * kp;
 }
 
-// slices X (rows x k) into caller-provided device memory
-static int oz_split_into(const double* X, int64_t rows, int64_t k, int64_t ldx, int S, int8_t* planes, int* exps,
+// slices X (rows x k) into caller-provided device memory (unit-major pre-swizzled layout)
+static int oz_split_into(const double* X, int64_t rows, int64_t k, int64_t ldx, int S, int8_t* units, int* exps,
                          OzOperand* o, cudaStream_t s) {
   o->rows_pad = (rows + OZ_BM - 1) / OZ_BM * OZ_BM;
   o->kp = (k + OZ_KPAD - 1) / OZ_KPAD * OZ_KPAD;
-  o->planes = planes;
+  o->units = units;
   o->exps = exps;
-  k_ozaki_split<<<ceil_div(o->rows_pad, 8), 256, 0, s>>>(X, rows, k, ldx, S, o->rows_pad, o->kp, o->planes, o->exps);
+  k_ozaki_split_sw<<<ceil_div(o->rows_pad, 8), 256, 0, s>>>(X, rows, k, ldx, S, o->rows_pad, o->kp, o->units, o->exps);
   SG_CUDA(cudaGetLastError());
   count_launch(KID_GEMM);
   return 0;
@@ -394,43 +431,51 @@ static int oz_split_into(const double* X, int64_t rows, int64_t k, int64_t ldx, 
 
 static int oz_launch(const OzOperand& oa, const OzOperand& ob, int64_t m, int64_t n, double alpha, double* C,
                      int64_t ldc, int S, int tri, cudaStream_t s, int* dbg_levels = nullptr) {
-  // unit width: 64 bytes (default, deep ring) or 128 bytes (SGDML_B200_OZAKI_BK=128, the plain 128-byte swizzle)
-  const char* bke = getenv("SGDML_B200_OZAKI_BK");
-  const int bk = (bke != nullptr && atoi(bke) == 128) ? 128 : 64;
-  CUtensorMap tmA, tmB;
-  SG_TRY(oz_make_map(&tmA, oa.planes, S, oa.rows_pad, oa.kp, OZ_BM, bk));
-  SG_TRY(oz_make_map(&tmB, ob.planes, S, ob.rows_pad, ob.kp, OZ_BN, bk));
   static bool configured[64] = {false};
   int dev = 0;
   SG_CUDA(cudaGetDevice(&dev));
   if (dev >= 0 && dev < 64 && !configured[dev]) {
-    SG_CUDA(cudaFuncSetAttribute(k_ozaki_gemm<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)OZ_SMEM_BYTES));
-    SG_CUDA(cudaFuncSetAttribute(k_ozaki_gemm<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)OZ_SMEM_BYTES));
+    SG_CUDA(cudaFuncSetAttribute(k_ozaki_gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)OZ_SMEM_BYTES));
     configured[dev] = true;
   }
+  SG_ARG(oa.kp == ob.kp);
   OzArgs a;
   a.m = m;
   a.n = n;
   a.kp = oa.kp;
+  a.rt_a = oa.rows_pad / OZ_BM;
+  a.rt_b = ob.rows_pad / OZ_BM;
   a.S = S;
   a.tri = tri;
   a.alpha = alpha;
+  a.ua = oa.units;
+  a.ub = ob.units;
   a.ea = oa.exps;
   a.eb = ob.exps;
   a.C = C;
   a.ldc = ldc;
   a.dbg_levels = dbg_levels;
-  dim3 grid((unsigned)ceil_div(n, OZ_BN), (unsigned)ceil_div(m, OZ_BM));
-  SG_ARG(grid.y <= 65535);
+  {
+    const char* df = getenv("SGDML_B200_OZAKI_DBG");
+    a.dbg_flags = df ? atoi(df) : 0;
+  }
+  const int64_t ntm = ceil_div(m, OZ_BM), ntn = ceil_div(n, OZ_BN);
+  int64_t n_super;
+  if (tri) {
+    const int64_t sr = (ntm + OZ_GSM - 1) / OZ_GSM;  // 1024-row super-tile rows; (GSM * BM == GSN * BN)
+    n_super = sr * (sr + 1) / 2;
+  } else {
+    n_super = ((ntm + OZ_GSM - 1) / OZ_GSM) * ((ntn + OZ_GSN - 1) / OZ_GSN);
+  }
+  const int64_t blocks = n_super * OZ_GSM * OZ_GSN;
+  SG_ARG(blocks < ((int64_t)1 << 31));
   ProfScope ps(KID_GEMM, s);
-  if (bk == 128)
-    k_ozaki_gemm<128><<<grid, 192, OZ_SMEM_BYTES, s>>>(tmA, tmB, a);
-  else
-    k_ozaki_gemm<64><<<grid, 192, OZ_SMEM_BYTES, s>>>(tmA, tmB, a);
+  k_ozaki_gemm<<<(unsigned)blocks, 192, OZ_SMEM_BYTES, s>>>(a);
   SG_CUDA(cudaGetLastError());
   count_launch(KID_GEMM);
   return 0;
 }
+static_assert(OZ_GSM * OZ_BM == OZ_GSN * OZ_BN, "square super-tiles (the triangular raster relies on it)");
 
 // Workspace of the symmetric update used by potrf: allocated once per factorisation (a cudaMalloc /
 // cudaFree pair costs ~20 ms in a process that holds tens of GB -- see csrc/core.cu), reused by every
@@ -489,8 +534,8 @@ int ozaki_gemm_nt_device(int64_t m, int64_t n, int64_t k, double alpha, const do
 }
 
 // Bring-up aid: runs the split and the int8 products and hands back every intermediate.
-//   planes_a [S][m_pad][kp] int8, exps_a [m_pad], planes_b / exps_b likewise, levels [S][m][n] int32
-// (all device pointers; any of them may be NULL).  C receives C + A B^T as usual.
+//   planes_a [S][m_pad][kp] int8 (plain row-major layout), exps_a [m_pad], planes_b / exps_b likewise,
+//   levels [S][m][n] int32 (all device pointers; any of them may be NULL).  C receives C + A B^T as usual.
 int ozaki_debug_device(int64_t m, int64_t n, int64_t k, const double* A, int64_t lda, const double* B, int64_t ldb,
                        double* C, int64_t ldc, int S, int8_t* planes_a, int* exps_a, int8_t* planes_b, int* exps_b,
                        int* levels, cudaStream_t s) {
@@ -506,16 +551,24 @@ int ozaki_debug_device(int64_t m, int64_t n, int64_t k, const double* A, int64_t
   auto body = [&]() -> int {
     OzOperand oa, ob;
     const size_t ba = oz_plane_bytes(m, k, S), bb = oz_plane_bytes(n, k, S);
-    const size_t ea = sizeof(int) * (size_t)((m + OZ_BM - 1) / OZ_BM * OZ_BM), eb = sizeof(int) * (size_t)((n + OZ_BM - 1) / OZ_BM * OZ_BM);
+    const int64_t mp = (m + OZ_BM - 1) / OZ_BM * OZ_BM, np = (n + OZ_BM - 1) / OZ_BM * OZ_BM, kp = (k + OZ_KPAD - 1) / OZ_KPAD * OZ_KPAD;
+    const size_t ea = sizeof(int) * (size_t)mp, eb = sizeof(int) * (size_t)np;
     SG_CUDA(cudaMalloc(&pa, ba));
     SG_CUDA(cudaMalloc(&xa, ea));
     SG_CUDA(cudaMalloc(&pb, bb));
     SG_CUDA(cudaMalloc(&xb, eb));
+    // the plain-layout planes for the caller (their exponents are the ones the GEMM uses too)
+    if (planes_a) {
+      k_ozaki_split<<<ceil_div(mp, 8), 256, 0, s>>>(A, m, k, lda, S, mp, kp, planes_a, xa);
+      SG_CUDA(cudaGetLastError());
+    }
+    if (planes_b) {
+      k_ozaki_split<<<ceil_div(np, 8), 256, 0, s>>>(B, n, k, ldb, S, np, kp, planes_b, xb);
+      SG_CUDA(cudaGetLastError());
+    }
     SG_TRY(oz_split_into(A, m, k, lda, S, pa, xa, &oa, s));
     SG_TRY(oz_split_into(B, n, k, ldb, S, pb, xb, &ob, s));
-    if (planes_a) SG_CUDA(cudaMemcpyAsync(planes_a, pa, ba, cudaMemcpyDeviceToDevice, s));
     if (exps_a) SG_CUDA(cudaMemcpyAsync(exps_a, xa, ea, cudaMemcpyDeviceToDevice, s));
-    if (planes_b) SG_CUDA(cudaMemcpyAsync(planes_b, pb, bb, cudaMemcpyDeviceToDevice, s));
     if (exps_b) SG_CUDA(cudaMemcpyAsync(exps_b, xb, eb, cudaMemcpyDeviceToDevice, s));
     if (C != nullptr) SG_TRY(oz_launch(oa, ob, m, n, 1.0, C, ldc, S, 0, s, levels));
     SG_CUDA(cudaStreamSynchronize(s));

@@ -1160,8 +1160,12 @@ int sgdml_b200_model_set_R_d_desc(sgdml_b200_model* m, const double* R_d_desc) {
   SG_TRY(require_device());
   SG_ARG(m != nullptr && R_d_desc != nullptr);
   const size_t bytes = sizeof(double) * (size_t)m->M * m->D * 3;
+  // this entry point has no stream argument: order it against work the caller may have in flight on ANY
+  // stream (k_set_alphas / predict kernels of a non-blocking torch stream read m->R_d_desc)
+  SG_CUDA(cudaDeviceSynchronize());
   if (m->R_d_desc == nullptr) SG_CUDA(cudaMalloc(&m->R_d_desc, bytes));
   SG_CUDA(cudaMemcpy(m->R_d_desc, R_d_desc, bytes, cudaMemcpyDefault));
+  SG_CUDA(cudaDeviceSynchronize());
   return 0;
 }
 
@@ -1218,9 +1222,18 @@ int sgdml_b200_predict_train(sgdml_b200_model* m, int64_t m_begin, int64_t m_end
   return 0;
 }
 
+int sgdml_b200_model_dims(const sgdml_b200_model* m, int64_t* n_atoms, int64_t* n_train, int64_t* n_perms) {
+  SG_ARG(m != nullptr);
+  if (n_atoms) *n_atoms = m->N;
+  if (n_train) *n_train = m->M;
+  if (n_perms) *n_perms = m->S;
+  return 0;
+}
+
 int sgdml_b200_model_get_R_d_desc_alpha(sgdml_b200_model* m, double* out) {
   SG_TRY(require_device());
   SG_ARG(m != nullptr && out != nullptr);
+  SG_CUDA(cudaDeviceSynchronize());  // no stream argument: wait for set_alphas kernels on the caller's streams
   Staged sO;
   SG_TRY(sO.init(out, sizeof(double) * (size_t)m->M * m->D, false, 0));
   const int64_t tot = (int64_t)m->M * m->D;

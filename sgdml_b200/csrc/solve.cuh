@@ -27,6 +27,14 @@ int potrs_device(const double* L, int64_t n, int64_t lda, double* B, int64_t nrh
 int trsm_right_lt_device(const double* L, int64_t m, int64_t ldl, double* X, int64_t n_rows, int64_t ldx,
                          cudaStream_t s);
 
+// csrc/nystroem.cu: the two halves of the preconditioner application on device vectors (stream-ordered, no
+// synchronisation); part must hold m * xtv_chunks(n_rows) doubles
+int64_t xtv_chunks(int64_t n_rows);
+int xt_v_device(const double* X, int64_t n_rows, int64_t m, int64_t ldx, const double* v_dev, double* t_dev,
+                double* part, cudaStream_t s);
+int x_t_minus_v_device(const double* X, int64_t n_rows, int64_t m, int64_t ldx, double lam, const double* t_dev,
+                       const double* v_dev, double* out_dev, cudaStream_t s);
+
 // csrc/ozaki.cu: C += alpha A B^T through n_slices int8 slices per operand on tcgen05 (experimental)
 int ozaki_gemm_nt_device(int64_t m, int64_t n, int64_t k, double alpha, const double* A, int64_t lda, const double* B,
                          int64_t ldb, double* C, int64_t ldc, int n_slices, int tri, cudaStream_t s);

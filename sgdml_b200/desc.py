@@ -98,6 +98,9 @@ class Desc(object):
             ),
             'vec_dot_d_desc',
         )
+        if out is not None:  # desc.py:388-408 fills a caller-provided array in place
+            out[...] = res.reshape(out.shape)
+            return out
         return res
 
     @staticmethod

@@ -44,28 +44,83 @@ def _device_for_backend(group=None):
     return torch.device('cuda', torch.cuda.current_device()) if backend == 'nccl' else torch.device('cpu')
 
 
+def all_reduce_min_scalar(value, group=None):
+    """min over the ranks of a host scalar (a memory budget every rank must agree on)."""
+    import torch
+
+    dist = _dist()
+    if world_info(group)[1] == 1:
+        return value
+    t = torch.tensor([float(value)], dtype=torch.float64, device=_device_for_backend(group))
+    dist.all_reduce(t, op=dist.ReduceOp.MIN, group=group)
+    return float(t.item())
+
+
 def all_gather_rows(local, n_total, group=None):
     """Gathers row-sharded arrays (shards as produced by shard_bounds) into the full array on
-    every rank.  One all_gather; shards are padded to the largest shard."""
+    every rank.  One all_gather; shards are padded to the largest shard.  A torch tensor stays a tensor
+    on its device (CUDA tensors never touch the host: NCCL moves them over NVLink); a NumPy array comes
+    back as a NumPy array."""
     import torch
 
     dist = _dist()
     rank, world = world_info(group)
-    local = np.ascontiguousarray(local, dtype=np.float64)
+    is_tensor = hasattr(local, 'data_ptr')
+    if not is_tensor:
+        local = np.ascontiguousarray(local, dtype=np.float64)
     if world == 1:
         return local
     dev = _device_for_backend(group)
-    tail = local.shape[1:]
+    loc_t = (local if is_tensor else torch.from_numpy(local)).to(dev)
+    tail = tuple(loc_t.shape[1:])
     max_rows = shard_bounds(n_total, world, 0)[1]
-    buf = torch.zeros((max_rows,) + tail, dtype=torch.float64, device=dev)
-    buf[: local.shape[0]] = torch.from_numpy(local).to(dev)
-    out = [torch.empty_like(buf) for _ in range(world)]
-    dist.all_gather(out, buf, group=group)
-    parts = []
+    if n_total % world == 0:  # equal shards: gather straight into the result
+        full = torch.empty((n_total,) + tail, dtype=torch.float64, device=dev)
+        dist.all_gather_into_tensor(full, loc_t.contiguous(), group=group)
+    else:
+        buf = torch.zeros((max_rows,) + tail, dtype=torch.float64, device=dev)
+        buf[: loc_t.shape[0]] = loc_t
+        out = torch.empty((world, max_rows) + tail, dtype=torch.float64, device=dev)
+        dist.all_gather_into_tensor(out, buf, group=group)
+        full = torch.cat([out[r, : shard_bounds(n_total, world, r)[1] - shard_bounds(n_total, world, r)[0]] for r in range(world)], dim=0)
+    if is_tensor:
+        return full.to(local.device)
+    return full.cpu().numpy()
+
+
+def exchange_on_workspace(ws, off, count, op, n_train, dim_i, group=None):
+    """The exchange function of `sgdml_b200_pcg` (include/sgdml_b200.h) on torch.distributed: `ws` is the
+    solver's device workspace (a flat float64 tensor), [off, off + count) the buffer of this exchange.
+      op 0: sum over the ranks in place (X^T v of the row-sharded Nystroem factor, m doubles);
+      op 1: all-gather of a replicated n-vector whose rows [lo*dim_i, hi*dim_i) this rank has just written
+            (K.v rows, P.v rows): in place when the shards are equal, through a padded staging tensor otherwise.
+    Collectives are enqueued in stream order on the backend's stream; nothing is copied to the host."""
+    import torch
+
+    dist = _dist()
+    rank, world = world_info(group)
+    view = ws[off : off + count]
+    if world == 1:
+        return
+    if op == 0:
+        dist.all_reduce(view, op=dist.ReduceOp.SUM, group=group)
+        return
+    if op != 1:
+        raise ValueError('unknown exchange op %r' % (op,))
+    assert count == n_train * dim_i
+    lo, hi = shard_bounds(n_train, world, rank)
+    if n_train % world == 0:
+        dist.all_gather_into_tensor(view, view[lo * dim_i : hi * dim_i], group=group)
+        return
+    max_rows = shard_bounds(n_train, world, 0)[1] * dim_i
+    buf = torch.zeros(max_rows, dtype=ws.dtype, device=ws.device)
+    buf[: (hi - lo) * dim_i] = view[lo * dim_i : hi * dim_i]
+    out = torch.empty(world * max_rows, dtype=ws.dtype, device=ws.device)
+    dist.all_gather_into_tensor(out, buf, group=group)
     for r in range(world):
-        lo, hi = shard_bounds(n_total, world, r)
-        parts.append(out[r][: hi - lo].cpu().numpy())
-    return np.concatenate(parts, axis=0)
+        rlo, rhi = shard_bounds(n_train, world, r)
+        if r != rank:
+            view[rlo * dim_i : rhi * dim_i] = out[r * max_rows : r * max_rows + (rhi - rlo) * dim_i]
 
 
 def predict_sharded(predict_fn, R, gather=True, group=None):
@@ -278,21 +333,40 @@ class TrainPointShardedPredictor(object):
         self.part = predictor_cls(model_shard(model, self.lo, self.hi)) if self.hi > self.lo else None
 
     def predict(self, R, return_E=True):
+        """R: NumPy array (B, 3N) -> NumPy (E, F); or a CUDA float64 tensor -> CUDA tensors, in which case the
+        partial results, the all-reduce (NCCL) and the scaling all stay on the device."""
         import torch
 
-        R = np.asarray(R, dtype=np.float64)
-        if R.ndim == 1:
-            R = R[None, :]  # predict.py:1183-1184
+        on_device = hasattr(R, 'data_ptr') and R.is_cuda
+        if not on_device:
+            R = np.asarray(R, dtype=np.float64)
+            if R.ndim == 1:
+                R = R[None, :]  # predict.py:1183-1184
+            B = R.shape[0]
+            buf = np.zeros((B, self.dim_i + 1))
+            if self.part is not None:
+                E, F = self.part.predict(R)
+                buf[:, 0], buf[:, 1:] = E, F.reshape(B, -1)
+            if world_info(self.group)[1] > 1:
+                t = torch.from_numpy(buf).to(_device_for_backend(self.group))
+                all_reduce_sum_(t, self.group)
+                buf = t.cpu().numpy()
+            F = buf[:, 1:] * self.std  # predict.py:1286-1288
+            if not return_E:
+                return (F,)
+            return buf[:, 0] * self.std + self.c, F
+        R = R.reshape(-1, self.dim_i)
         B = R.shape[0]
-        buf = np.zeros((B, self.dim_i + 1))
+        # one buffer [F | E] so that ONE all-reduce of B*(3N+1) doubles carries both (SURVEY 8e)
+        buf = torch.zeros(B * (self.dim_i + 1), dtype=torch.float64, device=R.device)
+        F_v = buf[: B * self.dim_i].view(B, self.dim_i)
+        E_v = buf[B * self.dim_i :]
         if self.part is not None:
-            E, F = self.part.predict(R)
-            buf[:, 0], buf[:, 1:] = E, F.reshape(B, -1)
-        if world_info(self.group)[1] > 1:
-            t = torch.from_numpy(buf).to(_device_for_backend(self.group))
-            all_reduce_sum_(t, self.group)
-            buf = t.cpu().numpy()
-        F = buf[:, 1:] * self.std  # predict.py:1286-1288
+            self.part.predict(R, out=(E_v, F_v))
+        all_reduce_sum_(buf, self.group)
+        F_v *= self.std
         if not return_E:
-            return (F,)
-        return buf[:, 0] * self.std + self.c, F
+            return (F_v,)
+        E_v *= self.std
+        E_v += self.c
+        return E_v, F_v

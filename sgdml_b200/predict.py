@@ -192,13 +192,38 @@ class GDMLPredict(object):
                 pin = (not R.is_cuda) and R.is_pinned()  # pinned host tensor in -> pinned host tensors out
                 F = torch.empty((n, dim_i), dtype=torch.float64, device=R.device, pin_memory=pin)
                 E = torch.empty((n,), dtype=torch.float64, device=R.device, pin_memory=pin) if return_E else None
-        if tuple(F.shape) != (n, dim_i) or (E is not None and tuple(E.shape) != (n,)):
-            raise ValueError('out buffers have the wrong shape')
+        if not return_E:
+            E = None  # the engine skips the energy output entirely
+        self._check_out(R, E, F, n, dim_i)
         _lib.check(
             L.sgdml_b200_predict(self._handle, _lib.ptr(R), n, _lib.ptr(E), _lib.ptr(F), _lib.current_stream()),
             'predict',
         )
         return (E, F) if return_E else (F,)
+
+    @staticmethod
+    def _check_out(R, E, F, n, dim_i):
+        """Output buffers go to the engine as raw double*: wrong dtype / layout / device would corrupt memory."""
+        for buf, shape, name in ((F, (n, dim_i), 'F'), (E, (n,), 'E')):
+            if buf is None:
+                continue
+            if tuple(buf.shape) != shape:
+                raise ValueError('out buffer %s has the wrong shape %s (expected %s)' % (name, tuple(buf.shape), shape))
+            if isinstance(buf, np.ndarray):
+                if buf.dtype != np.float64 or not buf.flags['C_CONTIGUOUS'] or not buf.flags['WRITEABLE']:
+                    raise ValueError('out buffer %s must be a writeable C-contiguous float64 array' % name)
+                if not isinstance(R, np.ndarray) and R.is_cuda:
+                    raise ValueError('out buffer %s is a host array but R is a CUDA tensor' % name)
+            else:
+                import torch
+
+                if buf.dtype != torch.float64 or not buf.is_contiguous():
+                    raise ValueError('out buffer %s must be a contiguous float64 tensor' % name)
+                r_dev = None if isinstance(R, np.ndarray) else R.device
+                if buf.is_cuda and (r_dev is None or buf.device != r_dev):
+                    raise ValueError('out buffer %s lives on %s but R does not' % (name, buf.device))
+                if (not buf.is_cuda) and r_dev is not None and r_dev.type == 'cuda':
+                    raise ValueError('out buffer %s is a host tensor but R is a CUDA tensor' % name)
 
     def kmatvec_train(self, m_begin=0, m_end=None, out=None):
         """Raw (std = 1, c = 0) force sums on training points [m_begin, m_end): the K.v operator

@@ -12,7 +12,8 @@ What is different: the (n x m) block K_nm never leaves HBM -- it is assembled th
 (`sgdml_b200_assemble` with a column list), factorised with the engine's FP64 Cholesky / TRSM /
 Gram kernels (`csrc/nystroem.cu`, `csrc/solve.cu`), and applied with two GEMV kernels per
 iteration; K v is one launch sequence of the fused predictor on the cached training descriptors.
-The O(n) vector updates of CG stay on the host (NumPy), like SciPy's `cg` in the reference.
+The CG loop itself runs on the device too (`sgdml_b200_pcg`, csrc/pcg.cu): vectors and scalars never leave HBM;
+the host sees a residual history every few iterations for the reference's callbacks, checkpoints and restarts.
 """
 
 import collections
@@ -224,6 +225,7 @@ class Iterative(object):
             return sdist.run_steps(sdist.precon_apply_steps(ops, X, m, lam, v, lo, hi, dim_i), n_train)
 
         _P_vec.keepalive = X
+        _P_vec.factor = (X, m, lo, hi)  # the device PCG applies the factor itself (sgdml_b200_pcg)
         return _P_vec, lev_scores
 
     def _init_precon_operator(self, task, R_desc, R_d_desc, tril_perms_lin, inducing_pts_idxs, callback=None):
@@ -249,6 +251,7 @@ class Iterative(object):
             return out
 
         _P_vec.keepalive = X
+        _P_vec.factor = (X, m, 0, R_desc.shape[0])
         return _P_vec, lev_scores
 
     def _init_kernel_operator(self, task, R_desc, R_d_desc, tril_perms_lin, lam, n, callback=None):
@@ -340,91 +343,66 @@ class Iterative(object):
         self.timings['precon_s'] = timeit.default_timer() - t_start
 
         n = lev_scores.size
-        K_vec = self._init_kernel_operator(task, R_desc, R_d_desc, tril_perms_lin, lam, n)
-
-        self.timings.update({'kvec_s': 0.0, 'pvec_s': 0.0})
-
-        def A_vec(v):  # -K_op: the SPD operator (-K + lam I), iterative.py:740-741
-            t_op = timeit.default_timer()
-            out = -K_vec(v)
-            self.timings['kvec_s'] += timeit.default_timer() - t_op
-            return out
-
-        def _timed_precon(fn):
-            def P(v):
-                t_op = timeit.default_timer()
-                out = fn(v)
-                self.timings['pvec_s'] += timeit.default_timer() - t_op
-                return out
-
-            return P
-
-        P_vec = _timed_precon(P_vec)
+        self._init_kernel_operator(task, R_desc, R_d_desc, tril_perms_lin, lam, n)  # -> self.gdml_predict
 
         y = np.ascontiguousarray(y, dtype=np.float64)
         norm_y = _norm(y)
-        x = np.zeros(n) if alphas0_F is None else -np.asarray(alphas0_F, dtype=np.float64).copy()
+        x0 = None if alphas0_F is None else -np.asarray(alphas0_F, dtype=np.float64).copy()
         maxiter = 3 * n_atoms * n_train * 10  # iterative.py:746-749
 
-        num_iters = num_iters0
-        num_restarts = 0
-        steps_hist = collections.deque(maxlen=CG_STEPS_HIST_LEN)
-        is_conv = False
-        t_cg = timeit.default_timer()
-        last_ckpt = t_cg
+        state = {
+            'num_iters': num_iters0,
+            'resid': None,
+            'steps_hist': collections.deque(maxlen=CG_STEPS_HIST_LEN),
+            'restart': False,
+            'last_ckpt': timeit.default_timer(),
+            'x_dev': None,
+        }
 
-        while True:  # restart loop (iterative.py:737-801)
-            r = y - A_vec(x) if np.any(x) else y.copy()
-            resid = _norm(r)
-            z = P_vec(r)
-            p = z.copy()
-            rz = _dot(r, z)
-            restart = False
-            it_this = 0
-            while resid > tol * norm_y and it_this < maxiter:
-                Ap = A_vec(p)
-                alpha = rz / _dot(p, Ap)
-                x += alpha * p
-                r -= alpha * Ap
-                old_resid, resid = resid, _norm(r)
-                num_iters += 1
-                it_this += 1
-
-                # solver effectiveness (iterative.py:640-653)
-                steps_hist.append(resid - old_resid)
-                arr = np.array(steps_hist)
+        def on_progress(resids):
+            """Host side of the solve, once per residual-history read-back: solver effectiveness and restart
+            decision (iterative.py:640-653, 726-735), progress display, periodic checkpoints (iterative.py:675-724)."""
+            for resid in resids:
+                old_resid = state['resid']
+                state['resid'] = resid
+                state['num_iters'] += 1
+                state['steps_hist'].append(resid - old_resid)
+                arr = np.array(state['steps_hist'])
                 tot = np.abs(arr).sum()
                 ratio = (-arr.clip(max=0).sum() / tot) if tot > 0 else 1
                 eff = (int(100 * ratio) - 50) * 2
-
                 if self.callback is not None:
                     self.callback(
                         NOT_DONE,
                         disp_str='Training error (RMSE): forces {:.4f}'.format(resid / np.sqrt(len(y))),
-                        sec_disp_str='{:d} iter, k={:d}'.format(num_iters, n_inducing_pts),
+                        sec_disp_str='{:d} iter, k={:d}'.format(state['num_iters'], n_inducing_pts),
                     )
-                now = timeit.default_timer()
-                if save_progr_callback is not None and now - last_ckpt > 120.0:  # iterative.py:675-724
-                    last_ckpt = now
-                    save_progr_callback(
-                        self._checkpoint_model(task, R_desc, R_d_desc, tril_perms_lin, y_std, x, tol, num_iters, resid, norm_y, inducing_pts_idxs)
+                if len(state['steps_hist']) == CG_STEPS_HIST_LEN and eff <= EFF_RESTART_THRESH and n_inducing_pts < n_train:
+                    state['restart'] = True  # iterative.py:726-735
+                    return 1
+            now = timeit.default_timer()
+            if save_progr_callback is not None and now - state['last_ckpt'] > 120.0:
+                state['last_ckpt'] = now
+                xk = state['x_dev'].cpu().numpy()
+                save_progr_callback(
+                    self._checkpoint_model(
+                        task, R_desc, R_d_desc, tril_perms_lin, y_std, xk, tol, state['num_iters'], state['resid'], norm_y, inducing_pts_idxs
                     )
+                )
+            return 0
 
-                if len(steps_hist) == CG_STEPS_HIST_LEN and eff <= EFF_RESTART_THRESH and n_inducing_pts < n_train:
-                    restart = True  # iterative.py:726-735
-                    break
-                if resid <= tol * norm_y:
-                    break
-                z = P_vec(r)
-                rz_new = _dot(r, z)
-                p = z + (rz_new / rz) * p
-                rz = rz_new
-
-            if not restart:
+        num_restarts = 0
+        is_conv = False
+        t_cg = timeit.default_timer()
+        x = x0
+        while True:  # restart loop (iterative.py:737-801)
+            state['restart'] = False
+            x, resid = self._pcg_device(P_vec.factor, lam, y, x, tol * norm_y, maxiter, dim_i, on_progress, state)
+            if not state['restart']:
                 is_conv = resid <= tol * norm_y
                 break
             num_restarts += 1
-            steps_hist.clear()
+            state['steps_hist'].clear()
             if num_restarts == MAX_NUM_RESTARTS:
                 is_conv = False
                 break
@@ -432,7 +410,7 @@ class Iterative(object):
             inducing_pts_idxs = self._bcast_idxs(self.inducing_pts_from_lev_scores(lev_scores, n_inducing_pts * dim_i))
             del P_vec
             P_vec, lev_scores = self._init_precon_operator(task, R_desc, R_d_desc, tril_perms_lin, inducing_pts_idxs)
-            P_vec = _timed_precon(P_vec)
+        num_iters = state['num_iters']
 
         self.timings['cg_s'] = timeit.default_timer() - t_cg
         self.timings['iters'] = num_iters - num_iters0
@@ -445,6 +423,73 @@ class Iterative(object):
                 sec_disp_str='{:d} iterations'.format(num_iters),
             )
         return alphas, tol, num_iters, resid, train_rmse, inducing_pts_idxs, is_conv
+
+    def _pcg_device(self, factor, lam, y, x0, tol_abs, maxiter, dim_i, on_progress, state, check_every=25):
+        """One run of the device-resident PCG (`sgdml_b200_pcg`, csrc/pcg.cu): every CG vector stays in HBM, the
+        host gets the residual history every <= check_every iterations.  With several ranks the K.v rows and the
+        Nystroem factor rows are those of this rank's training points and the three exchanges per iteration run
+        as torch.distributed collectives on views of the device workspace (dist.exchange_on_workspace)."""
+        import ctypes
+
+        import torch
+
+        from .. import dist as sdist
+
+        L = _lib.lib()
+        X, m, lo, hi = factor
+        rank, world = sdist.world_info()
+        n_train = self.gdml_predict.n_train
+        n = n_train * dim_i
+        if world == 1:
+            lo, hi = 0, n_train
+        n_rows_loc = (hi - lo) * dim_i
+        ws_doubles = int(L.sgdml_b200_pcg_workspace_doubles(n, n_rows_loc, m, check_every))
+        ws = torch.empty(ws_doubles, dtype=torch.float64, device='cuda')
+        state['x_dev'] = ws[:n]  # the solution vector is the first slot of the workspace (csrc/pcg.cu)
+        if state['resid'] is None:
+            state['resid'] = float(_norm(y)) if x0 is None else None
+
+        def _exchange(_ctx, op, buf, count):
+            try:
+                off = (int(buf) - ws.data_ptr()) // 8
+                sdist.exchange_on_workspace(ws, off, int(count), int(op), n_train, dim_i)
+                return 0
+            except Exception as e:  # noqa: BLE001 -- must not propagate through the C frame
+                self.log.error('exchange failed: %r' % (e,))
+                return 1
+
+        first = {'pending': x0 is not None}
+
+        def _progress(_ctx, iters_done, hist, n_new):
+            try:
+                resids = [hist[i] for i in range(n_new)]
+                if first['pending']:  # warm start: the step history starts from the first measured residual
+                    first['pending'] = False
+                    if state['resid'] is None:
+                        state['resid'] = resids[0]
+                return int(on_progress(resids))
+            except Exception as e:  # noqa: BLE001
+                self.log.error('progress callback failed: %r' % (e,))
+                state['error'] = e
+                return 1
+
+        exch = _lib.EXCHANGE_FN(_exchange) if world > 1 else ctypes.cast(None, _lib.EXCHANGE_FN)
+        prog = _lib.PROGRESS_FN(_progress)
+        x = np.zeros(n) if x0 is None else np.ascontiguousarray(x0, dtype=np.float64)
+        iters, resid = ctypes.c_int64(0), ctypes.c_double(0.0)
+        _lib.check(
+            L.sgdml_b200_pcg(
+                self.gdml_predict._handle, lo, hi, X.data_ptr() if m > 0 else None, m, X.shape[1] if m > 0 else 0,
+                float(lam), _lib.ptr(y), _lib.ptr(x), 1 if x0 is None else 0, float(tol_abs), int(maxiter),
+                int(check_every), ws.data_ptr(), ws_doubles, exch, None, prog, None,
+                ctypes.byref(iters), ctypes.byref(resid), _lib.current_stream(),
+            ),
+            'pcg',
+        )
+        if 'error' in state:
+            raise state.pop('error')
+        state['x_dev'] = None
+        return x, float(resid.value)
 
     @staticmethod
     def _bcast_idxs(idxs):

@@ -116,6 +116,11 @@ class GDMLTrain(object):
         est_bytes_analytic = Analytic.est_memory_requirement(n_train, n_atoms)
         free_bytes, _total = _torch().cuda.mem_get_info()
         max_bytes = free_bytes if self._max_memory is None else min(free_bytes, self._max_memory * 1024**3)
+        # several ranks must take the SAME decision (the iterative path issues collectives the analytic one
+        # never joins) and derive the same number of inducing points: agree on the smallest budget
+        from . import dist as sdist
+
+        max_bytes = sdist.all_reduce_min_scalar(max_bytes)
         use_analytic_solver = est_bytes_analytic < max_bytes
 
         solver_keys = {}

@@ -147,8 +147,24 @@ def _worker(rank, world, port, case, out_dir):
     X, lo, hi = sdist.run_steps(sdist.nystroem_factor_steps(ops, rank, world, n_train, dim_i, cols, lam), n_train)
     lev = sdist.run_steps(sdist.lev_scores_steps(ops, X, len(cols), dim_i), n_train)
     Pv = sdist.run_steps(sdist.precon_apply_steps(ops, X, len(cols), lam, g['v'], lo, hi, dim_i), n_train)
+    # 6. the exchange function of the device-resident PCG (sgdml_b200_pcg) on a workspace tensor: all-reduce of
+    #    an m-vector, in-place all-gather of a replicated n-vector with equal (8 points) and ragged (7 points) shards
+    import torch
+
+    exch = {}
+    for n_pts in (8, 7):
+        di = 3
+        ws = torch.zeros(5 + n_pts * di + 4, dtype=torch.float64)
+        ws[1:4] = torch.tensor([1.0, 2.0, 3.0]) * (rank + 1)
+        sdist.exchange_on_workspace(ws, 1, 3, 0, n_pts, di)
+        lo_, hi_ = sdist.shard_bounds(n_pts, world, rank)
+        full = np.arange(n_pts * di, dtype=np.float64) + 100.0
+        ws[5 + lo_ * di : 5 + hi_ * di] = torch.from_numpy(full[lo_ * di : hi_ * di])  # only the owned rows are valid
+        sdist.exchange_on_workspace(ws, 5, n_pts * di, 1, n_pts, di)
+        exch['ws%d' % n_pts] = ws.numpy().copy()
     np.savez(
-        os.path.join(out_dir, 'r%d.npz' % rank), E=E, F=F, Kv=Kv, a=a, c=c, std=std, E_tp=E_tp, F_tp=F_tp, lev=lev, Pv=Pv
+        os.path.join(out_dir, 'r%d.npz' % rank), E=E, F=F, Kv=Kv, a=a, c=c, std=std, E_tp=E_tp, F_tp=F_tp, lev=lev, Pv=Pv,
+        **exch
     )
     dist.barrier()
     dist.destroy_process_group()
@@ -183,6 +199,10 @@ def test_two_rank_gloo(tmp_path):
             assert float(f['c']) == float(g['c']) and float(f['std']) == float(g['std'])
             assert np.max(np.abs(f['F_tp'] - g['F_query'])) < 1e-10 * np.max(np.abs(g['F_query']))
             assert np.max(np.abs(f['E_tp'] - g['E_query'])) < 1e-10 * np.max(np.abs(g['E_query']))
+            for n_pts in (8, 7):
+                ws = f['ws%d' % n_pts]
+                assert np.array_equal(ws[1:4], np.array([3.0, 6.0, 9.0])) and ws[0] == 0 and ws[4] == 0
+                assert np.array_equal(ws[5 : 5 + n_pts * 3], np.arange(n_pts * 3) + 100.0) and not ws[5 + n_pts * 3 :].any()
             lev_ref, Pv_ref = _nystroem_reference(g)
             assert np.max(np.abs(f['lev'] - lev_ref)) < 1e-6 * np.max(np.abs(lev_ref))
             assert np.max(np.abs(f['Pv'] - Pv_ref)) < 1e-6 * np.max(np.abs(Pv_ref))

@@ -282,3 +282,150 @@ def test_train_point_sharded_predictor_single_rank():
     parts = [sgdml_b200.GDMLPredict(sdist.model_shard(model, lo, hi)).predict(gq['R_query']) for lo, hi in [(0, 7), (7, M)]]
     F_sum = (parts[0][1] + parts[1][1]) * float(model['std'])
     assert rel_err(F_sum, gq['F_query']) < 1e-9
+
+
+# --------------------------------------------------------------------------- device-resident PCG through the C ABI
+def _pcg_call(pred, X, m, lam, y, x0, tol_abs, max_iters, check_every=5, exchange=None, progress=None):
+    import ctypes
+
+    import torch
+
+    from sgdml_b200 import _lib
+
+    L = _lib.lib()
+    n = y.size
+    n_train = pred.n_train
+    n_rows = n
+    wsd = int(L.sgdml_b200_pcg_workspace_doubles(n, n_rows, m, check_every))
+    ws = torch.empty(wsd, dtype=torch.float64, device='cuda')
+    x = np.zeros(n) if x0 is None else np.array(x0, dtype=np.float64)
+    iters, resid = ctypes.c_int64(0), ctypes.c_double(0.0)
+    exch = _lib.EXCHANGE_FN(exchange) if exchange is not None else ctypes.cast(None, _lib.EXCHANGE_FN)
+    prog = _lib.PROGRESS_FN(progress) if progress is not None else ctypes.cast(None, _lib.PROGRESS_FN)
+    _lib.check(
+        L.sgdml_b200_pcg(
+            pred._handle, 0, n_train, X.data_ptr() if m else None, m, X.shape[1] if m else 0, float(lam), _lib.ptr(y), _lib.ptr(x),
+            1 if x0 is None else 0, float(tol_abs), int(max_iters), int(check_every), ws.data_ptr(), wsd, exch, None, prog, None,
+            ctypes.byref(iters), ctypes.byref(resid), _lib.current_stream(),
+        ),
+        'pcg',
+    )
+    return x, int(iters.value), float(resid.value)
+
+
+def _np_pcg(A, Pinv, y, x0, n_iters):
+    """Textbook PCG (the loop of scipy.sparse.linalg.cg the reference calls, iterative.py:740-752)."""
+    x = np.zeros_like(y) if x0 is None else x0.copy()
+    r = y - A @ x
+    z = Pinv(r)
+    p = z.copy()
+    rz = r @ z
+    hist = []
+    for _ in range(n_iters):
+        Ap = A @ p
+        alpha = rz / (p @ Ap)
+        x += alpha * p
+        r -= alpha * Ap
+        hist.append(np.linalg.norm(r))
+        z = Pinv(r)
+        rz_new = r @ z
+        p = z + (rz_new / rz) * p
+        rz = rz_new
+    return x, np.array(hist)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('precon', [False, True])
+@pytest.mark.parametrize('warm', [False, True])
+def test_pcg_c_abi_matches_numpy_cg(precon, warm):
+    """sgdml_b200_pcg against a NumPy PCG on the EXPLICIT system matrix of a reference fixture: same iterates."""
+    import sgdml_b200
+    from sgdml_b200.desc import Desc
+    from sgdml_b200.solvers.iterative import Iterative
+
+    g, task, N, M, R = _setup()
+    lam = float(g['lam'])
+    d = Desc(N)
+    x_desc, gd = d.from_R(R)
+    lin = odesc.tril_perms_lin(g['perms'])
+    t = sgdml_b200.GDMLTrain(max_memory=float(g['max_memory_gb']))
+    it = Iterative(t, d, float(g['max_memory_gb']), None, False)
+    n = 3 * N * M
+    it._init_kernel_operator(task, x_desc, gd, lin, lam, n)
+    from oracle import assemble as oassemble
+
+    K = oassemble.assemble(x_desc, gd, lin, int(g['sig']))
+    A = -K + lam * np.eye(n)
+    y = np.ascontiguousarray(g['y'], dtype=np.float64)
+    if precon:
+        P, _ = it._init_precon_operator(task, x_desc, gd, lin, g['inducing_pts_idxs'])
+        X, m = P.factor[0], P.factor[1]
+        Xh = X[:, :m].cpu().numpy()
+        Pinv = lambda v: (Xh @ (Xh.T @ v) - v) / lam  # noqa: E731  (iterative.py:136-138)
+    else:
+        X, m = None, 0
+        Pinv = lambda v: v.copy()  # noqa: E731
+    x0 = 0.01 * np.random.default_rng(5).standard_normal(n) if warm else None
+    n_it = 12
+    x_ref, hist_ref = _np_pcg(A, Pinv, y, x0, n_it)
+    seen = []
+
+    def progress(_ctx, iters_done, hist, n_new):
+        seen.extend(hist[i] for i in range(n_new))
+        return 0
+
+    x, iters, resid = _pcg_call(it.gdml_predict, X, m, lam, y, x0, 0.0, n_it, check_every=5, progress=progress)
+    assert iters == n_it and len(seen) == n_it
+    assert rel_err(np.array(seen), hist_ref) < 1e-6
+    assert rel_err(x, x_ref) < 1e-6
+    assert abs(resid - hist_ref[-1]) < 1e-6 * hist_ref[-1]
+
+
+@pytest.mark.gpu
+def test_pcg_stops_at_tolerance_and_on_request():
+    """The device-side freeze: x stops changing at the first iteration below the tolerance, even inside a chunk;
+    a non-zero return of the progress function ends the solve; the exchange hook is called in stream order."""
+    import sgdml_b200
+    from sgdml_b200.desc import Desc
+    from sgdml_b200.solvers.iterative import Iterative
+
+    g, task, N, M, R = _setup()
+    lam = float(g['lam'])
+    d = Desc(N)
+    x_desc, gd = d.from_R(R)
+    lin = odesc.tril_perms_lin(g['perms'])
+    t = sgdml_b200.GDMLTrain(max_memory=float(g['max_memory_gb']))
+    it = Iterative(t, d, float(g['max_memory_gb']), None, False)
+    n = 3 * N * M
+    it._init_kernel_operator(task, x_desc, gd, lin, lam, n)
+    P, _ = it._init_precon_operator(task, x_desc, gd, lin, g['inducing_pts_idxs'])
+    X, m = P.factor[0], P.factor[1]
+    y = np.ascontiguousarray(g['y'], dtype=np.float64)
+    tol_abs = 1e-4 * np.linalg.norm(y)
+    hist = []
+
+    def progress(_ctx, iters_done, h, n_new):
+        hist.extend(h[i] for i in range(n_new))
+        return 0
+
+    calls = []
+
+    def exchange(_ctx, op, buf, count):  # single rank: nothing to exchange, but every call is recorded
+        calls.append((op, count))
+        return 0
+
+    x, iters, resid = _pcg_call(it.gdml_predict, X, m, lam, y, None, tol_abs, 10000, check_every=50, exchange=exchange, progress=progress)
+    assert resid <= tol_abs and iters == len(hist)
+    assert all(h > tol_abs for h in hist[:-1]) and hist[-1] <= tol_abs  # stopped AT the first converged iteration
+    assert abs(iters - int(g['solver_iters'])) <= max(5, 0.2 * int(g['solver_iters']))
+    assert (0, m) in calls and (1, n) in calls and len(calls) >= 3 * iters
+    # the frozen x reproduces the reported residual
+    K = it._init_kernel_operator(task, x_desc, gd, lin, lam, n)
+    r = y + K(x)  # A x = -K_op(x)
+    assert abs(np.linalg.norm(r) - resid) < 1e-6 * resid + 1e-9
+
+    def stop_after_three(_ctx, iters_done, h, n_new):
+        return 1 if iters_done >= 3 else 0
+
+    _, iters2, _ = _pcg_call(it.gdml_predict, X, m, lam, y, None, 0.0, 1000, check_every=1, progress=stop_after_three)
+    assert iters2 == 3
