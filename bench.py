@@ -62,6 +62,13 @@ def parse_args():
     ap.add_argument('--cpu-seconds', type=float, default=15.0, help='target duration of the cpu_baseline sample')
     ap.add_argument('--no-cpu-baseline', action='store_true', help='skip the cpu_baseline leg (profiling runs)')
     ap.add_argument('--ref-batch', type=int, default=None, help='queries per step of the reference arm')
+    ap.add_argument('--no-extras', action='store_true', help='skip the ethanol and sharded-path legs of the default run')
+    ap.add_argument('--sharded-workload', default='c60', choices=['c60', 'synthetic100', 'ac-ala3-nhme'])
+    ap.add_argument('--sharded-n-train', type=int, default=None)
+    ap.add_argument('--sharded-batch', type=int, default=64, help='query geometries of the training-point-sharded predictor leg')
+    ap.add_argument('--sharded-iters', type=int, default=3, help='PCG iterations timed in the sharded leg')
+    ap.add_argument('--sharded-inducing', type=int, default=4096, help='columns of the (synthetic) Nystroem factor in the sharded leg')
+    ap.add_argument('--ref-torch-worker', default=None, help=argparse.SUPPRESS)  # internal: reference torch-CUDA arm
     ap.add_argument('--ref-worker', default=None, help=argparse.SUPPRESS)  # internal: JSON spec of a reference-arm subprocess
     ap.add_argument('--ref-train-worker', default=None, help=argparse.SUPPRESS)  # internal: reference training sample
     return ap.parse_args()
@@ -377,6 +384,93 @@ def reference_train_estimate(cfg, cores, seconds=6.0):
     }
 
 
+def ref_torch_worker_main(spec):
+    """Runs inside a subprocess WITH the GPU visible: the reference's own torch engine on CUDA --
+    GDMLPredict(model, use_torch=True).predict (predict.py:358-421, torchtools.py:877-1128; inputs are downcast to
+    float32 by the reference itself, predict.py:1197-1201, the model stays float64) and GDMLTorchAssemble through
+    GDMLTrain(use_torch=True)._assemble_kernel_mat (train.py:1412-1482, torchtools.py:110-392) on a bounded number
+    of block-columns.  Prints one JSON line."""
+    import logging
+
+    sys.path.insert(0, REF_DIR)
+    import torch
+
+    from sgdml_b200 import synth
+
+    cfg = spec['cfg']
+    perms, r0 = synth.config_perms_and_r0(cfg['name'])
+    N, M = cfg['n_atoms'], cfg['n_train']
+    out = {'device': torch.cuda.get_device_name(0) if torch.cuda.is_available() else 'cpu'}
+    try:
+        from sgdml.predict import GDMLPredict  # the reference, not this repo
+
+        model = oracle_random_model(cfg, perms)
+        pred = GDMLPredict(model, use_torch=True, log_level=logging.CRITICAL)
+        Bq = int(spec['batch'])
+        Rq = synth.geometries(N, Bq, 1, r0=r0).reshape(Bq, -1)
+        pred.predict(Rq)  # warm-up (its own batch-size back-off happens here)
+        torch.cuda.synchronize()
+        n_done, t0 = 0, time.perf_counter()
+        while time.perf_counter() - t0 < float(spec['seconds']):
+            E, F = pred.predict(Rq)
+            n_done += Bq
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        from oracle import predict as opredict
+
+        _, F_orc = opredict.Predictor(model).predict(Rq[:4])
+        out['predict'] = {'value': n_done / dt, 'unit': 'predictions/s', 'batch': Bq, 'seconds': dt,
+                          'rel_dev_from_f64_oracle': float(np.max(np.abs(F[:4] - F_orc)) / np.max(np.abs(F_orc)))}
+    except Exception as e:  # noqa: BLE001
+        out['predict'] = {'unavailable': repr(e)[:300]}
+    try:
+        from sgdml.train import GDMLTrain
+        from sgdml.utils.desc import Desc
+
+        R = synth.geometries(N, M, 0, r0=r0).reshape(M, -1)
+        desc = Desc(N, max_processes=1)
+        R_desc, R_d_desc = desc.from_R(R, max_processes=1)
+        tril_perms = np.array([Desc.perm(p) for p in perms])
+        tril_perms_lin = (tril_perms + np.arange(len(perms))[:, None] * desc.dim).flatten('F')
+        gdml = GDMLTrain(max_processes=1, use_torch=True)
+        k = max(1, min(M, int(spec['col_points'])))
+        gdml._assemble_kernel_mat(R_desc, R_d_desc, tril_perms_lin, cfg['sig'], desc, col_idxs=np.s_[: 3 * N])  # warm-up
+        t0 = time.perf_counter()
+        gdml._assemble_kernel_mat(R_desc, R_d_desc, tril_perms_lin, cfg['sig'], desc, col_idxs=np.s_[: k * 3 * N])
+        dt = time.perf_counter() - t0
+        out['assemble'] = {'col_points': k, 'seconds': dt, 'extrapolated_full_s': dt * M / k}
+    except Exception as e:  # noqa: BLE001
+        out['assemble'] = {'unavailable': repr(e)[:300]}
+    print(json.dumps(out))
+    sys.stdout.flush()
+    os._exit(0)
+
+
+def reference_torch_cuda(cfg, gpu_index, seconds=5.0):
+    """The reference's own torch-CUDA path timed on this B200 (SURVEY 8d "existing GPU
+    implementation" bar); None if the reference is not installed, {'unavailable': why} if it cannot run."""
+    if not reference_available():
+        return None
+    spec = {'cfg': cfg, 'batch': 1024, 'seconds': seconds, 'col_points': 16}
+    env = dict(os.environ)
+    env['CUDA_VISIBLE_DEVICES'] = str(gpu_index)
+    for k in ('RANK', 'WORLD_SIZE', 'LOCAL_RANK'):
+        env.pop(k, None)
+    try:
+        res = subprocess.run([sys.executable, os.path.abspath(__file__), '--ref-torch-worker', json.dumps(spec)],
+                             env=env, capture_output=True, text=True, timeout=240)
+        for ln in reversed(res.stdout.strip().splitlines()):
+            try:
+                out = json.loads(ln)
+                out['kind'] = 'reference (unmodified, its torch engine on cuda:%d of this box)' % gpu_index
+                return out
+            except ValueError:
+                continue
+        return {'unavailable': 'no output; stderr tail: ' + res.stderr.strip()[-300:]}
+    except Exception as e:  # noqa: BLE001
+        return {'unavailable': repr(e)[:300]}
+
+
 def run_reference_subprocess(cfg, cores, warmup, steps, per_step, seconds_per_step, timeout_s):
     """-> dict (see ref_worker_main) or None if the reference is not installed / failed / timed out."""
     if not reference_available():
@@ -481,60 +575,78 @@ def run_reference(args):
 
 
 # --------------------------------------------------------------------------- engine arm
-def run_engine(args):
+def _barrier(world):
     import torch
     import torch.distributed as dist
 
-    world = int(os.environ.get('WORLD_SIZE', '1'))
-    rank = int(os.environ.get('RANK', '0'))
-    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
-    torch.cuda.set_device(local_rank)
     if world > 1:
-        # keep stdout to the single JSON line (NCCL prints a version banner there at VERSION/INFO level)
-        os.environ['NCCL_DEBUG'] = os.environ.get('SGDML_B200_NCCL_DEBUG', 'WARN')
-        dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+        dist.barrier()
+    torch.cuda.synchronize()
+
+
+def _max_over_ranks(seconds, world):
+    import torch
+    import torch.distributed as dist
+
+    t = torch.tensor([seconds], dtype=torch.float64, device='cuda')
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def measure_workload(args, workload, batch, steps, warmup, world, rank, local_rank, compact=False):
+    """One full measurement of a named workload: training leg (rank 0), device-resident prediction steps,
+    end-to-end steps through the public API with host buffers, roofline of the dominant kernel and (not compact)
+    the CPU / reference baselines.  Returns the JSON line as a dict on rank 0, None elsewhere."""
+    import torch
+    import torch.distributed as dist
 
     import sgdml_b200
     from sgdml_b200 import _lib, synth
+    from sgdml_b200.diagnostics import residual_report
 
     L = _lib.lib()
-    cfg = workload_cfg(args)
+    wargs = argparse.Namespace(**vars(args))
+    wargs.workload = workload
+    cfg = workload_cfg(wargs)
+    no_train = args.no_train or workload in PREDICT_ONLY
     N, M = cfg['n_atoms'], cfg['n_train']
     D = N * (N - 1) // 2
     perms, r0 = synth.config_perms_and_r0(cfg['name'])
     S = len(perms)
     n = 3 * N * M
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
     # ---------------- training leg (rank 0), model broadcast to the other ranks
     train_info = None
-    task = synth.make_task(N, M, perms, cfg['sig'])
+    task = synth.make_task(N, M, perms, cfg['sig'], r0=r0)
     trainer = sgdml_b200.GDMLTrain()
-    if args.no_train:
+    if no_train:
         model = synth.random_model(N, M, perms, cfg['sig'], r0=r0)
     else:
         alphas_t = torch.empty(n + 2, dtype=torch.float64, device='cuda')
         if rank == 0:
             # warm-up: a small training run (kernel load, context, allocator)
-            log('warm-up training run')
-            trainer.train(synth.make_task(N, min(M, 40), perms, cfg['sig']))
-            log('timed training run: n = %d' % n)
+            log('[%s] warm-up training run' % workload)
+            trainer.train(synth.make_task(N, min(M, 40), perms, cfg['sig'], r0=r0))
+            log('[%s] timed training run: n = %d' % (workload, n))
             torch.cuda.synchronize()
             L.sgdml_b200_profile_reset()
             t0 = time.perf_counter()
             model0 = trainer.train(task)
             torch.cuda.synchronize()
             train_s = time.perf_counter() - t0
-            log('training done in %.3f s (%s)' % (train_s, trainer.timings))
+            log('[%s] training done in %.3f s (%s)' % (workload, train_s, trainer.timings))
             snap = _lib.profile_snapshot()
             tm = trainer.timings
             hbm_peak, hbm_src = measured_peak('hbm_gbs', 6650.0)
             fp64_peak = fp64_peak_tflops(L)
             asm_bytes = 8.0 * n * n + 8.0 * M * 4 * D
+            asm_flops = float(M) * M * 2.0 * D * 3 * N * (S + 6)  # SURVEY 8d: W_K = 2 D 3N (S + 6) per block
+            # independent check of the benchmarked training run: (K - lam I) alphas against the labels through the
+            # predictor kernels (none of the assembly / Cholesky code), and the forces on the training points
+            chk = residual_report(model0, task)
+            chk['ok'] = bool(chk['residual_rel'] < 1e-8 and chk['force_rel_max_train'] < 1e-3)
+            log('[%s] solution check: %s' % (workload, chk))
             train_info = {
                 'metric': 'K-assembly+solve wall-time',
                 'unit': 's',
@@ -547,6 +659,12 @@ def run_engine(args):
                 'what': 'GDMLTrain.train(task): host R/F/E in -> model dict out (descriptors, K assembly in HBM, '
                 'FP64 Cholesky + 2 triangular solves, R_d_desc_alpha, integration constant)',
                 'gpu_launches': int(sum(v[2] for v in snap.values())),
+                'solution_check': dict(
+                    chk,
+                    what='||(K - lam I) alphas - y|| / ||y|| with K.alphas evaluated by the predictor kernels '
+                    '(K.v identity, iterative.py:183-204): independent of the assembly and Cholesky kernels; '
+                    'force_rel_max_train = max |F_pred - F_label| / max |F_label| on ALL training points',
+                ),
                 'roofline_assemble': {
                     'bound': 'hbm',
                     'achieved': asm_bytes / tm['assemble_s'] * 1e-9,
@@ -555,6 +673,13 @@ def run_engine(args):
                     'frac': asm_bytes / tm['assemble_s'] * 1e-9 / hbm_peak,
                     'peak_source': hbm_src,
                     'algorithmic_bytes': asm_bytes,
+                    'fp64': {
+                        'algorithmic_flops': asm_flops,
+                        'achieved_tflops': asm_flops / tm['assemble_s'] * 1e-12,
+                        'frac_of_fp64_peak': asm_flops / tm['assemble_s'] * 1e-12 / fp64_peak,
+                        'note': 'SURVEY 8d: above ~5 flop/B the FP64 pipe governs; both terms are reported, '
+                        'the larger fraction names the binding roofline',
+                    },
                 },
                 'roofline_solve': {
                     'bound': 'fp64-tensor (DMMA)',
@@ -564,7 +689,10 @@ def run_engine(args):
                     'frac': (n**3 / 3.0) / tm['solve_s'] * 1e-12 / fp64_peak,
                     'peak_source': 'live DMMA m8n8k4 probe (sgdml_b200_fp64_peak_tflops); MEASURED_PEAKS.json has no FP64 entry',
                     'algorithmic_flops': n**3 / 3.0,
-                    'note': 'whole solve (potf2 + TRSM strips + DMMA trailing updates + 2 triangular solves) over n^3/3',
+                    'trailing_update': os.environ.get('SGDML_B200_OZAKI_SLICES', '0') not in ('', '0') and
+                    'tcgen05 kind::i8 slice products (SGDML_B200_OZAKI_SLICES=%s)' % os.environ.get('SGDML_B200_OZAKI_SLICES') or 'FP64 DMMA',
+                    'note': 'whole solve (potf2 + TRSM strips + trailing updates + 2 triangular solves) over n^3/3; a '
+                    'fraction above 1 means the trailing updates ran on the int8 tensor cores (error-free slicing)',
                 },
             }
             alphas_t[:n] = torch.from_numpy(model0['alphas_F']).cuda()
@@ -584,10 +712,10 @@ def run_engine(args):
             model['c'] = float(host[n])
 
     predictor = sgdml_b200.GDMLPredict(model)
-    log('predictor ready; batch %d' % args.batch)
+    log('[%s] predictor ready; batch %d' % (workload, batch))
 
     # ---------------- prediction steps, inputs resident in HBM
-    B = args.batch
+    B = batch
     Rq_host = synth.geometries(N, B, 1 + rank, r0=r0).reshape(B, -1)
     Rq_dev = torch.from_numpy(Rq_host).cuda()
     # the clock sampler (an nvidia-smi child process) is started BEFORE the warm-up so that its
@@ -596,52 +724,59 @@ def run_engine(args):
     if rank == 0:
         sampler.start()
         time.sleep(0.5)
-    for _ in range(max(args.warmup, 3)):
+    for _ in range(max(warmup, 3)):
         predictor.predict(Rq_dev)
     L.sgdml_b200_profile_reset()
-    barrier()
+    _barrier(world)
     if rank == 0:
         sampler.rows.clear()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(args.steps):
+    for _ in range(steps):
         E_dev, F_dev = predictor.predict(Rq_dev)
     e1.record()
-    barrier()
+    _barrier(world)
     clocks = sampler.stop() if rank == 0 else None
-    dt = torch.tensor([e0.elapsed_time(e1) * 1e-3], dtype=torch.float64, device='cuda')
-    if world > 1:
-        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
-    dt = float(dt.item())
+    dt = _max_over_ranks(e0.elapsed_time(e1) * 1e-3, world)
     launches_timed = int(sum(v[2] for v in _lib.profile_snapshot().values()))
-    value = world * B * args.steps / dt
-    log('device-resident steps done: %.3e predictions/s' % value)
+    value = world * B * steps / dt
+    log('[%s] device-resident steps done: %.3e predictions/s' % (workload, value))
 
     # ---------------- end to end through the public API with pinned HOST buffers
     R_pin = torch.from_numpy(Rq_host).pin_memory()
     out_pin = (torch.empty(B, dtype=torch.float64).pin_memory(), torch.empty((B, 3 * N), dtype=torch.float64).pin_memory())
     for _ in range(2):
         predictor.predict(R_pin, out=out_pin)
-    barrier()
+    _barrier(world)
     t0 = time.perf_counter()
-    for _ in range(args.steps):
+    for _ in range(steps):
         E_h, F_h = predictor.predict(R_pin, out=out_pin)
         _ = float(E_h[0])  # the step's result is read on the host
     torch.cuda.synchronize()
-    dt_e2e = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device='cuda')
-    barrier()
-    if world > 1:
-        dist.all_reduce(dt_e2e, op=dist.ReduceOp.MAX)
-    dt_e2e = float(dt_e2e.item())
-    e2e_value = world * B * args.steps / dt_e2e
-    log('e2e steps done: %.3e predictions/s' % e2e_value)
+    dt_e2e = _max_over_ranks(time.perf_counter() - t0, world)
+    e2e_value = world * B * steps / dt_e2e
+    log('[%s] e2e steps done: %.3e predictions/s' % (workload, e2e_value))
+
+    # ---------------- the same through the reference-shaped call: NumPy array in, NEW NumPy arrays out (pageable)
+    for _ in range(2):
+        predictor.predict(Rq_host)
+    _barrier(world)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        E_n, F_n = predictor.predict(Rq_host)
+        _ = float(E_n[0])
+    dt_np = _max_over_ranks(time.perf_counter() - t0, world)
+    e2e_numpy = world * B * steps / dt_np
+    log('[%s] e2e (NumPy in/out) steps done: %.3e predictions/s' % (workload, e2e_numpy))
 
     # parity spot check of the benchmarked path (tiny, after the timed regions)
     assert np.allclose(F_h[:8].numpy(), F_dev[:8].cpu().numpy(), rtol=0, atol=0), 'host and device paths disagree'
+    assert np.array_equal(F_n[:8], F_h[:8].numpy()), 'NumPy and pinned-tensor paths disagree'
 
     # ---------------- roofline of the dominant kernel (rank 0): device time of k_predict_main
     roofline = None
     cpu_baseline = None
+    ref_torch = None
     if rank == 0:
         L.sgdml_b200_profile_reset()
         L.sgdml_b200_profile_enable(1)
@@ -680,10 +815,10 @@ def run_engine(args):
             'kernel_ms_per_step': t_step * 1e3,
             'launches_per_step': main_launches / reps,
             'kernel_share_of_step': main_ms / max(main_ms + aux_ms, 1e-9),
-            'traffic': ncu_traffic(args.workload, B / max(main_launches / reps, 1)),
+            'traffic': ncu_traffic(workload, B / max(main_launches / reps, 1)),
         }
-        log('roofline probe done')
-        if world == 1 and not args.no_cpu_baseline:
+        log('[%s] roofline probe done' % workload)
+        if world == 1 and not args.no_cpu_baseline and not compact:
             cfg_named = dict(cfg)
             all_cores = os.cpu_count() or 1
             # the unmodified reference on all host threads when baseline/_ref is installed (one step of
@@ -720,53 +855,226 @@ def run_engine(args):
                     'sample': '%d query geometries of the same workload, NumPy oracle port of predict.py:84-245, process pool over all host threads (1 BLAS thread each)'
                     % nq,
                 }
+            # the reference's OWN GPU path (torch, CUDA) on this B200: the "existing GPU implementation" bar
+            ref_torch = reference_torch_cuda(cfg_named, local_rank)
+            log('reference torch-CUDA arm: %s' % (ref_torch,))
 
-    if rank == 0 and world == 1 and train_info is not None and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and train_info is not None and not args.no_cpu_baseline and not compact:
         # the reference's own CPU training path beside it (bounded samples, extrapolated: SURVEY.md section 8d)
         train_info['cpu_reference'] = reference_train_estimate(dict(cfg), os.cpu_count() or 1)
         log('reference training estimate: %s' % (train_info['cpu_reference'],))
 
-    if rank == 0:
-        line = {
-            'metric': 'force_predictions_per_s',
-            'value': value,
+    del predictor
+    if rank != 0:
+        return None
+    return {
+        'metric': 'force_predictions_per_s',
+        'value': value,
+        'unit': 'predictions/s',
+        'n_gpus': world,
+        'steps': steps,
+        'warmup': max(warmup, 3),
+        'ms_per_step': 1e3 * dt / steps,
+        'higher_is_better': True,
+        'scaling': 'weak',
+        'vs_baseline': None,
+        'dtype': 'f64',
+        'data': 'synthetic',
+        'config': {
+            'workload': WORKLOADS[workload][1],
+            'n_atoms': N,
+            'n_train': M,
+            'n_perms': S,
+            'sig': cfg['sig'],
+            'batch_per_gpu_per_step': B,
+            'parallelism': 'query batch sharded over %d GPU(s), model replicated, no data-path collective' % world,
+            'l2': 'no explicit flush: each step streams >= %.0f MB of per-row workspace (query rows + partial forces, > 126 MB L2); '
+            'the %.1f MB model is L2-resident by design' % (B * S * D * 8 * 2 / 1e6, 2 * M * D * 8 / 1e6),
+            'model': 'trained by the engine in this run' if not no_train else 'random coefficients',
+        },
+        'e2e': {
+            'value': e2e_value,
             'unit': 'predictions/s',
-            'n_gpus': world,
-            'steps': args.steps,
-            'warmup': max(args.warmup, 3),
-            'ms_per_step': 1e3 * dt / args.steps,
-            'higher_is_better': True,
-            'scaling': 'weak',
-            'vs_baseline': None,
-            'dtype': 'f64',
-            'data': 'synthetic',
-            'config': {
-                'workload': WORKLOADS[args.workload][1],
-                'n_atoms': N,
-                'n_train': M,
-                'n_perms': S,
-                'sig': cfg['sig'],
-                'batch_per_gpu_per_step': B,
-                'parallelism': 'query batch sharded over %d GPU(s), model replicated, no data-path collective' % world,
-                'l2': 'no explicit flush: each step streams >= %.0f MB of per-row workspace (query rows + partial forces, > 126 MB L2); '
-                'the %.1f MB model is L2-resident by design' % (B * S * D * 8 * 2 / 1e6, 2 * M * D * 8 / 1e6),
-                'model': 'trained by the engine in this run' if not args.no_train else 'random coefficients',
-            },
-            'e2e': {
-                'value': e2e_value,
+            'h2d_bytes_per_step': B * 3 * N * 8,
+            'd2h_bytes_per_step': B * (3 * N + 1) * 8,
+            'what': 'GDMLPredict.predict(pinned host R, out=pinned host E/F); H2D and D2H copies inside the timed region',
+            'numpy': {
+                'value': e2e_numpy,
                 'unit': 'predictions/s',
-                'h2d_bytes_per_step': B * 3 * N * 8,
-                'd2h_bytes_per_step': B * (3 * N + 1) * 8,
-                'what': 'GDMLPredict.predict(pinned host R, out=pinned host E/F); H2D and D2H copies inside the timed region',
+                'what': 'the reference-shaped call: GDMLPredict.predict(np.ndarray) -> NEW NumPy arrays (pageable host '
+                'memory both ways, output allocation inside the timed region)',
             },
-            'gpu_launches': launches_timed,
-            'clocks': clocks,
-            'roofline': roofline,
-            'cpu_baseline': cpu_baseline,
-            'train': train_info,
-        }
-        print(json.dumps(line))
+        },
+        'gpu_launches': launches_timed,
+        'clocks': clocks,
+        'roofline': roofline,
+        'cpu_baseline': cpu_baseline,
+        'ref_torch_cuda': ref_torch,
+        'train': train_info,
+    }
+
+
+def measure_sharded(args, world, rank, local_rank):
+    """The north-star splits on a large-molecule shape, at ANY number of GPUs (1 = the base of the
+    strong-scaling curve): (i) prediction with the TRAINING POINTS sharded over the ranks -- every rank evaluates the
+    whole batch against its M/G points, then ONE all-reduce of B*(3N+1) doubles on the device; (ii) iterations of
+    the device-resident PCG with row-sharded K.v (all-gather of n doubles) and row-sharded Nystroem factor
+    (all-reduce of m doubles + all-gather of n doubles).  Random coefficients / a random factor: the cost of both
+    paths does not depend on the values.  Timed with CUDA events, max over ranks."""
+    import ctypes
+
+    import torch
+
+    import sgdml_b200
+    from sgdml_b200 import _lib, synth
+    from sgdml_b200 import dist as sdist
+    from sgdml_b200.desc import Desc
+
+    name = args.sharded_workload
+    cfg = dict(synth.CONFIGS[name])
+    if args.sharded_n_train:
+        cfg['n_train'] = args.sharded_n_train
+    N, M = cfg['n_atoms'], cfg['n_train']
+    perms, r0 = synth.config_perms_and_r0(name)
+    S = len(perms)
+    dim_i = 3 * N
+    n = dim_i * M
+    D = N * (N - 1) // 2
+    L = _lib.lib()
+    model = synth.random_model(N, M, perms, cfg['sig'], r0=r0)
+    out = {'workload': WORKLOADS[name][1], 'n_atoms': N, 'n_train': M, 'n_perms': S, 'n': n, 'n_gpus': world}
+
+    # ---- (i) prediction sharded over training points
+    B = args.sharded_batch
+    tp = sdist.TrainPointShardedPredictor(model, sgdml_b200.GDMLPredict)
+    Rq = torch.from_numpy(synth.geometries(N, B, 1, r0=r0).reshape(B, -1)).cuda()
+    for _ in range(2):
+        tp.predict(Rq)
+    _barrier(world)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 3
+    e0.record()
+    for _ in range(reps):
+        E, F = tp.predict(Rq)
+    e1.record()
+    _barrier(world)
+    dt = _max_over_ranks(e0.elapsed_time(e1) * 1e-3, world) / reps
+    flops = 9.0 * M * S * D * B
+    fp64_peak = fp64_peak_tflops(L)
+    out['train_point_sharded_predict'] = {
+        'batch': B,
+        'ms_per_batch': dt * 1e3,
+        'predictions_per_s': B / dt,
+        'collective': 'one all-reduce (NCCL, device buffers) of B*(3N+1) doubles per batch',
+        'allreduce_bytes': B * (dim_i + 1) * 8,
+        'tflops_algorithmic_total': flops / dt * 1e-12,
+        'frac_of_fp64_peak_per_gpu': flops / dt * 1e-12 / world / fp64_peak,
+    }
+    del tp
+
+    # ---- (ii) PCG iterations, K.v rows and factor rows sharded by training point
+    lo, hi = sdist.shard_bounds(M, world, rank)
+    pred = sgdml_b200.GDMLPredict(model)
+    _, R_d_desc = Desc(N).from_R(synth.geometries(N, M, 0, r0=r0).reshape(M, -1))
+    pred.set_R_d_desc(R_d_desc)
+    del R_d_desc
+    m_ind = args.sharded_inducing
+    n_loc = (hi - lo) * dim_i
+    ldx = (m_ind + 1) // 2 * 2
+    X = 1e-3 * torch.randn((max(n_loc, 1), ldx), dtype=torch.float64, device='cuda')
+    y = np.random.default_rng(3).standard_normal(n)
+    check_every = 4
+    wsd = int(L.sgdml_b200_pcg_workspace_doubles(n, n_loc, m_ind, check_every))
+    ws = torch.empty(wsd, dtype=torch.float64, device='cuda')
+
+    def _exchange(_ctx, op, buf, count):
+        sdist.exchange_on_workspace(ws, (int(buf) - ws.data_ptr()) // 8, int(count), int(op), M, dim_i)
+        return 0
+
+    exch = _lib.EXCHANGE_FN(_exchange) if world > 1 else ctypes.cast(None, _lib.EXCHANGE_FN)
+    prog = ctypes.cast(None, _lib.PROGRESS_FN)
+    x = np.zeros(n)
+    iters, resid = ctypes.c_int64(0), ctypes.c_double(0.0)
+
+    def run(n_it):
+        _lib.check(
+            L.sgdml_b200_pcg(pred._handle, lo if world > 1 else 0, hi if world > 1 else M, X.data_ptr(), m_ind, ldx, 1e-10,
+                             _lib.ptr(y), _lib.ptr(x), 1, 0.0, n_it, check_every, ws.data_ptr(), wsd, exch, None, prog, None,
+                             ctypes.byref(iters), ctypes.byref(resid), _lib.current_stream()),
+            'pcg',
+        )
+
+    run(1)  # warm-up (also the set-up: r0, z0, p0)
+    _barrier(world)
+    n_it = args.sharded_iters
+    # set-up cost (one P.v, no K.v) is measured separately and subtracted
+    e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+    e[0].record()
+    run(0)
+    e[1].record()
+    run(n_it)
+    e[2].record()
+    _barrier(world)
+    t_setup = _max_over_ranks(e[0].elapsed_time(e[1]) * 1e-3, world)
+    t_total = _max_over_ranks(e[1].elapsed_time(e[2]) * 1e-3, world)
+    per_iter = max(t_total - t_setup, 1e-9) / max(int(iters.value), 1)
+    kv_flops = 9.0 * M * M * S * D
+    out['pcg_iteration'] = {
+        'iterations_timed': int(iters.value),
+        'ms_per_iteration': per_iter * 1e3,
+        'inducing_columns': m_ind,
+        'collectives_per_iteration': 'all-gather of n doubles (K.v rows), all-reduce of m doubles + all-gather of n doubles (P.v); '
+        'NCCL on device buffers inside the solver workspace, enqueued by the exchange hook of sgdml_b200_pcg',
+        'allgather_bytes_per_iteration': 2 * n * 8,
+        'allreduce_bytes_per_iteration': m_ind * 8,
+        'kv_tflops_algorithmic_total': kv_flops / per_iter * 1e-12,
+        'frac_of_fp64_peak_per_gpu': kv_flops / per_iter * 1e-12 / world / fp64_peak,
+        'limiting': 'K.v (FP64 tensor pipe); the collectives move %.1f MB per iteration' % ((2 * n + m_ind) * 8 / 1e6),
+    }
+    del pred, X, ws
+    torch.cuda.empty_cache()
+    return out if rank == 0 else None
+
+
+def run_engine(args):
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local_rank)
+    nccl_log = None
     if world > 1:
+        # NCCL's INFO log (rank count, rings/trees, NVLS) goes to a FILE per rank so that stdout stays the single
+        # JSON line and the driver can still verify the communicator (comm_nranks)
+        nccl_dir = os.path.join(ROOT, 'gpurun_out')
+        os.makedirs(nccl_dir, exist_ok=True)
+        os.environ.setdefault('NCCL_DEBUG', 'INFO')
+        os.environ.setdefault('NCCL_DEBUG_SUBSYS', 'INIT,ENV')
+        os.environ.setdefault('NCCL_DEBUG_FILE', os.path.join(nccl_dir, 'nccl_n%d_r%%h_%%p.log' % world))
+        nccl_log = os.environ['NCCL_DEBUG_FILE']
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+
+    line = measure_workload(args, args.workload, args.batch, args.steps, args.warmup, world, rank, local_rank)
+    default_run = args.workload == 'aspirin' and not args.no_train and args.n_train is None
+    if default_run and world == 1 and not args.no_extras:
+        # north_star's own target (ethanol: train < 1 s, >= 1e6 predictions/s at >= 60 % of the roofline) in the same
+        # driver-recorded line
+        eth = measure_workload(args, 'ethanol', args.batch, max(3, args.steps // 2), 3, world, rank, local_rank, compact=True)
+        if rank == 0:
+            line['north_star_ethanol'] = eth
+    if not args.no_extras and (world > 1 or default_run):
+        sh = measure_sharded(args, world, rank, local_rank)
+        if rank == 0:
+            line['sharded'] = sh
+            if nccl_log:
+                line['sharded']['nccl_debug_file'] = nccl_log
+    if rank == 0:
+        print(json.dumps(line))
+        sys.stdout.flush()
+    if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
 
 
@@ -806,6 +1114,9 @@ def main():
         return
     if args.ref_train_worker is not None:
         ref_train_worker_main(json.loads(args.ref_train_worker))
+        return
+    if args.ref_torch_worker is not None:
+        ref_torch_worker_main(json.loads(args.ref_torch_worker))
         return
     if args.workload in PREDICT_ONLY:
         args.no_train = True

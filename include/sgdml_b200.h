@@ -54,6 +54,13 @@ int sgdml_b200_tril_perms_lin(const int64_t* perms, int64_t n_perms, int64_t n_a
 int sgdml_b200_desc_from_R(const double* R, int64_t n_geo, int64_t n_atoms, double* R_desc,
                            double* R_d_desc, void* stream);
 
+/* Desc.from_R with periodic boundary conditions: utils/desc.py:44-77 (_pbc_diff), 100-108, 200-201.  lattice and
+ * lattice_inv are 3 x 3 row-major HOST arrays (lattice vectors as COLUMNS, as task['lattice'] / model['lattice'],
+ * train.py:524, 826-827; the inverse as np.linalg.inv gives it, train.py:908-911).  Every pair difference is
+ * clamped to the super cell, d -= lattice @ round(lattice_inv @ d), before the distance is taken. */
+int sgdml_b200_desc_from_R_pbc(const double* R, int64_t n_geo, int64_t n_atoms, const double* lattice,
+                               const double* lattice_inv, double* R_desc, double* R_d_desc, void* stream);
+
 /* Desc.d_desc_dot_vec: utils/desc.py:368-385.  R_d_desc (n_geo, D, 3), vecs (n_geo, 3N)
  * -> out (n_geo, D). */
 int sgdml_b200_d_desc_dot_vec(const double* R_d_desc, const double* vecs, int64_t n_geo,
@@ -85,6 +92,16 @@ int sgdml_b200_model_destroy(sgdml_b200_model* model);
  * R (B, 3N) -> E (B,) [may be NULL], F (B, 3N); outputs scaled: F*std, E*std + c. */
 int sgdml_b200_predict(sgdml_b200_model* model, const double* R, int64_t n_geo, double* E,
                        double* F, void* stream);
+
+/* Periodic model (predict.py:332-334: lat_and_inv from model['lattice']): query descriptors of
+ * sgdml_b200_predict are built with the minimum-image convention.  Both NULL: back to a free molecule. */
+int sgdml_b200_model_set_lattice(sgdml_b200_model* model, const double* lattice, const double* lattice_inv);
+
+/* Energy constraints in the kernel (use_E_cstr models; predict.py:219-229, 443-447, 594-601): alphas_E (M,) or
+ * NULL to switch the terms off.  With alphas_E set, every (virtual query row, training point) pair additionally
+ * contributes alphas_E[m] * c2 * delta to the descriptor-space force and alphas_E[m] * K_ee to the energy,
+ * K_ee = (1 + (n/sig)(1 + n/(3 sig))) exp(-n/sig). */
+int sgdml_b200_model_set_alphas_E(sgdml_b200_model* model, const double* alphas_E, void* stream);
 
 /* GDMLPredict.set_R_desc / set_R_d_desc: predict.py:511-549.  Caches the training
  * descriptor Jacobians (M, D, 3) on the device so that set_alphas and the training-point
@@ -133,6 +150,14 @@ int sgdml_b200_assemble_rows(const double* R_desc, const double* R_d_desc,
                              int64_t n_perms, double sig, const int64_t* col_idxs, int64_t n_cols,
                              double scale, int64_t m_begin, int64_t m_end, double* K, int64_t ldk,
                              void* stream);
+
+/* Energy constraints in the kernel (task['use_E_cstr'], train.py:234-300, 1325-1335): fills the M energy rows and
+ * columns and the M x M energy-energy block of the (3NM + M)-square matrix K (DEVICE pointer, row stride ldk >= 3NM + M)
+ * whose force-force part sgdml_b200_assemble has written with the same `scale`:
+ *   K[3NM + i, blk_j] = K[blk_j, 3NM + i] = scale * K_fe(i, j),   K[3NM + j, 3NM + i] = scale * K_ee(i, j). */
+int sgdml_b200_assemble_ecstr(const double* R_desc, const double* R_d_desc, const int64_t* tril_perms_lin,
+                              int64_t n_atoms, int64_t n_train, int64_t n_perms, double sig, double scale, double* K,
+                              int64_t ldk, void* stream);
 
 /* Tuning / test hook: 0 = kernel chosen by molecule size (default), 1 = always the large-molecule
  * kernel (tables in global memory), which molecules above ~50 atoms need; 1000 + r = at most r row

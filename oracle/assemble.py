@@ -1,7 +1,7 @@
 """Oracle (test infrastructure): Matern-5/2 Hessian-kernel matrix assembly.
 
 NumPy restatement of sgdml/train.py:97-232 (_assemble_kernel_mat_wkr, force-force
-blocks only; use_E_cstr is out of scope) and the column
+blocks) with its column selection logic, and train.py:234-300 (energy-constraint rows and columns) and the column
 selection logic of train.py:1260-1407 (_assemble_kernel_mat).
 
 Reference sign convention: this returns K as the reference's _assemble_kernel_mat
@@ -94,6 +94,43 @@ def assemble(R_desc, R_d_desc, tril_perms_lin, sig, col_idxs=None, n_procs=1):
         keep = col_idxs[m_idxs == j] - j * dim_i  # train.py:1393-1407 keep_idxs_3n
         K[:, pos : pos + len(keep)] = blk[:, keep]
         pos += len(keep)
+    return K
+
+
+def assemble_E_cstr(R_desc, R_d_desc, tril_perms_lin, sig):
+    """Kernel matrix with energy constraints, (3NM + M) x (3NM + M), reference sign (train.py:234-300, 1325-1335,
+    1370): the force-force part as :func:`assemble`, then for every pair of training points (i, j)
+      K[n + i, blk_j] = K_fe(i, j) = -sum_p c_p delta_p^T J_j^(p),  c_p = 5 (n_p + sig) e^{-n_p/sig} / (3 sig^3),
+                                      delta_p = x_i - x_j[perm_p]                       (train.py:237-248),
+      K[blk_i, n + j] = the same with the roles of i and j exchanged                     (train.py:266-294),
+      K[n + i, n + j] = -sum_p (1 + (n_p/sig)(1 + n_p/(3 sig))) e^{-n_p/sig},  delta = x_j - x_i[perm_p] (train.py:296-300)."""
+    R_desc = np.ascontiguousarray(R_desc, dtype=np.float64)
+    M, D = R_desc.shape
+    S = len(tril_perms_lin) // D
+    tril_perms = odesc.tril_perms_from_lin(tril_perms_lin, S)
+    N = odesc.n_atoms_from_dim(D)
+    dim_i = 3 * N
+    n = M * dim_i
+    K = np.zeros((n + M, n + M))
+    K[:n, :n] = assemble(R_desc, R_d_desc, tril_perms_lin, sig)
+    sqrt5 = np.sqrt(5.0)
+    J = odesc.d_desc_from_comp(R_d_desc)  # (M, D, 3N)
+    for j in range(M):
+        xj_perms = R_desc[j][tril_perms]  # (S, D)
+        Jj_perms = J[j][tril_perms, :]  # (S, D, 3N)
+        for i in range(M):
+            diff = R_desc[i][None, :] - xj_perms  # train.py:199
+            norm = sqrt5 * np.linalg.norm(diff, axis=1)
+            K_fe = 5 * diff / (3 * sig**3) * (norm[:, None] + sig) * np.exp(-norm / sig)[:, None]  # train.py:237-243
+            K[n + i, j * dim_i : (j + 1) * dim_i] = -np.einsum('pd,pdk->k', K_fe, Jj_perms)  # train.py:245-248
+            # column n + j (train.py:266-300): descriptor of j against the permuted copies of i
+            xi_perms = R_desc[i][tril_perms]
+            Ji_perms = J[i][tril_perms, :]
+            diff2 = R_desc[j][None, :] - xi_perms
+            norm2 = sqrt5 * np.linalg.norm(diff2, axis=1)
+            K_fe2 = 5 * diff2 / (3 * sig**3) * (norm2[:, None] + sig) * np.exp(-norm2 / sig)[:, None]
+            K[i * dim_i : (i + 1) * dim_i, n + j] = -np.einsum('pd,pdk->k', K_fe2, Ji_perms)
+            K[n + i, n + j] = -(1 + (norm2 / sig) * (1 + norm2 / (3 * sig))).dot(np.exp(-norm2 / sig))
     return K
 
 

@@ -19,11 +19,20 @@ def n_atoms_from_dim(dim_d):
     return int((1 + np.sqrt(8 * dim_d + 1)) / 2)
 
 
-def from_R(R):
-    """Descriptor and compressed Jacobian for M geometries (no lattice).
+def pbc_diff(diffs, lat_and_inv):
+    """Minimum-image convention (desc.py:44-77): d -= lat @ round(lat_inv @ d); lat holds the lattice vectors
+    as COLUMNS; np.around rounds half to even."""
+    lat, lat_inv = lat_and_inv
+    c = np.einsum('ij,...j->...i', np.asarray(lat_inv, dtype=np.float64), diffs)
+    return diffs - np.einsum('ij,...j->...i', np.asarray(lat, dtype=np.float64), np.around(c))
+
+
+def from_R(R, lat_and_inv=None):
+    """Descriptor and compressed Jacobian for M geometries.
 
     Follows desc.py:80-110 (_pdist), 139-163 (_r_to_desc), 166-205 (_r_to_d_desc),
-    288-365 (Desc.from_R): x_d = 1/|r_a - r_b|, g_d = (r_a - r_b)/|r_a - r_b|^3.
+    288-365 (Desc.from_R): x_d = 1/|r_a - r_b|, g_d = (r_a - r_b)/|r_a - r_b|^3; with a lattice the pair
+    differences are clamped to the super cell first (desc.py:100-108, 200-201).
 
     R : (M, 3N) or (M, N, 3) float64.  Returns R_desc (M, D), R_d_desc (M, D, 3).
     """
@@ -32,6 +41,8 @@ def from_R(R):
     r = R.reshape(M, -1, 3)
     a, b = tril_pairs(r.shape[1])
     pdiff = r[:, a, :] - r[:, b, :]  # desc.py:193-198
+    if lat_and_inv is not None:
+        pdiff = pbc_diff(pdiff, lat_and_inv)
     # SciPy's pdist (desc.py:103) computes sqrt of the sum of squared differences
     dist = np.sqrt(np.sum(pdiff * pdiff, axis=-1))
     R_desc = 1.0 / dist  # desc.py:163

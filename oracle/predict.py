@@ -2,7 +2,7 @@
 
 NumPy restatement of sgdml/predict.py:84-245 (_predict_wkr), the permuted caches of
 predict.py:424-441, set_alphas predict.py:551-601 and the output scaling of
-predict.py:1286-1288.  use_E_cstr / lattice are out of scope.
+predict.py:1286-1288, including the energy-constraint terms (predict.py:219-229) and lattices (predict.py:332-334).
 """
 
 import multiprocessing as mp
@@ -26,6 +26,15 @@ class Predictor(object):
         self.n_train = model['R_desc'].shape[1]
         self.R_d_desc = None
         self.R_desc_train = None
+        self.lat_and_inv = None
+        if 'lattice' in model:  # predict.py:332-334
+            lat = np.asarray(model['lattice'], dtype=np.float64)
+            self.lat_and_inv = (lat, np.linalg.inv(lat))
+        # energy constraints in the kernel: one coefficient per training point, repeated over the permutations
+        # (predict.py:443-447)
+        self.alphas_E_lin = None
+        if 'alphas_E' in model:
+            self.alphas_E_lin = np.tile(np.asarray(model['alphas_E'], dtype=np.float64)[:, None], (1, self.n_perms)).ravel()
 
         # predict.py:426-441: caches with row k = m*S + p
         self.R_desc_perms = self._perm_cache(np.asarray(model['R_desc']).T)
@@ -70,6 +79,10 @@ class Predictor(object):
         base = base * (norm + sig)  # predict.py:213
         Fd -= base.dot(self.R_d_desc_alpha_perms)  # predict.py:214
         E = a_x2.dot(base)  # predict.py:217
+        if self.alphas_E_lin is not None:  # predict.py:219-229
+            Fd += self.alphas_E_lin.dot(diff * base[:, None])
+            K_ee = (1 + (norm * sig_inv) * (1 + norm / (3 * sig))) * np.exp(-norm * sig_inv)
+            E += K_ee.dot(self.alphas_E_lin)
 
         out = np.empty(3 * self.n_atoms + 1)
         out[0] = E
@@ -86,7 +99,7 @@ class Predictor(object):
             R = np.asarray(R, dtype=np.float64)
             if R.ndim == 1:
                 R = R[None, :]  # predict.py:1183-1184
-            R_desc, R_d_desc = odesc.from_R(R.reshape(R.shape[0], -1))
+            R_desc, R_d_desc = odesc.from_R(R.reshape(R.shape[0], -1), self.lat_and_inv)
         E_F = np.array([self._raw(x, g) for x, g in zip(R_desc, R_d_desc)])
         E_F = E_F.reshape(-1, 3 * self.n_atoms + 1) * self.std  # predict.py:1286
         F = E_F[:, 1:]

@@ -500,6 +500,81 @@ __global__ void __launch_bounds__(256, 2)
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Energy constraints in the kernel (use_E_cstr; reference train.py:234-300): the M extra rows and columns of
+// the (3NM + M) x (3NM + M) matrix.  One CTA per pair (i, j), one thread per atom b of point j:
+//   delta_p[d(P^-1 b, P^-1 g)] = x_i[d(P^-1 b, P^-1 g)] - x_j[d(b, g)],   n_p = sqrt5 |delta_p|,
+//   v_p[b] = -sum_g G_j[b][g] delta_p[...]                                  (= J_j^(p)T delta_p, as in k_assemble)
+//   r[b]   = -sum_p c_p v_p[b],  c_p = 5 (n_p + sig) exp(-n_p/sig) / (3 sig^3)        (train.py:237-248)
+//   K[n + i, blk_j] = r  and, by the same formula with the roles exchanged (train.py:266-294), K[blk_j, n + i] = r;
+//   K[n + j, n + i] = -sum_p (1 + (n_p/sig)(1 + n_p/(3 sig))) exp(-n_p/sig)           (train.py:296-300)
+// No tables: the pair quantities are read straight from the compressed arrays (L1/L2 resident); the work is
+// O(S N^2) per pair against O(S N^2 * 33) for the force-force block.
+__global__ void __launch_bounds__(128) k_assemble_ecstr(const double* __restrict__ R_desc, const double* __restrict__ R_d_desc,
+                                                       const int* __restrict__ aperm_inv, int N, int D, int M, int S,
+                                                       double sig, double scale, double* __restrict__ K, int64_t ldk) {
+  __shared__ double red[4];
+  __shared__ double s_cp, s_kee;
+  const int i = blockIdx.y, j = blockIdx.x;
+  const int b = threadIdx.x;  // atom of point j (blockDim.x = N rounded up to a warp multiple)
+  const double* xi = R_desc + (int64_t)i * D;
+  const double* xj = R_desc + (int64_t)j * D;
+  const double* gj = R_d_desc + (int64_t)j * D * 3;
+  const int64_t n = (int64_t)M * 3 * N;
+  double r0 = 0.0, r1 = 0.0, r2 = 0.0, kee = 0.0;
+  for (int pp = 0; pp < S; ++pp) {
+    const int* Pi = aperm_inv + pp * N;
+    double v0 = 0.0, v1 = 0.0, v2 = 0.0, s2 = 0.0;
+    if (b < N) {
+      const int pb = Pi[b];
+      for (int g = 0; g < N; ++g) {
+        if (g == b) continue;
+        const int pg = Pi[g];
+        const int d1 = pb > pg ? pair_index(pb, pg) : pair_index(pg, pb);
+        const int d2 = b > g ? pair_index(b, g) : pair_index(g, b);
+        const double sgn = b > g ? 1.0 : -1.0;  // G_j[b][g] = +g_d for b > g, -g_d otherwise
+        const double dl = xi[d1] - xj[d2];
+        s2 = fma(dl, dl, s2);
+        v0 = fma(sgn * gj[d2 * 3 + 0], dl, v0);
+        v1 = fma(sgn * gj[d2 * 3 + 1], dl, v1);
+        v2 = fma(sgn * gj[d2 * 3 + 2], dl, v2);
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s2;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double n2 = 0.0;
+      for (int w = 0; w < (int)(blockDim.x >> 5); ++w) n2 += red[w];
+      const double nrm = sqrt(5.0) * sqrt(0.5 * n2);  // every pair was visited twice
+      const double e = exp(-nrm / sig);
+      s_cp = 5.0 * (nrm + sig) * e / (3.0 * sig * sig * sig);
+      const double t = nrm / sig;
+      s_kee = (1.0 + t * (1.0 + nrm / (3.0 * sig))) * e;
+    }
+    __syncthreads();
+    const double cp = s_cp;
+    // v_p = -(sum): r -= c_p v_p  ->  r += c_p (sum)
+    r0 = fma(cp, v0, r0);
+    r1 = fma(cp, v1, r1);
+    r2 = fma(cp, v2, r2);
+    if (threadIdx.x == 0) kee += s_kee;
+    __syncthreads();  // red / s_cp are rewritten by the next permutation
+  }
+  if (b < N) {
+    const int64_t col = (int64_t)j * 3 * N + 3 * b;
+    double* rowE = K + (n + i) * ldk + col;
+    rowE[0] = scale * r0;
+    rowE[1] = scale * r1;
+    rowE[2] = scale * r2;
+    K[(col + 0) * ldk + n + i] = scale * r0;
+    K[(col + 1) * ldk + n + i] = scale * r1;
+    K[(col + 2) * ldk + n + i] = scale * r2;
+  }
+  if (threadIdx.x == 0) K[(n + j) * ldk + n + i] = -scale * kee;
+}
+
 static size_t asm_large_slab_doubles(int N, int S) {
   const size_t N3 = 3 * (size_t)N, NN = (size_t)N * N;
   return 2 * (NN * 3 + NN) + (size_t)S * (2 * N3 + 3 * N3 + 2) + NN;
@@ -764,4 +839,53 @@ extern "C" int sgdml_b200_assemble(const double* R_desc, const double* R_d_desc,
                                    void* stream) {
   return sgdml_b200_assemble_rows(R_desc, R_d_desc, tril_perms_lin, n_atoms, n_train, n_perms, sig, col_idxs, n_cols,
                                   scale, 0, n_train, K, ldk, stream);
+}
+
+// GDMLTrain._assemble_kernel_mat(use_E_cstr=True), train.py:234-300: fills the M energy rows and columns (and the
+// M x M energy-energy block) of the (3NM + M)-square matrix whose force-force part sgdml_b200_assemble writes.
+extern "C" int sgdml_b200_assemble_ecstr(const double* R_desc, const double* R_d_desc, const int64_t* tril_perms_lin,
+                                         int64_t n_atoms, int64_t n_train, int64_t n_perms, double sig, double scale,
+                                         double* K, int64_t ldk, void* stream) {
+  SG_TRY(require_device());
+  SG_ARG(R_desc != nullptr && R_d_desc != nullptr && tril_perms_lin != nullptr && K != nullptr);
+  SG_ARG(n_atoms >= 2 && n_atoms <= 128 && n_train >= 1 && n_train <= 65535 && n_perms >= 1 && sig > 0);
+  const int N = (int)n_atoms, M = (int)n_train, S = (int)n_perms;
+  const int D = N * (N - 1) / 2;
+  const int64_t nt = (int64_t)M * 3 * N + M;
+  SG_ARG(ldk >= nt && is_device_ptr(K));
+  cudaStream_t s = (cudaStream_t)stream;
+  std::vector<int64_t> lin((size_t)S * D);
+  if (is_device_ptr(tril_perms_lin))
+    SG_CUDA(cudaMemcpy(lin.data(), tril_perms_lin, sizeof(int64_t) * lin.size(), cudaMemcpyDeviceToHost));
+  else
+    std::copy(tril_perms_lin, tril_perms_lin + lin.size(), lin.begin());
+  std::vector<int> dperm((size_t)D), aperm((size_t)N), apinv((size_t)S * N);
+  for (int pp = 0; pp < S; ++pp) {
+    for (int d = 0; d < D; ++d) {
+      const int64_t e = lin[(size_t)d * S + pp] - (int64_t)pp * D;
+      SG_ARG(e >= 0 && e < D);
+      dperm[(size_t)d] = (int)e;
+    }
+    if (!atom_perm_from_desc_perm(dperm.data(), N, aperm.data()))
+      return fail_arg("tril_perms_lin is not induced by atom permutations (utils/desc.py:509-539)");
+    for (int a = 0; a < N; ++a) apinv[(size_t)pp * N + aperm[(size_t)a]] = a;
+  }
+  Staged sX, sG;
+  SG_TRY(sX.init(R_desc, sizeof(double) * (size_t)M * D, true, s));
+  SG_TRY(sG.init(R_d_desc, sizeof(double) * (size_t)M * D * 3, true, s));
+  int* d_apinv = nullptr;
+  SG_CUDA(cudaMalloc(&d_apinv, sizeof(int) * apinv.size()));
+  auto body = [&]() -> int {
+    SG_CUDA(cudaMemcpyAsync(d_apinv, apinv.data(), sizeof(int) * apinv.size(), cudaMemcpyHostToDevice, s));
+    ProfScope ps(KID_ASSEMBLE, s);
+    k_assemble_ecstr<<<dim3((unsigned)M, (unsigned)M), (N + 31) / 32 * 32, 0, s>>>(
+        (const double*)sX.dev(), (const double*)sG.dev(), d_apinv, N, D, M, S, sig, scale, K, ldk);
+    SG_CUDA(cudaGetLastError());
+    count_launch(KID_ASSEMBLE);
+    SG_CUDA(cudaStreamSynchronize(s));
+    return 0;
+  };
+  int rc = body();
+  cudaFree(d_apinv);
+  return rc;
 }

@@ -8,8 +8,10 @@ namespace sgdml {
 
 // ---------------------------------------------------------------- a-D1: from_R
 // reference: utils/desc.py:80-110 (_pdist), 139-163, 166-205, 288-365
+// lat.on != 0: minimum-image convention (utils/desc.py:44-77): d -= lat @ rint(lat_inv @ d), lattice vectors as the
+// COLUMNS of lat; np.around and rint both round half to even
 __global__ void k_desc_from_R(const double* __restrict__ R, int64_t n_geo, int n_atoms, int dim_d,
-                              double* __restrict__ R_desc, double* __restrict__ R_d_desc) {
+                              double* __restrict__ R_desc, double* __restrict__ R_d_desc, const Lattice lat) {
   int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   int64_t total = n_geo * dim_d;
   if (idx >= total) return;
@@ -21,6 +23,14 @@ __global__ void k_desc_from_R(const double* __restrict__ R, int64_t n_geo, int n
   double dx = r[3 * a + 0] - r[3 * b + 0];
   double dy = r[3 * a + 1] - r[3 * b + 1];
   double dz = r[3 * a + 2] - r[3 * b + 2];
+  if (lat.on) {
+    const double c0 = rint(lat.inv[0] * dx + lat.inv[1] * dy + lat.inv[2] * dz);
+    const double c1 = rint(lat.inv[3] * dx + lat.inv[4] * dy + lat.inv[5] * dz);
+    const double c2 = rint(lat.inv[6] * dx + lat.inv[7] * dy + lat.inv[8] * dz);
+    dx -= lat.vec[0] * c0 + lat.vec[1] * c1 + lat.vec[2] * c2;
+    dy -= lat.vec[3] * c0 + lat.vec[4] * c1 + lat.vec[5] * c2;
+    dz -= lat.vec[6] * c0 + lat.vec[7] * c1 + lat.vec[8] * c2;
+  }
   double dist = sqrt(dx * dx + dy * dy + dz * dz);
   double inv = 1.0 / dist;
   double inv3 = 1.0 / (dist * dist * dist);
@@ -80,12 +90,15 @@ __global__ void k_vec_dot_d_desc(const double* __restrict__ R_d_desc, const doub
 }
 
 int launch_desc_from_R(const double* R, int64_t n_geo, int n_atoms, double* R_desc, double* R_d_desc,
-                       cudaStream_t s) {
+                       cudaStream_t s, const Lattice* lat) {
   if (n_geo == 0) return 0;
   const int D = n_atoms * (n_atoms - 1) / 2;
   int64_t total = n_geo * D;
+  Lattice l;
+  l.on = 0;
+  if (lat != nullptr) l = *lat;
   ProfScope ps(KID_DESC, s);
-  k_desc_from_R<<<ceil_div(total, 256), 256, 0, s>>>(R, n_geo, n_atoms, D, R_desc, R_d_desc);
+  k_desc_from_R<<<ceil_div(total, 256), 256, 0, s>>>(R, n_geo, n_atoms, D, R_desc, R_d_desc, l);
   SG_CUDA(cudaGetLastError());
   count_launch(KID_DESC);
   return 0;
@@ -113,6 +126,19 @@ int launch_vec_dot_d_desc(const double* R_d_desc, const double* vecs, int64_t n_
   return 0;
 }
 
+// lattice / lattice_inv: 9 HOST doubles each (3 x 3 row-major, lattice vectors as columns), or both NULL
+int lattice_from_host(const double* lattice, const double* lattice_inv, Lattice* l) {
+  l->on = 0;
+  if (lattice == nullptr && lattice_inv == nullptr) return 0;
+  SG_ARG(lattice != nullptr && lattice_inv != nullptr);
+  SG_ARG(!is_device_ptr(lattice) && !is_device_ptr(lattice_inv));
+  for (int i = 0; i < 9; ++i) {
+    l->vec[i] = lattice[i];
+    l->inv[i] = lattice_inv[i];
+  }
+  l->on = 1;
+  return 0;
+}
 }  // namespace sgdml
 
 using namespace sgdml;
@@ -142,6 +168,26 @@ int sgdml_b200_tril_perms_lin(const int64_t* perms, int64_t n_perms, int64_t n_a
       }
     }
   }
+  return 0;
+}
+
+int sgdml_b200_desc_from_R_pbc(const double* R, int64_t n_geo, int64_t n_atoms, const double* lattice,
+                               const double* lattice_inv, double* R_desc, double* R_d_desc, void* stream) {
+  SG_TRY(require_device());
+  SG_ARG(R != nullptr && n_geo >= 0 && n_atoms >= 2);
+  if (n_geo == 0) return 0;
+  Lattice l;
+  SG_TRY(lattice_from_host(lattice, lattice_inv, &l));
+  cudaStream_t s = (cudaStream_t)stream;
+  const int64_t D = n_atoms * (n_atoms - 1) / 2;
+  Staged sR, sX, sG;
+  SG_TRY(sR.init(R, sizeof(double) * n_geo * 3 * n_atoms, true, s));
+  SG_TRY(sX.init(R_desc, sizeof(double) * n_geo * D, false, s));
+  SG_TRY(sG.init(R_d_desc, sizeof(double) * n_geo * D * 3, false, s));
+  SG_TRY(launch_desc_from_R((const double*)sR.dev(), n_geo, (int)n_atoms, (double*)sX.dev(), (double*)sG.dev(), s, &l));
+  SG_TRY(sX.finish(s));
+  SG_TRY(sG.finish(s));
+  if (sR.staged() || sX.staged() || sG.staged()) SG_CUDA(cudaStreamSynchronize(s));
   return 0;
 }
 

@@ -19,9 +19,17 @@ __host__ __device__ __forceinline__ void pair_from_d(int d, int& a, int& b) {
   b = d - t * (t - 1) / 2;
 }
 
+// periodic cell for the minimum-image convention (utils/desc.py:44-77): 3 x 3 row-major, lattice vectors as columns
+struct Lattice {
+  int on;
+  double vec[9];
+  double inv[9];
+};
+int lattice_from_host(const double* lattice, const double* lattice_inv, Lattice* l);
+
 // host-side launchers defined in desc.cu (device pointers only), reused by predict.cu
 int launch_desc_from_R(const double* R, int64_t n_geo, int n_atoms, double* R_desc, double* R_d_desc,
-                       cudaStream_t s);
+                       cudaStream_t s, const Lattice* lat = nullptr);
 int launch_d_desc_dot_vec(const double* R_d_desc, const double* vecs, int64_t n_geo, int n_atoms, double* out,
                           int64_t out_stride, cudaStream_t s);
 int launch_vec_dot_d_desc(const double* R_d_desc, const double* vecs, int64_t n_geo, int n_atoms,

@@ -224,11 +224,6 @@ constexpr size_t OZ_SMEM_BYTES = (size_t)OZ_RING_BYTES + sizeof(OzSmemTail) + 10
 constexpr int OZ_STAGE_LD = 33;  // doubles per row of the epilogue transpose tiles (32 + 1: conflict-free both ways)
 static_assert(4 * 32 * OZ_STAGE_LD * 8 <= OZ_RING_BYTES, "the epilogue stages through the (then idle) ring");
 
-// slice visited at position idx of a k-block: 1, S, 2, S-1, ...  (1-based slice numbers)
-__device__ __forceinline__ int oz_order(int idx, int S) { return (idx & 1) ? S - (idx >> 1) : 1 + (idx >> 1); }
-// position of slice p in that order
-__device__ __forceinline__ int oz_pos(int p, int S) { return (2 * p <= S + 1) ? 2 * (p - 1) : 2 * (S - p) + 1; }
-
 // CTA number -> tile (tm, tn), super-tile by super-tile; false if the CTA has no tile
 __device__ __forceinline__ bool oz_tile_of_cta(const OzArgs& p, int64_t cta, int64_t& tm, int64_t& tn) {
   constexpr int PER = OZ_GSM * OZ_GSN;
@@ -255,11 +250,17 @@ __device__ __forceinline__ bool oz_tile_of_cta(const OzArgs& p, int64_t cta, int
   return true;
 }
 
+// S is a template parameter: the pair schedule of a k-block (28 pairs for S = 7) is then a compile-time list and the
+// single MMA-issuing thread runs straight-line code -- one tcgen05.mma per instruction slot, ring slots advanced
+// with adds and compares.  (The first version computed `unit % ring` with 64-bit runtime divisions, ~150 cycles
+// each, ~70 per k-block: the issuing thread, not the tensor pipe, set the pace -- 5.4 us per k-block against the
+// 0.9 us the MMAs need; profiles/r02_ozaki_bringup.md.)
+template <int S>
 __global__ void __launch_bounds__(192, 1) k_ozaki_gemm(const OzArgs p) {
   extern __shared__ unsigned char oz_raw[];
   // 1024-byte alignment for the swizzled tiles
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(oz_raw) + 1023) & ~(uintptr_t)1023);
-  const int S = p.S, R = oz_ring_slots(S);
+  constexpr int R = (2 * S + 4 < OZ_MAX_RING) ? 2 * S + 4 : OZ_MAX_RING;
   OzSmemTail* tail = reinterpret_cast<OzSmemTail*>(smem + (size_t)OZ_RING_BYTES);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
@@ -290,64 +291,93 @@ __global__ void __launch_bounds__(192, 1) k_ozaki_gemm(const OzArgs p) {
   tc_fence_after();
   const uint32_t tmem = tail->tmem_base;
   const int KB = (int)(p.kp / OZ_BK);
+  const uint32_t smem_base = smem_u32(smem);
 
   if (warp == 0) {
     // ===================================================== producer: two contiguous bulk copies per unit
     if (lane == 0) {
-      const int8_t* a_base = p.ua + tm * (int64_t)OZ_A_BYTES;
-      const int8_t* b_base = p.ub + (n0 / OZ_BM) * (int64_t)OZ_A_BYTES + (n0 % OZ_BM) * OZ_BK;
+      const int8_t* a_src = p.ua + tm * (int64_t)OZ_A_BYTES;
+      const int8_t* b_src = p.ub + (n0 / OZ_BM) * (int64_t)OZ_A_BYTES + (n0 % OZ_BM) * OZ_BK;
       const int64_t a_stride = p.rt_a * (int64_t)OZ_A_BYTES, b_stride = p.rt_b * (int64_t)OZ_A_BYTES;  // per (kb, slice)
-      int64_t u = 0;
+      int slot = 0;
+      uint32_t round = 0;
       for (int kb = 0; kb < KB; ++kb) {
-        for (int idx = 0; idx < S; ++idx, ++u) {
-          const int slot = (int)(u % R);
-          const uint32_t round = (uint32_t)(u / R);
+#pragma unroll
+        for (int idx = 0; idx < S; ++idx) {
           if (round > 0) mbar_wait(&tail->empty[slot], (round - 1) & 1);  // the slot's previous unit is dead
           unsigned char* base = smem + (size_t)slot * OZ_UNIT_BYTES;
-          const int64_t ks = (int64_t)kb * S + (oz_order(idx, S) - 1);
+          const int sl = (idx & 1) ? S - 1 - (idx >> 1) : (idx >> 1);  // 0-based slice in the order 1, S, 2, S-1, ...
           mbar_arrive_expect_tx(&tail->full[slot], (uint32_t)OZ_UNIT_BYTES);
-          bulk_g2s(base, a_base + ks * a_stride, OZ_A_BYTES, &tail->full[slot]);
-          bulk_g2s(base + OZ_A_BYTES, b_base + ks * b_stride, OZ_B_BYTES, &tail->full[slot]);
+          bulk_g2s(base, a_src + sl * a_stride, OZ_A_BYTES, &tail->full[slot]);
+          bulk_g2s(base + OZ_A_BYTES, b_src + sl * b_stride, OZ_B_BYTES, &tail->full[slot]);
+          if (++slot == R) {
+            slot = 0;
+            ++round;
+          }
         }
+        a_src += (int64_t)S * a_stride;
+        b_src += (int64_t)S * b_stride;
       }
     }
   } else if (warp == 1) {
     // ===================================================== MMA issuer
     if (lane == 0) {
       constexpr uint32_t IDESC = umma_idesc_s8(OZ_BM, OZ_BN);
-      uint32_t level_started = 0;  // bit L: accumulator of level L holds data
+      // descriptor of a tile at shared address 0, K offset 0: everything but the 14-bit start-address field
+      const uint64_t desc_hi = umma_desc_kmajor(0);
+      int base_slot = 0;       // ring slot of position 0 of this k-block
+      uint32_t base_round = 0;  // its round (parity of the full barrier)
       for (int kb = 0; kb < KB; ++kb) {
-        const int64_t ub = (int64_t)kb * S;
-        // group r = 1 needs every slice of this k-block
+        // slots, in position order, of the S units of this k-block; wait for all of them (group r = 1 needs all)
+        uint32_t a_lo[S], b_lo[S];  // start-address fields (>> 4) of slice p's A and B tiles, indexed by slice - 1
+        int slot_of_pos[S];
+#pragma unroll
         for (int idx = 0; idx < S; ++idx) {
-          const int64_t u = ub + idx;
-          mbar_wait(&tail->full[u % R], (uint32_t)(u / R) & 1);
+          int sl = base_slot + idx;
+          uint32_t rd = base_round;
+          if (sl >= R) {
+            sl -= R;
+            ++rd;
+          }
+          slot_of_pos[idx] = sl;
+          mbar_wait(&tail->full[sl], rd & 1);
+          const int slice = (idx & 1) ? S - 1 - (idx >> 1) : (idx >> 1);  // 0-based
+          const uint32_t addr = smem_base + (uint32_t)sl * OZ_UNIT_BYTES;
+          a_lo[slice] = (addr >> 4) & 0x3FFF;
+          b_lo[slice] = ((addr + OZ_A_BYTES) >> 4) & 0x3FFF;
         }
         tc_fence_after();
+#pragma unroll
         for (int r = 1; 2 * r <= S + 1; ++r) {
           // pairs with min(pa, pb) = r and pa + pb <= S + 1
+#pragma unroll
           for (int t = r; t <= S + 1 - r; ++t) {
+#pragma unroll
             for (int side = 0; side < 2; ++side) {
               if (side == 1 && t == r) continue;  // (r, r) only once
               const int pa = side == 0 ? r : t, pb = side == 0 ? t : r;
               const int level = pa + pb;  // 2 .. S + 1
-              const int64_t ua = ub + oz_pos(pa, S), ubb = ub + oz_pos(pb, S);
-              const uint32_t a_addr = smem_u32(smem + (size_t)(ua % R) * OZ_UNIT_BYTES);
-              const uint32_t b_addr = smem_u32(smem + (size_t)(ubb % R) * OZ_UNIT_BYTES + OZ_A_BYTES);
               const uint32_t d_addr = tmem + (uint32_t)(level - 2) * OZ_BN;
+              // the first product into a level accumulator (first k-block only) overwrites it
+              const bool first_of_level = (pa == 1 || (pb == 1 && pa == 1));
 #pragma unroll
               for (int ks = 0; ks < OZ_BK / OZ_UMMA_K; ++ks) {
-                // advancing along K inside the swizzle row: +32 bytes on the start address
-                const uint64_t da = umma_desc_kmajor(a_addr + ks * OZ_UMMA_K);
-                const uint64_t db = umma_desc_kmajor(b_addr + ks * OZ_UMMA_K);
-                if (!(p.dbg_flags & 2)) tc_mma_i8(d_addr, da, db, IDESC, (level_started >> level) & 1u);
-                level_started |= 1u << level;
+                // advancing along K inside the swizzle row: +32 bytes on the start address (+2 in the >> 4 field)
+                const uint64_t da = desc_hi | (uint64_t)(a_lo[pa - 1] + 2 * ks);
+                const uint64_t db = desc_hi | (uint64_t)(b_lo[pb - 1] + 2 * ks);
+                const uint32_t acc = (first_of_level && ks == 0 && kb == 0) ? 0u : 1u;
+                if (!(p.dbg_flags & 2)) tc_mma_i8(d_addr, da, db, IDESC, acc);
               }
             }
           }
-          // slices r and S + 1 - r are dead for this k-block: hand their slots back
-          tc_commit(&tail->empty[(ub + oz_pos(r, S)) % R]);
-          if (S + 1 - r != r) tc_commit(&tail->empty[(ub + oz_pos(S + 1 - r, S)) % R]);
+          // slices r and S + 1 - r are dead for this k-block: hand their slots back (positions 2(r-1), 2(r-1)+1)
+          tc_commit(&tail->empty[slot_of_pos[2 * (r - 1)]]);
+          if (S + 1 - r != r) tc_commit(&tail->empty[slot_of_pos[2 * (r - 1) + 1]]);
+        }
+        base_slot += S;
+        if (base_slot >= R) {
+          base_slot -= R;
+          ++base_round;
         }
       }
       tc_commit(&tail->acc_full);  // every accumulator is final (and every unit has been consumed)
@@ -363,19 +393,29 @@ __global__ void __launch_bounds__(192, 1) k_ozaki_gemm(const OzArgs p) {
     double* stage = reinterpret_cast<double*>(smem) + (size_t)quad * 32 * OZ_STAGE_LD;  // this warp's 32 x 32 tile
 #pragma unroll 1
     for (int half = 0; half < OZ_BN / 32; ++half) {
+      // the old values of C for this warp's 32 x 32 sub-tile: 32 independent row-contiguous loads in flight while
+      // the level sums are read from tensor memory
+      const int64_t gc = n0 + half * 32 + lane;
+      const int rows_here = (int)max((int64_t)0, min((int64_t)32, p.m - (m0 + quad * 32)));
+      const bool col_ok = gc < p.n && !(p.dbg_flags & 1);
+      double* cp = p.C + (m0 + quad * 32) * p.ldc + gc;
+      double cold[32];
+#pragma unroll
+      for (int r = 0; r < 32; ++r) cold[r] = (col_ok && r < rows_here) ? cp[(int64_t)r * p.ldc] : 0.0;
       double acc[32];
 #pragma unroll
       for (int j = 0; j < 32; ++j) acc[j] = 0.0;
+#pragma unroll 1
       for (int level = (p.dbg_flags & 4) ? 2 : S + 1; level >= 2; --level) {  // smallest contributions first
         int v[32];
         tmem_ld_32x32(tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)((level - 2) * OZ_BN + half * 32), v);
-        const double w = ldexp(1.0, -OZ_BITS * level);
+        const double w = __longlong_as_double((long long)(1023 - OZ_BITS * level) << 52);  // 2^(-7 level), exact
 #pragma unroll
         for (int j = 0; j < 32; ++j) acc[j] = fma((double)v[j], w, acc[j]);
         if (p.dbg_levels != nullptr && gr < p.m) {
           for (int j = 0; j < 32; ++j) {
-            const int64_t gc = n0 + half * 32 + j;
-            if (gc < p.n) p.dbg_levels[((int64_t)(level - 2) * p.m + gr) * p.n + gc] = v[j];
+            const int64_t gcj = n0 + half * 32 + j;
+            if (gcj < p.n) p.dbg_levels[((int64_t)(level - 2) * p.m + gr) * p.n + gcj] = v[j];
           }
         }
       }
@@ -385,14 +425,10 @@ __global__ void __launch_bounds__(192, 1) k_ozaki_gemm(const OzArgs p) {
 #pragma unroll
       for (int j = 0; j < 32; ++j) stage[lane * OZ_STAGE_LD + j] = acc[j] * row_scale * tail->col_scale[half * 32 + j];
       __syncwarp();
-      if (!(p.dbg_flags & 1)) {
-        const int64_t gc = n0 + half * 32 + lane;
-        const int rows_here = (int)max((int64_t)0, min((int64_t)32, p.m - (m0 + quad * 32)));
-        if (gc < p.n) {
-          double* cp = p.C + (m0 + quad * 32) * p.ldc + gc;
-#pragma unroll 4
-          for (int r = 0; r < rows_here; ++r) cp[(int64_t)r * p.ldc] += stage[r * OZ_STAGE_LD + lane];
-        }
+      if (col_ok) {
+#pragma unroll
+        for (int r = 0; r < 32; ++r)
+          if (r < rows_here) cp[(int64_t)r * p.ldc] = cold[r] + stage[r * OZ_STAGE_LD + lane];
       }
     }
     tc_fence_before();
@@ -435,7 +471,12 @@ static int oz_launch(const OzOperand& oa, const OzOperand& ob, int64_t m, int64_
   int dev = 0;
   SG_CUDA(cudaGetDevice(&dev));
   if (dev >= 0 && dev < 64 && !configured[dev]) {
-    SG_CUDA(cudaFuncSetAttribute(k_ozaki_gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)OZ_SMEM_BYTES));
+    SG_CUDA(cudaFuncSetAttribute(k_ozaki_gemm<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)OZ_SMEM_BYTES));
+    SG_CUDA(cudaFuncSetAttribute(k_ozaki_gemm<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)OZ_SMEM_BYTES));
+    SG_CUDA(cudaFuncSetAttribute(k_ozaki_gemm<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)OZ_SMEM_BYTES));
+    SG_CUDA(cudaFuncSetAttribute(k_ozaki_gemm<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)OZ_SMEM_BYTES));
+    SG_CUDA(cudaFuncSetAttribute(k_ozaki_gemm<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)OZ_SMEM_BYTES));
+    SG_CUDA(cudaFuncSetAttribute(k_ozaki_gemm<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)OZ_SMEM_BYTES));
     configured[dev] = true;
   }
   SG_ARG(oa.kp == ob.kp);
@@ -470,7 +511,15 @@ static int oz_launch(const OzOperand& oa, const OzOperand& ob, int64_t m, int64_
   const int64_t blocks = n_super * OZ_GSM * OZ_GSN;
   SG_ARG(blocks < ((int64_t)1 << 31));
   ProfScope ps(KID_GEMM, s);
-  k_ozaki_gemm<<<(unsigned)blocks, 192, OZ_SMEM_BYTES, s>>>(a);
+  switch (S) {
+    case 2: k_ozaki_gemm<2><<<(unsigned)blocks, 192, OZ_SMEM_BYTES, s>>>(a); break;
+    case 3: k_ozaki_gemm<3><<<(unsigned)blocks, 192, OZ_SMEM_BYTES, s>>>(a); break;
+    case 4: k_ozaki_gemm<4><<<(unsigned)blocks, 192, OZ_SMEM_BYTES, s>>>(a); break;
+    case 5: k_ozaki_gemm<5><<<(unsigned)blocks, 192, OZ_SMEM_BYTES, s>>>(a); break;
+    case 6: k_ozaki_gemm<6><<<(unsigned)blocks, 192, OZ_SMEM_BYTES, s>>>(a); break;
+    case 7: k_ozaki_gemm<7><<<(unsigned)blocks, 192, OZ_SMEM_BYTES, s>>>(a); break;
+    default: return fail_arg("2 <= n_slices <= 7");
+  }
   SG_CUDA(cudaGetLastError());
   count_launch(KID_GEMM);
   return 0;

@@ -60,7 +60,8 @@ struct PCfg {
   static constexpr int OFF_JA = OFF_X + 2 * BM * DS;      // [2][BM*DS]
   static constexpr int OFF_MM = OFF_JA + 2 * BM * DS;     // [2][BM]
   static constexpr int OFF_XJA = OFF_MM + 2 * BM;         // [2][BM]
-  static constexpr int OFF_P = OFF_XJA + 2 * BM;          // [W1K][2][BQ*CS]; set 0 becomes C1/C2
+  static constexpr int OFF_AE = OFF_XJA + 2 * BM;         // [2][BM] energy-constraint coefficients (zeros when unused)
+  static constexpr int OFF_P = OFF_AE + 2 * BM;           // [W1K][2][BQ*CS]; set 0 becomes C1/C2
   static constexpr int OFF_QQ = OFF_P + W1K * 2 * BQ * CS;
   static constexpr int OFF_CSUM = OFF_QQ + BQ;
   static constexpr int OFF_E = OFF_CSUM + BQ;
@@ -77,6 +78,8 @@ struct PredictArgs {
   const double* JA;     // (Mpad, DS) R_d_desc_alpha, zero padded
   const double* mm;     // (Mpad) |Xc_m|^2
   const double* xja;    // (Mpad) Xc_m . JA_m
+  const double* ae;     // (Mpad) alphas_E (use_E_cstr models, predict.py:219-229); zeros when use_ae == 0
+  int use_ae;
   int D, M, S, Mpad;
   double sig;
   // queries: virtual rows (b, p) prepared by k_query_rows
@@ -132,6 +135,19 @@ __device__ __forceinline__ void matern52(double x5, double a, const MaternK& k, 
   c1 = a * (e * k.k_c1);
   c2 = (e * k.k_base) * (nrm + k.sig);
 }
+// the same with the energy-constraint terms of predict.py:219-229 for a training point with coefficient ae:
+//   F_desc += ae c2 delta  (folded into c1: both multiply delta),  E += ae K_ee,
+//   K_ee = (1 + (n/sig)(1 + n/(3 sig))) exp(-n/sig);  returns the energy term a c2 + ae K_ee
+__device__ __forceinline__ double matern52_ecstr(double x5, double a, double ae, const MaternK& k, double& c1, double& c2) {
+  const double x = fmax(x5, 1e-300);
+  const double nrm = x * rsqrt(x);
+  const double t = nrm * k.sig_inv;
+  const double e = exp_neg(t);
+  c2 = (e * k.k_base) * (nrm + k.sig);
+  c1 = fma(ae, c2, a * (e * k.k_c1));
+  const double kee = fma(t, fma(t, 1.0 / 3.0, 1.0), 1.0) * e;
+  return fma(a, c2, ae * kee);
+}
 
 // ============================================================== main kernel
 template <class C>
@@ -142,6 +158,7 @@ __global__ void __launch_bounds__(256, C::MINB) k_predict_main(const PredictArgs
   double* JAs = smem + C::OFF_JA;
   double* mms = smem + C::OFF_MM;
   double* xjas = smem + C::OFF_XJA;
+  double* aes = smem + C::OFF_AE;
   double* Ps = smem + C::OFF_P;
   double* qq = smem + C::OFF_QQ;
   double* csum_s = smem + C::OFF_CSUM;
@@ -154,7 +171,7 @@ __global__ void __launch_bounds__(256, C::MINB) k_predict_main(const PredictArgs
   const int64_t r0 = (int64_t)blockIdx.x * C::BQ;
   const int t_begin = (int)blockIdx.y * p.tiles_per_split;
   const int n_tiles = min(p.Mpad / C::BM, t_begin + p.tiles_per_split);  // exclusive end of this CTA's range
-  constexpr uint32_t STAGE_BYTES = (uint32_t)((2 * C::BM * C::DS + 2 * C::BM) * 8);
+  constexpr uint32_t STAGE_BYTES = (uint32_t)((2 * C::BM * C::DS + 3 * C::BM) * 8);
 
   if (tid == 0) {
     mbar_init(&bars[0], 1);
@@ -172,6 +189,7 @@ __global__ void __launch_bounds__(256, C::MINB) k_predict_main(const PredictArgs
     bulk_g2s(JAs + s * C::BM * C::DS, p.JA + m0 * C::DS, C::BM * C::DS * 8, &bars[s]);
     bulk_g2s(mms + s * C::BM, p.mm + m0, C::BM * 8, &bars[s]);
     bulk_g2s(xjas + s * C::BM, p.xja + m0, C::BM * 8, &bars[s]);
+    bulk_g2s(aes + s * C::BM, p.ae + m0, C::BM * 8, &bars[s]);
   };
   if (tid == 0) {
     // the Q tile (BQ prepared virtual rows, contiguous) and its row norms: two bulk copies
@@ -230,6 +248,7 @@ __global__ void __launch_bounds__(256, C::MINB) k_predict_main(const PredictArgs
     const double* JAt = JAs + s * C::BM * C::DS;
     const double* mmt = mms + s * C::BM;
     const double* xjat = xjas + s * C::BM;
+    const double* aet = aes + s * C::BM;
     mbar_wait(&bars[s], (uint32_t)(((t - t_begin) >> 1) & 1));
     // real training points in this tile: the zero-padded tail of the last tile is skipped
     // (whole 8-point fragment columns in GEMM1, whole 4-point k-steps in GEMM2)
@@ -280,10 +299,15 @@ __global__ void __launch_bounds__(256, C::MINB) k_predict_main(const PredictArgs
               const double q5 = 5.0 * qq[r];
               double c1a_, c2a_, c1b_, c2b_;
               const double aa = a2[i][j][0] - xa, ab = a2[i][j][1] - xb2;
-              matern52(fma(-10.0, a1[i][j][0], q5 + m5a), aa, mk, c1a_, c2a_);
-              matern52(fma(-10.0, a1[i][j][1], q5 + m5b), ab, mk, c1b_, c2b_);
+              if (p.use_ae) {  // warp-uniform: models with energy constraints in the kernel
+                E_part[i] += matern52_ecstr(fma(-10.0, a1[i][j][0], q5 + m5a), aa, aet[mc], mk, c1a_, c2a_);
+                E_part[i] += matern52_ecstr(fma(-10.0, a1[i][j][1], q5 + m5b), ab, aet[mc + 1], mk, c1b_, c2b_);
+              } else {
+                matern52(fma(-10.0, a1[i][j][0], q5 + m5a), aa, mk, c1a_, c2a_);
+                matern52(fma(-10.0, a1[i][j][1], q5 + m5b), ab, mk, c1b_, c2b_);
+                E_part[i] = fma(aa, c2a_, fma(ab, c2b_, E_part[i]));
+              }
               csum_part[i] += c1a_ + c1b_;
-              E_part[i] = fma(aa, c2a_, fma(ab, c2b_, E_part[i]));
               const int off = r * C::CS + mc;
               *reinterpret_cast<double2*>(C1s + off) = make_double2(c1a_, c1b_);
               *reinterpret_cast<double2*>(C2s + off) = make_double2(c2a_, c2b_);
@@ -320,9 +344,13 @@ __global__ void __launch_bounds__(256, C::MINB) k_predict_main(const PredictArgs
         }
         const double a = s2 - xjat[mc];
         double c1, c2;
-        matern52(fma(-10.0, s1, 5.0 * (qq[r] + mmt[mc])), a, mk, c1, c2);
+        if (p.use_ae) {
+          E_part[j] += matern52_ecstr(fma(-10.0, s1, 5.0 * (qq[r] + mmt[mc])), a, aet[mc], mk, c1, c2);
+        } else {
+          matern52(fma(-10.0, s1, 5.0 * (qq[r] + mmt[mc])), a, mk, c1, c2);
+          E_part[j] = fma(a, c2, E_part[j]);
+        }
         csum_part[j] += c1;
-        E_part[j] = fma(a, c2, E_part[j]);
         C1s[off] = c1;
         C2s[off] = c2;
       }
@@ -487,7 +515,8 @@ __global__ void __launch_bounds__(256) k_query_rows(const double* __restrict__ x
 // Per (row, m) pair this adds 64 B of HBM traffic to >= 9 * 256 flop: far above the FP64 ridge.
 __global__ void __launch_bounds__(256) k_transform_rows(double* __restrict__ S1, double* __restrict__ S2, int64_t ldS,
                                                         const double* __restrict__ qq, const double* __restrict__ mm,
-                                                        const double* __restrict__ xja, int M, int Mpad,
+                                                        const double* __restrict__ xja,
+                                                        const double* __restrict__ ae, int M, int Mpad,
                                                         int64_t n_rows, MaternK mk, double* __restrict__ csum,
                                                         double* __restrict__ Erow) {
   const int lane = threadIdx.x & 31;
@@ -501,9 +530,13 @@ __global__ void __launch_bounds__(256) k_transform_rows(double* __restrict__ S1,
     double c1 = 0.0, c2 = 0.0;
     if (m < M) {
       const double a = s2[m] - xja[m];
-      matern52(fma(-10.0, s1[m], q5 + 5.0 * mm[m]), a, mk, c1, c2);
+      if (ae != nullptr) {
+        es += matern52_ecstr(fma(-10.0, s1[m], q5 + 5.0 * mm[m]), a, ae[m], mk, c1, c2);
+      } else {
+        matern52(fma(-10.0, s1[m], q5 + 5.0 * mm[m]), a, mk, c1, c2);
+        es = fma(a, c2, es);
+      }
       cs += c1;
-      es = fma(a, c2, es);
     }
     s1[m] = c1;
     s2[m] = c2;
@@ -690,6 +723,9 @@ struct sgdml_b200_model {
   double sig = 0, std = 1, c = 0;
   double *X = nullptr;    // (M, D) raw descriptors (training-point queries)
   double *Xc = nullptr, *JA = nullptr, *mm = nullptr, *xja = nullptr, *mu = nullptr;
+  double* ae = nullptr;                  // (Mpad) alphas_E, zeros unless use_ae
+  int use_ae = 0;
+  Lattice lat = {0, {0}, {0}};           // periodic cell of the query descriptors (predict.py:332-334)
   int *perm = nullptr, *pinv = nullptr;  // (S, D)
   double* R_d_desc = nullptr;            // (M, D, 3), optional
   // two workspace slots (slot 1 and the side streams are only used by the host-I/O pipeline)
@@ -866,7 +902,7 @@ int run_queries(sgdml_b200_model* m, int slot, const double* xq, const double* g
       SG_CUDA(cudaMemsetAsync(w.S2, 0, sizeof(double) * (size_t)n_rows * m->Mpad, s));
       SG_TRY(ozaki_gemm_nt_device(n_rows, m->Mpad, m->DS, 1.0, w.Qg, m->DS, m->Xc, m->DS, w.S1, m->Mpad, oz_s, 0, s));
       SG_TRY(ozaki_gemm_nt_device(n_rows, m->Mpad, m->DS, 1.0, w.Qg, m->DS, m->JA, m->DS, w.S2, m->Mpad, oz_s, 0, s));
-      k_transform_rows<<<(unsigned)((n_rows + 7) / 8), 256, 0, s>>>(w.S1, w.S2, m->Mpad, w.qq, m->mm, m->xja, m->M,
+      k_transform_rows<<<(unsigned)((n_rows + 7) / 8), 256, 0, s>>>(w.S1, w.S2, m->Mpad, w.qq, m->mm, m->xja, m->use_ae ? m->ae : nullptr, m->M,
                                                                      m->Mpad, n_rows, mk, w.csum, w.Erow);
       SG_CUDA(cudaGetLastError());
       SG_CUDA(cudaMemsetAsync(w.G, 0, sizeof(double) * (size_t)n_rows * m->DP, s));
@@ -887,7 +923,7 @@ int run_queries(sgdml_b200_model* m, int slot, const double* xq, const double* g
     g.B = m->JA;
     g.C = w.S2;
     SG_TRY(launch_gemm(g, s));
-    k_transform_rows<<<(unsigned)((n_rows + 7) / 8), 256, 0, s>>>(w.S1, w.S2, m->Mpad, w.qq, m->mm, m->xja, m->M,
+    k_transform_rows<<<(unsigned)((n_rows + 7) / 8), 256, 0, s>>>(w.S1, w.S2, m->Mpad, w.qq, m->mm, m->xja, m->use_ae ? m->ae : nullptr, m->M,
                                                                    m->Mpad, n_rows, mk, w.csum, w.Erow);
     SG_CUDA(cudaGetLastError());
     // acc = C1 XcT^T + C2 JAT^T   (rows x DP, contraction over the training points)
@@ -914,6 +950,8 @@ int run_queries(sgdml_b200_model* m, int slot, const double* xq, const double* g
     a.JA = m->JA;
     a.mm = m->mm;
     a.xja = m->xja;
+    a.ae = m->ae;
+    a.use_ae = m->use_ae;
     a.D = m->D;
     a.M = m->M;
     a.S = m->S;
@@ -1054,6 +1092,8 @@ int sgdml_b200_model_create(sgdml_b200_model** out, int64_t n_atoms, int64_t n_t
     SG_CUDA(cudaMalloc(&m->JA, sizeof(double) * m->Mpad * m->DS));
     SG_CUDA(cudaMalloc(&m->mm, sizeof(double) * m->Mpad));
     SG_CUDA(cudaMalloc(&m->xja, sizeof(double) * m->Mpad));
+    SG_CUDA(cudaMalloc(&m->ae, sizeof(double) * m->Mpad));
+    SG_CUDA(cudaMemset(m->ae, 0, sizeof(double) * m->Mpad));
     SG_CUDA(cudaMalloc(&m->mu, sizeof(double) * m->DS));
     SG_CUDA(cudaMemset(m->mu, 0, sizeof(double) * m->DS));
     Staged sJA;
@@ -1092,6 +1132,7 @@ int sgdml_b200_model_destroy(sgdml_b200_model* m) {
   cudaFree(m->JA);
   cudaFree(m->mm);
   cudaFree(m->xja);
+  cudaFree(m->ae);
   cudaFree(m->mu);
   cudaFree(m->perm);
   cudaFree(m->pinv);
@@ -1139,7 +1180,7 @@ int sgdml_b200_predict(sgdml_b200_model* m, const double* R, int64_t n_geo, doub
       SG_CUDA(cudaMemcpyAsync(w.R, Rd, sizeof(double) * ng * dimi, cudaMemcpyHostToDevice, st));
       Rd = w.R;
     }
-    SG_TRY(launch_desc_from_R(Rd, ng, m->N, w.xq, w.gq, st));
+    SG_TRY(launch_desc_from_R(Rd, ng, m->N, w.xq, w.gq, st, &m->lat));
     double* Fd = F_dev ? F + g0 * dimi : w.F;
     double* Ed = (E == nullptr) ? nullptr : (E_dev ? E + g0 : w.E);
     SG_TRY(run_queries(m, slot, w.xq, w.gq, ng, m->std, m->c, Ed, Fd, st));
@@ -1153,6 +1194,27 @@ int sgdml_b200_predict(sgdml_b200_model* m, const double* R, int64_t n_geo, doub
     }
   }
   if (host_io) SG_CUDA(cudaStreamSynchronize(s));
+  return 0;
+}
+
+int sgdml_b200_model_set_lattice(sgdml_b200_model* m, const double* lattice, const double* lattice_inv) {
+  SG_ARG(m != nullptr);
+  SG_CUDA(cudaDeviceSynchronize());  // no stream argument: kernels in flight copied the old cell by value, but keep calls ordered
+  return lattice_from_host(lattice, lattice_inv, &m->lat);
+}
+
+int sgdml_b200_model_set_alphas_E(sgdml_b200_model* m, const double* alphas_E, void* stream) {
+  SG_TRY(require_device());
+  SG_ARG(m != nullptr);
+  cudaStream_t s = (cudaStream_t)stream;
+  if (alphas_E == nullptr) {
+    SG_CUDA(cudaMemsetAsync(m->ae, 0, sizeof(double) * m->Mpad, s));
+    m->use_ae = 0;
+    return 0;
+  }
+  SG_CUDA(cudaMemcpyAsync(m->ae, alphas_E, sizeof(double) * m->M, cudaMemcpyDefault, s));
+  if (!is_device_ptr(alphas_E)) SG_CUDA(cudaStreamSynchronize(s));
+  m->use_ae = 1;
   return 0;
 }
 

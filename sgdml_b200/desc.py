@@ -38,8 +38,6 @@ class Desc(object):
     def from_R(self, R, lat_and_inv=None, max_processes=None, callback=None):
         """utils/desc.py:288-365: R (M, 3N) -> R_desc (M, D), R_d_desc (M, D, 3).
         A single geometry returns (D,), (D, 3) like the reference (desc.py:329-330)."""
-        if lat_and_inv is not None:
-            raise NotImplementedError('periodic boundary conditions are out of scope (SURVEY.md section 2 row 21)')
         R = _as_f64(R)
         if R.ndim == 1:
             R = R[None, :]
@@ -47,12 +45,24 @@ class Desc(object):
         M = R.shape[0]
         R_desc = np.empty((M, self.dim))
         R_d_desc = np.empty((M, self.dim, 3))
-        _lib.check(
-            _lib.lib().sgdml_b200_desc_from_R(
-                _lib.ptr(R), M, self.n_atoms, _lib.ptr(R_desc), _lib.ptr(R_d_desc), _lib.current_stream()
-            ),
-            'desc_from_R',
-        )
+        if lat_and_inv is not None:  # minimum-image convention (desc.py:44-77, 100-108, 200-201)
+            lat, lat_inv = (_as_f64(x) for x in lat_and_inv)
+            if lat.shape != (3, 3) or lat_inv.shape != (3, 3):
+                raise ValueError('lat_and_inv must be a pair of 3 x 3 matrices')
+            _lib.check(
+                _lib.lib().sgdml_b200_desc_from_R_pbc(
+                    _lib.ptr(R), M, self.n_atoms, _lib.ptr(lat), _lib.ptr(lat_inv), _lib.ptr(R_desc), _lib.ptr(R_d_desc),
+                    _lib.current_stream(),
+                ),
+                'desc_from_R_pbc',
+            )
+        else:
+            _lib.check(
+                _lib.lib().sgdml_b200_desc_from_R(
+                    _lib.ptr(R), M, self.n_atoms, _lib.ptr(R_desc), _lib.ptr(R_d_desc), _lib.current_stream()
+                ),
+                'desc_from_R',
+            )
         if callback is not None:
             callback(M, M)
         if M == 1:

@@ -38,16 +38,14 @@ class GDMLPredict(object):
         if 'type' not in model or not (model['type'] == 'm' or model['type'] == b'm'):
             raise ValueError('The provided data structure is not a valid model.')  # predict.py:326-328
 
-        if 'lattice' in model:
-            raise NotImplementedError('periodic boundary conditions are out of scope (SURVEY.md section 2 row 21)')
-        if 'alphas_E' in model:
-            raise NotImplementedError('use_E_cstr models are out of scope (SURVEY.md section 2 row 22)')
-
         _lib.require_gpu()
 
         self.n_atoms = int(np.asarray(model['z']).shape[0])
         self.desc = Desc(self.n_atoms, max_processes=max_processes)
         self.lat_and_inv = None
+        if 'lattice' in model:  # predict.py:332-334
+            lat = np.ascontiguousarray(model['lattice'], dtype=np.float64)
+            self.lat_and_inv = (lat, np.ascontiguousarray(np.linalg.inv(lat)))
 
         self.n_train = int(model['R_desc'].shape[1])
         self.sig = float(model['sig'])  # as stored (predict.py:346); no int() truncation (torchtools.py:476)
@@ -81,6 +79,13 @@ class GDMLPredict(object):
             'model_create',
         )
         self._handle = handle
+        if self.lat_and_inv is not None:
+            _lib.check(
+                _lib.lib().sgdml_b200_model_set_lattice(handle, _lib.ptr(self.lat_and_inv[0]), _lib.ptr(self.lat_and_inv[1])),
+                'model_set_lattice',
+            )
+        if 'alphas_E' in model:  # energy constraints in the kernel (predict.py:443-447)
+            self._set_alphas_E(model['alphas_E'])
 
     def __del__(self):
         h = getattr(self, '_handle', None)
@@ -105,10 +110,16 @@ class GDMLPredict(object):
                 raise ValueError('R_d_desc must have shape (n_train, D, 3)')
             _lib.check(_lib.lib().sgdml_b200_model_set_R_d_desc(self._handle, _lib.ptr(a)), 'model_set_R_d_desc')
 
+    def _set_alphas_E(self, alphas_E):
+        a = np.ascontiguousarray(np.asarray(alphas_E, dtype=np.float64).ravel())
+        if a.shape != (self.n_train,):
+            raise ValueError('alphas_E must have one entry per training point')
+        _lib.check(_lib.lib().sgdml_b200_model_set_alphas_E(self._handle, _lib.ptr(a), _lib.current_stream()), 'model_set_alphas_E')
+
     def set_alphas(self, alphas_F, alphas_E=None):
         """predict.py:551-601: new regression coefficients (used once per CG iteration)."""
         if alphas_E is not None:
-            raise NotImplementedError('use_E_cstr is out of scope (SURVEY.md section 2 row 22)')
+            self._set_alphas_E(alphas_E)  # predict.py:594-601
         assert self.R_d_desc is not None  # predict.py:575
         a = alphas_F if not isinstance(alphas_F, np.ndarray) else np.ascontiguousarray(alphas_F, dtype=np.float64)
         _lib.check(

@@ -34,8 +34,7 @@ class Analytic(object):
 
         sig = task['sig']
         lam = task['lam']
-        if task.get('use_E_cstr', False):
-            raise NotImplementedError('use_E_cstr is out of scope (SURVEY.md section 2 row 22)')
+        use_E_cstr = bool(task.get('use_E_cstr', False))
 
         n_train = R_d_desc.shape[0]
         if self.callback is not None:
@@ -45,16 +44,21 @@ class Analytic(object):
         # K lives in HBM from assembly to the factorisation; its allocation (a 32 GB cudaMalloc at
         # BASELINE config 2) is kept out of the assembly timing
         n = n_train * 3 * self.desc.n_atoms
-        ldk = (n + 1) // 2 * 2
         t_alloc = timeit.default_timer()
-        K = torch.empty((n, ldk), dtype=torch.float64, device='cuda')
+        if not use_E_cstr:
+            ldk = (n + 1) // 2 * 2
+            K = torch.empty((n, ldk), dtype=torch.float64, device='cuda')
         torch.cuda.synchronize()
         t_alloc = timeit.default_timer() - t_alloc
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
         ev[0].record()
-        K, n = self.gdml_train._assemble_kernel_mat_device(
-            R_desc, R_d_desc, tril_perms_lin, sig, scale=-1.0, out=K
-        )  # analytic.py:65 (flip sign to make convex)
+        if use_E_cstr:  # M extra rows and columns (train.py:234-300, analytic.py:53-73)
+            K = self.gdml_train._assemble_kernel_mat_ecstr_device(R_desc, R_d_desc, tril_perms_lin, sig, scale=-1.0)
+            n = n + n_train
+        else:
+            K, n = self.gdml_train._assemble_kernel_mat_device(
+                R_desc, R_d_desc, tril_perms_lin, sig, scale=-1.0, out=K
+            )  # analytic.py:65 (flip sign to make convex)
         ev[1].record()
 
         if self.callback is not None:
@@ -77,7 +81,10 @@ class Analytic(object):
             import scipy.linalg
 
             del K
-            K, n = self.gdml_train._assemble_kernel_mat_device(R_desc, R_d_desc, tril_perms_lin, sig, scale=-1.0)
+            if use_E_cstr:
+                K = self.gdml_train._assemble_kernel_mat_ecstr_device(R_desc, R_d_desc, tril_perms_lin, sig, scale=-1.0)
+            else:
+                K, n = self.gdml_train._assemble_kernel_mat_device(R_desc, R_d_desc, tril_perms_lin, sig, scale=-1.0)
             Kh = K[:, :n].cpu().numpy()
             Kh[np.diag_indices_from(Kh)] += lam
             alphas = -scipy.linalg.solve(Kh, y, overwrite_a=True, check_finite=False)

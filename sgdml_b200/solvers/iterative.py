@@ -187,7 +187,7 @@ class Iterative(object):
         from .. import dist as sdist
 
         if use_E_cstr:
-            raise NotImplementedError('use_E_cstr is out of scope (SURVEY.md section 2 row 22)')
+            raise NotImplementedError('use_E_cstr is supported with the analytic solver only (the reference marks its iterative path unfinished, iterative.py:602)')
         n_train, dim_d = R_d_desc.shape[:2]
         dim_i = 3 * int((1 + np.sqrt(8 * dim_d + 1)) / 2)
         cols = np.ascontiguousarray(col_idxs, dtype=np.int64)
@@ -293,7 +293,7 @@ class Iterative(object):
             from .. import dist as sdist
 
             if use_E_cstr:
-                raise NotImplementedError('use_E_cstr is out of scope (SURVEY.md section 2 row 22)')
+                raise NotImplementedError('use_E_cstr is supported with the analytic solver only (the reference marks its iterative path unfinished, iterative.py:602)')
             rank, world = sdist.world_info()
             lev_approx_idxs = self._bcast_idxs(lev_approx_idxs)  # one draw (rank 0's) for the shared factor
             ops = _EngineNystroemOps(self, R_desc, R_d_desc, tril_perms_lin, sig)

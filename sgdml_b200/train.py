@@ -92,22 +92,29 @@ class GDMLTrain(object):
         """train.py:836-1088.  Returns the model dict."""
         t_all = timeit.default_timer()
         task = dict(task)
-        if task.get('use_E_cstr', False):
-            raise NotImplementedError('use_E_cstr is out of scope (SURVEY.md section 2 row 22)')
-        if 'lattice' in task:
-            raise NotImplementedError('periodic boundary conditions are out of scope (SURVEY.md section 2 row 21)')
+        use_E_cstr = bool(task.get('use_E', False)) and bool(task.get('use_E_cstr', False))
+        task['use_E_cstr'] = use_E_cstr
 
         n_train, n_atoms = task['R_train'].shape[:2]
         desc = Desc(n_atoms, max_processes=self._max_processes)
 
         tril_perms_lin = _tril_perms_lin(task['perms'])  # train.py:897-904
 
+        lat_and_inv = None
+        if 'lattice' in task:  # train.py:906-911
+            lat = np.ascontiguousarray(task['lattice'], dtype=np.float64)
+            lat_and_inv = (lat, np.ascontiguousarray(np.linalg.inv(lat)))
         R = np.ascontiguousarray(task['R_train'], dtype=np.float64).reshape(n_train, -1)
-        R_desc, R_d_desc = desc.from_R(R)  # train.py:926-935
+        R_desc, R_d_desc = desc.from_R(R, lat_and_inv=lat_and_inv)  # train.py:926-935
         if n_train == 1:
             R_desc, R_d_desc = R_desc[None], R_d_desc[None]
 
         y = np.asarray(task['F_train'], dtype=np.float64).ravel().copy()  # train.py:939-947
+        E_train_mean = None
+        if use_E_cstr:
+            E_train = np.asarray(task['E_train'], dtype=np.float64).ravel().copy()
+            E_train_mean = np.mean(E_train)
+            y = np.hstack((y, -E_train + E_train_mean))
         y_std = np.std(y)
         y /= y_std
 
@@ -122,6 +129,10 @@ class GDMLTrain(object):
 
         max_bytes = sdist.all_reduce_min_scalar(max_bytes)
         use_analytic_solver = est_bytes_analytic < max_bytes
+        if use_E_cstr and not use_analytic_solver:
+            # the reference's own iterative path is unfinished for energy constraints (iterative.py:602 "TODO: ... this
+            # will not work with E_cstr"); the engine supports them with the analytic solver
+            raise NotImplementedError('use_E_cstr needs the analytic solver (the kernel matrix must fit the device memory)')
 
         solver_keys = {}
         if use_analytic_solver:
@@ -147,13 +158,20 @@ class GDMLTrain(object):
                 self.log.warning('Iterative solver did not converge! (train.py:1032-1052)')
 
         t0 = timeit.default_timer()
+        alphas_F, alphas_E = alphas, None
+        if use_E_cstr:  # train.py:1052-1056
+            alphas_E = alphas[-n_train:]
+            alphas_F = alphas[:-n_train]
         model = self.create_model(
-            task, 'analytic' if use_analytic_solver else 'cg', R_desc, R_d_desc, tril_perms_lin, y_std, alphas
+            task, 'analytic' if use_analytic_solver else 'cg', R_desc, R_d_desc, tril_perms_lin, y_std, alphas_F,
+            alphas_E=alphas_E,
         )
         model.update(solver_keys)
         t1 = timeit.default_timer()
-        if model['use_E']:  # train.py:1074-1086
-            model['c'] = self._recov_int_const(model, task, R_desc=R_desc, R_d_desc=R_d_desc)
+        if model['use_E']:  # train.py:1071-1086: with energy constraints c is the mean of the training energies
+            model['c'] = (
+                self._recov_int_const(model, task, R_desc=R_desc, R_d_desc=R_d_desc) if E_train_mean is None else E_train_mean
+            )
         t2 = timeit.default_timer()
         self.timings.update({'desc_s': t_desc, 'model_s': t1 - t0, 'int_const_s': t2 - t1, 'total_s': t2 - t_all})
         return model
@@ -234,6 +252,30 @@ class GDMLTrain(object):
         )
         return K, n_cols
 
+    def _assemble_kernel_mat_ecstr_device(self, R_desc, R_d_desc, tril_perms_lin, sig, scale=1.0):
+        """(3NM + M)-square kernel matrix with energy constraints (train.py:234-300) as a CUDA tensor
+        (n_tot, ldk): force-force part by the assembly kernel, energy rows / columns by k_assemble_ecstr."""
+        torch = _torch()
+        R_desc = np.ascontiguousarray(R_desc, dtype=np.float64)
+        R_d_desc = np.ascontiguousarray(R_d_desc, dtype=np.float64)
+        tril_perms_lin = np.ascontiguousarray(tril_perms_lin, dtype=np.int64)
+        n_train, dim_d = R_d_desc.shape[:2]
+        n_atoms = int((1 + np.sqrt(8 * dim_d + 1)) / 2)
+        n_perms = len(tril_perms_lin) // dim_d
+        n = n_train * 3 * n_atoms
+        n_tot = n + n_train
+        ldk = (n_tot + 1) // 2 * 2
+        K = torch.zeros((n_tot, ldk), dtype=torch.float64, device='cuda')
+        self._assemble_kernel_mat_device(R_desc, R_d_desc, tril_perms_lin, sig, scale=scale, out=K[:n])
+        _lib.check(
+            _lib.lib().sgdml_b200_assemble_ecstr(
+                _lib.ptr(R_desc), _lib.ptr(R_d_desc), _lib.ptr(tril_perms_lin), n_atoms, n_train, n_perms, float(sig),
+                float(scale), K.data_ptr(), ldk, _lib.current_stream(),
+            ),
+            'assemble_ecstr',
+        )
+        return K
+
     def _assemble_kernel_mat(
         self,
         R_desc,
@@ -248,11 +290,17 @@ class GDMLTrain(object):
     ):
         """train.py:1260-1535: returns K as a host array of shape (3NM + alloc_extra_rows, n_cols)
         in the reference's sign convention.  (The analytic path does not use this host copy.)"""
-        if use_E_cstr:
-            raise NotImplementedError('use_E_cstr is out of scope (SURVEY.md section 2 row 22)')
         n_train, dim_d = R_d_desc.shape[:2]
         dim_i = 3 * int((1 + np.sqrt(8 * dim_d + 1)) / 2)
         K_n_rows = n_train * dim_i
+        if use_E_cstr:  # train.py:1333-1335: M extra rows and columns; full matrix only (what the analytic solver needs)
+            if not (isinstance(col_idxs, slice) and col_idxs == np.s_[:]):
+                raise NotImplementedError('column subsets of the energy-constrained kernel matrix are not supported')
+            Kd = self._assemble_kernel_mat_ecstr_device(R_desc, R_d_desc, tril_perms_lin, sig, scale=1.0)
+            n_tot = K_n_rows + n_train
+            K = np.empty((n_tot + alloc_extra_rows, n_tot))
+            K[:n_tot, :] = Kd[:, :n_tot].cpu().numpy()
+            return K
         if isinstance(col_idxs, slice):
             cols = np.arange(K_n_rows)[col_idxs]
             if len(cols) == K_n_rows:

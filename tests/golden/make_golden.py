@@ -10,6 +10,7 @@ GPU box):
     PYTHONPATH=baseline/_ref:. python tests/golden/make_golden.py iterative
     PYTHONPATH=baseline/_ref:. python tests/golden/make_golden.py c60
     PYTHONPATH=baseline/_ref:. python tests/golden/make_golden.py n100
+    PYTHONPATH=baseline/_ref:. python tests/golden/make_golden.py pbc_ecstr
 
 Each fixture holds the inputs (geometries, labels, perms, sig, lam, query geometries) and
 the reference outputs of every hot-path stage: tril_perms_lin (Desc.perm / train.py:897-904),
@@ -105,6 +106,52 @@ def main():
             F_train_pred=F_t,
             v=v,
             Kv=Kv,
+        )
+        print(name, 'K', K.shape, 'size %.0f KB' % (os.path.getsize(out) / 1024))
+
+
+def main_pbc_ecstr():
+    """(f)4 rows: periodic boundary conditions (utils/desc.py:44-77: minimum-image pair differences; the
+    lattice travels in the task and the model, train.py:524, 826-827, predict.py:332-334) and energy
+    constraints in the kernel (train.py:234-300, 940-947, 1052-1086; predict.py:219-229).  Two fixtures:
+    pbc_n6_m8 (lattice, no energy constraints) and ecstr_n6_m8 (use_E_cstr, no lattice)."""
+    gdml_train = GDMLTrain(max_processes=1, use_torch=False)
+    N, M, sig, n_query = 6, 8, 15, 5
+    perms = synth.rotor_swap_group(N, 1, 1)
+    for name in ('pbc_n6_m8', 'ecstr_n6_m8'):
+        task = synth.make_task(N, M, perms, sig)
+        lat = None
+        if name.startswith('pbc'):
+            # a cell smaller than the molecule's extent, so that the minimum-image convention is active for many pairs
+            lat = np.array([[2.6, 0.3, 0.0], [0.0, 2.4, 0.2], [0.1, 0.0, 2.9]])  # columns = lattice vectors
+            task['lattice'] = lat
+        else:
+            task['use_E_cstr'] = True
+        desc = Desc(N, max_processes=1)
+        lat_and_inv = None if lat is None else (lat, np.linalg.inv(lat))
+        tril_perms = np.array([Desc.perm(p) for p in task['perms']])
+        tril_perms_lin = (tril_perms + np.arange(len(perms))[:, None] * desc.dim).flatten('F')
+        R = task['R_train'].reshape(M, -1)
+        R_desc, R_d_desc = desc.from_R(R, lat_and_inv=lat_and_inv, max_processes=1)
+        use_E_cstr = bool(task['use_E_cstr'])
+        K = gdml_train._assemble_kernel_mat(R_desc, R_d_desc, tril_perms_lin, sig, desc, use_E_cstr=use_E_cstr)
+        model = gdml_train.train(task)
+        predictor = GDMLPredict(model, max_processes=1, use_torch=False)
+        R_query = synth.geometries(N, n_query, 1).reshape(n_query, -1)
+        E_q, F_q = predictor.predict(R_query)
+        E_t, F_t = predictor.predict(R)
+        extra = {}
+        if lat is not None:
+            extra['lattice'] = lat
+        if use_E_cstr:
+            extra['alphas_E'] = model['alphas_E']
+        out = os.path.join(HERE, name + '.npz')
+        np.savez_compressed(
+            out, reference_version=sgdml.__version__, n_atoms=N, perms=perms, sig=sig, lam=task['lam'], z=task['z'],
+            R_train=task['R_train'], F_train=task['F_train'], E_train=task['E_train'], tril_perms_lin=tril_perms_lin,
+            R_desc=R_desc, R_d_desc=R_d_desc, K=K, alphas_F=model['alphas_F'], R_d_desc_alpha=model['R_d_desc_alpha'],
+            model_R_desc=model['R_desc'], std=model['std'], c=model['c'], R_query=R_query, E_query=E_q, F_query=F_q,
+            E_train_pred=E_t, F_train_pred=F_t, use_E_cstr=use_E_cstr, **extra
         )
         print(name, 'K', K.shape, 'size %.0f KB' % (os.path.getsize(out) / 1024))
 
@@ -274,6 +321,8 @@ if __name__ == '__main__':
         main_n100()
     elif len(sys.argv) > 1 and sys.argv[1] == 'c60':
         main_c60()
+    elif len(sys.argv) > 1 and sys.argv[1] == 'pbc_ecstr':
+        main_pbc_ecstr()
     elif len(sys.argv) > 1 and sys.argv[1] == 'iterative':
         main_iterative()   # separate process: the reference allows one GDMLTrain instance (train.py:336-342)
     else:

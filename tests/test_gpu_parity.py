@@ -328,6 +328,51 @@ def test_assemble_row_ranges(eng, golden, large):
         _lib.lib().sgdml_b200_set_assemble_variant(0)
 
 
+def test_assemble_multi_launch_row_chunks(eng, golden):
+    """Row ranges above the grid limit (65535 row points) run as several launches with their own first row point
+    and K row offset; the test hook lowers the limit to 3 row points so that a small fixture takes that path
+    (full matrix -- symmetric mode switched off -- and a column subset)."""
+    from sgdml_b200 import _lib
+
+    n = golden['K'].shape[0]
+    t = eng.GDMLTrain()
+    args = (golden['R_desc'], golden['R_d_desc'], golden['tril_perms_lin'], int(golden['sig']))
+    cols = np.unique(np.random.default_rng(5).integers(0, n, size=31))
+    K_ref, _ = t._assemble_kernel_mat_device(*args)
+    Kc_ref, nc = t._assemble_kernel_mat_device(*args, col_idxs=cols)
+    _lib.lib().sgdml_b200_set_assemble_variant(1003)
+    try:
+        K, _ = t._assemble_kernel_mat_device(*args)
+        Kc, _ = t._assemble_kernel_mat_device(*args, col_idxs=cols)
+    finally:
+        _lib.lib().sgdml_b200_set_assemble_variant(1000 + 65535)
+    assert rel_err(K[:, :n].cpu().numpy(), golden['K']) < 1e-12
+    assert rel_err(K[:, :n].cpu().numpy(), K_ref[:, :n].cpu().numpy()) < 1e-14  # mirrored vs directly computed blocks
+    assert np.array_equal(Kc[:, :nc].cpu().numpy(), Kc_ref[:, :nc].cpu().numpy())
+
+
+def test_predict_rejects_bad_out_buffers(eng, golden):
+    """Output buffers reach the engine as raw double*: wrong dtype / shape / device must raise, not corrupt memory."""
+    import torch
+
+    p = eng.GDMLPredict(golden_model(golden))
+    R = golden['R_query']
+    B, dim_i = R.shape
+    with pytest.raises(ValueError):
+        p.predict(R, out=(np.empty(B, dtype=np.float32), np.empty((B, dim_i))))
+    with pytest.raises(ValueError):
+        p.predict(R, out=(np.empty(B), np.empty((B, dim_i), dtype=np.float32)))
+    with pytest.raises(ValueError):
+        p.predict(R, out=(np.empty(B), np.empty((B + 1, dim_i))))
+    with pytest.raises(ValueError):
+        p.predict(torch.from_numpy(R).cuda(), out=(np.empty(B), np.empty((B, dim_i))))
+    with pytest.raises(ValueError):
+        p.predict(R, out=(torch.empty(B, dtype=torch.float64, device='cuda'), torch.empty((B, dim_i), dtype=torch.float64, device='cuda')))
+    E, F = np.full(B, np.nan), np.empty((B, dim_i))
+    (F2,) = p.predict(R, return_E=False, out=(E, F))  # E is not written when no energies are asked for
+    assert F2 is F and np.all(np.isnan(E)) and rel_err(F, golden['F_query']) < 1e-10
+
+
 def test_c60_icosahedral_config(eng):
     """BASELINE config 5 shape: buckyball, 60 atoms, the 120 permutations of I_h (reduced M)."""
     from sgdml_b200 import synth
@@ -435,6 +480,55 @@ def test_potrf_potrs(eng, variant, n):
     assert rel_err(x1, x[:, 0]) < 1e-12
 
 
+@pytest.mark.parametrize('oz_slices', [0, 7])
+def test_potrf_potrs_large_outer_block(eng, oz_slices, monkeypatch):
+    """n >= 16384 takes the NBO = 1024 outer blocking and the triangular super-tile order of the trailing GEMM --
+    the configuration BASELINE config 2 (n = 63000) runs -- against scipy's LAPACK dpotrf / dpotrs
+    (analytic.py:94-99).  oz_slices = 7: the same factorisation with the tcgen05 int8 trailing updates."""
+    import scipy.linalg
+    import torch
+    from sgdml_b200 import _lib
+
+    L = _lib.lib()
+    n = 16500  # not a multiple of any block size
+    rng = np.random.default_rng(7)
+    X = rng.standard_normal((n, 64))
+    d = rng.uniform(0.5, 2.0, size=n)
+    A = X @ X.T  # rank 64 + a positive diagonal: condition ~1e5, cheap to build
+    A[np.diag_indices(n)] += d
+    b = rng.standard_normal((n, 2))
+    c, low = scipy.linalg.cho_factor(A, lower=True, check_finite=False)
+    x_ref = scipy.linalg.cho_solve((c, low), b, check_finite=False)
+    if oz_slices:
+        monkeypatch.setenv('SGDML_B200_OZAKI_SLICES', str(oz_slices))
+    Ad = torch.from_numpy(A).cuda()
+    _lib.check(L.sgdml_b200_potrf(Ad.data_ptr(), n, n, _lib.current_stream()), 'potrf')
+    xd = torch.from_numpy(b.copy()).cuda()
+    _lib.check(L.sgdml_b200_potrs(Ad.data_ptr(), n, n, xd.data_ptr(), 2, 2, _lib.current_stream()), 'potrs')
+    torch.cuda.synchronize()
+    Lg = np.tril(Ad.cpu().numpy())
+    tol = 1e-11 if not oz_slices else 1e-9
+    assert rel_err(Lg, np.tril(c)) < tol
+    x = xd.cpu().numpy()
+    assert rel_err(x, x_ref) < tol * 10
+    assert rel_err(A @ x, b) < tol * 10
+
+
+def test_train_analytic_large_outer_block_residual(eng):
+    """Aspirin shape at M = 270 (n = 17010 >= 16384: NBO = 1024 path) through GDMLTrain.train, checked by the
+    K.v identity: (K - lam I) alphas reproduces the labels through the predictor kernels, which share no code with
+    the assembly and Cholesky kernels (sgdml_b200/diagnostics.py; analytic.py:65-99)."""
+    from sgdml_b200 import synth
+    from sgdml_b200.diagnostics import residual_report
+
+    task = synth.make_config_task('aspirin', n_train=270)
+    model = eng.GDMLTrain().train(task)
+    assert model['solver_name'] == 'analytic'
+    rep = residual_report(model, task)
+    assert rep['residual_rel'] < 1e-10, rep
+    assert rep['force_rel_max_train'] < 1e-4, rep
+
+
 def test_potrf_not_positive_definite(eng):
     from sgdml_b200 import _lib
 
@@ -454,7 +548,7 @@ def test_solve_analytic_golden(eng, golden):
     from sgdml_b200 import _lib
 
     task = golden_task(golden)
-    y, _ = otrain.labels(task)
+    y, _, _ = otrain.labels(task)
     n = golden['K'].shape[0]
     Kneg = -golden['K'].copy()
     alphas = np.empty(n)
@@ -552,4 +646,67 @@ def test_predict_small_batches_split_over_training_points(eng, B):
     Rq2 = synth.geometries(N2, min(B, 40), 1).reshape(min(B, 40), -1)
     E_ref, F_ref = opredict.Predictor(model2).predict(Rq2)
     E, F = eng.GDMLPredict(model2).predict(Rq2)
+    assert rel_err(F, F_ref) < 1e-10 and rel_err(E, E_ref) < 1e-10
+
+
+# --------------------------------------------------------------------------- (f)4: lattices and energy constraints
+def _pbc_ecstr_task(g):
+    from sgdml_b200 import synth
+
+    N = int(g['n_atoms'])
+    t = synth.make_task(N, g['R_train'].shape[0], g['perms'], int(g['sig']), lam=float(g['lam']))
+    if 'lattice' in g:
+        t['lattice'] = g['lattice']
+    t['use_E_cstr'] = bool(g['use_E_cstr'])
+    return t
+
+
+def _pbc_ecstr_model(g):
+    m = golden_model(g)
+    if 'lattice' in g:
+        m['lattice'] = g['lattice']
+    if 'alphas_E' in g:
+        m['alphas_E'] = g['alphas_E']
+    return m
+
+
+@pytest.mark.parametrize('name', ['pbc_n6_m8', 'ecstr_n6_m8'])
+def test_pbc_and_energy_constraints_vs_reference(eng, name):
+    """Engine against fixtures generated by the unmodified reference with a lattice (utils/desc.py:44-77) and with
+    energy constraints in the kernel (train.py:234-300, predict.py:219-229): descriptors, K (incl. the M extra rows /
+    columns), predictions of the reference's model, and the engine's own training run (1e-6 rel, north_star)."""
+    from sgdml_b200.desc import Desc
+
+    g = load_golden(name)
+    N, M = int(g['n_atoms']), g['R_train'].shape[0]
+    d = Desc(N)
+    lat_and_inv = (g['lattice'], np.linalg.inv(g['lattice'])) if 'lattice' in g else None
+    x, gd = d.from_R(g['R_train'].reshape(M, -1), lat_and_inv=lat_and_inv)
+    assert rel_err(x, g['R_desc']) < 1e-14 and rel_err(gd, g['R_d_desc']) < 1e-13
+    t = eng.GDMLTrain()
+    K = t._assemble_kernel_mat(g['R_desc'], g['R_d_desc'], g['tril_perms_lin'], int(g['sig']), d, use_E_cstr=bool(g['use_E_cstr']))
+    assert K.shape == g['K'].shape and rel_err(K, g['K']) < 1e-12
+    p = eng.GDMLPredict(_pbc_ecstr_model(g))
+    E, F = p.predict(g['R_query'])
+    assert rel_err(F, g['F_query']) < 1e-9 and rel_err(E, g['E_query']) < 1e-9
+    E, F = p.predict(g['R_train'].reshape(M, -1))
+    assert rel_err(F, g['F_train_pred']) < 1e-9 and rel_err(E, g['E_train_pred']) < 1e-9
+    model = t.train(_pbc_ecstr_task(g))
+    assert ('alphas_E' in model) == bool(g['use_E_cstr']) and ('lattice' in model) == ('lattice' in g)
+    assert abs(float(model['c']) - float(g['c'])) < 1e-6 * abs(float(g['c']))
+    E2, F2 = eng.GDMLPredict(model).predict(g['R_query'])
+    assert rel_err(F2, g['F_query']) < 1e-6 and rel_err(E2, g['E_query']) < 1e-6
+
+
+def test_energy_constraints_large_descriptor_path(eng):
+    """The energy-constraint terms in the GEMM-composed predictor (D > 256) against the oracle."""
+    from sgdml_b200 import synth
+
+    N, M = 24, 12
+    perms = synth.rotor_swap_group(N, 1, 1)
+    model, x, g = _oracle_model(N, M, perms, 30)
+    model['alphas_E'] = np.random.default_rng(4).standard_normal(M)
+    Rq = synth.geometries(N, 7, 1).reshape(7, -1)
+    E, F = eng.GDMLPredict(model).predict(Rq)
+    E_ref, F_ref = opredict.Predictor(model).predict(Rq)
     assert rel_err(F, F_ref) < 1e-10 and rel_err(E, E_ref) < 1e-10
