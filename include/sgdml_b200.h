@@ -38,6 +38,9 @@ extern "C" {
 #define SGDML_B200_ERR_NO_DEVICE (-1002)
 
 int sgdml_b200_abi_version(void);
+/* Frees the persistent device workspaces of the current device (the Cholesky panel workspace, the int8 slice
+ * planes): they are kept between calls so that a sigma grid of training runs (cli.py:802-806) pays for them once. */
+int sgdml_b200_release_workspaces(void);
 const char* sgdml_b200_last_error(void);
 /* Number of visible CUDA devices (0 => every compute entry point fails loudly). */
 int sgdml_b200_device_count(void);

@@ -23,6 +23,7 @@ i64 = C.c_int64
 # name -> (restype, argtypes); mirrors include/sgdml_b200.h one to one
 SIGNATURES = {
     'sgdml_b200_abi_version': (C.c_int, []),
+    'sgdml_b200_release_workspaces': (C.c_int, []),
     'sgdml_b200_last_error': (C.c_char_p, []),
     'sgdml_b200_device_count': (C.c_int, []),
     'sgdml_b200_tril_perms_lin': (C.c_int, [c_void_p, i64, i64, c_void_p]),

@@ -69,6 +69,15 @@ class Staged {
   bool owns_ = false;
 };
 
+// Persistent device workspaces for calls that run once per training run or more often (the Cholesky panel
+// workspace is 516 MB at BASELINE config 2; a cudaMalloc / cudaFree pair of that size costs milliseconds and
+// synchronises the device).  One buffer per (device, slot), grown on demand, kept until
+// sgdml_b200_release_workspaces().  The caller must have finished with the buffer (stream synchronised) before the
+// next ws_get of the same slot -- true for every user: they all synchronise before returning.
+enum WsSlot { WS_POTRF_W0 = 0, WS_POTRF_W1 = 1, WS_OZ_PLANES = 2, WS_OZ_EXPS = 3, WS_POTRF_INFO = 4, WS_SOLVE_TMP = 5,
+              WS_SLOT_COUNT = 6 };
+int ws_get(int slot, size_t bytes, void** out);
+
 inline int ceil_div(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 
 int num_sms();

@@ -127,6 +127,30 @@ int Staged::finish(cudaStream_t s) {
   return 0;
 }
 
+namespace {
+struct WsBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+};
+WsBuf g_ws[64][WS_SLOT_COUNT];
+}  // namespace
+
+int ws_get(int slot, size_t bytes, void** out) {
+  int dev = 0;
+  SG_CUDA(cudaGetDevice(&dev));
+  SG_ARG(dev >= 0 && dev < 64 && slot >= 0 && slot < WS_SLOT_COUNT);
+  WsBuf& b = g_ws[dev][slot];
+  if (b.cap < bytes) {
+    if (b.p != nullptr) cudaFree(b.p);
+    b.p = nullptr;
+    b.cap = 0;
+    SG_CUDA(cudaMalloc(&b.p, bytes));
+    b.cap = bytes;
+  }
+  *out = b.p;
+  return 0;
+}
+
 int num_sms() {
   static int cached[64] = {0};
   int dev = 0;
@@ -194,6 +218,17 @@ int sgdml_b200_profile_get(int kid, double* total_ms, int64_t* scopes, int64_t* 
   if (total_ms) *total_ms = sgdml::g_prof_ms[kid];
   if (scopes) *scopes = sgdml::g_prof_n[kid];
   if (launches) *launches = sgdml::g_launches[kid];
+  return 0;
+}
+
+int sgdml_b200_release_workspaces(void) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 0;
+  cudaDeviceSynchronize();
+  for (int i = 0; i < sgdml::WS_SLOT_COUNT; ++i) {
+    if (sgdml::g_ws[dev][i].p != nullptr) cudaFree(sgdml::g_ws[dev][i].p);
+    sgdml::g_ws[dev][i] = sgdml::WsBuf();
+  }
   return 0;
 }
 

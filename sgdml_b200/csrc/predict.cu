@@ -736,6 +736,19 @@ struct sgdml_b200_model {
   } ws[2];
   cudaStream_t pipe_stream[2] = {nullptr, nullptr};
   cudaEvent_t pipe_event[3] = {nullptr, nullptr, nullptr};
+  // MD latency path: the launch sequence of a small host-buffer batch, captured once per batch size into a CUDA graph
+  struct GraphSlot {
+    int64_t n_geo = 0;
+    int with_E = 0;
+    int n_kernels = 0;
+    uint64_t generation = 0;
+    cudaGraphExec_t exec = nullptr;
+    double *hR = nullptr, *hF = nullptr, *hE = nullptr;  // pinned staging
+  } graphs[4];
+  int graph_next = 0;
+  uint64_t generation = 1;  // bumped whenever something a captured graph has baked in changes (workspace, cell, alphas_E)
+  cudaStream_t graph_stream = nullptr;
+  cudaEvent_t graph_event = nullptr;
 };
 
 namespace {
@@ -810,6 +823,7 @@ int ensure_ws(sgdml_b200_model* m, int slot, int64_t n_geo) {
     n_geo = std::max<int64_t>(n_geo, std::min<int64_t>(min_geo, chunk_geos(m)));
   }
   if (n_geo <= w.geo) return 0;
+  ++m->generation;  // captured graphs hold the old workspace pointers
   cudaFree(w.xq);
   cudaFree(w.gq);
   cudaFree(w.G);
@@ -1125,8 +1139,102 @@ int sgdml_b200_model_create(sgdml_b200_model** out, int64_t n_atoms, int64_t n_t
   return 0;
 }
 
+namespace {
+
+constexpr int64_t GRAPH_MAX_GEO = 16;  // batches up to this size with host buffers replay a captured graph
+
+void free_graph_slot(sgdml_b200_model::GraphSlot& g) {
+  if (g.exec) cudaGraphExecDestroy(g.exec);
+  cudaFreeHost(g.hR);
+  cudaFreeHost(g.hF);
+  cudaFreeHost(g.hE);
+  g = sgdml_b200_model::GraphSlot();
+}
+
+// Small host-buffer batch (molecular dynamics: one geometry per call, ase_calc.py:98-110): pinned staging buffers and
+// the whole launch sequence (H2D copy, descriptor kernel, query rows, main kernel, finishing kernel, D2H copies)
+// replayed from a CUDA graph -- one launch call instead of seven.
+int predict_graph(sgdml_b200_model* m, const double* R, int64_t n_geo, double* E, double* F, cudaStream_t s) {
+  const int dimi = 3 * m->N;
+  const int with_E = E != nullptr ? 1 : 0;
+  SG_TRY(ensure_ws(m, 0, n_geo));
+  if (m->graph_stream == nullptr) {
+    SG_CUDA(cudaStreamCreateWithFlags(&m->graph_stream, cudaStreamNonBlocking));
+    SG_CUDA(cudaEventCreateWithFlags(&m->graph_event, cudaEventDisableTiming));
+  }
+  cudaStream_t gs = m->graph_stream;
+  sgdml_b200_model::WS& w = m->ws[0];
+  sgdml_b200_model::GraphSlot* g = nullptr;
+  for (auto& c : m->graphs)
+    if (c.exec != nullptr && c.n_geo == n_geo && c.with_E == with_E && c.generation == m->generation) g = &c;
+  // work queued on the caller's stream (set_alphas, ...) comes first
+  SG_CUDA(cudaEventRecord(m->graph_event, s));
+  SG_CUDA(cudaStreamWaitEvent(gs, m->graph_event, 0));
+  auto enqueue = [&](sgdml_b200_model::GraphSlot* q) -> int {
+    SG_CUDA(cudaMemcpyAsync(w.R, q->hR, sizeof(double) * n_geo * dimi, cudaMemcpyHostToDevice, gs));
+    SG_TRY(launch_desc_from_R(w.R, n_geo, m->N, w.xq, w.gq, gs, &m->lat));
+    SG_TRY(run_queries(m, 0, w.xq, w.gq, n_geo, m->std, m->c, with_E ? w.E : nullptr, w.F, gs));
+    SG_CUDA(cudaMemcpyAsync(q->hF, w.F, sizeof(double) * n_geo * dimi, cudaMemcpyDeviceToHost, gs));
+    if (with_E) SG_CUDA(cudaMemcpyAsync(q->hE, w.E, sizeof(double) * n_geo, cudaMemcpyDeviceToHost, gs));
+    return 0;
+  };
+  if (g == nullptr) {
+    g = &m->graphs[m->graph_next];
+    m->graph_next = (m->graph_next + 1) % 4;
+    free_graph_slot(*g);
+    SG_CUDA(cudaMallocHost(&g->hR, sizeof(double) * n_geo * dimi));
+    SG_CUDA(cudaMallocHost(&g->hF, sizeof(double) * n_geo * dimi));
+    SG_CUDA(cudaMallocHost(&g->hE, sizeof(double) * n_geo));
+    std::copy(R, R + n_geo * dimi, g->hR);
+    // first call: run the sequence un-captured (sets the kernels' shared-memory attributes) ...
+    SG_TRY(enqueue(g));
+    SG_CUDA(cudaStreamSynchronize(gs));
+    // ... then capture it
+    long long before = 0, after = 0;
+    for (int k = 0; k < KID_COUNT; ++k) {
+      int64_t ln = 0;
+      sgdml_b200_profile_get(k, nullptr, nullptr, &ln);
+      before += ln;
+    }
+    cudaGraph_t graph = nullptr;
+    SG_CUDA(cudaStreamBeginCapture(gs, cudaStreamCaptureModeThreadLocal));
+    int rc = enqueue(g);
+    cudaError_t e = cudaStreamEndCapture(gs, &graph);
+    if (rc != 0) {
+      if (graph) cudaGraphDestroy(graph);
+      return rc;
+    }
+    SG_CUDA(e);
+    e = cudaGraphInstantiate(&g->exec, graph, 0);
+    cudaGraphDestroy(graph);
+    SG_CUDA(e);
+    for (int k = 0; k < KID_COUNT; ++k) {
+      int64_t ln = 0;
+      sgdml_b200_profile_get(k, nullptr, nullptr, &ln);
+      after += ln;
+    }
+    g->n_kernels = (int)(after - before);
+    g->n_geo = n_geo;
+    g->with_E = with_E;
+    g->generation = m->generation;
+  } else {
+    std::copy(R, R + n_geo * dimi, g->hR);
+    SG_CUDA(cudaGraphLaunch(g->exec, gs));
+    count_launch(KID_PREDICT_AUX, g->n_kernels);  // the kernels of a replay are launches too
+    SG_CUDA(cudaStreamSynchronize(gs));
+  }
+  std::copy(g->hF, g->hF + n_geo * dimi, F);
+  if (with_E) std::copy(g->hE, g->hE + n_geo, E);
+  return 0;
+}
+
+}  // namespace
+
 int sgdml_b200_model_destroy(sgdml_b200_model* m) {
   if (m == nullptr) return 0;
+  for (auto& g : m->graphs) free_graph_slot(g);
+  if (m->graph_stream) cudaStreamDestroy(m->graph_stream);
+  if (m->graph_event) cudaEventDestroy(m->graph_event);
   cudaFree(m->X);
   cudaFree(m->Xc);
   cudaFree(m->JA);
@@ -1156,6 +1264,9 @@ int sgdml_b200_predict(sgdml_b200_model* m, const double* R, int64_t n_geo, doub
   const bool R_dev = is_device_ptr(R), F_dev = is_device_ptr(F), E_dev = (E != nullptr) && is_device_ptr(E);
   const bool host_io = !R_dev || !F_dev || (E != nullptr && !E_dev);
   const int dimi = 3 * m->N;
+  if (!R_dev && !F_dev && (E == nullptr || !E_dev) && n_geo <= GRAPH_MAX_GEO && !profiling_enabled() &&
+      getenv("SGDML_B200_NO_GRAPH") == nullptr)
+    return predict_graph(m, R, n_geo, E, F, s);
   int64_t chunk = std::min<int64_t>(chunk_geos(m), n_geo);
   // Host buffers: split the batch into >= 4 chunks and run them on two side streams so that the
   // H2D copy of chunk k+1 and the D2H copy of chunk k-1 overlap the kernels of chunk k.
@@ -1200,6 +1311,7 @@ int sgdml_b200_predict(sgdml_b200_model* m, const double* R, int64_t n_geo, doub
 int sgdml_b200_model_set_lattice(sgdml_b200_model* m, const double* lattice, const double* lattice_inv) {
   SG_ARG(m != nullptr);
   SG_CUDA(cudaDeviceSynchronize());  // no stream argument: kernels in flight copied the old cell by value, but keep calls ordered
+  ++m->generation;  // captured graphs carry the cell as a kernel argument
   return lattice_from_host(lattice, lattice_inv, &m->lat);
 }
 
@@ -1207,6 +1319,7 @@ int sgdml_b200_model_set_alphas_E(sgdml_b200_model* m, const double* alphas_E, v
   SG_TRY(require_device());
   SG_ARG(m != nullptr);
   cudaStream_t s = (cudaStream_t)stream;
+  ++m->generation;  // captured graphs carry use_ae as a kernel argument
   if (alphas_E == nullptr) {
     SG_CUDA(cudaMemsetAsync(m->ae, 0, sizeof(double) * m->Mpad, s));
     m->use_ae = 0;

@@ -868,12 +868,7 @@ int potrf_device(double* A, int64_t n, int64_t lda, int* info_host, cudaStream_t
   const int oz_slices = (oz != nullptr) ? std::max(0, std::min(7, atoi(oz))) : 0;
   int8_t* oz_planes = nullptr;  // slice planes of the current outer panel (experimental tcgen05 path)
   int* oz_exps = nullptr;
-  auto cleanup = [&]() {
-    cudaFree(oz_planes);
-    cudaFree(oz_exps);
-    cudaFree(d_info);
-    cudaFree(W[0]);
-    cudaFree(W[1]);
+  auto cleanup = [&]() {  // (the device buffers are persistent workspaces: csrc/core.cu ws_get)
     if (s2) cudaStreamDestroy(s2);
     for (int i = 0; i < 2; ++i) {
       if (evI[i]) cudaEventDestroy(evI[i]);
@@ -881,16 +876,16 @@ int potrf_device(double* A, int64_t n, int64_t lda, int* info_host, cudaStream_t
     }
   };
   auto body = [&]() -> int {
-    SG_CUDA(cudaMalloc(&d_info, sizeof(int)));
-    SG_CUDA(cudaMalloc(&W[0], sizeof(double) * (size_t)n * NBO));
+    SG_TRY(ws_get(WS_POTRF_INFO, sizeof(int), (void**)&d_info));
+    SG_TRY(ws_get(WS_POTRF_W0, sizeof(double) * (size_t)n * NBO, (void**)&W[0]));
     if (oz_slices > 0 && !lookahead) {
       size_t pb = 0, eb = 0;
       SG_TRY(ozaki_syrk_workspace_bytes(n, NBO, oz_slices, &pb, &eb));
-      SG_CUDA(cudaMalloc(&oz_planes, pb));
-      SG_CUDA(cudaMalloc(&oz_exps, eb));
+      SG_TRY(ws_get(WS_OZ_PLANES, pb, (void**)&oz_planes));
+      SG_TRY(ws_get(WS_OZ_EXPS, eb, (void**)&oz_exps));
     }
     if (lookahead) {
-      SG_CUDA(cudaMalloc(&W[1], sizeof(double) * (size_t)n * NBO));
+      SG_TRY(ws_get(WS_POTRF_W1, sizeof(double) * (size_t)n * NBO, (void**)&W[1]));
       int lo = 0, hi = 0;
       SG_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));  // lo = least priority
       SG_CUDA(cudaStreamCreateWithPriority(&s2, cudaStreamNonBlocking, lo));
@@ -1154,7 +1149,7 @@ int sgdml_b200_solve_analytic(double* Kneg, int64_t n, int64_t lda, double lam, 
     return info;
   }
   double* tmp = nullptr;
-  SG_CUDA(cudaMalloc(&tmp, sizeof(double) * (size_t)n));
+  SG_TRY(ws_get(WS_SOLVE_TMP, sizeof(double) * (size_t)n, (void**)&tmp));
   auto body = [&]() -> int {
     SG_CUDA(cudaMemcpyAsync(tmp, sY.dev(), sizeof(double) * (size_t)n, cudaMemcpyDeviceToDevice, s));
     SG_TRY(potrs_device(K, n, lda, tmp, 1, 1, s));  // analytic.py:97-99
@@ -1164,9 +1159,7 @@ int sgdml_b200_solve_analytic(double* Kneg, int64_t n, int64_t lda, double lam, 
     SG_CUDA(cudaStreamSynchronize(s));
     return 0;
   };
-  int rc = body();
-  cudaFree(tmp);
-  return rc;
+  return body();
 }
 
 int sgdml_b200_dgemm_nt(int64_t m, int64_t n, int64_t k, double alpha, const double* A, int64_t lda, const double* B,

@@ -47,7 +47,7 @@ class Analytic(object):
         t_alloc = timeit.default_timer()
         if not use_E_cstr:
             ldk = (n + 1) // 2 * 2
-            K = torch.empty((n, ldk), dtype=torch.float64, device='cuda')
+            K = self.gdml_train._kernel_matrix_buffer(n, ldk)  # kept across the tasks of a sigma grid
         torch.cuda.synchronize()
         t_alloc = timeit.default_timer() - t_alloc
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
@@ -81,6 +81,7 @@ class Analytic(object):
             import scipy.linalg
 
             del K
+            self.gdml_train._K_buf = None  # the factorisation destroyed it; assemble a fresh matrix
             if use_E_cstr:
                 K = self.gdml_train._assemble_kernel_mat_ecstr_device(R_desc, R_d_desc, tril_perms_lin, sig, scale=-1.0)
             else:
@@ -96,7 +97,7 @@ class Analytic(object):
             'alloc_s': t_alloc,
         }
         t_free = timeit.default_timer()
-        del K
+        del K  # (the buffer itself stays with the GDMLTrain instance for the next task; release_buffers() frees it)
         torch.cuda.synchronize()
         self.timings['free_s'] = timeit.default_timer() - t_free
 

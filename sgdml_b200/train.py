@@ -41,6 +41,54 @@ class GDMLTrain(object):
         self._max_memory = max_memory
         self._max_processes = max_processes
         self._use_torch = use_torch
+        # Residency across the tasks of a sigma grid (`sgdml all` retrains the same points for several length scales
+        # with ONE GDMLTrain instance, cli.py:802-806, 923-932, 981-1083): descriptors and Jacobians are
+        # sigma-independent and stay on the device, the kernel-matrix buffer (31.8 GB at BASELINE config 2) and the
+        # factorisation workspaces are allocated once.  release_buffers() drops them.
+        self._desc_cache = {}
+        self._K_buf = None
+        self.cache_stats = {'desc_hits': 0, 'desc_misses': 0, 'K_reused': 0, 'K_allocated': 0}
+
+    def release_buffers(self):
+        """Frees the device buffers kept between train() calls (descriptor cache, K, factorisation workspaces)."""
+        self._desc_cache.clear()
+        self._K_buf = None
+        _lib.lib().sgdml_b200_release_workspaces()
+        _torch().cuda.empty_cache()
+
+    def _descriptors(self, desc, R, lat_and_inv):
+        """R_desc, R_d_desc of the training geometries as host arrays AND device tensors, cached by content."""
+        import hashlib
+
+        torch = _torch()
+        h = hashlib.blake2b(R.tobytes(), digest_size=16)
+        if lat_and_inv is not None:
+            h.update(np.ascontiguousarray(lat_and_inv[0]).tobytes())
+        key = (R.shape, h.hexdigest())
+        hit = self._desc_cache.get(key)
+        if hit is not None:
+            self.cache_stats['desc_hits'] += 1
+            return hit
+        self.cache_stats['desc_misses'] += 1
+        R_desc, R_d_desc = desc.from_R(R, lat_and_inv=lat_and_inv)  # train.py:926-935
+        if R.shape[0] == 1:
+            R_desc, R_d_desc = R_desc[None], R_d_desc[None]
+        entry = (R_desc, R_d_desc, torch.from_numpy(R_desc).cuda(), torch.from_numpy(R_d_desc).cuda())
+        if len(self._desc_cache) >= 4:  # a handful of training sets at most
+            self._desc_cache.pop(next(iter(self._desc_cache)))
+        self._desc_cache[key] = entry
+        return entry
+
+    def _kernel_matrix_buffer(self, n_rows, ldk):
+        """A (n_rows, ldk) float64 CUDA tensor, reused between train() calls of the same size."""
+        torch = _torch()
+        if self._K_buf is not None and tuple(self._K_buf.shape) == (n_rows, ldk):
+            self.cache_stats['K_reused'] += 1
+            return self._K_buf
+        self._K_buf = None  # free the old one first
+        self._K_buf = torch.empty((n_rows, ldk), dtype=torch.float64, device='cuda')
+        self.cache_stats['K_allocated'] += 1
+        return self._K_buf
 
     # ------------------------------------------------------------------ model assembly
     def create_model(self, task, solver, R_desc, R_d_desc, tril_perms_lin, std, alphas_F, alphas_E=None):
@@ -105,9 +153,8 @@ class GDMLTrain(object):
             lat = np.ascontiguousarray(task['lattice'], dtype=np.float64)
             lat_and_inv = (lat, np.ascontiguousarray(np.linalg.inv(lat)))
         R = np.ascontiguousarray(task['R_train'], dtype=np.float64).reshape(n_train, -1)
-        R_desc, R_d_desc = desc.from_R(R, lat_and_inv=lat_and_inv)  # train.py:926-935
-        if n_train == 1:
-            R_desc, R_d_desc = R_desc[None], R_d_desc[None]
+        R_desc, R_d_desc, R_desc_dev, R_d_desc_dev = self._descriptors(desc, R, lat_and_inv)
+        self._dev_views = {id(R_desc): R_desc_dev, id(R_d_desc): R_d_desc_dev}  # device twins of the host arrays
 
         y = np.asarray(task['F_train'], dtype=np.float64).ravel().copy()  # train.py:939-947
         E_train_mean = None
@@ -209,8 +256,10 @@ class GDMLTrain(object):
         rows=(m_begin, m_end): only the block rows of these training points (row-sharded
         assembly); the tensor then has (m_end - m_begin)*3N rows."""
         torch = _torch()
-        R_desc = np.ascontiguousarray(R_desc, dtype=np.float64)
-        R_d_desc = np.ascontiguousarray(R_d_desc, dtype=np.float64)
+        # device-resident copies of the training descriptors (cached by train()) are used in place: no H2D copy
+        views = getattr(self, '_dev_views', {})
+        R_desc = views.get(id(R_desc), None) if id(R_desc) in views else np.ascontiguousarray(R_desc, dtype=np.float64)
+        R_d_desc = views.get(id(R_d_desc), None) if id(R_d_desc) in views else np.ascontiguousarray(R_d_desc, dtype=np.float64)
         tril_perms_lin = np.ascontiguousarray(tril_perms_lin, dtype=np.int64)
         n_train, dim_d = R_d_desc.shape[:2]
         n_atoms = int((1 + np.sqrt(8 * dim_d + 1)) / 2)

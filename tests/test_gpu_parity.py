@@ -710,3 +710,42 @@ def test_energy_constraints_large_descriptor_path(eng):
     E, F = eng.GDMLPredict(model).predict(Rq)
     E_ref, F_ref = opredict.Predictor(model).predict(Rq)
     assert rel_err(F, F_ref) < 1e-10 and rel_err(E, E_ref) < 1e-10
+
+
+# --------------------------------------------------------------------------- (f)2: residency across a sigma grid
+def test_sigma_grid_reuses_descriptors_and_buffers(eng):
+    """`sgdml all` retrains the same points for several length scales with one GDMLTrain instance (cli.py:802-806,
+    981-1083): the engine keeps the (sigma-independent) descriptors on the device and reuses the kernel-matrix
+    buffer; the models equal those of fresh, independent training runs bit for bit."""
+    from sgdml_b200 import synth
+
+    N, M = 9, 30
+    perms = synth.rotor_swap_group(N, 1, 1)
+    t = eng.GDMLTrain()
+    models = []
+    for sig in (10, 20, 30):
+        models.append(t.train(synth.make_task(N, M, perms, sig)))
+    assert t.cache_stats['desc_misses'] == 1 and t.cache_stats['desc_hits'] == 2
+    assert t.cache_stats['K_allocated'] == 1 and t.cache_stats['K_reused'] == 2
+    for sig, m in zip((10, 20, 30), models):
+        fresh = eng.GDMLTrain().train(synth.make_task(N, M, perms, sig))
+        assert np.array_equal(m['alphas_F'], fresh['alphas_F']) and float(m['c']) == float(fresh['c'])
+    # a different training set is a cache miss, and release_buffers() empties everything
+    t.train(synth.make_task(N, M, perms, 20, seed=3))
+    assert t.cache_stats['desc_misses'] == 2
+    t.release_buffers()
+    assert not t._desc_cache and t._K_buf is None
+
+
+def test_ase_calculator_core_units(eng, golden):
+    """intf/ase_calc.py:81-110 without ASE: positions in Angstrom -> energy in eV, forces (N, 3) in eV/Ang."""
+    from sgdml_b200.intf.ase_calc import _KCAL_PER_MOL_IN_EV, SGDMLCalculatorCore
+
+    calc = SGDMLCalculatorCore()
+    calc._setup(golden_model(golden), _KCAL_PER_MOL_IN_EV, _KCAL_PER_MOL_IN_EV)
+    N = int(golden['n_atoms'])
+    res = calc.compute(golden['R_query'][0].reshape(N, 3))
+    assert res['forces'].shape == (N, 3)
+    assert rel_err(res['forces'].ravel(), golden['F_query'][0] * _KCAL_PER_MOL_IN_EV) < 1e-10
+    assert rel_err(res['energy'], golden['E_query'][:1] * _KCAL_PER_MOL_IN_EV) < 1e-10
+    assert abs(_KCAL_PER_MOL_IN_EV - 0.0433641) < 1e-6
