@@ -123,6 +123,11 @@ int sgdml_b200_model_set_alphas(sgdml_b200_model* model, const double* alphas_F,
 int sgdml_b200_predict_train(sgdml_b200_model* model, int64_t m_begin, int64_t m_end, int scaled,
                              double* E, double* F, void* stream);
 
+/* Test / tuning hook: main kernel of the fused predictor for 72 < D <= 256.  1 = two warp groups running the sweep
+ * half a tile apart so that one group's transform / barrier phases overlap the other's tensor phases (default),
+ * 0 = the single-group kernel. */
+int sgdml_b200_set_predict_variant(int variant);
+
 /* Shape of a model: n_atoms, n_train, n_perms (any pointer may be NULL). */
 int sgdml_b200_model_dims(const sgdml_b200_model* model, int64_t* n_atoms, int64_t* n_train, int64_t* n_perms);
 

@@ -208,6 +208,7 @@ struct OzArgs {
   double* C;
   int64_t ldc;
   int* dbg_levels;   // bring-up: raw int32 level sums, [S][m][n] (NULL in production)
+  int overwrite;     // 1: C = alpha A B^T (the old contents of C are not read)
   int dbg_flags;     // timing experiments (SGDML_B200_OZAKI_DBG): 1 = no global read-modify-write in the epilogue,
                      // 2 = no tcgen05.mma issued, 4 = epilogue reads only one level
 };
@@ -401,7 +402,7 @@ __global__ void __launch_bounds__(192, 1) k_ozaki_gemm(const OzArgs p) {
       double* cp = p.C + (m0 + quad * 32) * p.ldc + gc;
       double cold[32];
 #pragma unroll
-      for (int r = 0; r < 32; ++r) cold[r] = (col_ok && r < rows_here) ? cp[(int64_t)r * p.ldc] : 0.0;
+      for (int r = 0; r < 32; ++r) cold[r] = (col_ok && !p.overwrite && r < rows_here) ? cp[(int64_t)r * p.ldc] : 0.0;
       double acc[32];
 #pragma unroll
       for (int j = 0; j < 32; ++j) acc[j] = 0.0;
@@ -441,12 +442,6 @@ __global__ void __launch_bounds__(192, 1) k_ozaki_gemm(const OzArgs p) {
 }
 
 // ---------------------------------------------------------------- host side
-struct OzOperand {
-  int8_t* units = nullptr;   // [kb][p][rt][8192]
-  int* exps = nullptr;
-  int64_t rows_pad = 0, kp = 0;
-};
-
 static size_t oz_plane_bytes(int64_t rows, int64_t k, int S) {
   const int64_t rows_pad = (rows + OZ_BM - 1) / OZ_BM * OZ_BM, kp = (k + OZ_KPAD - 1) / OZ_KPAD * OZ_KPAD;
   return (size_t)S * rows_pad * kp;
@@ -466,7 +461,7 @@ static int oz_split_into(const double* X, int64_t rows, int64_t k, int64_t ldx, 
 }
 
 static int oz_launch(const OzOperand& oa, const OzOperand& ob, int64_t m, int64_t n, double alpha, double* C,
-                     int64_t ldc, int S, int tri, cudaStream_t s, int* dbg_levels = nullptr) {
+                     int64_t ldc, int S, int tri, cudaStream_t s, int* dbg_levels = nullptr, int overwrite = 0) {
   static bool configured[64] = {false};
   int dev = 0;
   SG_CUDA(cudaGetDevice(&dev));
@@ -496,6 +491,7 @@ static int oz_launch(const OzOperand& oa, const OzOperand& ob, int64_t m, int64_
   a.C = C;
   a.ldc = ldc;
   a.dbg_levels = dbg_levels;
+  a.overwrite = overwrite;
   {
     const char* df = getenv("SGDML_B200_OZAKI_DBG");
     a.dbg_flags = df ? atoi(df) : 0;
@@ -525,6 +521,20 @@ static int oz_launch(const OzOperand& oa, const OzOperand& ob, int64_t m, int64_
   return 0;
 }
 static_assert(OZ_GSM * OZ_BM == OZ_GSN * OZ_BN, "square super-tiles (the triangular raster relies on it)");
+
+// ---- operand-level interface (csrc/predict.cu keeps the slices of the model matrices between calls)
+size_t ozaki_units_bytes(int64_t rows, int64_t k, int S) { return oz_plane_bytes(rows, k, S); }
+size_t ozaki_exps_bytes(int64_t rows) { return sizeof(int) * (size_t)((rows + OZ_BM - 1) / OZ_BM * OZ_BM); }
+int ozaki_split(const double* X, int64_t rows, int64_t k, int64_t ldx, int S, int8_t* units, int* exps, OzOperand* o,
+                cudaStream_t s) {
+  SG_ARG(S >= 2 && S <= OZ_MAX_S && rows >= 1 && k >= 1 && k <= (1 << 14));
+  return oz_split_into(X, rows, k, ldx, S, units, exps, o, s);
+}
+int ozaki_gemm(const OzOperand& a, const OzOperand& b, int64_t m, int64_t n, double alpha, int overwrite, double* C,
+               int64_t ldc, int S, cudaStream_t s) {
+  SG_ARG(a.kp == b.kp && m <= a.rows_pad && n <= b.rows_pad);
+  return oz_launch(a, b, m, n, alpha, C, ldc, S, 0, s, nullptr, overwrite);
+}
 
 // Workspace of the symmetric update used by potrf: allocated once per factorisation (a cudaMalloc /
 // cudaFree pair costs ~20 ms in a process that holds tens of GB -- see csrc/core.cu), reused by every

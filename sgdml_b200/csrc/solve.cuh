@@ -35,6 +35,20 @@ int xt_v_device(const double* X, int64_t n_rows, int64_t m, int64_t ldx, const d
 int x_t_minus_v_device(const double* X, int64_t n_rows, int64_t m, int64_t ldx, double lam, const double* t_dev,
                        const double* v_dev, double* out_dev, cudaStream_t s);
 
+// csrc/ozaki.cu: an operand cut into int8 slices (unit-major pre-swizzled layout) and the GEMM on such operands
+struct OzOperand {
+  int8_t* units = nullptr;   // [k-block][slice][row tile][8192]
+  int* exps = nullptr;       // row exponents
+  int64_t rows_pad = 0, kp = 0;
+};
+size_t ozaki_units_bytes(int64_t rows, int64_t k, int n_slices);
+size_t ozaki_exps_bytes(int64_t rows);
+int ozaki_split(const double* X, int64_t rows, int64_t k, int64_t ldx, int n_slices, int8_t* units, int* exps,
+                OzOperand* out, cudaStream_t s);
+// C (m x n, ldc) = (overwrite ? 0 : C) + alpha * A B^T for pre-split operands; stream-ordered, no allocation
+int ozaki_gemm(const OzOperand& a, const OzOperand& b, int64_t m, int64_t n, double alpha, int overwrite, double* C,
+               int64_t ldc, int n_slices, cudaStream_t s);
+
 // csrc/ozaki.cu: C += alpha A B^T through n_slices int8 slices per operand on tcgen05 (experimental)
 int ozaki_gemm_nt_device(int64_t m, int64_t n, int64_t k, double alpha, const double* A, int64_t lda, const double* B,
                          int64_t ldb, double* C, int64_t ldc, int n_slices, int tri, cudaStream_t s);

@@ -192,3 +192,27 @@ def test_large_descriptor_predictor_on_int8_path(monkeypatch):
         monkeypatch.setenv('SGDML_B200_OZAKI_PREDICT_SLICES', str(S))
         E, F = sgdml_b200.GDMLPredict(model).predict(Rq)
         assert rel_err(F, F_ref) < tol and rel_err(E, E_ref) < tol
+
+
+def test_large_descriptor_kmatvec_on_int8_path(monkeypatch):
+    """K.v of a large-descriptor model (set_alphas refreshes the slices of JA / JA^T; predict_train runs the four
+    contractions on the int8 path) against the FP64 DMMA path, 5 slices."""
+    import sgdml_b200
+    from sgdml_b200 import synth
+    from sgdml_b200.desc import Desc
+
+    N, M = 30, 40
+    perms = synth.rotor_swap_group(N, 1, 1)
+    model = synth.random_model(N, M, perms, 30, seed=2)
+    _, R_d_desc = Desc(N).from_R(synth.geometries(N, M, 2).reshape(M, -1))
+    v = np.random.default_rng(3).standard_normal(M * 3 * N)
+    out = {}
+    for S in ('0', '5'):
+        monkeypatch.setenv('SGDML_B200_OZAKI_PREDICT_SLICES', S)
+        p = sgdml_b200.GDMLPredict(model)
+        p.set_R_d_desc(R_d_desc)
+        p.set_alphas(v)
+        out[S] = p.kmatvec_train().copy()
+        p.set_alphas(2.0 * v)  # a second set of coefficients through the same handle
+        assert rel_err(p.kmatvec_train(), 2.0 * out[S]) < 1e-9
+    assert rel_err(out['5'], out['0']) < 1e-8

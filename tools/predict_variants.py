@@ -1,0 +1,42 @@
+"""Device-resident throughput of the fused predictor for both main-kernel variants (0 = single group, 1 = two
+ping-pong groups) and B = 1 latency with and without the CUDA-graph replay."""
+import os, sys, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+import sgdml_b200
+from sgdml_b200 import synth, _lib
+L = _lib.lib()
+peak = __import__('ctypes').c_double()
+L.sgdml_b200_fp64_peak_tflops(__import__('ctypes').byref(peak))
+for wl, B in (('aspirin', 65536), ('ethanol', 65536)):
+    cfg = synth.CONFIGS[wl]
+    N, M = cfg['n_atoms'], cfg['n_train']
+    perms = synth.rotor_swap_group(N, cfg['n_rotors'], cfg['n_swaps'])
+    S, D = len(perms), N * (N - 1) // 2
+    model = synth.random_model(N, M, perms, cfg['sig'])
+    p = sgdml_b200.GDMLPredict(model)
+    R = torch.from_numpy(synth.geometries(N, B, 1).reshape(B, -1)).cuda()
+    ref = None
+    for variant in (0, 1, 0, 1):
+        L.sgdml_b200_set_predict_variant(variant)
+        for _ in range(3): E, F = p.predict(R)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(5): E, F = p.predict(R)
+        e1.record(); torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 5
+        if ref is None: ref = F.clone()
+        dev = float((F - ref).abs().max() / ref.abs().max())
+        print('%s B=%d variant %d: %.3f ms/call, %.3e pred/s, %.1f TF/s algorithmic (%.2f of %.1f), max rel dev vs variant 0: %.1e' % (
+            wl, B, variant, ms, B / ms * 1e3, 9.0 * M * S * D * B / ms * 1e-9, 9.0 * M * S * D * B / ms * 1e-9 / peak.value, peak.value, dev), flush=True)
+    L.sgdml_b200_set_predict_variant(1)
+    R1 = synth.geometries(N, 1, 1).reshape(1, -1)
+    for env in (None, '1'):
+        if env: os.environ['SGDML_B200_NO_GRAPH'] = env
+        else: os.environ.pop('SGDML_B200_NO_GRAPH', None)
+        for _ in range(20): p.predict(R1)
+        t0 = time.perf_counter()
+        for _ in range(500): p.predict(R1)
+        print('%s B=1 host NumPy in/out, %s: %.1f us per call' % (wl, 'graph replay' if not env else 'plain launches', (time.perf_counter() - t0) / 500 * 1e6), flush=True)
+    os.environ.pop('SGDML_B200_NO_GRAPH', None)

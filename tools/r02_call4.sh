@@ -9,5 +9,6 @@ run c4_oz_probe 200 python tools/ozaki_probe.py
 SGDML_B200_OZAKI_SLICES=7 run c4_oz_solve_m1000 400 python tools/solve_check.py --workload aspirin
 run c4_iterative 600 python -m pytest tests/test_iterative.py -x -q -m gpu
 run c4_gpu_parity 900 python -m pytest tests/test_gpu_parity.py tests/test_dropin_cli.py -x -q -m gpu
+run c4_variants 300 python tools/predict_variants.py
 run c4_bench 900 python bench.py --steps 5 --warmup 3
 OZ_N=4096 timeout 300 ncu --set full --clock-control none --import-source on -k regex:k_ozaki_gemm -s 3 -c 1 -f -o $O/c4_oz_gemm python tools/ozaki_probe2.py > $O/c4_oz_ncu.log 2>&1
