@@ -1130,7 +1130,7 @@ int launch_main_t(const PredictArgs& a, int n_splits, cudaStream_t s) {
   return 0;
 }
 
-int g_predict_variant = 1;  // 1: two-group ping-pong kernel for the split-k configurations (default), 0: single-group kernel
+int g_predict_variant = 0;  // 1: two-group ping-pong kernel for the split-k configurations, 0: single-group kernel
 
 int launch_main(int cfg, const PredictArgs& a, int n_splits, cudaStream_t s) {
   if (g_predict_variant == 1) {
@@ -1542,6 +1542,11 @@ int sgdml_b200_model_create(sgdml_b200_model** out, int64_t n_atoms, int64_t n_t
 
 namespace {
 
+// SGDML_B200_GRAPH=1 / 0 switches the CUDA-graph replay of small host-buffer batches on / off (default below)
+bool g_graph_enabled() {
+  const char* e = getenv("SGDML_B200_GRAPH");
+  return e != nullptr ? (e[0] == '1') : false;
+}
 constexpr int64_t GRAPH_MAX_GEO = 16;  // batches up to this size with host buffers replay a captured graph
 
 void free_graph_slot(sgdml_b200_model::GraphSlot& g) {
@@ -1670,7 +1675,7 @@ int sgdml_b200_predict(sgdml_b200_model* m, const double* R, int64_t n_geo, doub
   const bool host_io = !R_dev || !F_dev || (E != nullptr && !E_dev);
   const int dimi = 3 * m->N;
   if (!R_dev && !F_dev && (E == nullptr || !E_dev) && n_geo <= GRAPH_MAX_GEO && !profiling_enabled() &&
-      getenv("SGDML_B200_NO_GRAPH") == nullptr)
+      g_graph_enabled())
     return predict_graph(m, R, n_geo, E, F, s);
   int64_t chunk = std::min<int64_t>(chunk_geos(m), n_geo);
   // Host buffers: split the batch into >= 4 chunks and run them on two side streams so that the

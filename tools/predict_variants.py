@@ -32,11 +32,10 @@ for wl, B in (('aspirin', 65536), ('ethanol', 65536)):
             wl, B, variant, ms, B / ms * 1e3, 9.0 * M * S * D * B / ms * 1e-9, 9.0 * M * S * D * B / ms * 1e-9 / peak.value, peak.value, dev), flush=True)
     L.sgdml_b200_set_predict_variant(1)
     R1 = synth.geometries(N, 1, 1).reshape(1, -1)
-    for env in (None, '1'):
-        if env: os.environ['SGDML_B200_NO_GRAPH'] = env
-        else: os.environ.pop('SGDML_B200_NO_GRAPH', None)
+    for env in ('1', '0'):
+        os.environ['SGDML_B200_GRAPH'] = env
         for _ in range(20): p.predict(R1)
         t0 = time.perf_counter()
         for _ in range(500): p.predict(R1)
-        print('%s B=1 host NumPy in/out, %s: %.1f us per call' % (wl, 'graph replay' if not env else 'plain launches', (time.perf_counter() - t0) / 500 * 1e6), flush=True)
-    os.environ.pop('SGDML_B200_NO_GRAPH', None)
+        print('%s B=1 host NumPy in/out, %s: %.1f us per call' % (wl, 'graph replay' if env == '1' else 'plain launches', (time.perf_counter() - t0) / 500 * 1e6), flush=True)
+    os.environ.pop('SGDML_B200_GRAPH', None)
