@@ -69,6 +69,8 @@ __device__ void load_pair_tables(const double* __restrict__ g, const double* __r
 // compiles to an XU-pipe sequence that throttled the first version of this kernel
 __device__ __forceinline__ int fastdiv(int x, unsigned m) { return (int)__umulhi((unsigned)x, m); }
 
+__device__ __forceinline__ int ceil_div_dev(int a, int b) { return (a + b - 1) / b; }
+
 constexpr int ASM_NI = 4;  // 3x3 atom-pair sub-blocks per thread (accumulators live in registers)
 
 // One CTA: row point i, a tile of TJ column points.  Permutations are the OUTER loop; for each
@@ -291,6 +293,233 @@ __global__ void __launch_bounds__(256, 2) k_assemble(const AsmArgs p) {
         double* Krow = p.K + ((int64_t)j * N3 + 3 * b + c2i) * p.ldk + (int64_t)i * N3 + 3 * a;
 #pragma unroll
         for (int c = 0; c < 3; ++c) Krow[c] = p.scale * acc[q][c * 3 + c2i];
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// k_assemble_v3: the same mathematics, restructured around what the first kernel's profile showed
+// (profiles/r01_ncu_assemble.txt: 24.6 % warps active, 14.4 % FP64 pipe, barrier / short-scoreboard / wait stalls):
+//  * permutations are processed in CHUNKS of PG: phase A computes the per-(point, permutation) vectors u, v, Dg of
+//    the whole chunk in one go -- tj * PG * 5N independent row tasks instead of tj * 5N, so all 256 threads have
+//    work -- with the delta table evaluated on the fly (delta_p[Pa][Pg] = x_i[a][g] - x_j[Pa][Pg]; no staged table,
+//    no barrier between "delta" and "vectors"); |delta_p|^2 falls out of the v rows;
+//  * three CTA barriers per chunk (after the vectors, after the Matern factors, before the vectors are overwritten)
+//    instead of two per permutation;
+//  * a CTA walks over `tiles_per_cta` column tiles with the row point's tables (G_i, X_i, permutations) resident.
+// Phase B (the 3x3 sub-block accumulation in registers) is unchanged.
+__global__ void __launch_bounds__(256, 2) k_assemble_v3(const AsmArgs p, int PG, int tiles_per_cta) {
+  extern __shared__ __align__(16) double sm[];
+  const int N = p.N, S = p.S, TJ = p.TJ;
+  const int N3 = 3 * N, NN = N * N, NN3 = NN * 3;
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const int warp = tid >> 5, lane = tid & 31, nw = nt >> 5;
+  const int i = p.i0 + blockIdx.y;
+
+  double* Gi = sm;                      // NN3
+  double* Xi = Gi + NN3;                // NN
+  double* Gj = Xi + NN;                 // TJ*NN3
+  double* Xj = Gj + TJ * NN3;           // TJ*NN
+  double* uS = Xj + TJ * NN;            // TJ*PG*N3
+  double* vS = uS + TJ * PG * N3;       // TJ*PG*N3
+  double* DgS = vS + TJ * PG * N3;      // TJ*PG*3*N3
+  double* n2p = DgS + TJ * PG * 3 * N3; // TJ*PG*N   per-row sums of squared deltas (each pair twice)
+  double* cc = n2p + TJ * PG * N;       // TJ*PG*2
+  int* sP = reinterpret_cast<int*>(cc + TJ * PG * 2);  // S*N
+  int* sPi = sP + S * N;                                    // S*N
+
+  load_pair_tables(p.R_d_desc + (int64_t)i * p.D * 3, p.R_desc + (int64_t)i * p.D, N, Gi, Xi, warp, lane, nw);
+  for (int idx = tid; idx < S * N; idx += nt) {
+    sP[idx] = p.aperm[idx];
+    sPi[idx] = p.apinv[idx];
+  }
+  const double sig = p.sig;
+  const double sig2 = sig * sig;
+  const double inv_div = 1.0 / (3.0 * sig2 * sig2);  // 1/mat52_base_div (train.py:179)
+  const int per = 5 * N;  // row tasks per (point, permutation): N (u) + N (v) + 3N (Dg rows a,c)
+
+  const int tile_begin = blockIdx.x * tiles_per_cta;
+  const int tile_end = min(tile_begin + tiles_per_cta, ceil_div_dev(p.nJ, TJ));
+  for (int tile = tile_begin; tile < tile_end; ++tile) {
+    const int jt0 = tile * TJ;
+    const int tj = min(TJ, p.nJ - jt0);
+    if (p.sym && jt0 + tj - 1 < i) continue;  // (sym: jpts is the identity) every column point of the tile is < i
+    __syncthreads();  // the previous tile's phase B has finished with Gj / the vectors
+    for (int t = 0; t < tj; ++t) {
+      const int j = p.jpts[jt0 + t];
+      load_pair_tables(p.R_d_desc + (int64_t)j * p.D * 3, p.R_desc + (int64_t)j * p.D, N, Gj + t * NN3, Xj + t * NN, warp,
+                       lane, nw);
+    }
+    // this thread's output items: (t, a, b) = column point, row atom, column atom
+    int it_t[ASM_NI], it_a[ASM_NI], it_b[ASM_NI];
+    double acc[ASM_NI][9];
+#pragma unroll
+    for (int q = 0; q < ASM_NI; ++q) {
+      const int it = (int)blockIdx.z * ASM_NI * nt + tid + q * nt;  // grid.z splits the sub-blocks of large molecules
+      bool ok = it < tj * NN;
+      const int t = ok ? fastdiv(it, p.mNN) : 0;
+      if (p.sym && jt0 + t < i) ok = false;  // mirrored from block (j, i) instead
+      const int ab = ok ? it - t * NN : 0;
+      it_a[q] = fastdiv(ab, p.mN);
+      it_b[q] = ab - it_a[q] * N;
+      if (ok && !p.sym) {
+        const int64_t* dst = p.dest + (int64_t)(jt0 + t) * N3 + 3 * it_b[q];
+        if (dst[0] < 0 && dst[1] < 0 && dst[2] < 0) ok = false;  // column subset: never stored, never accumulated
+      }
+      it_t[q] = ok ? t : -1;
+#pragma unroll
+      for (int e = 0; e < 9; ++e) acc[q][e] = 0.0;
+    }
+    __syncthreads();
+
+    for (int p0 = 0; p0 < S; p0 += PG) {
+      const int pg = min(PG, S - p0);
+      // ---- phase A: u, v (+ row sums of delta^2), Dg for every (column point, permutation) of the chunk
+      for (int idx = tid; idx < tj * pg * per; idx += nt) {
+        const int tp = fastdiv(idx, p.mPer);
+        const int r = idx - tp * per;
+        const int t = tp / pg, pl = tp - t * pg;
+        const int* P = sP + (p0 + pl) * N;
+        const int* Pi = sPi + (p0 + pl) * N;
+        const double* Gjt = Gj + t * NN3;
+        const double* Xjt = Xj + t * NN;
+        const int slot = t * PG + pl;
+        if (r < N) {  // u[a] = -sum_g G_i[a][g] delta[Pa][Pg],  delta[Pa][Pg] = x_i[a][g] - x_j[Pa][Pg]
+          const int a = r;
+          const double* gi = Gi + a * N3;
+          const double* xi = Xi + a * N;
+          const double* xj = Xjt + P[a] * N;
+          double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+          for (int g = 0; g < N; ++g) {
+            const double d = xi[g] - xj[P[g]];
+            s0 = fma(gi[g * 3 + 0], d, s0);
+            s1 = fma(gi[g * 3 + 1], d, s1);
+            s2 = fma(gi[g * 3 + 2], d, s2);
+          }
+          double* u = uS + slot * N3 + 3 * a;
+          u[0] = -s0;
+          u[1] = -s1;
+          u[2] = -s2;
+        } else if (r < 2 * N) {  // v[b] = -sum_g G_j[b][g] delta[b][g],  delta[b][g] = x_i[P^-1 b][P^-1 g] - x_j[b][g]
+          const int b = r - N;
+          const double* gj = Gjt + b * N3;
+          const double* xj = Xjt + b * N;
+          const double* xi = Xi + Pi[b] * N;
+          double s0 = 0.0, s1 = 0.0, s2 = 0.0, q2 = 0.0;
+          for (int g = 0; g < N; ++g) {
+            const double d = xi[Pi[g]] - xj[g];
+            q2 = fma(d, d, q2);
+            s0 = fma(gj[g * 3 + 0], d, s0);
+            s1 = fma(gj[g * 3 + 1], d, s1);
+            s2 = fma(gj[g * 3 + 2], d, s2);
+          }
+          double* v = vS + slot * N3 + 3 * b;
+          v[0] = -s0;
+          v[1] = -s1;
+          v[2] = -s2;
+          n2p[slot * N + b] = q2;
+        } else {  // Dg[a][c][0..2] = sum_g G_i[a][g][c] G_j[Pa][Pg][0..2]
+          const int ac = r - 2 * N;
+          const int a = (int)__umulhi((unsigned)ac, 0x55555556u), c = ac - 3 * a;
+          const double* gi = Gi + a * N3 + c;
+          const double* gj = Gjt + P[a] * N3;
+          double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+          for (int g = 0; g < N; ++g) {
+            const double x = gi[g * 3];
+            const double* y = gj + P[g] * 3;
+            s0 = fma(x, y[0], s0);
+            s1 = fma(x, y[1], s1);
+            s2 = fma(x, y[2], s2);
+          }
+          double* dg = DgS + slot * 3 * N3 + ac * 3;
+          dg[0] = s0;
+          dg[1] = s1;
+          dg[2] = s2;
+        }
+      }
+      __syncthreads();
+      // ---- Matern factors of the chunk (fixed-order sum of the row partials: bit-reproducible K)
+      if (tid < tj * pg) {
+        const int t = tid / pg, pl = tid - t * pg;
+        const int slot = t * PG + pl;
+        double n2 = 0.0;
+        for (int b = 0; b < N; ++b) n2 += n2p[slot * N + b];
+        const double nrm = sqrt(5.0) * sqrt(0.5 * n2);  // every pair twice; train.py:201
+        const double base = exp(-nrm / sig) * inv_div * 5.0;          // train.py:202
+        cc[slot * 2 + 0] = base * 5.0;                                 // c1 (train.py:211)
+        cc[slot * 2 + 1] = (sig2 + sig * nrm) * base;                  // c2 (train.py:219)
+      }
+      __syncthreads();
+      // ---- phase B: acc[a][b] += c1 u[a] (x) v[b] - c2 T[a][b] for the permutations of the chunk
+      for (int pl = 0; pl < pg; ++pl) {
+        const int* P = sP + (p0 + pl) * N;
+        const int* Pi = sPi + (p0 + pl) * N;
+#pragma unroll
+        for (int q = 0; q < ASM_NI; ++q) {
+          const int t = it_t[q];
+          if (t < 0) continue;
+          const int slot = t * PG + pl;
+          const int a = it_a[q], b = it_b[q];
+          const double c1 = cc[slot * 2 + 0], c2 = cc[slot * 2 + 1];
+          const double* ua = uS + slot * N3 + 3 * a;
+          const double* vb = vS + slot * N3 + 3 * b;
+          const int pa = P[a];
+          if (b != pa) {
+            const double* gi = Gi + (a * N + Pi[b]) * 3;
+            const double* gj = Gj + t * NN3 + (pa * N + b) * 3;
+            double t0[3], t1[3];  // T[a][b] = -gi (x) gj  ->  -c2 T = +c2 gi (x) gj
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+              t0[c] = c2 * gi[c];
+              t1[c] = gj[c];
+            }
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+              const double cu = c1 * ua[c];
+#pragma unroll
+              for (int c2i = 0; c2i < 3; ++c2i)
+                acc[q][c * 3 + c2i] = fma(t0[c], t1[c2i], fma(cu, vb[c2i], acc[q][c * 3 + c2i]));
+            }
+          } else {
+            const double* dg = DgS + slot * 3 * N3 + 9 * a;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+              const double cu = c1 * ua[c];
+#pragma unroll
+              for (int c2i = 0; c2i < 3; ++c2i)
+                acc[q][c * 3 + c2i] = fma(-c2, dg[c * 3 + c2i], fma(cu, vb[c2i], acc[q][c * 3 + c2i]));
+            }
+          }
+        }
+      }
+      if (p0 + PG < S) __syncthreads();  // the next chunk overwrites the vectors
+    }
+
+    // ---- single store of the finished 3x3 sub-blocks (+ the mirrored block in symmetric mode)
+#pragma unroll
+    for (int q = 0; q < ASM_NI; ++q) {
+      const int t = it_t[q];
+      if (t < 0) continue;
+      const int a = it_a[q], b = it_b[q];
+      const int64_t* dst = p.dest + (int64_t)(jt0 + t) * N3 + 3 * b;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        double* Krow = p.K + ((int64_t)(i - p.i0) * N3 + 3 * a + c) * p.ldk;
+#pragma unroll
+        for (int c2i = 0; c2i < 3; ++c2i) {
+          const int64_t col = dst[c2i];
+          if (col >= 0) Krow[col] = p.scale * acc[q][c * 3 + c2i];
+        }
+      }
+      if (p.sym && jt0 + t > i) {  // (sym implies i0 == 0)
+        const int j = jt0 + t;
+#pragma unroll
+        for (int c2i = 0; c2i < 3; ++c2i) {
+          double* Krow = p.K + ((int64_t)j * N3 + 3 * b + c2i) * p.ldk + (int64_t)i * N3 + 3 * a;
+#pragma unroll
+          for (int c = 0; c < 3; ++c) Krow[c] = p.scale * acc[q][c * 3 + c2i];
+        }
       }
     }
   }
@@ -580,6 +809,12 @@ static size_t asm_large_slab_doubles(int N, int S) {
   return 2 * (NN * 3 + NN) + (size_t)S * (2 * N3 + 3 * N3 + 2) + NN;
 }
 
+static size_t asm_v3_smem_bytes(int N, int S, int TJ, int PG) {
+  const size_t N3 = 3 * (size_t)N, NN = (size_t)N * N;
+  const size_t dbl = NN * 3 + NN + (size_t)TJ * (NN * 3 + NN) + (size_t)TJ * PG * (2 * N3 + 3 * N3 + N + 2);
+  return dbl * 8 + 2 * (size_t)S * N * 4;
+}
+
 static size_t asm_smem_bytes(int N, int D, int S, int TJ) {
   (void)D;
   const size_t N3 = 3 * (size_t)N, NN = (size_t)N * N;
@@ -636,6 +871,7 @@ static bool atom_perm_from_desc_perm(const int* dperm, int N, int* P) {
 }
 
 static int g_asm_variant = 0;  // 0: by size; 1: always the large-molecule kernel (tests)
+static int g_asm_kernel = 2;  // small-molecule kernel: 2 = k_assemble (per-permutation phases), 3 = k_assemble_v3 (chunked)
 static int g_asm_max_rowpts = 65535;  // row points per launch of k_assemble (grid.y limit; lowered by tests)
 
 extern "C" int sgdml_b200_set_assemble_variant(int variant) {
@@ -643,6 +879,10 @@ extern "C" int sgdml_b200_set_assemble_variant(int variant) {
   if (variant >= 1000) {
     SG_ARG(variant - 1000 >= 1 && variant - 1000 <= 65535);
     g_asm_max_rowpts = variant - 1000;
+    return 0;
+  }
+  if (variant == 2 || variant == 3) {  // which small-molecule kernel
+    g_asm_kernel = variant;
     return 0;
   }
   SG_ARG(variant == 0 || variant == 1);
@@ -792,17 +1032,32 @@ extern "C" int sgdml_b200_assemble_rows(const double* R_desc, const double* R_d_
       // rows on grid.y, column tiles on grid.x; grid.y is limited to 65535, so longer row ranges (the
       // iterative solver assembles K_nm over ALL training points of a rank) run as several launches,
       // each with its own first row point and K row offset
-      SG_CUDA(cudaFuncSetAttribute(k_assemble, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       const int max_rows_per_launch = g_asm_max_rowpts;
       if (n_rowpts > max_rows_per_launch) a.sym = 0;  // the mirrored store addresses absolute row points
+      // v3 kernel: permutation chunk PG = as many permutations as keep the shared memory within ~100 KB (two CTAs per
+      // SM) -- all of them for small groups; a CTA walks over 4 column tiles with the row tables resident
+      int PG = S;
+      while (PG > 1 && asm_v3_smem_bytes(N, S, TJ, PG) > 100 * 1024) PG = (PG + 1) / 2;
+      const size_t smem3 = asm_v3_smem_bytes(N, S, TJ, PG);
+      const bool use_v3 = g_asm_kernel == 3 && smem3 <= 220 * 1024 && TJ * PG <= 256;
+      const int tiles_per_cta = 4;
+      if (use_v3)
+        SG_CUDA(cudaFuncSetAttribute(k_assemble_v3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3));
+      else
+        SG_CUDA(cudaFuncSetAttribute(k_assemble, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       ProfScope ps(KID_ASSEMBLE, s);
       for (int r0 = 0; r0 < n_rowpts; r0 += max_rows_per_launch) {
         const int nr = std::min(max_rows_per_launch, n_rowpts - r0);
         AsmArgs ac = a;
         ac.i0 = (int)m_begin + r0;
         ac.K = a.K + (int64_t)r0 * N3 * ldk;
-        dim3 grid((unsigned)ceil_div(nJ, TJ), (unsigned)nr, (unsigned)n_chunks);
-        k_assemble<<<grid, 256, smem, s>>>(ac);
+        if (use_v3) {
+          dim3 grid((unsigned)ceil_div(ceil_div(nJ, TJ), tiles_per_cta), (unsigned)nr, (unsigned)n_chunks);
+          k_assemble_v3<<<grid, 256, smem3, s>>>(ac, PG, tiles_per_cta);
+        } else {
+          dim3 grid((unsigned)ceil_div(nJ, TJ), (unsigned)nr, (unsigned)n_chunks);
+          k_assemble<<<grid, 256, smem, s>>>(ac);
+        }
         SG_CUDA(cudaGetLastError());
         count_launch(KID_ASSEMBLE);
       }

@@ -21,12 +21,15 @@
 //            14 GB/s per SM -- measured, profiles/r02_ozaki_bringup.md.)
 //   warp 0   producer: units travel through a ring of 18 slots (216 KB, two and a half k-blocks of all 7
 //            slices) with full/empty mbarriers
-//   warp 1   MMA issuer (one elected lane): per k-block the pairs are issued in groups r = 1, 2, ...
-//            (all pairs with min(p, q) = r), after which slices r and S + 1 - r are dead and their
-//            slots are handed back with tcgen05.commit -- the same order the producer refills them in
-//   warps 2-5 epilogue: the S level accumulators (S x 64 TMEM columns) are read with tcgen05.ld, summed
-//            smallest level first in FP64 registers, scaled by 2^(ea_i + eb_j), transposed through shared
-//            memory and added to C with row-contiguous (coalesced) accesses
+//   warps 1-4 MMA issuers AND epilogue.  Issue: the level accumulators are dealt out to the four warps (levels of one
+//            warp hold 7 of the 28 slice pairs for S = 7: {8}, {7,2}, {6,3}, {5,4}); products into one accumulator
+//            must come from one thread (in-order), different accumulators are independent, so four elected lanes
+//            issue concurrently -- a single issuing thread needed ~110 cycles per tcgen05.mma (descriptor
+//            arithmetic, uniform-register moves) against the 32 the tensor core takes (measured, r02).  Every
+//            warp commits each slot of the k-block once it has issued its products (empty barriers count 4).
+//            Epilogue: the S level accumulators (S x 64 TMEM columns) are read with tcgen05.ld, summed smallest
+//            level first in FP64 registers, scaled by 2^(ea_i + eb_j), transposed through shared memory and added
+//            to C with row-contiguous (coalesced) accesses
 //   raster   CTAs are numbered super-tile by super-tile (8 x 16 tiles = 1024 x 1024 of C, one wave of CTAs), so
 //            the slices a wave reads (2 x 1024 rows) stay L2-resident while they are reused
 //
@@ -139,6 +142,18 @@ __global__ void __launch_bounds__(256) k_ozaki_split_sw(const double* __restrict
 }
 
 // ---------------------------------------------------------------- tcgen05 / TMEM helpers
+// one lane of the (converged) warp; the compiler keeps the elected lane's address arithmetic on the uniform datapath
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "elect.sync _|p, 0xffffffff;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 // arrives (count 1) on an mbarrier once every tcgen05.mma issued so far by this thread has completed
@@ -256,8 +271,34 @@ __device__ __forceinline__ bool oz_tile_of_cta(const OzArgs& p, int64_t cta, int
 // with adds and compares.  (The first version computed `unit % ring` with 64-bit runtime divisions, ~150 cycles
 // each, ~70 per k-block: the issuing thread, not the tensor pipe, set the pace -- 5.4 us per k-block against the
 // 0.9 us the MMAs need; profiles/r02_ozaki_bringup.md.)
+// the tcgen05.mma sequence of issuing warp IW for one k-block: all slice pairs (pa, pb) of its level accumulators
+template <int S, int IW>
+__device__ __forceinline__ void oz_issue_levels(uint32_t tmem, uint64_t desc_hi, const uint32_t (&a_lo)[S],
+                                                const uint32_t (&b_lo)[S], uint32_t idesc, bool first_kb, bool no_mma) {
+#pragma unroll
+  for (int half = 0; half < 2; ++half) {
+    const int level = half == 0 ? S + 1 - IW : IW + 1;
+    if (level < 2 || (half == 1 && level > S - 3)) continue;  // half 1 deals out the levels 2 .. S-3 left over by half 0
+    const uint32_t d_addr = tmem + (uint32_t)(level - 2) * OZ_BN;
+#pragma unroll
+    for (int pa = 1; pa <= S; ++pa) {
+      const int pb = level - pa;
+      if (pb < 1 || pb > S) continue;
+#pragma unroll
+      for (int ks = 0; ks < OZ_BK / OZ_UMMA_K; ++ks) {
+        // advancing along K inside the swizzle row: +32 bytes on the start address (+2 in the >> 4 field)
+        const uint64_t da = desc_hi | (uint64_t)(a_lo[pa - 1] + 2 * ks);
+        const uint64_t db = desc_hi | (uint64_t)(b_lo[pb - 1] + 2 * ks);
+        const uint32_t acc = (pa == 1 && ks == 0 && first_kb) ? 0u : 1u;  // first product into this accumulator
+        if (!no_mma) tc_mma_i8(d_addr, da, db, idesc, acc);
+      }
+    }
+  }
+}
+
+constexpr int OZ_THREADS = 160;  // warp 0: producer; warps 1-4: MMA issue + epilogue
 template <int S>
-__global__ void __launch_bounds__(192, 1) k_ozaki_gemm(const OzArgs p) {
+__global__ void __launch_bounds__(OZ_THREADS, 1) k_ozaki_gemm(const OzArgs p) {
   extern __shared__ unsigned char oz_raw[];
   // 1024-byte alignment for the swizzled tiles
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(oz_raw) + 1023) & ~(uintptr_t)1023);
@@ -272,9 +313,9 @@ __global__ void __launch_bounds__(192, 1) k_ozaki_gemm(const OzArgs p) {
   if (tid == 0) {
     for (int i = 0; i < R; ++i) {
       mbar_init(&tail->full[i], 1);
-      mbar_init(&tail->empty[i], 1);
+      mbar_init(&tail->empty[i], 4);  // one tcgen05.commit per issuing warp
     }
-    mbar_init(&tail->acc_full, 1);
+    mbar_init(&tail->acc_full, 4);
     fence_mbar_init();
   }
   if (warp == 0) {  // one warp allocates the tensor memory (and frees it at the end)
@@ -283,8 +324,8 @@ __global__ void __launch_bounds__(192, 1) k_ozaki_gemm(const OzArgs p) {
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
-  if (tid >= 64 && tid < 64 + OZ_BN) {  // column scales 2^(eb_j) of this tile
-    const int j = tid - 64;
+  if (tid >= 32 && tid < 32 + OZ_BN) {  // column scales 2^(eb_j) of this tile
+    const int j = tid - 32;
     tail->col_scale[j] = (n0 + j < p.n) ? ldexp(1.0, p.eb[n0 + j]) : 0.0;
   }
   tc_fence_before();
@@ -320,16 +361,15 @@ __global__ void __launch_bounds__(192, 1) k_ozaki_gemm(const OzArgs p) {
         b_src += (int64_t)S * b_stride;
       }
     }
-  } else if (warp == 1) {
-    // ===================================================== MMA issuer
-    if (lane == 0) {
+  } else {
+    // ===================================================== warps 1-4: MMA issue, then epilogue
+    {
       constexpr uint32_t IDESC = umma_idesc_s8(OZ_BM, OZ_BN);
-      // descriptor of a tile at shared address 0, K offset 0: everything but the 14-bit start-address field
-      const uint64_t desc_hi = umma_desc_kmajor(0);
-      int base_slot = 0;       // ring slot of position 0 of this k-block
+      const uint64_t desc_hi = umma_desc_kmajor(0);  // everything but the 14-bit start-address field
+      const int iw = warp - 1;                        // issuing warp 0..3
+      int base_slot = 0;        // ring slot of position 0 of this k-block
       uint32_t base_round = 0;  // its round (parity of the full barrier)
       for (int kb = 0; kb < KB; ++kb) {
-        // slots, in position order, of the S units of this k-block; wait for all of them (group r = 1 needs all)
         uint32_t a_lo[S], b_lo[S];  // start-address fields (>> 4) of slice p's A and B tiles, indexed by slice - 1
         int slot_of_pos[S];
 #pragma unroll
@@ -341,50 +381,39 @@ __global__ void __launch_bounds__(192, 1) k_ozaki_gemm(const OzArgs p) {
             ++rd;
           }
           slot_of_pos[idx] = sl;
-          mbar_wait(&tail->full[sl], rd & 1);
+          mbar_wait(&tail->full[sl], rd & 1);  // (whole warp: the elected lane must not run ahead of the data)
           const int slice = (idx & 1) ? S - 1 - (idx >> 1) : (idx >> 1);  // 0-based
           const uint32_t addr = smem_base + (uint32_t)sl * OZ_UNIT_BYTES;
           a_lo[slice] = (addr >> 4) & 0x3FFF;
           b_lo[slice] = ((addr + OZ_A_BYTES) >> 4) & 0x3FFF;
         }
         tc_fence_after();
-#pragma unroll
-        for (int r = 1; 2 * r <= S + 1; ++r) {
-          // pairs with min(pa, pb) = r and pa + pb <= S + 1
-#pragma unroll
-          for (int t = r; t <= S + 1 - r; ++t) {
-#pragma unroll
-            for (int side = 0; side < 2; ++side) {
-              if (side == 1 && t == r) continue;  // (r, r) only once
-              const int pa = side == 0 ? r : t, pb = side == 0 ? t : r;
-              const int level = pa + pb;  // 2 .. S + 1
-              const uint32_t d_addr = tmem + (uint32_t)(level - 2) * OZ_BN;
-              // the first product into a level accumulator (first k-block only) overwrites it
-              const bool first_of_level = (pa == 1 || (pb == 1 && pa == 1));
-#pragma unroll
-              for (int ks = 0; ks < OZ_BK / OZ_UMMA_K; ++ks) {
-                // advancing along K inside the swizzle row: +32 bytes on the start address (+2 in the >> 4 field)
-                const uint64_t da = desc_hi | (uint64_t)(a_lo[pa - 1] + 2 * ks);
-                const uint64_t db = desc_hi | (uint64_t)(b_lo[pb - 1] + 2 * ks);
-                const uint32_t acc = (first_of_level && ks == 0 && kb == 0) ? 0u : 1u;
-                if (!(p.dbg_flags & 2)) tc_mma_i8(d_addr, da, db, IDESC, acc);
-              }
-            }
+        if (elect_one()) {
+          // levels of this warp (compile-time per warp, so that the pair list is straight-line code):
+          //   warp w takes level S + 1 - w and, of the levels 2 .. S - 3 that leaves over, level w + 1
+          //   [S = 7: {8}, {7,2}, {6,3}, {5,4};  S = 4: {5}, {4}, {3}, {2}]
+          const bool first_kb = kb == 0;
+          const bool no_mma = (p.dbg_flags & 2) != 0;
+          switch (iw) {
+            case 0: oz_issue_levels<S, 0>(tmem, desc_hi, a_lo, b_lo, IDESC, first_kb, no_mma); break;
+            case 1: oz_issue_levels<S, 1>(tmem, desc_hi, a_lo, b_lo, IDESC, first_kb, no_mma); break;
+            case 2: oz_issue_levels<S, 2>(tmem, desc_hi, a_lo, b_lo, IDESC, first_kb, no_mma); break;
+            default: oz_issue_levels<S, 3>(tmem, desc_hi, a_lo, b_lo, IDESC, first_kb, no_mma); break;
           }
-          // slices r and S + 1 - r are dead for this k-block: hand their slots back (positions 2(r-1), 2(r-1)+1)
-          tc_commit(&tail->empty[slot_of_pos[2 * (r - 1)]]);
-          if (S + 1 - r != r) tc_commit(&tail->empty[slot_of_pos[2 * (r - 1) + 1]]);
+          // this warp is done with the k-block's units (the slots are refilled once all four warps have committed)
+#pragma unroll
+          for (int idx = 0; idx < S; ++idx) tc_commit(&tail->empty[slot_of_pos[idx]]);
+          if (kb == KB - 1) tc_commit(&tail->acc_full);  // this warp's accumulators are final
         }
+        __syncwarp();
         base_slot += S;
         if (base_slot >= R) {
           base_slot -= R;
           ++base_round;
         }
       }
-      tc_commit(&tail->acc_full);  // every accumulator is final (and every unit has been consumed)
     }
-  } else {
-    // ===================================================== epilogue (warps 2..5 = 128 threads)
+    // ----------------------------------------------------- epilogue (all four warps = 128 threads)
     const int quad = warp & 3;               // TMEM lane quadrant this warp may read
     const int row = quad * 32 + lane;        // row of the tile owned by this thread
     const int64_t gr = m0 + row;
@@ -508,12 +537,12 @@ static int oz_launch(const OzOperand& oa, const OzOperand& ob, int64_t m, int64_
   SG_ARG(blocks < ((int64_t)1 << 31));
   ProfScope ps(KID_GEMM, s);
   switch (S) {
-    case 2: k_ozaki_gemm<2><<<(unsigned)blocks, 192, OZ_SMEM_BYTES, s>>>(a); break;
-    case 3: k_ozaki_gemm<3><<<(unsigned)blocks, 192, OZ_SMEM_BYTES, s>>>(a); break;
-    case 4: k_ozaki_gemm<4><<<(unsigned)blocks, 192, OZ_SMEM_BYTES, s>>>(a); break;
-    case 5: k_ozaki_gemm<5><<<(unsigned)blocks, 192, OZ_SMEM_BYTES, s>>>(a); break;
-    case 6: k_ozaki_gemm<6><<<(unsigned)blocks, 192, OZ_SMEM_BYTES, s>>>(a); break;
-    case 7: k_ozaki_gemm<7><<<(unsigned)blocks, 192, OZ_SMEM_BYTES, s>>>(a); break;
+    case 2: k_ozaki_gemm<2><<<(unsigned)blocks, OZ_THREADS, OZ_SMEM_BYTES, s>>>(a); break;
+    case 3: k_ozaki_gemm<3><<<(unsigned)blocks, OZ_THREADS, OZ_SMEM_BYTES, s>>>(a); break;
+    case 4: k_ozaki_gemm<4><<<(unsigned)blocks, OZ_THREADS, OZ_SMEM_BYTES, s>>>(a); break;
+    case 5: k_ozaki_gemm<5><<<(unsigned)blocks, OZ_THREADS, OZ_SMEM_BYTES, s>>>(a); break;
+    case 6: k_ozaki_gemm<6><<<(unsigned)blocks, OZ_THREADS, OZ_SMEM_BYTES, s>>>(a); break;
+    case 7: k_ozaki_gemm<7><<<(unsigned)blocks, OZ_THREADS, OZ_SMEM_BYTES, s>>>(a); break;
     default: return fail_arg("2 <= n_slices <= 7");
   }
   SG_CUDA(cudaGetLastError());

@@ -1542,10 +1542,11 @@ int sgdml_b200_model_create(sgdml_b200_model** out, int64_t n_atoms, int64_t n_t
 
 namespace {
 
-// SGDML_B200_GRAPH=1 / 0 switches the CUDA-graph replay of small host-buffer batches on / off (default below)
+// SGDML_B200_GRAPH=0 switches the CUDA-graph replay of small host-buffer batches off (measured on B200, B = 1,
+// NumPy in/out: 54 vs 65 us per call at BASELINE config 1, 92 vs 105 us at config 2)
 bool g_graph_enabled() {
   const char* e = getenv("SGDML_B200_GRAPH");
-  return e != nullptr ? (e[0] == '1') : false;
+  return e != nullptr ? (e[0] == '1') : true;
 }
 constexpr int64_t GRAPH_MAX_GEO = 16;  // batches up to this size with host buffers replay a captured graph
 

@@ -537,7 +537,8 @@ def test_potrf_not_positive_definite(eng):
     X = rng.standard_normal((n, n))
     A = X @ X.T + np.eye(n)
     A[170, 170] = -1.0  # leading minor of order 171 fails
-    rc = _lib.lib().sgdml_b200_potrf(_lib.ptr(A.copy()), n, n, None)
+    Af = A.copy()  # (keep a reference: the engine reads the buffer behind the raw pointer)
+    rc = _lib.lib().sgdml_b200_potrf(_lib.ptr(Af), n, n, None)
     assert rc == 171
     with pytest.raises(np.linalg.LinAlgError, match='not positive definite'):
         _lib.check(rc, 'potrf')
@@ -749,3 +750,86 @@ def test_ase_calculator_core_units(eng, golden):
     assert rel_err(res['forces'].ravel(), golden['F_query'][0] * _KCAL_PER_MOL_IN_EV) < 1e-10
     assert rel_err(res['energy'], golden['E_query'][:1] * _KCAL_PER_MOL_IN_EV) < 1e-10
     assert abs(_KCAL_PER_MOL_IN_EV - 0.0433641) < 1e-6
+
+
+# --------------------------------------------------------------------------- assembly kernel v3 (chunked permutations)
+def test_assemble_v3_kernel(eng, golden):
+    """k_assemble_v3 (permutation chunks, delta on the fly, resident row tables) against the reference's K: full
+    matrix (symmetric mode), a column subset, row ranges, and the multi-launch row path."""
+    from sgdml_b200 import _lib
+
+    N, M = int(golden['n_atoms']), golden['R_desc'].shape[0]
+    n = golden['K'].shape[0]
+    t = eng.GDMLTrain()
+    args = (golden['R_desc'], golden['R_d_desc'], golden['tril_perms_lin'], int(golden['sig']))
+    cols = np.unique(np.random.default_rng(11).integers(0, n, size=37))
+    L = _lib.lib()
+    L.sgdml_b200_set_assemble_variant(3)
+    try:
+        K, _ = t._assemble_kernel_mat_device(*args)
+        assert rel_err(K[:, :n].cpu().numpy(), golden['K']) < 1e-12
+        Kc, nc = t._assemble_kernel_mat_device(*args, col_idxs=cols)
+        assert rel_err(Kc[:, :nc].cpu().numpy(), golden['K'][:, cols]) < 1e-12
+        lo, hi = M // 3, 2 * M // 3 + 1
+        Kr, nc = t._assemble_kernel_mat_device(*args, col_idxs=cols, rows=(lo, hi))
+        assert rel_err(Kr[:, :nc].cpu().numpy(), golden['K'][lo * 3 * N : hi * 3 * N][:, cols]) < 1e-12
+        L.sgdml_b200_set_assemble_variant(1002)
+        K2, _ = t._assemble_kernel_mat_device(*args)
+        assert rel_err(K2[:, :n].cpu().numpy(), golden['K']) < 1e-12
+    finally:
+        L.sgdml_b200_set_assemble_variant(1000 + 65535)
+        L.sgdml_b200_set_assemble_variant(2)
+
+
+def test_assemble_v3_many_permutations(eng):
+    """A permutation group too large for one chunk (S = 81, 12 atoms... PG < S) and a mid-sized molecule whose sub-blocks
+    are split over grid.z (N = 36): v3 against the per-permutation kernel."""
+    from sgdml_b200 import _lib, synth
+    from sgdml_b200.desc import Desc, tril_perms_lin
+
+    L = _lib.lib()
+    t = eng.GDMLTrain()
+    for N, M, rot, swap in ((13, 5, 4, 0), (36, 4, 3, 1)):
+        perms = synth.rotor_swap_group(N, rot, swap)
+        R = synth.geometries(N, M, 0).reshape(M, -1)
+        x, g = Desc(N).from_R(R)
+        lin = tril_perms_lin(perms)
+        out = {}
+        for v in (2, 3):
+            L.sgdml_b200_set_assemble_variant(v)
+            try:
+                K, nc = t._assemble_kernel_mat_device(x, g, lin, 25)
+                out[v] = K[:, :nc].cpu().numpy()
+            finally:
+                L.sgdml_b200_set_assemble_variant(2)
+        assert rel_err(out[3], out[2]) < 1e-12
+        assert rel_err(out[3], out[3].T) < 1e-12  # the mirrored blocks
+
+
+# --------------------------------------------------------------------------- (f)3: MD latency path (graph replay)
+def test_small_batch_graph_replay(eng, golden, monkeypatch):
+    """Host-buffer batches of <= 16 geometries replay a captured CUDA graph (csrc/predict.cu predict_graph): same
+    results as plain launches, across batch sizes, repeated calls, new coefficients (set_alphas keeps the graph valid)
+    and with / without the energy output."""
+    from sgdml_b200.desc import Desc
+
+    model = golden_model(golden)
+    N, M = int(golden['n_atoms']), golden['R_train'].shape[0]
+    p = eng.GDMLPredict(model)
+    monkeypatch.setenv('SGDML_B200_GRAPH', '0')
+    ref = {B: p.predict(golden['R_query'][:B]) for B in (1, 3)}
+    monkeypatch.setenv('SGDML_B200_GRAPH', '1')
+    for rep in range(3):  # first call captures, later calls replay
+        for B in (1, 3):
+            E, F = p.predict(golden['R_query'][:B])
+            assert np.array_equal(F, ref[B][1]) and np.array_equal(E, ref[B][0])
+    (F1,) = p.predict(golden['R_query'][:1], return_E=False)
+    assert np.array_equal(F1, ref[1][1])
+    E, F = p.predict(golden['R_query'][1])  # a different geometry through the replayed graph
+    assert rel_err(F[0], golden['F_query'][1]) < 1e-10 and rel_err(E, golden['E_query'][1:2]) < 1e-10
+    # new coefficients through the same handle: the graph reads the updated device arrays
+    _, gd = Desc(N).from_R(golden['R_train'].reshape(M, -1))
+    p.set_R_d_desc(gd)
+    p.set_alphas(2.0 * golden['alphas_F'])
+    E2, F2 = p.predict(golden['R_query'][:1])
+    assert rel_err(F2, 2.0 * golden['F_query'][:1]) < 1e-10

@@ -1,0 +1,14 @@
+#!/bin/bash
+mkdir -p gpurun_out/r02
+O=gpurun_out/r02
+run() { local name=$1 to=$2; shift 2; echo "=== $name" | tee -a $O/call5.log; timeout $to "$@" > $O/$name.log 2>&1; local rc=$?; echo "rc=$rc" | tee -a $O/call5.log; tail -n 8 $O/$name.log | tee -a $O/call5.log; return $rc; }
+run c5_oz_tests 400 python -m pytest tests/test_ozaki.py -x -q
+for dbg in 0 1 3 7; do SGDML_B200_OZAKI_DBG=$dbg timeout 120 python tools/ozaki_probe2.py 2>&1 | tee -a $O/c5_oz_probe2.log; done
+OZ_S=4 timeout 120 python tools/ozaki_probe2.py 2>&1 | tee -a $O/c5_oz_probe2.log
+OZ_S=5 timeout 120 python tools/ozaki_probe2.py 2>&1 | tee -a $O/c5_oz_probe2.log
+SGDML_B200_OZAKI_SLICES=7 run c5_oz_solve_m1000 400 python tools/solve_check.py --workload aspirin
+run c5_gpu_tests 1200 python -m pytest tests -q -m gpu --deselect tests/test_ozaki.py
+run c5_asm 300 python tools/asm_variants.py
+run c5_latency 200 python tools/latency_probe.py
+for s in 0 4 5; do SGDML_B200_OZAKI_PREDICT_SLICES=$s run c5_bench_acala_s$s 400 python bench.py --workload ac-ala3-nhme --steps 3 --warmup 3 --no-cpu-baseline --no-extras; done
+OZ_N=4096 timeout 300 ncu --set full --clock-control none --import-source on -k regex:k_ozaki_gemm -s 3 -c 1 -f -o $O/c5_oz_gemm python tools/ozaki_probe2.py > $O/c5_oz_ncu.log 2>&1
