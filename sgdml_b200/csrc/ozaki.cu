@@ -19,17 +19,14 @@
 //            with two 1-D bulk copies (cp.async.bulk, A 8 KB + B 4 KB) that stream whole DRAM pages.  (The first
 //            version read row-major planes through 3-D tensor maps: 64-byte fragments 1 KB apart, which ran at
 //            14 GB/s per SM -- measured, profiles/r02_ozaki_bringup.md.)
-//   warp 0   producer: units travel through a ring of 18 slots (216 KB, two and a half k-blocks of all 7
-//            slices) with full/empty mbarriers
-//   warps 1-4 MMA issuers AND epilogue.  Issue: the level accumulators are dealt out to the four warps (levels of one
-//            warp hold 7 of the 28 slice pairs for S = 7: {8}, {7,2}, {6,3}, {5,4}); products into one accumulator
-//            must come from one thread (in-order), different accumulators are independent, so four elected lanes
-//            issue concurrently -- a single issuing thread needed ~110 cycles per tcgen05.mma (descriptor
-//            arithmetic, uniform-register moves) against the 32 the tensor core takes (measured, r02).  Every
-//            warp commits each slot of the k-block once it has issued its products (empty barriers count 4).
-//            Epilogue: the S level accumulators (S x 64 TMEM columns) are read with tcgen05.ld, summed smallest
-//            level first in FP64 registers, scaled by 2^(ea_i + eb_j), transposed through shared memory and added
-//            to C with row-contiguous (coalesced) accesses
+//   warp 0   producer: a pipeline stage holds one k-block -- the S slices of A (8 KB each), then the S slices of B
+//            (4 KB each) in slice order -- filled by 2 S bulk copies; 2 stages at S = 7 (168 KB), more for fewer slices
+//   warp 1   MMA issuer (whole warp waits on the stage, one elected lane issues): slice pa of A times up to four
+//            CONSECUTIVE slices of B in one M = 128, N <= 256 instruction -- consecutive B slices are consecutive
+//            levels, whose accumulators are consecutive 64-column blocks of tensor memory (see oz_issue_kblock)
+//   warps 2-5 epilogue: the S level accumulators (S x 64 TMEM columns) are read with tcgen05.ld, summed
+//            smallest level first in FP64 registers, scaled by 2^(ea_i + eb_j), transposed through shared
+//            memory and added to C with row-contiguous (coalesced) accesses
 //   raster   CTAs are numbered super-tile by super-tile (8 x 16 tiles = 1024 x 1024 of C, one wave of CTAs), so
 //            the slices a wave reads (2 x 1024 rows) stay L2-resident while they are reused
 //
@@ -271,38 +268,47 @@ __device__ __forceinline__ bool oz_tile_of_cta(const OzArgs& p, int64_t cta, int
 // with adds and compares.  (The first version computed `unit % ring` with 64-bit runtime divisions, ~150 cycles
 // each, ~70 per k-block: the issuing thread, not the tensor pipe, set the pace -- 5.4 us per k-block against the
 // 0.9 us the MMAs need; profiles/r02_ozaki_bringup.md.)
-// the tcgen05.mma sequence of issuing warp IW for one k-block: all slice pairs (pa, pb) of its level accumulators
-template <int S, int IW>
-__device__ __forceinline__ void oz_issue_levels(uint32_t tmem, uint64_t desc_hi, const uint32_t (&a_lo)[S],
-                                                const uint32_t (&b_lo)[S], uint32_t idesc, bool first_kb, bool no_mma) {
+// The tcgen05.mma sequence of one k-block.  Several level accumulators are updated by ONE instruction: for slice
+// pa of A, the slices pb = q, q+1, ... of B contribute to the CONSECUTIVE levels pa+q, pa+q+1, ..., whose accumulators
+// are consecutive 64-column blocks of tensor memory, and the B tiles of consecutive slices are consecutive in shared
+// memory -- so A_pa x [B_q; B_q+1; B_q+2; B_q+3]^T is a single M = 128, N = 256 product into 256 consecutive columns.
+// That quarters the number of times an A tile is read from shared memory: an N = 64 product reads 6 KB of operands
+// for 32 tensor-core cycles (192 B/cycle, above the 128 B/cycle the shared memory delivers -- measured: 69 cycles
+// per product, r02), an N = 256 one 12 KB for 128 cycles.  All products come from one thread (they overlap in the
+// accumulators they touch), 13 wide instructions x 2 k-halves per k-block for S = 7 instead of 56.
+template <int S>
+__device__ __forceinline__ void oz_issue_kblock(uint32_t tmem, uint64_t desc_hi, uint32_t a0_lo, uint32_t b0_lo,
+                                                bool first_kb, bool no_mma) {
 #pragma unroll
-  for (int half = 0; half < 2; ++half) {
-    const int level = half == 0 ? S + 1 - IW : IW + 1;
-    if (level < 2 || (half == 1 && level > S - 3)) continue;  // half 1 deals out the levels 2 .. S-3 left over by half 0
-    const uint32_t d_addr = tmem + (uint32_t)(level - 2) * OZ_BN;
+  for (int pa = 1; pa <= S; ++pa) {
+    constexpr int GMAX = 4;  // consecutive B slices per instruction (N = 64 * g <= 256)
 #pragma unroll
-    for (int pa = 1; pa <= S; ++pa) {
-      const int pb = level - pa;
-      if (pb < 1 || pb > S) continue;
+    for (int q0 = 1; q0 <= S + 1 - pa; q0 += GMAX) {
+      const int g = (S + 1 - pa - q0 + 1) < GMAX ? (S + 1 - pa - q0 + 1) : GMAX;
+      const uint32_t idesc = umma_idesc_s8(OZ_BM, OZ_BN * g);
+      const uint32_t d_addr = tmem + (uint32_t)(pa + q0 - 2) * OZ_BN;
 #pragma unroll
       for (int ks = 0; ks < OZ_BK / OZ_UMMA_K; ++ks) {
-        // advancing along K inside the swizzle row: +32 bytes on the start address (+2 in the >> 4 field)
-        const uint64_t da = desc_hi | (uint64_t)(a_lo[pa - 1] + 2 * ks);
-        const uint64_t db = desc_hi | (uint64_t)(b_lo[pb - 1] + 2 * ks);
-        const uint32_t acc = (pa == 1 && ks == 0 && first_kb) ? 0u : 1u;  // first product into this accumulator
+        // tiles are 8192 B (A) / 4096 B (B) apart: +512 / +256 in the >> 4 address field; K advance: +2
+        const uint64_t da = desc_hi | (uint64_t)((a0_lo + (uint32_t)(pa - 1) * (OZ_A_BYTES >> 4) + 2 * ks) & 0x3FFF);
+        const uint64_t db = desc_hi | (uint64_t)((b0_lo + (uint32_t)(q0 - 1) * (OZ_B_BYTES >> 4) + 2 * ks) & 0x3FFF);
+        const uint32_t acc = (pa == 1 && ks == 0 && first_kb) ? 0u : 1u;  // slice 1 of A opens every accumulator
         if (!no_mma) tc_mma_i8(d_addr, da, db, idesc, acc);
       }
     }
   }
 }
 
-constexpr int OZ_THREADS = 160;  // warp 0: producer; warps 1-4: MMA issue + epilogue
+constexpr int OZ_THREADS = 192;  // warp 0: producer; warp 1: MMA issuer; warps 2-5: epilogue
 template <int S>
 __global__ void __launch_bounds__(OZ_THREADS, 1) k_ozaki_gemm(const OzArgs p) {
   extern __shared__ unsigned char oz_raw[];
   // 1024-byte alignment for the swizzled tiles
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(oz_raw) + 1023) & ~(uintptr_t)1023);
-  constexpr int R = (2 * S + 4 < OZ_MAX_RING) ? 2 * S + 4 : OZ_MAX_RING;
+  // a pipeline stage holds one k-block: the S slices of A (8 KB each), then the S slices of B (4 KB each) in slice order
+  constexpr int STAGE_BYTES = S * OZ_UNIT_BYTES;
+  constexpr int NST = (OZ_RING_BYTES / STAGE_BYTES) < OZ_MAX_RING ? (OZ_RING_BYTES / STAGE_BYTES) : OZ_MAX_RING;
+  static_assert(NST >= 2, "at least two k-blocks in flight");
   OzSmemTail* tail = reinterpret_cast<OzSmemTail*>(smem + (size_t)OZ_RING_BYTES);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
@@ -311,11 +317,11 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) k_ozaki_gemm(const OzArgs p) {
   const int64_t m0 = tm * OZ_BM, n0 = tn * OZ_BN;
 
   if (tid == 0) {
-    for (int i = 0; i < R; ++i) {
+    for (int i = 0; i < NST; ++i) {
       mbar_init(&tail->full[i], 1);
-      mbar_init(&tail->empty[i], 4);  // one tcgen05.commit per issuing warp
+      mbar_init(&tail->empty[i], 1);
     }
-    mbar_init(&tail->acc_full, 4);
+    mbar_init(&tail->acc_full, 1);
     fence_mbar_init();
   }
   if (warp == 0) {  // one warp allocates the tensor memory (and frees it at the end)
@@ -324,8 +330,8 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) k_ozaki_gemm(const OzArgs p) {
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
-  if (tid >= 32 && tid < 32 + OZ_BN) {  // column scales 2^(eb_j) of this tile
-    const int j = tid - 32;
+  if (tid >= 64 && tid < 64 + OZ_BN) {  // column scales 2^(eb_j) of this tile
+    const int j = tid - 64;
     tail->col_scale[j] = (n0 + j < p.n) ? ldexp(1.0, p.eb[n0 + j]) : 0.0;
   }
   tc_fence_before();
@@ -336,84 +342,53 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) k_ozaki_gemm(const OzArgs p) {
   const uint32_t smem_base = smem_u32(smem);
 
   if (warp == 0) {
-    // ===================================================== producer: two contiguous bulk copies per unit
+    // ===================================================== producer: 2 S contiguous bulk copies per k-block
     if (lane == 0) {
       const int8_t* a_src = p.ua + tm * (int64_t)OZ_A_BYTES;
       const int8_t* b_src = p.ub + (n0 / OZ_BM) * (int64_t)OZ_A_BYTES + (n0 % OZ_BM) * OZ_BK;
       const int64_t a_stride = p.rt_a * (int64_t)OZ_A_BYTES, b_stride = p.rt_b * (int64_t)OZ_A_BYTES;  // per (kb, slice)
-      int slot = 0;
+      int st = 0;
       uint32_t round = 0;
       for (int kb = 0; kb < KB; ++kb) {
+        if (round > 0) mbar_wait(&tail->empty[st], (round - 1) & 1);  // the stage's previous k-block is consumed
+        unsigned char* base = smem + (size_t)st * STAGE_BYTES;
+        mbar_arrive_expect_tx(&tail->full[st], (uint32_t)STAGE_BYTES);
 #pragma unroll
-        for (int idx = 0; idx < S; ++idx) {
-          if (round > 0) mbar_wait(&tail->empty[slot], (round - 1) & 1);  // the slot's previous unit is dead
-          unsigned char* base = smem + (size_t)slot * OZ_UNIT_BYTES;
-          const int sl = (idx & 1) ? S - 1 - (idx >> 1) : (idx >> 1);  // 0-based slice in the order 1, S, 2, S-1, ...
-          mbar_arrive_expect_tx(&tail->full[slot], (uint32_t)OZ_UNIT_BYTES);
-          bulk_g2s(base, a_src + sl * a_stride, OZ_A_BYTES, &tail->full[slot]);
-          bulk_g2s(base + OZ_A_BYTES, b_src + sl * b_stride, OZ_B_BYTES, &tail->full[slot]);
-          if (++slot == R) {
-            slot = 0;
-            ++round;
-          }
+        for (int sl = 0; sl < S; ++sl) {
+          bulk_g2s(base + sl * OZ_A_BYTES, a_src + sl * a_stride, OZ_A_BYTES, &tail->full[st]);
+          bulk_g2s(base + S * OZ_A_BYTES + sl * OZ_B_BYTES, b_src + sl * b_stride, OZ_B_BYTES, &tail->full[st]);
         }
         a_src += (int64_t)S * a_stride;
         b_src += (int64_t)S * b_stride;
+        if (++st == NST) {
+          st = 0;
+          ++round;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================================== MMA issuer (whole warp waits, one elected lane issues)
+    const uint64_t desc_hi = umma_desc_kmajor(0);  // everything but the 14-bit start-address field
+    int st = 0;
+    uint32_t round = 0;
+    for (int kb = 0; kb < KB; ++kb) {
+      mbar_wait(&tail->full[st], round & 1);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t a0 = smem_base + (uint32_t)st * STAGE_BYTES;
+        oz_issue_kblock<S>(tmem, desc_hi, (a0 >> 4) & 0x3FFF, ((a0 + S * OZ_A_BYTES) >> 4) & 0x3FFF, kb == 0,
+                           (p.dbg_flags & 2) != 0);
+        tc_commit(&tail->empty[st]);                    // the stage is free once these products have completed
+        if (kb == KB - 1) tc_commit(&tail->acc_full);  // every accumulator is final
+      }
+      __syncwarp();
+      if (++st == NST) {
+        st = 0;
+        ++round;
       }
     }
   } else {
-    // ===================================================== warps 1-4: MMA issue, then epilogue
-    {
-      constexpr uint32_t IDESC = umma_idesc_s8(OZ_BM, OZ_BN);
-      const uint64_t desc_hi = umma_desc_kmajor(0);  // everything but the 14-bit start-address field
-      const int iw = warp - 1;                        // issuing warp 0..3
-      int base_slot = 0;        // ring slot of position 0 of this k-block
-      uint32_t base_round = 0;  // its round (parity of the full barrier)
-      for (int kb = 0; kb < KB; ++kb) {
-        uint32_t a_lo[S], b_lo[S];  // start-address fields (>> 4) of slice p's A and B tiles, indexed by slice - 1
-        int slot_of_pos[S];
-#pragma unroll
-        for (int idx = 0; idx < S; ++idx) {
-          int sl = base_slot + idx;
-          uint32_t rd = base_round;
-          if (sl >= R) {
-            sl -= R;
-            ++rd;
-          }
-          slot_of_pos[idx] = sl;
-          mbar_wait(&tail->full[sl], rd & 1);  // (whole warp: the elected lane must not run ahead of the data)
-          const int slice = (idx & 1) ? S - 1 - (idx >> 1) : (idx >> 1);  // 0-based
-          const uint32_t addr = smem_base + (uint32_t)sl * OZ_UNIT_BYTES;
-          a_lo[slice] = (addr >> 4) & 0x3FFF;
-          b_lo[slice] = ((addr + OZ_A_BYTES) >> 4) & 0x3FFF;
-        }
-        tc_fence_after();
-        if (elect_one()) {
-          // levels of this warp (compile-time per warp, so that the pair list is straight-line code):
-          //   warp w takes level S + 1 - w and, of the levels 2 .. S - 3 that leaves over, level w + 1
-          //   [S = 7: {8}, {7,2}, {6,3}, {5,4};  S = 4: {5}, {4}, {3}, {2}]
-          const bool first_kb = kb == 0;
-          const bool no_mma = (p.dbg_flags & 2) != 0;
-          switch (iw) {
-            case 0: oz_issue_levels<S, 0>(tmem, desc_hi, a_lo, b_lo, IDESC, first_kb, no_mma); break;
-            case 1: oz_issue_levels<S, 1>(tmem, desc_hi, a_lo, b_lo, IDESC, first_kb, no_mma); break;
-            case 2: oz_issue_levels<S, 2>(tmem, desc_hi, a_lo, b_lo, IDESC, first_kb, no_mma); break;
-            default: oz_issue_levels<S, 3>(tmem, desc_hi, a_lo, b_lo, IDESC, first_kb, no_mma); break;
-          }
-          // this warp is done with the k-block's units (the slots are refilled once all four warps have committed)
-#pragma unroll
-          for (int idx = 0; idx < S; ++idx) tc_commit(&tail->empty[slot_of_pos[idx]]);
-          if (kb == KB - 1) tc_commit(&tail->acc_full);  // this warp's accumulators are final
-        }
-        __syncwarp();
-        base_slot += S;
-        if (base_slot >= R) {
-          base_slot -= R;
-          ++base_round;
-        }
-      }
-    }
-    // ----------------------------------------------------- epilogue (all four warps = 128 threads)
+    // ===================================================== epilogue (warps 2..5 = 128 threads)
     const int quad = warp & 3;               // TMEM lane quadrant this warp may read
     const int row = quad * 32 + lane;        // row of the tile owned by this thread
     const int64_t gr = m0 + row;

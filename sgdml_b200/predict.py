@@ -58,6 +58,13 @@ class GDMLPredict(object):
         self.R_desc = None
         self.R_d_desc = None
 
+        # knobs of the reference's CPU engine that its callers read back (cli.py:1526-1530, predict.py:462-509):
+        # there are no worker processes and no chunking here
+        self.num_workers = 0
+        self.chunk_size = self.n_train
+        self.bulk_mp = False
+        self.use_torch = use_torch
+
         R_desc = np.ascontiguousarray(np.asarray(model['R_desc'], dtype=np.float64).T)  # (M, D); stored (D, M)
         R_d_desc_alpha = np.ascontiguousarray(model['R_d_desc_alpha'], dtype=np.float64)
         import ctypes
@@ -131,6 +138,18 @@ class GDMLPredict(object):
         out = np.empty((self.n_train, self.desc.dim))
         _lib.check(_lib.lib().sgdml_b200_model_get_R_d_desc_alpha(self._handle, _lib.ptr(out)), 'get_R_d_desc_alpha')
         return out
+
+    def _set_num_workers(self, num_workers=None, force_reset=False):
+        """predict.py:603-649 (CPU worker pool): nothing to configure on the engine."""
+        self.num_workers = 0
+
+    def _set_chunk_size(self, chunk_size=None):
+        """predict.py:651-673."""
+        self.chunk_size = self.n_train
+
+    def _set_bulk_mp(self, bulk_mp=False):
+        """predict.py:710-725."""
+        self.bulk_mp = False
 
     # ------------------------------------------------------------------ CPU autotuner stubs
     def prepare_parallel(self, n_bulk=1, n_reps=1, return_is_from_cache=False):
