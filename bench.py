@@ -689,12 +689,43 @@ def measure_workload(args, workload, batch, steps, warmup, world, rank, local_ra
                     'frac': (n**3 / 3.0) / tm['solve_s'] * 1e-12 / fp64_peak,
                     'peak_source': 'live DMMA m8n8k4 probe (sgdml_b200_fp64_peak_tflops); MEASURED_PEAKS.json has no FP64 entry',
                     'algorithmic_flops': n**3 / 3.0,
-                    'trailing_update': os.environ.get('SGDML_B200_OZAKI_SLICES', '0') not in ('', '0') and
-                    'tcgen05 kind::i8 slice products (SGDML_B200_OZAKI_SLICES=%s)' % os.environ.get('SGDML_B200_OZAKI_SLICES') or 'FP64 DMMA',
+                    'trailing_update': 'FP64 DMMA',
                     'note': 'whole solve (potf2 + TRSM strips + trailing updates + 2 triangular solves) over n^3/3; a '
                     'fraction above 1 means the trailing updates ran on the int8 tensor cores (error-free slicing)',
                 },
             }
+            slices_env = os.environ.get('SGDML_B200_OZAKI_SLICES')
+            int8_default = slices_env is None and n >= 16384
+            if int8_default or (slices_env not in (None, '', '0')):
+                train_info['roofline_solve']['trailing_update'] = (
+                    'tcgen05.mma kind::i8 on %s signed 7-bit slices per operand (exact int32 accumulation in tensor memory, '
+                    'FP64 level sums); default for n >= 16384, sgdml_b200_set_solve_slices(0) / SGDML_B200_OZAKI_SLICES=0 = FP64 DMMA'
+                    % (slices_env or '7'))
+                train_info['roofline_solve']['bound'] = 'int8 tensor pipe + shared-memory operand bandwidth (csrc/ozaki.cu); fraction quoted against the FP64 DMMA peak it replaces'
+            if int8_default and not compact:
+                # the same training run with all-FP64 trailing updates, for comparison (and as a second, independent solution)
+                L.sgdml_b200_set_solve_slices(0)
+                try:
+                    torch.cuda.synchronize()
+                    t0 = time.perf_counter()
+                    model_fp64 = trainer.train(task)
+                    torch.cuda.synchronize()
+                    t_fp64 = time.perf_counter() - t0
+                    chk64 = residual_report(model_fp64, task)
+                    a0, a1 = model0['alphas_F'], model_fp64['alphas_F']
+                    train_info['fp64_dmma'] = {
+                        'total_s': t_fp64,
+                        'solve_s': trainer.timings['solve_s'],
+                        'residual_rel': chk64['residual_rel'],
+                        'force_rel_max_train': chk64['force_rel_max_train'],
+                        'solve_tflops': (n**3 / 3.0) / trainer.timings['solve_s'] * 1e-12,
+                        'frac_of_fp64_peak': (n**3 / 3.0) / trainer.timings['solve_s'] * 1e-12 / fp64_peak,
+                        'alphas_rel_diff_int8_vs_fp64': float(np.max(np.abs(a0 - a1)) / np.max(np.abs(a1))),
+                        'what': 'the same GDMLTrain.train with sgdml_b200_set_solve_slices(0): every trailing update on the FP64 DMMA pipe',
+                    }
+                    log('[%s] FP64-DMMA training run: %.3f s (solve %.3f s)' % (workload, t_fp64, trainer.timings['solve_s']))
+                finally:
+                    L.sgdml_b200_set_solve_slices(-1)
             alphas_t[:n] = torch.from_numpy(model0['alphas_F']).cuda()
             alphas_t[n] = float(model0['c'])
             alphas_t[n + 1] = float(model0['std'])

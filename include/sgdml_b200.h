@@ -299,6 +299,13 @@ int sgdml_b200_fp64_peak_tflops(double* tflops);
  * kernels timed inside a long step (clocks settle under the power cap). */
 int sgdml_b200_fp64_peak_tflops_sustained(double seconds, double* tflops);
 
+/* Trailing updates of the Cholesky factorisation: -1 = automatic (default), 0 = FP64 DMMA, 2..7 = that many signed 7-bit
+ * slices per operand on the tcgen05 tensor cores (kind::i8, exact int32 accumulation in tensor memory, summed in FP64;
+ * csrc/ozaki.cu).  Automatic = the environment variable SGDML_B200_OZAKI_SLICES if set, otherwise 7 slices inside
+ * sgdml_b200_solve_analytic for n >= 16384 (BASELINE config 2: residual 3.7e-11, training forces equal to the FP64
+ * factorisation's to 2e-11 relative) and FP64 everywhere else (sgdml_b200_potrf, the Nystroem factor). */
+int sgdml_b200_set_solve_slices(int n_slices);
+
 /* Test / tuning hook: selects the GEMM kernel used by dgemm_nt and potrf's trailing update.
  * 0 = 128x128 DMMA tiles fed by cp.async, 1 = 128x64 DMMA tiles, 2 = scalar FMA reference kernel,
  * 3 = 128x128 DMMA tiles fed by TMA tensor maps (cp.async.bulk.tensor + mbarrier ring; default). */

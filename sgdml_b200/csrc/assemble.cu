@@ -871,7 +871,7 @@ static bool atom_perm_from_desc_perm(const int* dperm, int N, int* P) {
 }
 
 static int g_asm_variant = 0;  // 0: by size; 1: always the large-molecule kernel (tests)
-static int g_asm_kernel = 2;  // small-molecule kernel: 2 = k_assemble (per-permutation phases), 3 = k_assemble_v3 (chunked)
+static int g_asm_kernel = 0;  // small-molecule kernel: 0 = by permutation count (default), 2 = k_assemble (per-permutation phases), 3 = k_assemble_v3 (chunked)
 static int g_asm_max_rowpts = 65535;  // row points per launch of k_assemble (grid.y limit; lowered by tests)
 
 extern "C" int sgdml_b200_set_assemble_variant(int variant) {
@@ -887,6 +887,7 @@ extern "C" int sgdml_b200_set_assemble_variant(int variant) {
   }
   SG_ARG(variant == 0 || variant == 1);
   g_asm_variant = variant;
+  if (variant == 0) g_asm_kernel = 0;  // back to the defaults
   return 0;
 }
 
@@ -1039,7 +1040,10 @@ extern "C" int sgdml_b200_assemble_rows(const double* R_desc, const double* R_d_
       int PG = S;
       while (PG > 1 && asm_v3_smem_bytes(N, S, TJ, PG) > 100 * 1024) PG = (PG + 1) / 2;
       const size_t smem3 = asm_v3_smem_bytes(N, S, TJ, PG);
-      const bool use_v3 = g_asm_kernel == 3 && smem3 <= 220 * 1024 && TJ * PG <= 256;
+      // measured on B200 (tools/asm_variants.py): 35.9 vs 41.3 ms at BASELINE config 2 (S = 6, one chunk); with many
+      // permutations (S = 243, chunks of 8) the chunked kernel is 15 % SLOWER than the per-permutation one, so it is
+      // only used when all permutations fit one chunk -- unless a test forces it (variant 3)
+      const bool use_v3 = smem3 <= 220 * 1024 && TJ * PG <= 256 && (g_asm_kernel == 3 || (g_asm_kernel == 0 && PG == S));
       const int tiles_per_cta = 4;
       if (use_v3)
         SG_CUDA(cudaFuncSetAttribute(k_assemble_v3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3));

@@ -852,7 +852,19 @@ constexpr int NBO_MAX = 1024;
 // GEMMs) then runs concurrently with (b) instead of leaving the GPU to one CTA at a time.
 // Dependencies: inner(ob+1) needs a(ob); a(ob+1) and b(ob+1) need b(ob) (same tiles, += updates);
 // b(ob) reads the -X workspace of block ob, so the workspace is double buffered.
-int potrf_device(double* A, int64_t n, int64_t lda, int* info_host, cudaStream_t s) {
+// Slice count of the lazy trailing updates (csrc/ozaki.cu): -1 = automatic, 0 = FP64 DMMA, 2..7 = int8 slices on the
+// tcgen05 tensor cores.  Automatic: SGDML_B200_OZAKI_SLICES if set; otherwise 7 slices for the analytic solver's
+// factorisation when n >= 16384 (where the trailing updates are > 90 % of the time), FP64 for every other caller
+// (the Nystroem factor's inner matrix tolerates no more than 1e-14 of regularisation, iterative.py:305-307).
+static int g_solve_slices = -1;
+static int resolve_slices(int64_t n, bool analytic_solver) {
+  if (g_solve_slices >= 0) return g_solve_slices;
+  const char* oz = getenv("SGDML_B200_OZAKI_SLICES");
+  if (oz != nullptr) return std::max(0, std::min(7, atoi(oz)));
+  return (analytic_solver && n >= 16384) ? 7 : 0;
+}
+
+int potrf_device(double* A, int64_t n, int64_t lda, int* info_host, cudaStream_t s, bool analytic_solver) {
   int* d_info = nullptr;
   double* W[2] = {nullptr, nullptr};
   cudaStream_t s2 = nullptr;
@@ -864,9 +876,8 @@ int potrf_device(double* A, int64_t n, int64_t lda, int* info_host, cudaStream_t
   // environment switch (SGDML_B200_LOOKAHEAD=1) until the trailing GEMM is made persistent on a subset of SMs.
   const char* la = getenv("SGDML_B200_LOOKAHEAD");
   const bool lookahead = (la && la[0] == '1') && (n > 2 * (int64_t)NBO) && !profiling_enabled();
-  const char* oz = getenv("SGDML_B200_OZAKI_SLICES");  // 0 / unset: FP64 DMMA trailing updates (default)
-  const int oz_slices = (oz != nullptr) ? std::max(0, std::min(7, atoi(oz))) : 0;
-  int8_t* oz_planes = nullptr;  // slice planes of the current outer panel (experimental tcgen05 path)
+  const int oz_slices = resolve_slices(n, analytic_solver);
+  int8_t* oz_planes = nullptr;  // slice planes of the current outer panel (tcgen05 path)
   int* oz_exps = nullptr;
   auto cleanup = [&]() {  // (the device buffers are persistent workspaces: csrc/core.cu ws_get)
     if (s2) cudaStreamDestroy(s2);
@@ -1141,7 +1152,7 @@ int sgdml_b200_solve_analytic(double* Kneg, int64_t n, int64_t lda, double lam, 
   SG_CUDA(cudaGetLastError());
   count_launch(KID_MISC, 2);
   int info = 0;
-  SG_TRY(potrf_device(K, n, lda, &info, s));  // analytic.py:94-96
+  SG_TRY(potrf_device(K, n, lda, &info, s, true));  // analytic.py:94-96
   if (info > 0) {
     char buf[160];
     snprintf(buf, sizeof(buf), "%d-th leading minor of the array is not positive definite", info);
@@ -1259,6 +1270,12 @@ int sgdml_b200_fp64_peak_tflops_sustained(double seconds, double* tflops) {
 }
 
 // test / tuning hook: 0 = 128x128 tiles, 1 = 128x64 tiles, 2 = naive kernel
+int sgdml_b200_set_solve_slices(int n_slices) {
+  SG_ARG(n_slices == -1 || n_slices == 0 || (n_slices >= 2 && n_slices <= 7));
+  g_solve_slices = n_slices;
+  return 0;
+}
+
 int sgdml_b200_set_gemm_variant(int v) {
   g_gemm_variant = v;
   return 0;

@@ -22,7 +22,7 @@ struct GemmArgs {
 
 // device pointers only
 int launch_gemm(const GemmArgs& a, cudaStream_t s);
-int potrf_device(double* A, int64_t n, int64_t lda, int* info_host, cudaStream_t s);
+int potrf_device(double* A, int64_t n, int64_t lda, int* info_host, cudaStream_t s, bool analytic_solver = false);
 int potrs_device(const double* L, int64_t n, int64_t lda, double* B, int64_t nrhs, int64_t ldb, cudaStream_t s);
 int trsm_right_lt_device(const double* L, int64_t m, int64_t ldl, double* X, int64_t n_rows, int64_t ldx,
                          cudaStream_t s);

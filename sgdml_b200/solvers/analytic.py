@@ -76,19 +76,37 @@ class Analytic(object):
                 'solve_analytic',
             )
         except np.linalg.LinAlgError:
-            # analytic.py:101-114: try a solver that makes fewer assumptions (host LU, as the reference)
-            self.log.warning('Cholesky factorisation failed (matrix not positive definite); falling back to LU.')
+            # The factorisation overwrote K: assemble it again.  First retry with all-FP64 trailing updates (the
+            # default for large n runs them through int8 slices on the tcgen05 tensor cores, whose 2e-14 error
+            # could push a borderline matrix over the edge); only then the reference's fallback, a solver that
+            # makes fewer assumptions (host LU, analytic.py:101-114).
             import scipy.linalg
 
+            def reassemble():
+                self.gdml_train._K_buf = None
+                if use_E_cstr:
+                    return self.gdml_train._assemble_kernel_mat_ecstr_device(R_desc, R_d_desc, tril_perms_lin, sig, scale=-1.0)
+                return self.gdml_train._assemble_kernel_mat_device(R_desc, R_d_desc, tril_perms_lin, sig, scale=-1.0)[0]
+
             del K
-            self.gdml_train._K_buf = None  # the factorisation destroyed it; assemble a fresh matrix
-            if use_E_cstr:
-                K = self.gdml_train._assemble_kernel_mat_ecstr_device(R_desc, R_d_desc, tril_perms_lin, sig, scale=-1.0)
-            else:
-                K, n = self.gdml_train._assemble_kernel_mat_device(R_desc, R_d_desc, tril_perms_lin, sig, scale=-1.0)
-            Kh = K[:, :n].cpu().numpy()
-            Kh[np.diag_indices_from(Kh)] += lam
-            alphas = -scipy.linalg.solve(Kh, y, overwrite_a=True, check_finite=False)
+            K = reassemble()
+            L = _lib.lib()
+            L.sgdml_b200_set_solve_slices(0)
+            try:
+                _lib.check(
+                    L.sgdml_b200_solve_analytic(K.data_ptr(), n, K.shape[1], float(lam), _lib.ptr(y), _lib.ptr(alphas), _lib.current_stream()),
+                    'solve_analytic',
+                )
+                self.log.warning('Cholesky factorisation with int8-sliced trailing updates failed; the FP64 factorisation succeeded.')
+            except np.linalg.LinAlgError:
+                self.log.warning('Cholesky factorisation failed (matrix not positive definite); falling back to LU.')
+                del K
+                K = reassemble()
+                Kh = K[:, :n].cpu().numpy()
+                Kh[np.diag_indices_from(Kh)] += lam
+                alphas = -scipy.linalg.solve(Kh, y, overwrite_a=True, check_finite=False)
+            finally:
+                L.sgdml_b200_set_solve_slices(-1)
         ev[2].record()
         torch.cuda.synchronize()
         self.timings = {

@@ -521,12 +521,26 @@ def test_train_analytic_large_outer_block_residual(eng):
     from sgdml_b200 import synth
     from sgdml_b200.diagnostics import residual_report
 
+    from sgdml_b200 import _lib
+
     task = synth.make_config_task('aspirin', n_train=270)
-    model = eng.GDMLTrain().train(task)
-    assert model['solver_name'] == 'analytic'
-    rep = residual_report(model, task)
-    assert rep['residual_rel'] < 1e-10, rep
-    assert rep['force_rel_max_train'] < 1e-4, rep
+    models = {}
+    for slices, tol in ((-1, 1e-9), (0, 1e-12)):  # default (int8-sliced trailing updates at this size) and all-FP64
+        _lib.lib().sgdml_b200_set_solve_slices(slices)
+        try:
+            model = eng.GDMLTrain().train(task)
+        finally:
+            _lib.lib().sgdml_b200_set_solve_slices(-1)
+        assert model['solver_name'] == 'analytic'
+        rep = residual_report(model, task)
+        assert rep['residual_rel'] < tol, rep
+        assert rep['force_rel_max_train'] < 1e-4, rep
+        models[slices] = model
+    # the two factorisations give the same force field far inside the 1e-6 bound of north_star
+    Rq = synth.geometries(21, 32, 1).reshape(32, -1)
+    _, F_a = eng.GDMLPredict(models[-1]).predict(Rq)
+    _, F_b = eng.GDMLPredict(models[0]).predict(Rq)
+    assert rel_err(F_a, F_b) < 1e-8
 
 
 def test_potrf_not_positive_definite(eng):
@@ -778,7 +792,7 @@ def test_assemble_v3_kernel(eng, golden):
         assert rel_err(K2[:, :n].cpu().numpy(), golden['K']) < 1e-12
     finally:
         L.sgdml_b200_set_assemble_variant(1000 + 65535)
-        L.sgdml_b200_set_assemble_variant(2)
+        L.sgdml_b200_set_assemble_variant(0)
 
 
 def test_assemble_v3_many_permutations(eng):
@@ -801,7 +815,7 @@ def test_assemble_v3_many_permutations(eng):
                 K, nc = t._assemble_kernel_mat_device(x, g, lin, 25)
                 out[v] = K[:, :nc].cpu().numpy()
             finally:
-                L.sgdml_b200_set_assemble_variant(2)
+                L.sgdml_b200_set_assemble_variant(0)
         assert rel_err(out[3], out[2]) < 1e-12
         assert rel_err(out[3], out[3].T) < 1e-12  # the mirrored blocks
 

@@ -26,7 +26,7 @@ def run(name, N, M, perms, sig, cols):
         print('%s kernel %d: %.2f ms (%.1f GB written, %.0f GB/s), rel dev vs kernel 2: %.1e' % (
             name, v, e0.elapsed_time(e1), K.shape[0] * nc * 8 / 1e9, K.shape[0] * nc * 8 / 1e6 / e0.elapsed_time(e1), dev), flush=True)
         del K
-    L.sgdml_b200_set_assemble_variant(2)
+    L.sgdml_b200_set_assemble_variant(0)
 perms = synth.rotor_swap_group(21, 1, 1)
 run('aspirin M=1000 S=6 full', 21, 1000, perms, 20, None)
 perms = synth.rotor_swap_group(42, 5, 0)
