@@ -1110,10 +1110,10 @@ def run_engine(args):
 
 
 def ncu_traffic(workload, queries_per_launch):
-    """DRAM bytes per launch of k_predict_main from the committed ncu capture (profiles/r01_traffic.json),
+    """DRAM bytes per launch of k_predict_main from the committed ncu capture (profiles/r02_traffic.json),
     scaled to this run's launch size; None if no capture exists for the workload."""
     try:
-        with open(os.path.join(ROOT, 'profiles', 'r01_traffic.json')) as f:
+        with open(os.path.join(ROOT, 'profiles', 'r02_traffic.json')) as f:
             return float(json.load(f)[workload]['bytes_per_query']) * queries_per_launch
     except Exception:
         return None

@@ -151,6 +151,9 @@ __device__ __forceinline__ bool elect_one() {
       : "=r"(pred));
   return pred != 0;
 }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 // arrives (count 1) on an mbarrier once every tcgen05.mma issued so far by this thread has completed
@@ -229,13 +232,12 @@ struct OzSmemTail {
   uint64_t full[OZ_MAX_RING];
   uint64_t empty[OZ_MAX_RING];
   uint64_t acc_full;
+  uint64_t tmem_empty;
   uint32_t tmem_base;
-  double col_scale[OZ_BN];
 };
 
 constexpr size_t OZ_SMEM_BYTES = (size_t)OZ_RING_BYTES + sizeof(OzSmemTail) + 1024;
 constexpr int OZ_STAGE_LD = 33;  // doubles per row of the epilogue transpose tiles (32 + 1: conflict-free both ways)
-static_assert(4 * 32 * OZ_STAGE_LD * 8 <= OZ_RING_BYTES, "the epilogue stages through the (then idle) ring");
 
 // CTA number -> tile (tm, tn), super-tile by super-tile; false if the CTA has no tile
 __device__ __forceinline__ bool oz_tile_of_cta(const OzArgs& p, int64_t cta, int64_t& tm, int64_t& tn) {
@@ -300,21 +302,27 @@ __device__ __forceinline__ void oz_issue_kblock(uint32_t tmem, uint64_t desc_hi,
 }
 
 constexpr int OZ_THREADS = 192;  // warp 0: producer; warp 1: MMA issuer; warps 2-5: epilogue
+constexpr int OZ_STAGING_BYTES = 4 * 32 * OZ_STAGE_LD * 8;  // the epilogue's transpose tiles (one 32 x 32 per warp)
+
+// PERSISTENT: a CTA walks over the tiles  blockIdx.x, blockIdx.x + gridDim.x, ...  of the super-tile raster (so the
+// CTAs that run at the same time still work on neighbouring tiles).  The producer streams the k-block stages of one
+// tile after the other without a bubble; the issuer starts a tile as soon as the epilogue warps have READ the previous
+// tile's accumulators out of tensor memory (mbarrier `tmem_empty`); the read-modify-write of C -- and tensor-memory
+// allocation, barrier set-up, CTA launch -- overlap the next tile's products.  Measured before (one tile per CTA,
+// 8192^2 x 1024): 32.8 us per tile of which ~6 us set-up / launch and ~2 us the update of C.
 template <int S>
-__global__ void __launch_bounds__(OZ_THREADS, 1) k_ozaki_gemm(const OzArgs p) {
+__global__ void __launch_bounds__(OZ_THREADS, 1) k_ozaki_gemm(const OzArgs p, int64_t n_ids) {
   extern __shared__ unsigned char oz_raw[];
   // 1024-byte alignment for the swizzled tiles
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(oz_raw) + 1023) & ~(uintptr_t)1023);
   // a pipeline stage holds one k-block: the S slices of A (8 KB each), then the S slices of B (4 KB each) in slice order
   constexpr int STAGE_BYTES = S * OZ_UNIT_BYTES;
-  constexpr int NST = (OZ_RING_BYTES / STAGE_BYTES) < OZ_MAX_RING ? (OZ_RING_BYTES / STAGE_BYTES) : OZ_MAX_RING;
+  constexpr int NST_FIT = (OZ_RING_BYTES - OZ_STAGING_BYTES) / STAGE_BYTES;
+  constexpr int NST = NST_FIT < OZ_MAX_RING ? NST_FIT : OZ_MAX_RING;
   static_assert(NST >= 2, "at least two k-blocks in flight");
+  double* staging = reinterpret_cast<double*>(smem + (size_t)NST * STAGE_BYTES);
   OzSmemTail* tail = reinterpret_cast<OzSmemTail*>(smem + (size_t)OZ_RING_BYTES);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-
-  int64_t tm, tn;
-  if (!oz_tile_of_cta(p, (int64_t)blockIdx.x, tm, tn)) return;
-  const int64_t m0 = tm * OZ_BM, n0 = tn * OZ_BN;
 
   if (tid == 0) {
     for (int i = 0; i < NST; ++i) {
@@ -322,6 +330,7 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) k_ozaki_gemm(const OzArgs p) {
       mbar_init(&tail->empty[i], 1);
     }
     mbar_init(&tail->acc_full, 1);
+    mbar_init(&tail->tmem_empty, 4);  // one arrival per epilogue warp
     fence_mbar_init();
   }
   if (warp == 0) {  // one warp allocates the tensor memory (and frees it at the end)
@@ -329,10 +338,6 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) k_ozaki_gemm(const OzArgs p) {
                  "n"(OZ_TMEM_COLS)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-  }
-  if (tid >= 64 && tid < 64 + OZ_BN) {  // column scales 2^(eb_j) of this tile
-    const int j = tid - 64;
-    tail->col_scale[j] = (n0 + j < p.n) ? ldexp(1.0, p.eb[n0 + j]) : 0.0;
   }
   tc_fence_before();
   __syncthreads();
@@ -344,25 +349,30 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) k_ozaki_gemm(const OzArgs p) {
   if (warp == 0) {
     // ===================================================== producer: 2 S contiguous bulk copies per k-block
     if (lane == 0) {
-      const int8_t* a_src = p.ua + tm * (int64_t)OZ_A_BYTES;
-      const int8_t* b_src = p.ub + (n0 / OZ_BM) * (int64_t)OZ_A_BYTES + (n0 % OZ_BM) * OZ_BK;
       const int64_t a_stride = p.rt_a * (int64_t)OZ_A_BYTES, b_stride = p.rt_b * (int64_t)OZ_A_BYTES;  // per (kb, slice)
       int st = 0;
       uint32_t round = 0;
-      for (int kb = 0; kb < KB; ++kb) {
-        if (round > 0) mbar_wait(&tail->empty[st], (round - 1) & 1);  // the stage's previous k-block is consumed
-        unsigned char* base = smem + (size_t)st * STAGE_BYTES;
-        mbar_arrive_expect_tx(&tail->full[st], (uint32_t)STAGE_BYTES);
+      for (int64_t id = blockIdx.x; id < n_ids; id += gridDim.x) {
+        int64_t tm, tn;
+        if (!oz_tile_of_cta(p, id, tm, tn)) continue;
+        const int64_t n0 = tn * OZ_BN;
+        const int8_t* a_src = p.ua + tm * (int64_t)OZ_A_BYTES;
+        const int8_t* b_src = p.ub + (n0 / OZ_BM) * (int64_t)OZ_A_BYTES + (n0 % OZ_BM) * OZ_BK;
+        for (int kb = 0; kb < KB; ++kb) {
+          if (round > 0) mbar_wait(&tail->empty[st], (round - 1) & 1);  // the stage's previous k-block is consumed
+          unsigned char* base = smem + (size_t)st * STAGE_BYTES;
+          mbar_arrive_expect_tx(&tail->full[st], (uint32_t)STAGE_BYTES);
 #pragma unroll
-        for (int sl = 0; sl < S; ++sl) {
-          bulk_g2s(base + sl * OZ_A_BYTES, a_src + sl * a_stride, OZ_A_BYTES, &tail->full[st]);
-          bulk_g2s(base + S * OZ_A_BYTES + sl * OZ_B_BYTES, b_src + sl * b_stride, OZ_B_BYTES, &tail->full[st]);
-        }
-        a_src += (int64_t)S * a_stride;
-        b_src += (int64_t)S * b_stride;
-        if (++st == NST) {
-          st = 0;
-          ++round;
+          for (int sl = 0; sl < S; ++sl) {
+            bulk_g2s(base + sl * OZ_A_BYTES, a_src + sl * a_stride, OZ_A_BYTES, &tail->full[st]);
+            bulk_g2s(base + S * OZ_A_BYTES + sl * OZ_B_BYTES, b_src + sl * b_stride, OZ_B_BYTES, &tail->full[st]);
+          }
+          a_src += (int64_t)S * a_stride;
+          b_src += (int64_t)S * b_stride;
+          if (++st == NST) {
+            st = 0;
+            ++round;
+          }
         }
       }
     }
@@ -370,74 +380,119 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) k_ozaki_gemm(const OzArgs p) {
     // ===================================================== MMA issuer (whole warp waits, one elected lane issues)
     const uint64_t desc_hi = umma_desc_kmajor(0);  // everything but the 14-bit start-address field
     int st = 0;
-    uint32_t round = 0;
-    for (int kb = 0; kb < KB; ++kb) {
-      mbar_wait(&tail->full[st], round & 1);
-      tc_fence_after();
-      if (elect_one()) {
-        const uint32_t a0 = smem_base + (uint32_t)st * STAGE_BYTES;
-        oz_issue_kblock<S>(tmem, desc_hi, (a0 >> 4) & 0x3FFF, ((a0 + S * OZ_A_BYTES) >> 4) & 0x3FFF, kb == 0,
-                           (p.dbg_flags & 2) != 0);
-        tc_commit(&tail->empty[st]);                    // the stage is free once these products have completed
-        if (kb == KB - 1) tc_commit(&tail->acc_full);  // every accumulator is final
+    uint32_t round = 0, tile_it = 0;
+    for (int64_t id = blockIdx.x; id < n_ids; id += gridDim.x) {
+      int64_t tm, tn;
+      if (!oz_tile_of_cta(p, id, tm, tn)) continue;
+      if (tile_it > 0) {  // the previous tile's accumulators have been read out of tensor memory
+        mbar_wait(&tail->tmem_empty, (tile_it - 1) & 1);
+        tc_fence_after();
       }
-      __syncwarp();
-      if (++st == NST) {
-        st = 0;
-        ++round;
+      for (int kb = 0; kb < KB; ++kb) {
+        mbar_wait(&tail->full[st], round & 1);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t a0 = smem_base + (uint32_t)st * STAGE_BYTES;
+          oz_issue_kblock<S>(tmem, desc_hi, (a0 >> 4) & 0x3FFF, ((a0 + S * OZ_A_BYTES) >> 4) & 0x3FFF, kb == 0,
+                             (p.dbg_flags & 2) != 0);
+          tc_commit(&tail->empty[st]);                    // the stage is free once these products have completed
+          if (kb == KB - 1) tc_commit(&tail->acc_full);  // every accumulator of this tile is final
+        }
+        __syncwarp();
+        if (++st == NST) {
+          st = 0;
+          ++round;
+        }
       }
+      ++tile_it;
     }
   } else {
     // ===================================================== epilogue (warps 2..5 = 128 threads)
     const int quad = warp & 3;               // TMEM lane quadrant this warp may read
-    const int row = quad * 32 + lane;        // row of the tile owned by this thread
-    const int64_t gr = m0 + row;
-    mbar_wait(&tail->acc_full, 0);
-    tc_fence_after();
-    const double row_scale = (gr < p.m) ? p.alpha * ldexp(1.0, p.ea[gr]) : 0.0;
-    double* stage = reinterpret_cast<double*>(smem) + (size_t)quad * 32 * OZ_STAGE_LD;  // this warp's 32 x 32 tile
-#pragma unroll 1
-    for (int half = 0; half < OZ_BN / 32; ++half) {
-      // the old values of C for this warp's 32 x 32 sub-tile: 32 independent row-contiguous loads in flight while
-      // the level sums are read from tensor memory
-      const int64_t gc = n0 + half * 32 + lane;
+    const int ew = warp - 2;                 // epilogue warp 0..3 (staging tile)
+    double* stage = staging + (size_t)ew * 32 * OZ_STAGE_LD;  // this warp's 32 x 32 transpose tile
+    uint32_t tile_it = 0;
+    for (int64_t id = blockIdx.x; id < n_ids; id += gridDim.x) {
+      int64_t tm, tn;
+      if (!oz_tile_of_cta(p, id, tm, tn)) continue;
+      const int64_t m0 = tm * OZ_BM, n0 = tn * OZ_BN;
+      const int64_t gr = m0 + quad * 32 + lane;  // row of the tile owned by this thread on the TMEM side
+      const double row_scale = (gr < p.m) ? p.alpha * ldexp(1.0, p.ea[gr]) : 0.0;
+      // column scales 2^(eb_j): lane j holds those of columns j and 32 + j, handed round with shuffles
+      const double cs0 = (n0 + lane < p.n) ? ldexp(1.0, p.eb[n0 + lane]) : 0.0;
+      const double cs1 = (n0 + 32 + lane < p.n) ? ldexp(1.0, p.eb[n0 + 32 + lane]) : 0.0;
       const int rows_here = (int)max((int64_t)0, min((int64_t)32, p.m - (m0 + quad * 32)));
-      const bool col_ok = gc < p.n && !(p.dbg_flags & 1);
-      double* cp = p.C + (m0 + quad * 32) * p.ldc + gc;
+      // the old values of C (first half): 32 independent row-contiguous loads in flight during the wait
       double cold[32];
+      {
+        const int64_t gc = n0 + lane;
+        const bool ok = gc < p.n && !(p.dbg_flags & 1) && !p.overwrite;
+        const double* cp = p.C + (m0 + quad * 32) * p.ldc + gc;
 #pragma unroll
-      for (int r = 0; r < 32; ++r) cold[r] = (col_ok && !p.overwrite && r < rows_here) ? cp[(int64_t)r * p.ldc] : 0.0;
-      double acc[32];
-#pragma unroll
-      for (int j = 0; j < 32; ++j) acc[j] = 0.0;
+        for (int r = 0; r < 32; ++r) cold[r] = (ok && r < rows_here) ? cp[(int64_t)r * p.ldc] : 0.0;
+      }
+      mbar_wait(&tail->acc_full, tile_it & 1);
+      tc_fence_after();
+      double acc1[32];  // second half, kept in registers until the first half has left the staging tile
 #pragma unroll 1
-      for (int level = (p.dbg_flags & 4) ? 2 : S + 1; level >= 2; --level) {  // smallest contributions first
-        int v[32];
-        tmem_ld_32x32(tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)((level - 2) * OZ_BN + half * 32), v);
-        const double w = __longlong_as_double((long long)(1023 - OZ_BITS * level) << 52);  // 2^(-7 level), exact
+      for (int half = 0; half < OZ_BN / 32; ++half) {
+        double acc[32];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) acc[j] = fma((double)v[j], w, acc[j]);
-        if (p.dbg_levels != nullptr && gr < p.m) {
-          for (int j = 0; j < 32; ++j) {
-            const int64_t gcj = n0 + half * 32 + j;
-            if (gcj < p.n) p.dbg_levels[((int64_t)(level - 2) * p.m + gr) * p.n + gcj] = v[j];
+        for (int j = 0; j < 32; ++j) acc[j] = 0.0;
+#pragma unroll 1
+        for (int level = (p.dbg_flags & 4) ? 2 : S + 1; level >= 2; --level) {  // smallest contributions first
+          int v[32];
+          tmem_ld_32x32(tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)((level - 2) * OZ_BN + half * 32), v);
+          const double w = __longlong_as_double((long long)(1023 - OZ_BITS * level) << 52);  // 2^(-7 level), exact
+#pragma unroll
+          for (int j = 0; j < 32; ++j) acc[j] = fma((double)v[j], w, acc[j]);
+          if (p.dbg_levels != nullptr && gr < p.m) {
+            for (int j = 0; j < 32; ++j) {
+              const int64_t gcj = n0 + half * 32 + j;
+              if (gcj < p.n) p.dbg_levels[((int64_t)(level - 2) * p.m + gr) * p.n + gcj] = v[j];
+            }
           }
         }
-      }
-      // transpose through shared memory: thread = row on the TMEM side, lane = column on the global side, so
-      // that every warp-wide access to C covers 256 contiguous bytes of one row
-      __syncwarp();
+        const double cs = half == 0 ? cs0 : cs1;
+        if (half == 0) {
+          __syncwarp();
 #pragma unroll
-      for (int j = 0; j < 32; ++j) stage[lane * OZ_STAGE_LD + j] = acc[j] * row_scale * tail->col_scale[half * 32 + j];
-      __syncwarp();
-      if (col_ok) {
+          for (int j = 0; j < 32; ++j) stage[lane * OZ_STAGE_LD + j] = acc[j] * row_scale * __shfl_sync(0xffffffffu, cs, j);
+        } else {
 #pragma unroll
-        for (int r = 0; r < 32; ++r)
-          if (r < rows_here) cp[(int64_t)r * p.ldc] = cold[r] + stage[r * OZ_STAGE_LD + lane];
+          for (int j = 0; j < 32; ++j) acc1[j] = acc[j] * row_scale * __shfl_sync(0xffffffffu, cs, j);
+        }
       }
+      // tensor memory has been read: the issuer may start the next tile while C is updated
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tail->tmem_empty);
+      // ---- C update, transposed through shared memory: thread = row on the TMEM side, lane = column on the global
+      //      side, so that every warp-wide access to C covers 256 contiguous bytes of one row
+#pragma unroll 1
+      for (int half = 0; half < OZ_BN / 32; ++half) {
+        const int64_t gc = n0 + half * 32 + lane;
+        const bool col_ok = gc < p.n && !(p.dbg_flags & 1);
+        double* cp = p.C + (m0 + quad * 32) * p.ldc + gc;
+        if (half == 1) {
+          const bool ok = col_ok && !p.overwrite;
+#pragma unroll
+          for (int r = 0; r < 32; ++r) cold[r] = (ok && r < rows_here) ? cp[(int64_t)r * p.ldc] : 0.0;
+          __syncwarp();  // every lane has read the first half out of the staging tile
+#pragma unroll
+          for (int j = 0; j < 32; ++j) stage[lane * OZ_STAGE_LD + j] = acc1[j];
+        }
+        __syncwarp();
+        if (col_ok) {
+#pragma unroll
+          for (int r = 0; r < 32; ++r)
+            if (r < rows_here) cp[(int64_t)r * p.ldc] = cold[r] + stage[r * OZ_STAGE_LD + lane];
+        }
+      }
+      ++tile_it;
     }
-    tc_fence_before();
   }
+  tc_fence_before();
   __syncthreads();
   if (warp == 0) {
     tc_fence_after();
@@ -510,14 +565,15 @@ static int oz_launch(const OzOperand& oa, const OzOperand& ob, int64_t m, int64_
   }
   const int64_t blocks = n_super * OZ_GSM * OZ_GSN;
   SG_ARG(blocks < ((int64_t)1 << 31));
+  const unsigned grid = (unsigned)std::min<int64_t>(blocks, (int64_t)num_sms());
   ProfScope ps(KID_GEMM, s);
   switch (S) {
-    case 2: k_ozaki_gemm<2><<<(unsigned)blocks, OZ_THREADS, OZ_SMEM_BYTES, s>>>(a); break;
-    case 3: k_ozaki_gemm<3><<<(unsigned)blocks, OZ_THREADS, OZ_SMEM_BYTES, s>>>(a); break;
-    case 4: k_ozaki_gemm<4><<<(unsigned)blocks, OZ_THREADS, OZ_SMEM_BYTES, s>>>(a); break;
-    case 5: k_ozaki_gemm<5><<<(unsigned)blocks, OZ_THREADS, OZ_SMEM_BYTES, s>>>(a); break;
-    case 6: k_ozaki_gemm<6><<<(unsigned)blocks, OZ_THREADS, OZ_SMEM_BYTES, s>>>(a); break;
-    case 7: k_ozaki_gemm<7><<<(unsigned)blocks, OZ_THREADS, OZ_SMEM_BYTES, s>>>(a); break;
+    case 2: k_ozaki_gemm<2><<<grid, OZ_THREADS, OZ_SMEM_BYTES, s>>>(a, blocks); break;
+    case 3: k_ozaki_gemm<3><<<grid, OZ_THREADS, OZ_SMEM_BYTES, s>>>(a, blocks); break;
+    case 4: k_ozaki_gemm<4><<<grid, OZ_THREADS, OZ_SMEM_BYTES, s>>>(a, blocks); break;
+    case 5: k_ozaki_gemm<5><<<grid, OZ_THREADS, OZ_SMEM_BYTES, s>>>(a, blocks); break;
+    case 6: k_ozaki_gemm<6><<<grid, OZ_THREADS, OZ_SMEM_BYTES, s>>>(a, blocks); break;
+    case 7: k_ozaki_gemm<7><<<grid, OZ_THREADS, OZ_SMEM_BYTES, s>>>(a, blocks); break;
     default: return fail_arg("2 <= n_slices <= 7");
   }
   SG_CUDA(cudaGetLastError());

@@ -270,8 +270,14 @@ def test_assemble_large_kernel_matches_small(eng, golden):
     t = eng.GDMLTrain()
     args = (golden['R_desc'], golden['R_d_desc'], golden['tril_perms_lin'], int(golden['sig']), Desc(N))
     cols = np.unique(np.random.default_rng(1).integers(0, n, size=31))
-    K_small_full = t._assemble_kernel_mat(*args)
-    K_small_cols = t._assemble_kernel_mat(*args, col_idxs=cols)
+    K_default_cols = t._assemble_kernel_mat(*args, col_idxs=cols)  # default small-molecule kernel (k_assemble_v3 here)
+    _lib.lib().sgdml_b200_set_assemble_variant(2)  # the per-permutation kernel whose summation order the large one keeps
+    try:
+        K_small_full = t._assemble_kernel_mat(*args)
+        K_small_cols = t._assemble_kernel_mat(*args, col_idxs=cols)
+    finally:
+        _lib.lib().sgdml_b200_set_assemble_variant(0)
+    assert rel_err(K_default_cols, K_small_cols) < 1e-13
     _lib.lib().sgdml_b200_set_assemble_variant(1)
     try:
         K_full = t._assemble_kernel_mat(*args)
