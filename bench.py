@@ -1085,7 +1085,11 @@ def run_engine(args):
         os.environ.setdefault('NCCL_DEBUG_SUBSYS', 'INIT,ENV')
         os.environ.setdefault('NCCL_DEBUG_FILE', os.path.join(nccl_dir, 'nccl_n%d_r%%h_%%p.log' % world))
         nccl_log = os.environ['NCCL_DEBUG_FILE']
-        dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+        import datetime
+
+        # a mismatched collective must fail in minutes, not in NCCL's default 10 (the slowest legitimate wait is rank > 0
+        # waiting for rank 0's training legs: a few seconds)
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank), timeout=datetime.timedelta(seconds=240))
 
     line = measure_workload(args, args.workload, args.batch, args.steps, args.warmup, world, rank, local_rank)
     default_run = args.workload == 'aspirin' and not args.no_train and args.n_train is None

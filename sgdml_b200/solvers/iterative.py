@@ -153,6 +153,16 @@ class Iterative(object):
         self._use_torch = use_torch
         self.timings = {}
 
+    def _world(self):
+        """(rank, world) this solve is spread over: torch.distributed's, if the trainer was told that EVERY rank runs
+        the training (`GDMLTrain.distributed = True`); (0, 1) otherwise -- e.g. rank 0 training alone while the other
+        ranks wait for the coefficients, in which case no collective may be issued from here."""
+        from .. import dist as sdist
+
+        if not getattr(self.gdml_train, 'distributed', False):
+            return 0, 1
+        return sdist.world_info()
+
     # ------------------------------------------------------------------ preconditioner
     def _cho_factor_stable(self, M, pre_reg=False, eps_mag_max=1):
         """iterative.py:414-471: factorises the (m x m) CUDA tensor M in place, adding more and more
@@ -195,13 +205,10 @@ class Iterative(object):
         X, _, _ = sdist.run_steps_virtual([sdist.nystroem_factor_steps(ops, 0, 1, n_train, dim_i, cols, lam)])[0]
         return X, len(cols)
 
-    @staticmethod
-    def _shard_precon(n_train):
+    def _shard_precon(self, n_train):
         """Row-shard the Nystroem factor over the ranks whenever there are
         several ranks and every rank gets at least one training point."""
-        from .. import dist as sdist
-
-        rank, world = sdist.world_info()
+        rank, world = self._world()
         return world > 1 and n_train >= world
 
     def _init_precon_operator_sharded(self, task, R_desc, R_d_desc, tril_perms_lin, inducing_pts_idxs):
@@ -210,7 +217,7 @@ class Iterative(object):
         all-reduce and one n-vector all-gather per application."""
         from .. import dist as sdist
 
-        rank, world = sdist.world_info()
+        rank, world = self._world()
         lam = float(task['lam'])
         n_train = R_desc.shape[0]
         dim_i = 3 * task['R_train'].shape[1]
@@ -266,7 +273,7 @@ class Iterative(object):
 
         from .. import dist as sdist
 
-        rank, world = sdist.world_info()
+        rank, world = self._world()
         n_train = R_desc.shape[0]
 
         def _K_vec(v):
@@ -294,7 +301,7 @@ class Iterative(object):
 
             if use_E_cstr:
                 raise NotImplementedError('use_E_cstr is supported with the analytic solver only (the reference marks its iterative path unfinished, iterative.py:602)')
-            rank, world = sdist.world_info()
+            rank, world = self._world()
             lev_approx_idxs = self._bcast_idxs(lev_approx_idxs)  # one draw (rank 0's) for the shared factor
             ops = _EngineNystroemOps(self, R_desc, R_d_desc, tril_perms_lin, sig)
             X, lo, hi = sdist.run_steps(
@@ -437,7 +444,7 @@ class Iterative(object):
 
         L = _lib.lib()
         X, m, lo, hi = factor
-        rank, world = sdist.world_info()
+        rank, world = self._world()
         n_train = self.gdml_predict.n_train
         n = n_train * dim_i
         if world == 1:
@@ -491,13 +498,12 @@ class Iterative(object):
         state['x_dev'] = None
         return x, float(resid.value)
 
-    @staticmethod
-    def _bcast_idxs(idxs):
+    def _bcast_idxs(self, idxs):
         """The leverage-score sampling is random (iterative.py:404-409): with several ranks, rank 0's draw is
         broadcast so that every rank builds the same preconditioner."""
         from .. import dist as sdist
 
-        rank, world = sdist.world_info()
+        rank, world = self._world()
         if world == 1:
             return idxs
         import torch

@@ -41,6 +41,12 @@ class GDMLTrain(object):
         self._max_memory = max_memory
         self._max_processes = max_processes
         self._use_torch = use_torch
+        # Set to True when EVERY rank of an initialised torch.distributed job calls train() with the same task: the
+        # ranks then agree on the solver and its memory budget (one all-reduce) and the iterative solver shards its
+        # work over them (row-sharded Nystroem factor and K.v).  False (default): this process
+        # trains alone and issues no collective, whatever torch.distributed's state (e.g. rank 0 of a benchmark
+        # trains while the other ranks wait for the coefficients).
+        self.distributed = False
         # Residency across the tasks of a sigma grid (`sgdml all` retrains the same points for several length scales
         # with ONE GDMLTrain instance, cli.py:802-806, 923-932, 981-1083): descriptors and Jacobians are
         # sigma-independent and stay on the device, the kernel-matrix buffer (31.8 GB at BASELINE config 2) and the
@@ -172,9 +178,10 @@ class GDMLTrain(object):
         max_bytes = free_bytes if self._max_memory is None else min(free_bytes, self._max_memory * 1024**3)
         # several ranks must take the SAME decision (the iterative path issues collectives the analytic one
         # never joins) and derive the same number of inducing points: agree on the smallest budget
-        from . import dist as sdist
+        if self.distributed:
+            from . import dist as sdist
 
-        max_bytes = sdist.all_reduce_min_scalar(max_bytes)
+            max_bytes = sdist.all_reduce_min_scalar(max_bytes)
         use_analytic_solver = est_bytes_analytic < max_bytes
         if use_E_cstr and not use_analytic_solver:
             # the reference's own iterative path is unfinished for energy constraints (iterative.py:602 "TODO: ... this

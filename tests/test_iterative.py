@@ -201,7 +201,9 @@ def _cg_rank(rank, world, port, out_dir):
     perms = synth.rotor_swap_group(N, 1, 1)
     task = synth.make_task(N, M, perms, 20)
     np.random.seed(3 + rank)  # different draws per rank: rank 0's inducing columns must win
-    model = sgdml_b200.GDMLTrain(max_memory=0.01).train(task)
+    trainer = sgdml_b200.GDMLTrain(max_memory=0.01)
+    trainer.distributed = True  # every rank trains: sharded Nystroem factor and K.v, agreed solver choice
+    model = trainer.train(task)
     # prediction with the sum over training points sharded across the ranks + one all-reduce
     from conftest import golden_model
 

@@ -37,6 +37,7 @@ task = synth.make_config_task(a.workload, n_train=a.n_train)
 N = task['R_train'].shape[1]
 np.random.seed(0)
 trainer = sgdml_b200.GDMLTrain(max_memory=a.max_memory)
+trainer.distributed = world > 1  # every rank runs this script: the iterative solver shards over them
 torch.cuda.synchronize()
 t0 = time.perf_counter()
 _n_cb = [0]
