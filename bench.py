@@ -1068,23 +1068,25 @@ def measure_sharded(args, world, rank, local_rank):
 
 
 def run_engine(args):
-    import torch
-    import torch.distributed as dist
-
     world = int(os.environ.get('WORLD_SIZE', '1'))
     rank = int(os.environ.get('RANK', '0'))
     local_rank = int(os.environ.get('LOCAL_RANK', '0'))
-    torch.cuda.set_device(local_rank)
     nccl_log = None
     if world > 1:
         # NCCL's INFO log (rank count, rings/trees, NVLS) goes to a FILE per rank so that stdout stays the single
-        # JSON line and the driver can still verify the communicator (comm_nranks)
+        # JSON line and the driver can still verify the communicator (comm_nranks).  Set BEFORE torch is imported:
+        # NCCL latches its debug settings at its first call.
         nccl_dir = os.path.join(ROOT, 'gpurun_out')
         os.makedirs(nccl_dir, exist_ok=True)
         os.environ.setdefault('NCCL_DEBUG', 'INFO')
         os.environ.setdefault('NCCL_DEBUG_SUBSYS', 'INIT,ENV')
-        os.environ.setdefault('NCCL_DEBUG_FILE', os.path.join(nccl_dir, 'nccl_n%d_r%%h_%%p.log' % world))
+        os.environ.setdefault('NCCL_DEBUG_FILE', os.path.join(nccl_dir, 'nccl_n%d_%%h_%%p.log' % world))
         nccl_log = os.environ['NCCL_DEBUG_FILE']
+    import torch
+    import torch.distributed as dist
+
+    torch.cuda.set_device(local_rank)
+    if world > 1:
         import datetime
 
         # a mismatched collective must fail in minutes, not in NCCL's default 10 (the slowest legitimate wait is rank > 0
