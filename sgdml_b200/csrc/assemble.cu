@@ -101,6 +101,7 @@ __global__ void __launch_bounds__(256, 2) k_assemble(const AsmArgs p) {
   double* n2p = cc + S * TJ * 2;   // TJ*8  per-warp partial sums of squared deltas (each pair twice)
   int* sP = reinterpret_cast<int*>(n2p + TJ * 8);  // S*N
   int* sPi = sP + S * N;                                // S*N
+  int* need = sPi + S * N;                              // TJ*N: column atom b of point t has at least one kept column
 
   load_pair_tables(p.R_d_desc + (int64_t)i * p.D * 3, p.R_desc + (int64_t)i * p.D, N, Gi, Xi, warp, lane, nw);
   for (int t = 0; t < tj; ++t) {
@@ -111,6 +112,12 @@ __global__ void __launch_bounds__(256, 2) k_assemble(const AsmArgs p) {
   for (int idx = tid; idx < S * N; idx += nt) {
     sP[idx] = p.aperm[idx];
     sPi[idx] = p.apinv[idx];
+  }
+  // column subsets (the Nystroem set-up keeps ~10 of a point's 3N columns): the per-permutation vectors v[b] and the
+  // diagonal sums Dg[P^-1 b] are only needed for column atoms b with a kept column
+  for (int idx = tid; idx < tj * N; idx += nt) {
+    const int64_t* dst = p.dest + (int64_t)(jt0 + idx / N) * N3 + 3 * (idx % N);
+    need[idx] = (dst[0] >= 0 || dst[1] >= 0 || dst[2] >= 0) ? 1 : 0;
   }
 
   // this thread's output items: (t, a, b) = column point, row atom, column atom
@@ -197,6 +204,7 @@ __global__ void __launch_bounds__(256, 2) k_assemble(const AsmArgs p) {
           u[t * N3 + 3 * a + 2] = -s2;
         } else if (r < 2 * N) {  // v[b][0..2]
           const int b = r - N;
+          if (!need[t * N + b]) continue;
           const double* gj = Gjt + b * N3;
           const double* dl = Dlt + b * N;
           double s0 = 0.0, s1 = 0.0, s2 = 0.0;
@@ -212,6 +220,7 @@ __global__ void __launch_bounds__(256, 2) k_assemble(const AsmArgs p) {
         } else {  // Dg[a][c][0..2]
           const int ac = r - 2 * N;
           const int a = (int)__umulhi((unsigned)ac, 0x55555556u), c = ac - 3 * a;
+          if (!need[t * N + P[a]]) continue;  // only read for the sub-block (a, b = P a)
           const double* gi = Gi + a * N3 + c;
           const double* gj = Gjt + P[a] * N3;
           double s0 = 0.0, s1 = 0.0, s2 = 0.0;
@@ -328,6 +337,7 @@ __global__ void __launch_bounds__(256, 2) k_assemble_v3(const AsmArgs p, int PG,
   double* cc = n2p + TJ * PG * N;       // TJ*PG*2
   int* sP = reinterpret_cast<int*>(cc + TJ * PG * 2);  // S*N
   int* sPi = sP + S * N;                                    // S*N
+  int* need = sPi + S * N;                                  // TJ*N: column atom b of point t has a kept column
 
   load_pair_tables(p.R_d_desc + (int64_t)i * p.D * 3, p.R_desc + (int64_t)i * p.D, N, Gi, Xi, warp, lane, nw);
   for (int idx = tid; idx < S * N; idx += nt) {
@@ -350,6 +360,10 @@ __global__ void __launch_bounds__(256, 2) k_assemble_v3(const AsmArgs p, int PG,
       const int j = p.jpts[jt0 + t];
       load_pair_tables(p.R_d_desc + (int64_t)j * p.D * 3, p.R_desc + (int64_t)j * p.D, N, Gj + t * NN3, Xj + t * NN, warp,
                        lane, nw);
+    }
+    for (int idx = tid; idx < tj * N; idx += nt) {  // column atoms with at least one kept column (column subsets)
+      const int64_t* dst = p.dest + (int64_t)(jt0 + idx / N) * N3 + 3 * (idx % N);
+      need[idx] = (dst[0] >= 0 || dst[1] >= 0 || dst[2] >= 0) ? 1 : 0;
     }
     // this thread's output items: (t, a, b) = column point, row atom, column atom
     int it_t[ASM_NI], it_a[ASM_NI], it_b[ASM_NI];
@@ -407,12 +421,19 @@ __global__ void __launch_bounds__(256, 2) k_assemble_v3(const AsmArgs p, int PG,
           const double* xj = Xjt + b * N;
           const double* xi = Xi + Pi[b] * N;
           double s0 = 0.0, s1 = 0.0, s2 = 0.0, q2 = 0.0;
-          for (int g = 0; g < N; ++g) {
-            const double d = xi[Pi[g]] - xj[g];
-            q2 = fma(d, d, q2);
-            s0 = fma(gj[g * 3 + 0], d, s0);
-            s1 = fma(gj[g * 3 + 1], d, s1);
-            s2 = fma(gj[g * 3 + 2], d, s2);
+          if (need[t * N + b]) {
+            for (int g = 0; g < N; ++g) {
+              const double d = xi[Pi[g]] - xj[g];
+              q2 = fma(d, d, q2);
+              s0 = fma(gj[g * 3 + 0], d, s0);
+              s1 = fma(gj[g * 3 + 1], d, s1);
+              s2 = fma(gj[g * 3 + 2], d, s2);
+            }
+          } else {  // v[b] is never read: only this row's share of |delta|^2 (same summation order)
+            for (int g = 0; g < N; ++g) {
+              const double d = xi[Pi[g]] - xj[g];
+              q2 = fma(d, d, q2);
+            }
           }
           double* v = vS + slot * N3 + 3 * b;
           v[0] = -s0;
@@ -422,6 +443,7 @@ __global__ void __launch_bounds__(256, 2) k_assemble_v3(const AsmArgs p, int PG,
         } else {  // Dg[a][c][0..2] = sum_g G_i[a][g][c] G_j[Pa][Pg][0..2]
           const int ac = r - 2 * N;
           const int a = (int)__umulhi((unsigned)ac, 0x55555556u), c = ac - 3 * a;
+          if (!need[t * N + P[a]]) continue;  // only read for the sub-block (a, b = P a)
           const double* gi = Gi + a * N3 + c;
           const double* gj = Gjt + P[a] * N3;
           double s0 = 0.0, s1 = 0.0, s2 = 0.0;
@@ -812,14 +834,14 @@ static size_t asm_large_slab_doubles(int N, int S) {
 static size_t asm_v3_smem_bytes(int N, int S, int TJ, int PG) {
   const size_t N3 = 3 * (size_t)N, NN = (size_t)N * N;
   const size_t dbl = NN * 3 + NN + (size_t)TJ * (NN * 3 + NN) + (size_t)TJ * PG * (2 * N3 + 3 * N3 + N + 2);
-  return dbl * 8 + 2 * (size_t)S * N * 4;
+  return dbl * 8 + 2 * (size_t)S * N * 4 + (size_t)TJ * N * 4;
 }
 
 static size_t asm_smem_bytes(int N, int D, int S, int TJ) {
   (void)D;
   const size_t N3 = 3 * (size_t)N, NN = (size_t)N * N;
   size_t dbl = NN * 3 + NN + (size_t)TJ * (NN * 3 + NN + NN + 2 * N3 + 3 * N3) + (size_t)S * TJ * 2 + (size_t)TJ * 8;
-  return dbl * 8 + 2 * (size_t)S * N * 4;
+  return dbl * 8 + 2 * (size_t)S * N * 4 + (size_t)TJ * N * 4;
 }
 
 }  // namespace sgdml

@@ -853,3 +853,24 @@ def test_small_batch_graph_replay(eng, golden, monkeypatch):
     p.set_alphas(2.0 * golden['alphas_F'])
     E2, F2 = p.predict(golden['R_query'][:1])
     assert rel_err(F2, 2.0 * golden['F_query'][:1]) < 1e-10
+
+
+@pytest.mark.parametrize('N,M,rot,swap,sig', [(15, 40, 2, 0, 30), (18, 21, 1, 1, 40), (21, 50, 1, 1, 20), (23, 19, 0, 1, 20)])
+def test_predict_two_group_kernel_variant(eng, N, M, rot, swap, sig):
+    """The two-group ("ping-pong") main kernel (sgdml_b200_set_predict_variant(1); measured slower, off by default) gives
+    the same predictions as the single-group kernel on every split-k configuration (DP = 112, 160, 224, 256)."""
+    from sgdml_b200 import _lib, synth
+
+    perms = synth.rotor_swap_group(N, rot, swap)
+    model, _, _ = _oracle_model(N, M, perms, sig)
+    Rq = synth.geometries(N, 70, 1).reshape(70, -1)
+    p = eng.GDMLPredict(model)
+    E0, F0 = p.predict(Rq)
+    _lib.lib().sgdml_b200_set_predict_variant(1)
+    try:
+        E1, F1 = p.predict(Rq)
+        E1s, F1s = p.predict(Rq[:1])  # small batch: the sweep over the training points split across CTAs
+    finally:
+        _lib.lib().sgdml_b200_set_predict_variant(0)
+    assert rel_err(F1, F0) < 1e-12 and rel_err(E1, E0) < 1e-12
+    assert rel_err(F1s, F0[:1]) < 1e-12

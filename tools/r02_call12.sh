@@ -1,0 +1,7 @@
+#!/bin/bash
+mkdir -p gpurun_out/r02
+O=gpurun_out/r02
+run() { local name=$1 to=$2; shift 2; echo "=== $name" | tee -a $O/call12.log; timeout $to "$@" > $O/$name.log 2>&1; local rc=$?; echo "rc=$rc" | tee -a $O/call12.log; tail -n 6 $O/$name.log | tee -a $O/call12.log; return $rc; }
+run c12_gpu_tests 1500 python -m pytest tests -q -m gpu -x
+run c12_asm 300 python tools/asm_variants.py
+SGDML_B200_OZAKI_PREDICT_SLICES=5 run c12_cg_acala_m1000 900 python tools/cg_probe.py --workload ac-ala3-nhme --n-train 1000 --max-memory 60 --profile
