@@ -35,6 +35,8 @@ struct AsmArgs {
   int N, D, M, S, nJ, TJ;
   int i0;                  // first row point of this call (row-sharded assembly): K row block = i - i0
   unsigned mN, mNN, mPer;  // ceil(2^32 / d) for d = N, N*N, 5N
+  int NK;                  // kept column atoms per column point, at most (N unless a column subset is assembled)
+  unsigned mNK, mNNK;      // ceil(2^32 / d) for d = NK, N*NK
   int sym;                 // full square matrix: compute blocks j >= i only and mirror them (K_ji = K_ij^T)
   double sig, scale;
   double* K;
@@ -102,6 +104,8 @@ __global__ void __launch_bounds__(256, 2) k_assemble(const AsmArgs p) {
   int* sP = reinterpret_cast<int*>(n2p + TJ * 8);  // S*N
   int* sPi = sP + S * N;                                // S*N
   int* need = sPi + S * N;                              // TJ*N: column atom b of point t has at least one kept column
+  int* klist = need + TJ * N;                           // TJ*N: the kept column atoms of point t, compact
+  int* nk = klist + TJ * N;                             // TJ: how many
 
   load_pair_tables(p.R_d_desc + (int64_t)i * p.D * 3, p.R_desc + (int64_t)i * p.D, N, Gi, Xi, warp, lane, nw);
   for (int t = 0; t < tj; ++t) {
@@ -119,30 +123,36 @@ __global__ void __launch_bounds__(256, 2) k_assemble(const AsmArgs p) {
     const int64_t* dst = p.dest + (int64_t)(jt0 + idx / N) * N3 + 3 * (idx % N);
     need[idx] = (dst[0] >= 0 || dst[1] >= 0 || dst[2] >= 0) ? 1 : 0;
   }
+  // compact list of the kept column atoms of every column point: the sub-blocks are dealt out over (row atom, kept
+  // column atom) pairs, so a column subset with few kept atoms per point needs no grid.z split
+  if (tid < tj) {
+    int c = 0;
+    for (int b = 0; b < N; ++b) {
+      const int64_t* dst = p.dest + (int64_t)(jt0 + tid) * N3 + 3 * b;
+      if (dst[0] >= 0 || dst[1] >= 0 || dst[2] >= 0) klist[tid * N + c++] = b;
+    }
+    nk[tid] = c;
+  }
+  __syncthreads();
 
-  // this thread's output items: (t, a, b) = column point, row atom, column atom
+  // this thread's output items: (t, a, b) = column point, row atom, kept column atom
   int it_t[ASM_NI], it_a[ASM_NI], it_b[ASM_NI];
   double acc[ASM_NI][9];
 #pragma unroll
   for (int q = 0; q < ASM_NI; ++q) {
     const int it = (int)blockIdx.z * ASM_NI * nt + tid + q * nt;  // grid.z splits the sub-blocks of large molecules
-    bool ok = it < tj * NN;
-    const int t = ok ? fastdiv(it, p.mNN) : 0;
+    bool ok = it < tj * N * p.NK;
+    const int t = ok ? fastdiv(it, p.mNNK) : 0;
     if (p.sym && jt0 + t < i) ok = false;  // mirrored from block (j, i) instead
-    const int ab = ok ? it - t * NN : 0;
-    it_a[q] = fastdiv(ab, p.mN);
-    it_b[q] = ab - it_a[q] * N;
-    if (ok && !p.sym) {
-      // column subsets (Nystroem set-up): a sub-block none of whose three columns is kept is never stored,
-      // so it is not accumulated either
-      const int64_t* dst = p.dest + (int64_t)(jt0 + t) * N3 + 3 * it_b[q];
-      if (dst[0] < 0 && dst[1] < 0 && dst[2] < 0) ok = false;
-    }
+    const int ak = ok ? it - t * N * p.NK : 0;
+    it_a[q] = fastdiv(ak, p.mNK);
+    const int k = ak - it_a[q] * p.NK;
+    if (k >= nk[t]) ok = false;
+    it_b[q] = ok ? klist[t * N + k] : 0;
     it_t[q] = ok ? t : -1;
 #pragma unroll
     for (int e = 0; e < 9; ++e) acc[q][e] = 0.0;
   }
-  __syncthreads();
 
   const double sig = p.sig;
   const double sig2 = sig * sig;
@@ -338,6 +348,8 @@ __global__ void __launch_bounds__(256, 2) k_assemble_v3(const AsmArgs p, int PG,
   int* sP = reinterpret_cast<int*>(cc + TJ * PG * 2);  // S*N
   int* sPi = sP + S * N;                                    // S*N
   int* need = sPi + S * N;                                  // TJ*N: column atom b of point t has a kept column
+  int* klist = need + TJ * N;                               // TJ*N: the kept column atoms of point t, compact
+  int* nk = klist + TJ * N;                                 // TJ: how many
 
   load_pair_tables(p.R_d_desc + (int64_t)i * p.D * 3, p.R_desc + (int64_t)i * p.D, N, Gi, Xi, warp, lane, nw);
   for (int idx = tid; idx < S * N; idx += nt) {
@@ -365,27 +377,33 @@ __global__ void __launch_bounds__(256, 2) k_assemble_v3(const AsmArgs p, int PG,
       const int64_t* dst = p.dest + (int64_t)(jt0 + idx / N) * N3 + 3 * (idx % N);
       need[idx] = (dst[0] >= 0 || dst[1] >= 0 || dst[2] >= 0) ? 1 : 0;
     }
-    // this thread's output items: (t, a, b) = column point, row atom, column atom
+    if (tid < tj) {  // compact list of the kept column atoms of every column point
+      int c = 0;
+      for (int b = 0; b < N; ++b) {
+        const int64_t* dst = p.dest + (int64_t)(jt0 + tid) * N3 + 3 * b;
+        if (dst[0] >= 0 || dst[1] >= 0 || dst[2] >= 0) klist[tid * N + c++] = b;
+      }
+      nk[tid] = c;
+    }
+    __syncthreads();
+    // this thread's output items: (t, a, b) = column point, row atom, kept column atom
     int it_t[ASM_NI], it_a[ASM_NI], it_b[ASM_NI];
     double acc[ASM_NI][9];
 #pragma unroll
     for (int q = 0; q < ASM_NI; ++q) {
       const int it = (int)blockIdx.z * ASM_NI * nt + tid + q * nt;  // grid.z splits the sub-blocks of large molecules
-      bool ok = it < tj * NN;
-      const int t = ok ? fastdiv(it, p.mNN) : 0;
+      bool ok = it < tj * N * p.NK;
+      const int t = ok ? fastdiv(it, p.mNNK) : 0;
       if (p.sym && jt0 + t < i) ok = false;  // mirrored from block (j, i) instead
-      const int ab = ok ? it - t * NN : 0;
-      it_a[q] = fastdiv(ab, p.mN);
-      it_b[q] = ab - it_a[q] * N;
-      if (ok && !p.sym) {
-        const int64_t* dst = p.dest + (int64_t)(jt0 + t) * N3 + 3 * it_b[q];
-        if (dst[0] < 0 && dst[1] < 0 && dst[2] < 0) ok = false;  // column subset: never stored, never accumulated
-      }
+      const int ak = ok ? it - t * N * p.NK : 0;
+      it_a[q] = fastdiv(ak, p.mNK);
+      const int k = ak - it_a[q] * p.NK;
+      if (k >= nk[t]) ok = false;
+      it_b[q] = ok ? klist[t * N + k] : 0;
       it_t[q] = ok ? t : -1;
 #pragma unroll
       for (int e = 0; e < 9; ++e) acc[q][e] = 0.0;
     }
-    __syncthreads();
 
     for (int p0 = 0; p0 < S; p0 += PG) {
       const int pg = min(PG, S - p0);
@@ -834,14 +852,14 @@ static size_t asm_large_slab_doubles(int N, int S) {
 static size_t asm_v3_smem_bytes(int N, int S, int TJ, int PG) {
   const size_t N3 = 3 * (size_t)N, NN = (size_t)N * N;
   const size_t dbl = NN * 3 + NN + (size_t)TJ * (NN * 3 + NN) + (size_t)TJ * PG * (2 * N3 + 3 * N3 + N + 2);
-  return dbl * 8 + 2 * (size_t)S * N * 4 + (size_t)TJ * N * 4;
+  return dbl * 8 + 2 * (size_t)S * N * 4 + 2 * (size_t)TJ * N * 4 + (size_t)TJ * 4 + 16;
 }
 
 static size_t asm_smem_bytes(int N, int D, int S, int TJ) {
   (void)D;
   const size_t N3 = 3 * (size_t)N, NN = (size_t)N * N;
   size_t dbl = NN * 3 + NN + (size_t)TJ * (NN * 3 + NN + NN + 2 * N3 + 3 * N3) + (size_t)S * TJ * 2 + (size_t)TJ * 8;
-  return dbl * 8 + 2 * (size_t)S * N * 4 + (size_t)TJ * N * 4;
+  return dbl * 8 + 2 * (size_t)S * N * 4 + 2 * (size_t)TJ * N * 4 + (size_t)TJ * 4 + 16;
 }
 
 }  // namespace sgdml
@@ -976,6 +994,17 @@ extern "C" int sgdml_b200_assemble_rows(const double* R_desc, const double* R_d_
     }
   }
   const int nJ = (int)jpts.size();
+  // kept column atoms per column point, at most: the sub-blocks of a block are dealt out over N * NK (row atom, kept
+  // column atom) pairs -- N * N for the full matrix, far fewer for the column subsets of the Nystroem set-up
+  int NK = 1;
+  for (int jt = 0; jt < nJ; ++jt) {
+    int c = 0;
+    for (int b = 0; b < N; ++b) {
+      const int64_t* d3 = &dest[(size_t)jt * N3 + 3 * b];
+      if (d3[0] >= 0 || d3[1] >= 0 || d3[2] >= 0) ++c;
+    }
+    NK = std::max(NK, c);
+  }
 
   // ---- tile size: at most ASM_NI 3x3 sub-blocks per thread, and shared memory small enough for
   //      two co-resident CTAs per SM
@@ -990,7 +1019,7 @@ extern "C" int sgdml_b200_assemble_rows(const double* R_desc, const double* R_d_
     // mid-sized molecule: one column point per CTA, its N*N sub-blocks split over grid.z (the
     // per-permutation vectors are then recomputed by every chunk)
     TJ = 1;
-    n_chunks = (int)(((int64_t)N * N + ASM_NI * 256 - 1) / (ASM_NI * 256));
+    n_chunks = (int)(((int64_t)N * NK + ASM_NI * 256 - 1) / (ASM_NI * 256));
     if (asm_smem_bytes(N, D, S, 1) > 220 * 1024) large = true;  // tables beyond shared memory: k_assemble_large
   }
   if (large) TJ = 1;
@@ -1047,6 +1076,9 @@ extern "C" int sgdml_b200_assemble_rows(const double* R_desc, const double* R_d_
     a.mN = (unsigned)((0x100000000ull + N - 1) / N);
     a.mNN = (unsigned)((0x100000000ull + (uint64_t)N * N - 1) / ((uint64_t)N * N));
     a.mPer = (unsigned)((0x100000000ull + 5 * N - 1) / (5 * N));
+    a.NK = NK;
+    a.mNK = (unsigned)((0x100000000ull + NK - 1) / NK);
+    a.mNNK = (unsigned)((0x100000000ull + (uint64_t)N * NK - 1) / ((uint64_t)N * NK));
     a.sig = sig;
     a.scale = scale;
     a.K = (double*)sK.dev();
