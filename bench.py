@@ -716,6 +716,7 @@ def measure_workload(args, workload, batch, steps, warmup, world, rank, local_ra
                     train_info['fp64_dmma'] = {
                         'total_s': t_fp64,
                         'solve_s': trainer.timings['solve_s'],
+                        'timings': {k: float(v) for k, v in trainer.timings.items()},
                         'residual_rel': chk64['residual_rel'],
                         'force_rel_max_train': chk64['force_rel_max_train'],
                         'solve_tflops': (n**3 / 3.0) / trainer.timings['solve_s'] * 1e-12,

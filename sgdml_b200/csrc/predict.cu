@@ -30,8 +30,15 @@
 namespace sgdml {
 
 // ============================================================== tile configuration
-template <int DP_, int BQ_, int BM_, int W1Q_, int W1M_, int W1K_, int W2Q_, int W2D_, int MINB_ = 1, int W2S_ = 1>
+template <int DP_, int BQ_, int BM_, int W1Q_, int W1M_, int W1K_, int W2Q_, int W2D_, int MINB_ = 1, int W2S_ = 1,
+          int OB_ = 0>
 struct PCfg {
+  // OB = 1 (fused configurations, W1K == 1): C1 / C2 double-buffered over tiles, ONE CTA-wide barrier per tile --
+  // GEMM2 of tile t and GEMM1 + transform of tile t + 1 share a barrier interval, so warps drift apart and the tensor
+  // pipe sees DMMA work from one warp while another runs the Matern transform; the bulk copies of tile t + 1 are issued
+  // right after the barrier of tile t (its stage was last read by GEMM2 of tile t - 1)
+  static constexpr int OB = OB_;
+  static_assert(OB_ == 0 || W1K_ == 1, "one-barrier form needs the transform on the accumulator fragments");
   static constexpr int W2S = W2S_;      // 2: GEMM2 split by operand (warps 0-3: C1*Xc, warps 4-7: C2*JA)
   static constexpr int MINB = MINB_;    // CTAs per SM the kernel is compiled for
   static constexpr int DP = DP_;        // padded descriptor size (multiple of 8)
@@ -48,6 +55,9 @@ struct PCfg {
   static constexpr int TR2 = BQ / (8 * W2Q);
   static constexpr int TD2 = DP / (8 * W2D);
   static constexpr int EPT = BQ * BM / NT;  // epilogue-1 elements per thread
+  // a warp that owns a single 8 x 8 fragment of S1 / S2 runs two interleaved accumulation chains over k (summed in
+  // registers before the transform): four independent DMMAs in flight per warp instead of two
+  static constexpr int KI = (W1K_ == 1 && TR1 * TC1 == 1 && KS1 % 2 == 0) ? 2 : 1;
   static_assert(W1Q * W1M * W1K == 8 && W2Q * W2D * W2S == 8 && (W2S == 1 || W2S == 2), "8 warps");
   static_assert(W2S == 1 || W1K * 2 * BQ_ * (BM_ + 4) >= BQ_ * DP_, "combine scratch must fit in the S/C region");
   static_assert(BQ % (8 * W1Q) == 0 && BM % (8 * W1M) == 0 && (DP / 4) % W1K == 0, "GEMM1 tiling");
@@ -62,7 +72,7 @@ struct PCfg {
   static constexpr int OFF_XJA = OFF_MM + 2 * BM;         // [2][BM]
   static constexpr int OFF_AE = OFF_XJA + 2 * BM;         // [2][BM] energy-constraint coefficients (zeros when unused)
   static constexpr int OFF_P = OFF_AE + 2 * BM;           // [W1K][2][BQ*CS]; set 0 becomes C1/C2
-  static constexpr int OFF_QQ = OFF_P + W1K * 2 * BQ * CS;
+  static constexpr int OFF_QQ = OFF_P + (OB_ ? 2 : 1) * W1K * 2 * BQ * CS;
   static constexpr int OFF_CSUM = OFF_QQ + BQ;
   static constexpr int OFF_E = OFF_CSUM + BQ;
   static constexpr int OFF_BAR = OFF_E + BQ;              // 3 x uint64
@@ -197,7 +207,7 @@ __global__ void __launch_bounds__(256, C::MINB) k_predict_main(const PredictArgs
     bulk_g2s(Qs, p.Qg + r0 * C::DS, C::BQ * C::DS * 8, &bars[2]);
     bulk_g2s(qq, p.qqg + r0, C::BQ * 8, &bars[2]);
     issue_tile(t_begin);
-    if (t_begin + 1 < n_tiles) issue_tile(t_begin + 1);
+    if (!C::OB && t_begin + 1 < n_tiles) issue_tile(t_begin + 1);
   }
   if (tid < C::BQ) {
     csum_s[tid] = 0.0;
@@ -244,6 +254,10 @@ __global__ void __launch_bounds__(256, C::MINB) k_predict_main(const PredictArgs
 
   for (int t = t_begin; t < n_tiles; ++t) {
     const int s = (t - t_begin) & 1;
+    if constexpr (C::OB) {
+      C1s = Ps + s * 2 * C::BQ * C::CS;
+      C2s = C1s + C::BQ * C::CS;
+    }
     const double* Xt = Xs + s * C::BM * C::DS;
     const double* JAt = JAs + s * C::BM * C::DS;
     const double* mmt = mms + s * C::BM;
@@ -264,23 +278,44 @@ __global__ void __launch_bounds__(256, C::MINB) k_predict_main(const PredictArgs
       const double* qa = Qs + (row1 + lr) * C::DS + k1 + lc;
       const double* xb = Xt + (col1 + lr) * C::DS + k1 + lc;
       const double* jb = JAt + (col1 + lr) * C::DS + k1 + lc;
+      if constexpr (C::KI == 2) {
+        // one fragment per warp: even and odd k-steps accumulate into separate registers
+        double b1[2] = {0.0, 0.0}, b2[2] = {0.0, 0.0};
+        if (col1 < mvalid) {  // warp-uniform
 #pragma unroll 2
-      for (int ks = 0; ks < C::KS1; ++ks) {
-        double fa[C::TR1], fx[C::TC1], fj[C::TC1];
-#pragma unroll
-        for (int i = 0; i < C::TR1; ++i) fa[i] = qa[i * 8 * C::DS + ks * 4];
-#pragma unroll
-        for (int j = 0; j < C::TC1; ++j) {
-          fx[j] = xb[j * 8 * C::DS + ks * 4];
-          fj[j] = jb[j * 8 * C::DS + ks * 4];
+          for (int ks = 0; ks < C::KS1; ks += 2) {
+            const double fa0 = qa[ks * 4], fa1 = qa[ks * 4 + 4];
+            const double fx0 = xb[ks * 4], fx1 = xb[ks * 4 + 4];
+            const double fj0 = jb[ks * 4], fj1 = jb[ks * 4 + 4];
+            dmma884(a1[0][0][0], a1[0][0][1], fa0, fx0);
+            dmma884(a2[0][0][0], a2[0][0][1], fa0, fj0);
+            dmma884(b1[0], b1[1], fa1, fx1);
+            dmma884(b2[0], b2[1], fa1, fj1);
+          }
         }
+        a1[0][0][0] += b1[0];
+        a1[0][0][1] += b1[1];
+        a2[0][0][0] += b2[0];
+        a2[0][0][1] += b2[1];
+      } else {
+#pragma unroll 2
+        for (int ks = 0; ks < C::KS1; ++ks) {
+          double fa[C::TR1], fx[C::TC1], fj[C::TC1];
 #pragma unroll
-        for (int j = 0; j < C::TC1; ++j) {
-          if (col1 + j * 8 < mvalid) {  // warp-uniform
+          for (int i = 0; i < C::TR1; ++i) fa[i] = qa[i * 8 * C::DS + ks * 4];
 #pragma unroll
-            for (int i = 0; i < C::TR1; ++i) {
-              dmma884(a1[i][j][0], a1[i][j][1], fa[i], fx[j]);
-              dmma884(a2[i][j][0], a2[i][j][1], fa[i], fj[j]);
+          for (int j = 0; j < C::TC1; ++j) {
+            fx[j] = xb[j * 8 * C::DS + ks * 4];
+            fj[j] = jb[j * 8 * C::DS + ks * 4];
+          }
+#pragma unroll
+          for (int j = 0; j < C::TC1; ++j) {
+            if (col1 + j * 8 < mvalid) {  // warp-uniform
+#pragma unroll
+              for (int i = 0; i < C::TR1; ++i) {
+                dmma884(a1[i][j][0], a1[i][j][1], fa[i], fx[j]);
+                dmma884(a2[i][j][0], a2[i][j][1], fa[i], fj[j]);
+              }
             }
           }
         }
@@ -328,6 +363,9 @@ __global__ void __launch_bounds__(256, C::MINB) k_predict_main(const PredictArgs
       }
     }
     __syncthreads();
+    if constexpr (C::OB) {
+      if (tid == 0 && t + 1 < n_tiles) issue_tile(t + 1);
+    }
 
     if constexpr (C::W1K > 1) {
       // ---------------- split-k: sum the partials, Matern transform in place
@@ -403,8 +441,10 @@ __global__ void __launch_bounds__(256, C::MINB) k_predict_main(const PredictArgs
         }
       }
     }
-    __syncthreads();
-    if (tid == 0 && t + 2 < n_tiles) issue_tile(t + 2);
+    if constexpr (!C::OB) {
+      __syncthreads();
+      if (tid == 0 && t + 2 < n_tiles) issue_tile(t + 2);
+    }
   }
 
   // ---- row sums csum[r] = sum_m c1, E[r] = sum_m a c2
@@ -438,6 +478,7 @@ __global__ void __launch_bounds__(256, C::MINB) k_predict_main(const PredictArgs
     }
   }
   if constexpr (C::W2S == 2) {
+    if constexpr (C::OB) __syncthreads();  // GEMM2 of the last tile still reads C1 / C2
     // the JA group parks its partial sums in the (now free) S/C region
     if (w2s == 1) {
 #pragma unroll
@@ -833,6 +874,66 @@ __global__ void __launch_bounds__(256) k_query_rows(const double* __restrict__ x
   if (lane == 0) qqg[row] = s;
 }
 
+// Small host-buffer batches (the CUDA-graph path): descriptor, its derivative factors and the S query rows of one
+// geometry in ONE launch, one CTA per geometry.  R may live in pinned host memory (read once into shared memory through
+// the unified address space); the arithmetic is that of k_desc_from_R (csrc/desc.cu) followed by k_query_rows.
+__global__ void __launch_bounds__(256) k_desc_query_rows(const double* __restrict__ R, int n_atoms,
+                                                         const int* __restrict__ pinv, const double* __restrict__ mu,
+                                                         int D, int DS, int S, int64_t n_rows, int64_t n_rows_pad,
+                                                         double* __restrict__ gq, double* __restrict__ Qg,
+                                                         double* __restrict__ qqg, const Lattice lat) {
+  extern __shared__ double dq_sm[];  // r: 3N, x: D
+  double* r = dq_sm;
+  double* x = dq_sm + 3 * n_atoms;
+  const int64_t b = blockIdx.x;
+  for (int i = threadIdx.x; i < 3 * n_atoms; i += blockDim.x) r[i] = R[b * 3 * n_atoms + i];
+  __syncthreads();
+  for (int d = threadIdx.x; d < D; d += blockDim.x) {
+    int a, c;
+    pair_from_d(d, a, c);
+    double dx = r[3 * a + 0] - r[3 * c + 0];
+    double dy = r[3 * a + 1] - r[3 * c + 1];
+    double dz = r[3 * a + 2] - r[3 * c + 2];
+    if (lat.on) {
+      const double c0 = rint(lat.inv[0] * dx + lat.inv[1] * dy + lat.inv[2] * dz);
+      const double c1 = rint(lat.inv[3] * dx + lat.inv[4] * dy + lat.inv[5] * dz);
+      const double c2 = rint(lat.inv[6] * dx + lat.inv[7] * dy + lat.inv[8] * dz);
+      dx -= lat.vec[0] * c0 + lat.vec[1] * c1 + lat.vec[2] * c2;
+      dy -= lat.vec[3] * c0 + lat.vec[4] * c1 + lat.vec[5] * c2;
+      dz -= lat.vec[6] * c0 + lat.vec[7] * c1 + lat.vec[8] * c2;
+    }
+    const double dist = sqrt(dx * dx + dy * dy + dz * dz);
+    const double inv3 = 1.0 / (dist * dist * dist);
+    x[d] = 1.0 / dist;
+    double* g = gq + (b * D + d) * 3;
+    g[0] = dx * inv3;
+    g[1] = dy * inv3;
+    g[2] = dz * inv3;
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
+  // rows b*S .. b*S+S-1; the last CTA also clears the padding rows of the last main-kernel tile
+  const int extra = b == (int64_t)gridDim.x - 1 ? (int)(n_rows_pad - n_rows) : 0;
+  for (int pp = warp; pp < S + extra; pp += n_warps) {
+    const int64_t row = b * S + pp;
+    double s = 0.0;
+    if (pp < S) {
+      const int* pi = pinv + pp * D;
+      for (int e = lane; e < DS; e += 32) {
+        double v = 0.0;
+        if (e < D) v = x[pi[e]] - mu[e];
+        Qg[row * DS + e] = v;
+        s = fma(v, v, s);
+      }
+    } else {
+      for (int e = lane; e < DS; e += 32) Qg[row * DS + e] = 0.0;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) qqg[row] = s;
+  }
+}
+
 // ============================================================== large descriptors (D > 256)
 // The accumulator tile G (BQ x DP) of the fused kernel no longer fits the register file, so the
 // same four contractions run as plain DMMA GEMMs (csrc/solve.cu) around two element-wise kernels:
@@ -1093,6 +1194,18 @@ using Cfg112 = PCfg<112, 64, 16, 4, 1, 2, 4, 2>;
 using Cfg160 = PCfg<160, 32, 16, 2, 1, 4, 2, 4>;
 using Cfg224 = PCfg<224, 32, 16, 2, 1, 4, 2, 4>;
 using Cfg256 = PCfg<256, 32, 8, 2, 1, 4, 2, 4>;
+// variant 2: the same tiles without the split over k -- every warp owns whole S1 / S2 fragments, the Matern transform
+// runs on the accumulator registers and one of the three barriers per tile (and the partial-sum round trip through
+// shared memory) goes away; the price is three operand loads per two DMMAs in GEMM1
+using Cfg112f = PCfg<112, 64, 16, 4, 2, 1, 4, 2>;
+using Cfg160f = PCfg<160, 32, 16, 4, 2, 1, 2, 4>;
+using Cfg224f = PCfg<224, 32, 16, 4, 2, 1, 2, 4>;
+// variant 3: variant 2 with one barrier per tile (OB), for every descriptor size up to 224
+using Cfg40o = PCfg<40, 64, 32, 4, 2, 1, 4, 1, 2, 2, 1>;
+using Cfg72o = PCfg<72, 64, 32, 4, 2, 1, 8, 1, 1, 1, 1>;
+using Cfg112o = PCfg<112, 64, 16, 4, 2, 1, 4, 2, 1, 1, 1>;
+using Cfg160o = PCfg<160, 32, 16, 4, 2, 1, 2, 4, 1, 1, 1>;
+using Cfg224o = PCfg<224, 32, 16, 4, 2, 1, 2, 4, 1, 1, 1>;
 
 struct CfgInfo {
   int DP, BQ, BM;
@@ -1139,6 +1252,22 @@ int launch_main(int cfg, const PredictArgs& a, int n_splits, cudaStream_t s) {
       case 3: return launch_main_pp_t<Cfg160>(a, n_splits, s);
       case 4: return launch_main_pp_t<Cfg224>(a, n_splits, s);
       case 5: return launch_main_pp_t<Cfg256>(a, n_splits, s);
+    }
+  }
+  if (g_predict_variant == 2) {
+    switch (cfg) {
+      case 2: return launch_main_t<Cfg112f>(a, n_splits, s);
+      case 3: return launch_main_t<Cfg160f>(a, n_splits, s);
+      case 4: return launch_main_t<Cfg224f>(a, n_splits, s);
+    }
+  }
+  if (g_predict_variant == 3) {
+    switch (cfg) {
+      case 0: return launch_main_t<Cfg40o>(a, n_splits, s);
+      case 1: return launch_main_t<Cfg72o>(a, n_splits, s);
+      case 2: return launch_main_t<Cfg112o>(a, n_splits, s);
+      case 3: return launch_main_t<Cfg160o>(a, n_splits, s);
+      case 4: return launch_main_t<Cfg224o>(a, n_splits, s);
     }
   }
   switch (cfg) {
@@ -1260,13 +1389,14 @@ int64_t chunk_geos(const sgdml_b200_model* m) {
 }
 
 // Runs the predictor on n_geo queries whose descriptors (xq, gq) are on the device.
+// xq == nullptr: the query rows (w.Qg, w.qq) are already in place (k_desc_query_rows)
 int run_queries(sgdml_b200_model* m, int slot, const double* xq, const double* gq, int64_t n_geo, double std,
                 double c, double* E_dev, double* F_dev, cudaStream_t s) {
   sgdml_b200_model::WS& w = m->ws[slot];
   const int64_t n_rows = n_geo * m->S;
   const int64_t n_rows_pad = (n_rows + m->BQ - 1) / m->BQ * m->BQ;
   int n_splits = 1;
-  {
+  if (xq != nullptr) {
     ProfScope ps(KID_PREDICT_AUX, s);
     k_query_rows<<<(unsigned)((n_rows_pad + 7) / 8), 256, 0, s>>>(xq, m->pinv, m->mu, m->D, m->DS, m->S, n_rows,
                                                                  n_rows_pad, w.Qg, w.qq);
@@ -1548,6 +1678,10 @@ bool g_graph_enabled() {
   const char* e = getenv("SGDML_B200_GRAPH");
   return e != nullptr ? (e[0] == '1') : true;
 }
+bool g_graph_zero_copy() {
+  const char* e = getenv("SGDML_B200_GRAPH_ZEROCOPY");
+  return e != nullptr ? (e[0] == '1') : true;
+}
 constexpr int64_t GRAPH_MAX_GEO = 16;  // batches up to this size with host buffers replay a captured graph
 
 void free_graph_slot(sgdml_b200_model::GraphSlot& g) {
@@ -1577,7 +1711,25 @@ int predict_graph(sgdml_b200_model* m, const double* R, int64_t n_geo, double* E
   // work queued on the caller's stream (set_alphas, ...) comes first
   SG_CUDA(cudaEventRecord(m->graph_event, s));
   SG_CUDA(cudaStreamWaitEvent(gs, m->graph_event, 0));
+  // Three kernel nodes and no copy nodes: the first kernel reads the geometries straight from the pinned staging
+  // buffer (unified addressing) and builds descriptors + query rows, the finishing kernel stores E and F straight
+  // into pinned host memory.  SGDML_B200_GRAPH_ZEROCOPY=0: the earlier form (H2D copy, descriptor kernel, query-row
+  // kernel, ..., two D2H copies).
+  const size_t dq_bytes = sizeof(double) * (size_t)(dimi + m->D);
+  const bool zero_copy = g_graph_zero_copy() && dq_bytes <= 200 * 1024;
   auto enqueue = [&](sgdml_b200_model::GraphSlot* q) -> int {
+    if (zero_copy) {
+      const int64_t n_rows = n_geo * m->S;
+      const int64_t n_rows_pad = (n_rows + m->BQ - 1) / m->BQ * m->BQ;
+      if (dq_bytes > 48 * 1024)
+        SG_CUDA(cudaFuncSetAttribute(k_desc_query_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dq_bytes));
+      k_desc_query_rows<<<(unsigned)n_geo, 256, dq_bytes, gs>>>(q->hR, m->N, m->pinv, m->mu, m->D, m->DS, m->S, n_rows,
+                                                               n_rows_pad, w.gq, w.Qg, w.qq, m->lat);
+      SG_CUDA(cudaGetLastError());
+      count_launch(KID_PREDICT_AUX);
+      SG_TRY(run_queries(m, 0, nullptr, w.gq, n_geo, m->std, m->c, with_E ? q->hE : nullptr, q->hF, gs));
+      return 0;
+    }
     SG_CUDA(cudaMemcpyAsync(w.R, q->hR, sizeof(double) * n_geo * dimi, cudaMemcpyHostToDevice, gs));
     SG_TRY(launch_desc_from_R(w.R, n_geo, m->N, w.xq, w.gq, gs, &m->lat));
     SG_TRY(run_queries(m, 0, w.xq, w.gq, n_geo, m->std, m->c, with_E ? w.E : nullptr, w.F, gs));
@@ -1812,7 +1964,7 @@ int sgdml_b200_predict_train(sgdml_b200_model* m, int64_t m_begin, int64_t m_end
 }
 
 int sgdml_b200_set_predict_variant(int variant) {
-  SG_ARG(variant == 0 || variant == 1);
+  SG_ARG(variant >= 0 && variant <= 3);
   g_predict_variant = variant;
   return 0;
 }

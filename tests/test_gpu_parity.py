@@ -827,11 +827,15 @@ def test_assemble_v3_many_permutations(eng):
 
 
 # --------------------------------------------------------------------------- (f)3: MD latency path (graph replay)
-def test_small_batch_graph_replay(eng, golden, monkeypatch):
+@pytest.mark.parametrize('zero_copy', ['1', '0'])
+def test_small_batch_graph_replay(eng, golden, monkeypatch, zero_copy):
     """Host-buffer batches of <= 16 geometries replay a captured CUDA graph (csrc/predict.cu predict_graph): same
     results as plain launches, across batch sizes, repeated calls, new coefficients (set_alphas keeps the graph valid)
-    and with / without the energy output."""
+    and with / without the energy output.  zero_copy: three kernel nodes reading / writing pinned host memory directly
+    (k_desc_query_rows; the default) vs copy nodes around the four kernels of the large-batch path."""
     from sgdml_b200.desc import Desc
+
+    monkeypatch.setenv('SGDML_B200_GRAPH_ZEROCOPY', zero_copy)
 
     model = golden_model(golden)
     N, M = int(golden['n_atoms']), golden['R_train'].shape[0]
@@ -855,18 +859,24 @@ def test_small_batch_graph_replay(eng, golden, monkeypatch):
     assert rel_err(F2, 2.0 * golden['F_query'][:1]) < 1e-10
 
 
-@pytest.mark.parametrize('N,M,rot,swap,sig', [(15, 40, 2, 0, 30), (18, 21, 1, 1, 40), (21, 50, 1, 1, 20), (23, 19, 0, 1, 20)])
-def test_predict_two_group_kernel_variant(eng, N, M, rot, swap, sig):
-    """The two-group ("ping-pong") main kernel (sgdml_b200_set_predict_variant(1); measured slower, off by default) gives
-    the same predictions as the single-group kernel on every split-k configuration (DP = 112, 160, 224, 256)."""
+@pytest.mark.parametrize('variant', [1, 2, 3])
+@pytest.mark.parametrize(
+    'N,M,rot,swap,sig', [(9, 70, 1, 1, 20), (12, 45, 2, 0, 20), (15, 40, 2, 0, 30), (18, 21, 1, 1, 40), (21, 50, 1, 1, 20), (23, 19, 0, 1, 20)]
+)
+def test_predict_main_kernel_variants(eng, N, M, rot, swap, sig, variant):
+    """The alternative main kernels (sgdml_b200_set_predict_variant) give the same predictions as the default one on
+    every tile configuration (DP = 40, 72, 112, 160, 224, 256; a variant without a kernel for a size runs the default):
+    1 = two warp groups half a tile apart ("ping-pong"; measured slower), 2 = no split over k in GEMM1 (transform on
+    the accumulator fragments, two barriers per tile), 3 = 2 with double-buffered C1 / C2 and one barrier per tile."""
     from sgdml_b200 import _lib, synth
 
     perms = synth.rotor_swap_group(N, rot, swap)
     model, _, _ = _oracle_model(N, M, perms, sig)
     Rq = synth.geometries(N, 70, 1).reshape(70, -1)
     p = eng.GDMLPredict(model)
+    _lib.lib().sgdml_b200_set_predict_variant(0)
     E0, F0 = p.predict(Rq)
-    _lib.lib().sgdml_b200_set_predict_variant(1)
+    _lib.lib().sgdml_b200_set_predict_variant(variant)
     try:
         E1, F1 = p.predict(Rq)
         E1s, F1s = p.predict(Rq[:1])  # small batch: the sweep over the training points split across CTAs

@@ -1,5 +1,6 @@
-"""Device-resident throughput of the fused predictor for both main-kernel variants (0 = single group, 1 = two
-ping-pong groups) and B = 1 latency with and without the CUDA-graph replay."""
+"""Device-resident throughput of the fused predictor for the main-kernel variants (0 = default, 2 = no split over k,
+3 = 2 + one barrier per tile; see include/sgdml_b200.h) and B = 1 latency: CUDA-graph replay with zero-copy host
+buffers, graph replay with copy nodes, plain launches."""
 import os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
@@ -17,7 +18,7 @@ for wl, B in (('aspirin', 65536), ('ethanol', 65536)):
     p = sgdml_b200.GDMLPredict(model)
     R = torch.from_numpy(synth.geometries(N, B, 1).reshape(B, -1)).cuda()
     ref = None
-    for variant in (0, 1, 0, 1):
+    for variant in (0, 2, 3, 0, 2, 3):
         L.sgdml_b200_set_predict_variant(variant)
         for _ in range(3): E, F = p.predict(R)
         torch.cuda.synchronize()
@@ -30,12 +31,16 @@ for wl, B in (('aspirin', 65536), ('ethanol', 65536)):
         dev = float((F - ref).abs().max() / ref.abs().max())
         print('%s B=%d variant %d: %.3f ms/call, %.3e pred/s, %.1f TF/s algorithmic (%.2f of %.1f), max rel dev vs variant 0: %.1e' % (
             wl, B, variant, ms, B / ms * 1e3, 9.0 * M * S * D * B / ms * 1e-9, 9.0 * M * S * D * B / ms * 1e-9 / peak.value, peak.value, dev), flush=True)
-    L.sgdml_b200_set_predict_variant(1)
+    L.sgdml_b200_set_predict_variant(0)
     R1 = synth.geometries(N, 1, 1).reshape(1, -1)
-    for env in ('1', '0'):
-        os.environ['SGDML_B200_GRAPH'] = env
-        for _ in range(20): p.predict(R1)
+    for name, env in (('graph replay, zero-copy', {'SGDML_B200_GRAPH': '1', 'SGDML_B200_GRAPH_ZEROCOPY': '1'}),
+                      ('graph replay, copy nodes', {'SGDML_B200_GRAPH': '1', 'SGDML_B200_GRAPH_ZEROCOPY': '0'}),
+                      ('plain launches', {'SGDML_B200_GRAPH': '0'})):
+        os.environ.update(env)
+        p1 = sgdml_b200.GDMLPredict(model)  # a fresh handle: the graph cache is per model
+        for _ in range(20): p1.predict(R1)
         t0 = time.perf_counter()
-        for _ in range(500): p.predict(R1)
-        print('%s B=1 host NumPy in/out, %s: %.1f us per call' % (wl, 'graph replay' if env == '1' else 'plain launches', (time.perf_counter() - t0) / 500 * 1e6), flush=True)
+        for _ in range(1000): p1.predict(R1)
+        print('%s B=1 host NumPy in/out, %s: %.1f us per call' % (wl, name, (time.perf_counter() - t0) / 1000 * 1e6), flush=True)
     os.environ.pop('SGDML_B200_GRAPH', None)
+    os.environ.pop('SGDML_B200_GRAPH_ZEROCOPY', None)
