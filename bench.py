@@ -702,6 +702,15 @@ def measure_workload(args, workload, batch, steps, warmup, world, rank, local_ra
                     'FP64 level sums); default for n >= 16384, sgdml_b200_set_solve_slices(0) / SGDML_B200_OZAKI_SLICES=0 = FP64 DMMA'
                     % (slices_env or '7'))
                 train_info['roofline_solve']['bound'] = 'int8 tensor pipe + shared-memory operand bandwidth (csrc/ozaki.cu); fraction quoted against the FP64 DMMA peak it replaces'
+            if not compact:
+                # the same training run once more (workspaces and the K buffer now exist): shows how much of total_s
+                # above is first-use allocation and how much the run-to-run spread is
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                trainer.train(task)
+                torch.cuda.synchronize()
+                train_info['second_run'] = {'total_s': time.perf_counter() - t0, 'timings': {k: float(v) for k, v in trainer.timings.items()}}
+                log('[%s] second training run: %.3f s (%s)' % (workload, train_info['second_run']['total_s'], trainer.timings))
             if int8_default and not compact:
                 # the same training run with all-FP64 trailing updates, for comparison (and as a second, independent solution)
                 L.sgdml_b200_set_solve_slices(0)

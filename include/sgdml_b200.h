@@ -123,10 +123,11 @@ int sgdml_b200_model_set_alphas(sgdml_b200_model* model, const double* alphas_F,
 int sgdml_b200_predict_train(sgdml_b200_model* model, int64_t m_begin, int64_t m_end, int scaled,
                              double* E, double* F, void* stream);
 
-/* Test / tuning hook: main kernel of the fused predictor (D <= 256).  0 = default; 1 = two warp groups running the
- * sweep half a tile apart (72 < D; measured slower); 2 = no split over k in the first contraction: Matern transform on
- * the accumulator fragments, two CTA-wide barriers per tile instead of three (72 < D <= 224); 3 = 2 with C1 / C2
- * double-buffered and ONE barrier per tile (D <= 224).  A variant without a kernel for a size runs the default. */
+/* Test / tuning hook: main kernel of the fused predictor (D <= 256).  0 = default (the measured-fastest kernel per
+ * descriptor size); 1 = two warp groups running the sweep half a tile apart (72 < D; measured slower); 2 = no split
+ * over k in the first contraction: Matern transform on the accumulator fragments, two CTA-wide barriers per tile
+ * instead of three (72 < D <= 224); 3 = 2 with C1 / C2 double-buffered and ONE barrier per tile (D <= 224); 4 = the
+ * round-1 kernels for every size.  A variant without a kernel for a size runs the round-1 kernel. */
 int sgdml_b200_set_predict_variant(int variant);
 
 /* Shape of a model: n_atoms, n_train, n_perms (any pointer may be NULL). */

@@ -152,7 +152,7 @@ def ptr(x):
     if x is None:
         return None
     if isinstance(x, np.ndarray):
-        if not x.flags['C_CONTIGUOUS']:
+        if not x.flags.c_contiguous:
             raise ValueError('array must be C-contiguous')
         return x.ctypes.data
     # torch tensor
@@ -161,13 +161,30 @@ def ptr(x):
     return x.data_ptr()
 
 
+_stream_state = None  # (cuda available, torch._C._cuda_getCurrentRawStream or None, torch._C._cuda_getDevice or None)
+
+
 def current_stream():
     """cudaStream_t of torch's current stream (so that the engine's kernels are ordered
-    with torch work and visible to torch.cuda.Event timing)."""
+    with torch work and visible to torch.cuda.Event timing).  This sits on the B = 1 latency path (MD): the
+    availability check is cached and the raw-stream accessor is used where torch has it (~0.3 us instead of ~4)."""
+    global _stream_state
+    if _stream_state is None:
+        import torch
+
+        avail = torch.cuda.is_available()
+        _stream_state = (
+            avail,
+            getattr(torch._C, '_cuda_getCurrentRawStream', None) if avail else None,
+            getattr(torch._C, '_cuda_getDevice', None) if avail else None,
+        )
+    avail, raw, dev = _stream_state
+    if not avail:
+        return None
+    if raw is not None and dev is not None:
+        return raw(dev())
     import torch
 
-    if not torch.cuda.is_available():
-        return None
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 

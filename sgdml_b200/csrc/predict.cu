@@ -1243,7 +1243,7 @@ int launch_main_t(const PredictArgs& a, int n_splits, cudaStream_t s) {
   return 0;
 }
 
-int g_predict_variant = 0;  // 1: two-group ping-pong kernel for the split-k configurations, 0: single-group kernel
+int g_predict_variant = 0;  // see sgdml_b200_set_predict_variant (include/sgdml_b200.h)
 
 int launch_main(int cfg, const PredictArgs& a, int n_splits, cudaStream_t s) {
   if (g_predict_variant == 1) {
@@ -1270,7 +1270,12 @@ int launch_main(int cfg, const PredictArgs& a, int n_splits, cudaStream_t s) {
       case 4: return launch_main_t<Cfg224o>(a, n_splits, s);
     }
   }
-  switch (cfg) {
+  if (g_predict_variant == 0) {  // default: the measured-fastest kernel per size (tools/predict_variants.py)
+    switch (cfg) {
+      case 4: return launch_main_t<Cfg224o>(a, n_splits, s);
+    }
+  }
+  switch (cfg) {  // (variant 4: the round-1 kernels for every size)
     case 0: return launch_main_t<Cfg40>(a, n_splits, s);
     case 1: return launch_main_t<Cfg72>(a, n_splits, s);
     case 2: return launch_main_t<Cfg112>(a, n_splits, s);
@@ -1964,7 +1969,7 @@ int sgdml_b200_predict_train(sgdml_b200_model* m, int64_t m_begin, int64_t m_end
 }
 
 int sgdml_b200_set_predict_variant(int variant) {
-  SG_ARG(variant >= 0 && variant <= 3);
+  SG_ARG(variant >= 0 && variant <= 4);
   g_predict_variant = variant;
   return 0;
 }

@@ -224,7 +224,8 @@ class GDMLPredict(object):
                 E = torch.empty((n,), dtype=torch.float64, device=R.device, pin_memory=pin) if return_E else None
         if not return_E:
             E = None  # the engine skips the energy output entirely
-        self._check_out(R, E, F, n, dim_i)
+        if out is not None:  # (buffers allocated above are right by construction)
+            self._check_out(R, E, F, n, dim_i)
         _lib.check(
             L.sgdml_b200_predict(self._handle, _lib.ptr(R), n, _lib.ptr(E), _lib.ptr(F), _lib.current_stream()),
             'predict',
