@@ -170,8 +170,9 @@ int sgdml_b200_assemble_ecstr(const double* R_desc, const double* R_d_desc, cons
                               int64_t ldk, void* stream);
 
 /* Tuning / test hook: 0 = kernel chosen by molecule size (default), 1 = always the large-molecule
- * kernel (tables in global memory), which molecules above ~50 atoms need; 2 / 3 = small-molecule kernel with
- * per-permutation phases (k_assemble) / with permutation chunks and resident row tables (k_assemble_v3);
+ * kernel (tables in global memory), which molecules above ~50 atoms need; 2 / 3 / 4 = small-molecule kernel with
+ * per-permutation phases (k_assemble) / with permutation chunks and resident row tables (k_assemble_v3) / chunks of
+ * up to 16 permutations with byte permutation tables and per-kind phases over the kept column atoms (k_assemble_v4);
  * 1000 + r = at most r row
  * points per launch of the small-molecule kernel (default 65535, the grid limit; tests lower it to
  * cover the multi-launch path that row ranges above 65535 training points take). */

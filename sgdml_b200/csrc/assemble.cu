@@ -566,6 +566,284 @@ __global__ void __launch_bounds__(256, 2) k_assemble_v3(const AsmArgs p, int PG,
 }
 
 // ---------------------------------------------------------------------------------------------
+// k_assemble_v4: the chunked kernel for MANY permutations and column subsets (BASELINE config 3: N = 42, S = 243, the
+// Nystroem set-up keeps ~9 of a point's 126 columns).  Against k_assemble_v3:
+//  * the atom-permutation tables are bytes (20 KB instead of 82 KB at S = 243, N = 42), which leaves room for chunks of
+//    up to 16 permutations next to the four pair tables of a 42-atom block;
+//  * the pair tables have ODD row strides (3N | 1, N | 1 doubles): threads of a warp work on different table rows, and
+//    with N = 42 the even strides of v3 put every fourth row on the same banks;
+//  * phase A is enumerated TYPE-major over the chunk -- all u rows, then the v rows, then the Dg rows -- so a warp runs
+//    one kind of row task (v3 interleaves the three kinds per permutation: divergent warps), and v / Dg rows exist only
+//    for column atoms with a kept column (compact list); |delta|^2 comes out of the u rows, which are always needed.
+// Phase B (3x3 sub-blocks in registers) is that of v3.
+__device__ void load_pair_tables_strided(const double* __restrict__ g, const double* __restrict__ x, int N, int gs, int xs,
+                                         double* __restrict__ G, double* __restrict__ X, int warp, int lane, int nw) {
+  for (int a = warp; a < N; a += nw)
+    for (int b = lane; b < N; b += 32) {
+      double v0 = 0.0, v1 = 0.0, v2 = 0.0, xv = 0.0;
+      if (a != b) {
+        const int hi = a > b ? a : b, lo = a > b ? b : a;
+        const int d = pair_index(hi, lo);
+        const double sgn = a > b ? 1.0 : -1.0;
+        v0 = sgn * g[d * 3 + 0];
+        v1 = sgn * g[d * 3 + 1];
+        v2 = sgn * g[d * 3 + 2];
+        xv = x[d];
+      }
+      G[a * gs + b * 3 + 0] = v0;
+      G[a * gs + b * 3 + 1] = v1;
+      G[a * gs + b * 3 + 2] = v2;
+      X[a * xs + b] = xv;
+    }
+}
+
+__global__ void __launch_bounds__(256, 2) k_assemble_v4(const AsmArgs p, int PG, int tiles_per_cta) {
+  extern __shared__ __align__(16) double sm[];
+  const int N = p.N, S = p.S, TJ = p.TJ, NK = p.NK;
+  const int N3 = 3 * N;
+  const int GS = N3 | 1, XS = N | 1;  // odd row strides of the pair tables
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const int warp = tid >> 5, lane = tid & 31, nw = nt >> 5;
+  const int i = p.i0 + blockIdx.y;
+
+  double* Gi = sm;                        // N*GS
+  double* Xi = Gi + N * GS;               // N*XS
+  double* Gj = Xi + N * XS;               // TJ*N*GS
+  double* Xj = Gj + TJ * N * GS;          // TJ*N*XS
+  double* uS = Xj + TJ * N * XS;          // TJ*PG*N3
+  double* vS = uS + TJ * PG * N3;         // TJ*PG*N3   (rows of kept column atoms only)
+  double* DgS = vS + TJ * PG * N3;        // TJ*PG*3*N3 (rows a = P^-1 b of kept column atoms b only)
+  double* n2p = DgS + TJ * PG * 3 * N3;   // TJ*PG*N    per-u-row sums of squared deltas (each pair twice)
+  double* cc = n2p + TJ * PG * N;         // TJ*PG*2
+  int* klist = reinterpret_cast<int*>(cc + TJ * PG * 2);  // TJ*N: the kept column atoms of point t, compact
+  int* nk = klist + TJ * N;                                    // TJ: how many
+  unsigned char* sP = reinterpret_cast<unsigned char*>(nk + TJ);  // S*N
+  unsigned char* sPi = sP + S * N;                                     // S*N
+
+  load_pair_tables_strided(p.R_d_desc + (int64_t)i * p.D * 3, p.R_desc + (int64_t)i * p.D, N, GS, XS, Gi, Xi, warp, lane,
+                           nw);
+  for (int idx = tid; idx < S * N; idx += nt) {
+    sP[idx] = (unsigned char)p.aperm[idx];
+    sPi[idx] = (unsigned char)p.apinv[idx];
+  }
+  const double sig = p.sig;
+  const double sig2 = sig * sig;
+  const double inv_div = 1.0 / (3.0 * sig2 * sig2);  // 1/mat52_base_div (train.py:179)
+
+  const int tile_begin = blockIdx.x * tiles_per_cta;
+  const int tile_end = min(tile_begin + tiles_per_cta, ceil_div_dev(p.nJ, TJ));
+  for (int tile = tile_begin; tile < tile_end; ++tile) {
+    const int jt0 = tile * TJ;
+    const int tj = min(TJ, p.nJ - jt0);
+    if (p.sym && jt0 + tj - 1 < i) continue;  // (sym: jpts is the identity) every column point of the tile is < i
+    __syncthreads();  // the previous tile's phase B has finished with Gj / the vectors
+    for (int t = 0; t < tj; ++t) {
+      const int j = p.jpts[jt0 + t];
+      load_pair_tables_strided(p.R_d_desc + (int64_t)j * p.D * 3, p.R_desc + (int64_t)j * p.D, N, GS, XS, Gj + t * N * GS,
+                               Xj + t * N * XS, warp, lane, nw);
+    }
+    for (int tw = warp; tw < tj; tw += nw) {  // compact list of the kept column atoms of point tw (ballot over atoms)
+      int c = 0;
+      for (int b0 = 0; b0 < N; b0 += 32) {
+        const int b = b0 + lane;
+        bool kept = false;
+        if (b < N) {
+          const int64_t* dst = p.dest + (int64_t)(jt0 + tw) * N3 + 3 * b;
+          kept = dst[0] >= 0 || dst[1] >= 0 || dst[2] >= 0;
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, kept);
+        if (kept) klist[tw * N + c + __popc(m & ((1u << lane) - 1u))] = b;
+        c += __popc(m);
+      }
+      if (lane == 0) nk[tw] = c;
+    }
+    __syncthreads();
+    // this thread's output items: (t, a, b) = column point, row atom, kept column atom
+    int it_t[ASM_NI], it_a[ASM_NI], it_b[ASM_NI];
+    double acc[ASM_NI][9];
+#pragma unroll
+    for (int q = 0; q < ASM_NI; ++q) {
+      const int it = (int)blockIdx.z * ASM_NI * nt + tid + q * nt;  // grid.z splits the sub-blocks of large molecules
+      bool ok = it < tj * N * NK;
+      const int t = ok ? fastdiv(it, p.mNNK) : 0;
+      if (p.sym && jt0 + t < i) ok = false;  // mirrored from block (j, i) instead
+      const int ak = ok ? it - t * N * NK : 0;
+      it_a[q] = fastdiv(ak, p.mNK);
+      const int k = ak - it_a[q] * NK;
+      if (k >= nk[t]) ok = false;
+      it_b[q] = ok ? klist[t * N + k] : 0;
+      it_t[q] = ok ? t : -1;
+#pragma unroll
+      for (int e = 0; e < 9; ++e) acc[q][e] = 0.0;
+    }
+
+    for (int p0 = 0; p0 < S; p0 += PG) {
+      const int pg = min(PG, S - p0);
+      // ---- phase A, type-major over the chunk's (column point, permutation) slots
+      const int n_slots = tj * pg;
+      const int nU = n_slots * N, nV = n_slots * NK, nD = 3 * nV;
+      for (int idx = tid; idx < nU + nV + nD; idx += nt) {
+        if (idx < nU) {
+          // u[a] = -sum_g G_i[a][g] delta[a][g],  delta[a][g] = x_i[a][g] - x_j[Pa][Pg]  (i frame)
+          const int sl = fastdiv(idx, p.mN);
+          const int a = idx - sl * N;
+          const int t = sl / pg, pl = sl - t * pg;
+          const unsigned char* P = sP + (p0 + pl) * N;
+          const double* gi = Gi + a * GS;
+          const double* xi = Xi + a * XS;
+          const double* xj = Xj + t * N * XS + P[a] * XS;
+          double s0 = 0.0, s1 = 0.0, s2 = 0.0, q2 = 0.0;
+          for (int g = 0; g < N; ++g) {
+            const double d = xi[g] - xj[P[g]];
+            q2 = fma(d, d, q2);
+            s0 = fma(gi[g * 3 + 0], d, s0);
+            s1 = fma(gi[g * 3 + 1], d, s1);
+            s2 = fma(gi[g * 3 + 2], d, s2);
+          }
+          const int slot = t * PG + pl;
+          double* u = uS + slot * N3 + 3 * a;
+          u[0] = -s0;
+          u[1] = -s1;
+          u[2] = -s2;
+          n2p[slot * N + a] = q2;
+        } else if (idx < nU + nV) {
+          // v[b] = -sum_g G_j[b][g] delta[P^-1 b][P^-1 g]  for the kept column atoms b
+          const int e = idx - nU;
+          const int sl = fastdiv(e, p.mNK);
+          const int k = e - sl * NK;
+          const int t = sl / pg, pl = sl - t * pg;
+          if (k >= nk[t]) continue;
+          const int b = klist[t * N + k];
+          const unsigned char* Pi = sPi + (p0 + pl) * N;
+          const double* gj = Gj + t * N * GS + b * GS;
+          const double* xj = Xj + t * N * XS + b * XS;
+          const double* xi = Xi + Pi[b] * XS;
+          double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+          for (int g = 0; g < N; ++g) {
+            const double d = xi[Pi[g]] - xj[g];
+            s0 = fma(gj[g * 3 + 0], d, s0);
+            s1 = fma(gj[g * 3 + 1], d, s1);
+            s2 = fma(gj[g * 3 + 2], d, s2);
+          }
+          double* v = vS + (t * PG + pl) * N3 + 3 * b;
+          v[0] = -s0;
+          v[1] = -s1;
+          v[2] = -s2;
+        } else {
+          // Dg[a][c][0..2] = sum_g G_i[a][g][c] G_j[Pa][Pg][0..2]  for a = P^-1 b, b a kept column atom
+          const int e = idx - nU - nV;
+          const int e3 = (int)__umulhi((unsigned)e, 0x55555556u), c = e - 3 * e3;
+          const int sl = fastdiv(e3, p.mNK);
+          const int k = e3 - sl * NK;
+          const int t = sl / pg, pl = sl - t * pg;
+          if (k >= nk[t]) continue;
+          const int b = klist[t * N + k];
+          const unsigned char* P = sP + (p0 + pl) * N;
+          const int a = sPi[(p0 + pl) * N + b];
+          const double* gi = Gi + a * GS + c;
+          const double* gj = Gj + t * N * GS + b * GS;  // b = P a
+          double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+          for (int g = 0; g < N; ++g) {
+            const double x = gi[g * 3];
+            const double* y = gj + P[g] * 3;
+            s0 = fma(x, y[0], s0);
+            s1 = fma(x, y[1], s1);
+            s2 = fma(x, y[2], s2);
+          }
+          double* dg = DgS + (t * PG + pl) * 3 * N3 + (a * 3 + c) * 3;
+          dg[0] = s0;
+          dg[1] = s1;
+          dg[2] = s2;
+        }
+      }
+      __syncthreads();
+      // ---- Matern factors of the chunk (fixed-order sum of the row partials: bit-reproducible K)
+      if (tid < n_slots) {
+        const int t = tid / pg, pl = tid - t * pg;
+        const int slot = t * PG + pl;
+        double n2 = 0.0;
+        for (int a = 0; a < N; ++a) n2 += n2p[slot * N + a];
+        const double nrm = sqrt(5.0) * sqrt(0.5 * n2);  // every pair twice; train.py:201
+        const double base = exp(-nrm / sig) * inv_div * 5.0;          // train.py:202
+        cc[slot * 2 + 0] = base * 5.0;                                 // c1 (train.py:211)
+        cc[slot * 2 + 1] = (sig2 + sig * nrm) * base;                  // c2 (train.py:219)
+      }
+      __syncthreads();
+      // ---- phase B: acc[a][b] += c1 u[a] (x) v[b] - c2 T[a][b] for the permutations of the chunk
+      for (int pl = 0; pl < pg; ++pl) {
+        const unsigned char* P = sP + (p0 + pl) * N;
+        const unsigned char* Pi = sPi + (p0 + pl) * N;
+#pragma unroll
+        for (int q = 0; q < ASM_NI; ++q) {
+          const int t = it_t[q];
+          if (t < 0) continue;
+          const int slot = t * PG + pl;
+          const int a = it_a[q], b = it_b[q];
+          const double c1 = cc[slot * 2 + 0], c2 = cc[slot * 2 + 1];
+          const double* ua = uS + slot * N3 + 3 * a;
+          const double* vb = vS + slot * N3 + 3 * b;
+          const int pa = P[a];
+          if (b != pa) {
+            const double* gi = Gi + a * GS + Pi[b] * 3;
+            const double* gj = Gj + t * N * GS + pa * GS + b * 3;
+            double t0[3], t1[3];  // T[a][b] = -gi (x) gj  ->  -c2 T = +c2 gi (x) gj
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+              t0[c] = c2 * gi[c];
+              t1[c] = gj[c];
+            }
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+              const double cu = c1 * ua[c];
+#pragma unroll
+              for (int c2i = 0; c2i < 3; ++c2i)
+                acc[q][c * 3 + c2i] = fma(t0[c], t1[c2i], fma(cu, vb[c2i], acc[q][c * 3 + c2i]));
+            }
+          } else {
+            const double* dg = DgS + slot * 3 * N3 + 9 * a;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+              const double cu = c1 * ua[c];
+#pragma unroll
+              for (int c2i = 0; c2i < 3; ++c2i)
+                acc[q][c * 3 + c2i] = fma(-c2, dg[c * 3 + c2i], fma(cu, vb[c2i], acc[q][c * 3 + c2i]));
+            }
+          }
+        }
+      }
+      if (p0 + PG < S) __syncthreads();  // the next chunk overwrites the vectors
+    }
+
+    // ---- single store of the finished 3x3 sub-blocks (+ the mirrored block in symmetric mode)
+#pragma unroll
+    for (int q = 0; q < ASM_NI; ++q) {
+      const int t = it_t[q];
+      if (t < 0) continue;
+      const int a = it_a[q], b = it_b[q];
+      const int64_t* dst = p.dest + (int64_t)(jt0 + t) * N3 + 3 * b;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        double* Krow = p.K + ((int64_t)(i - p.i0) * N3 + 3 * a + c) * p.ldk;
+#pragma unroll
+        for (int c2i = 0; c2i < 3; ++c2i) {
+          const int64_t col = dst[c2i];
+          if (col >= 0) Krow[col] = p.scale * acc[q][c * 3 + c2i];
+        }
+      }
+      if (p.sym && jt0 + t > i) {  // (sym implies i0 == 0)
+        const int j = jt0 + t;
+#pragma unroll
+        for (int c2i = 0; c2i < 3; ++c2i) {
+          double* Krow = p.K + ((int64_t)j * N3 + 3 * b + c2i) * p.ldk + (int64_t)i * N3 + 3 * a;
+#pragma unroll
+          for (int c = 0; c < 3; ++c) Krow[c] = p.scale * acc[q][c * 3 + c2i];
+        }
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // Large molecules (N > ~50: the atom tables of one block no longer fit in shared memory; BASELINE
 // configs 4 and 5).  Same mathematics and the same summation order as k_assemble, but the tables
 // live in a private slab of global memory per CTA (L1/L2 resident), the CTAs are persistent
@@ -855,6 +1133,12 @@ static size_t asm_v3_smem_bytes(int N, int S, int TJ, int PG) {
   return dbl * 8 + 2 * (size_t)S * N * 4 + 2 * (size_t)TJ * N * 4 + (size_t)TJ * 4 + 16;
 }
 
+static size_t asm_v4_smem_bytes(int N, int S, int TJ, int PG) {
+  const size_t N3 = 3 * (size_t)N, GS = N3 | 1, XS = (size_t)N | 1;
+  const size_t dbl = (size_t)N * (GS + XS) * (1 + TJ) + (size_t)TJ * PG * (2 * N3 + 3 * N3 + N + 2);
+  return dbl * 8 + ((size_t)TJ * N + TJ) * 4 + 2 * (size_t)S * N + 16;
+}
+
 static size_t asm_smem_bytes(int N, int D, int S, int TJ) {
   (void)D;
   const size_t N3 = 3 * (size_t)N, NN = (size_t)N * N;
@@ -911,7 +1195,7 @@ static bool atom_perm_from_desc_perm(const int* dperm, int N, int* P) {
 }
 
 static int g_asm_variant = 0;  // 0: by size; 1: always the large-molecule kernel (tests)
-static int g_asm_kernel = 0;  // small-molecule kernel: 0 = by permutation count (default), 2 = k_assemble (per-permutation phases), 3 = k_assemble_v3 (chunked)
+static int g_asm_kernel = 0;  // small-molecule kernel: 0 = by size (default), 2 = k_assemble (per-permutation phases), 3 = k_assemble_v3 (chunked), 4 = k_assemble_v4 (chunked, byte permutation tables, type-major phase A)
 static int g_asm_max_rowpts = 65535;  // row points per launch of k_assemble (grid.y limit; lowered by tests)
 
 extern "C" int sgdml_b200_set_assemble_variant(int variant) {
@@ -921,7 +1205,7 @@ extern "C" int sgdml_b200_set_assemble_variant(int variant) {
     g_asm_max_rowpts = variant - 1000;
     return 0;
   }
-  if (variant == 2 || variant == 3) {  // which small-molecule kernel
+  if (variant >= 2 && variant <= 4) {  // which small-molecule kernel
     g_asm_kernel = variant;
     return 0;
   }
@@ -1098,8 +1382,20 @@ extern "C" int sgdml_b200_assemble_rows(const double* R_desc, const double* R_d_
       // permutations (S = 243, chunks of 8) the chunked kernel is 15 % SLOWER than the per-permutation one, so it is
       // only used when all permutations fit one chunk -- unless a test forces it (variant 3)
       const bool use_v3 = smem3 <= 220 * 1024 && TJ * PG <= 256 && (g_asm_kernel == 3 || (g_asm_kernel == 0 && PG == S));
+      // v4 kernel: chunks of up to 16 permutations; two CTAs per SM when everything fits in ~110 KB, else one
+      int PG4 = std::min(S, 16);
+      while (PG4 > 1 && (asm_v4_smem_bytes(N, S, TJ, PG4) > 220 * 1024 || TJ * PG4 > 256)) --PG4;
+      if (PG4 == S && asm_v4_smem_bytes(N, S, TJ, PG4) > 110 * 1024) {
+        int q = PG4;
+        while (q > 8 && asm_v4_smem_bytes(N, S, TJ, q) > 110 * 1024) --q;
+        if (asm_v4_smem_bytes(N, S, TJ, q) <= 110 * 1024) PG4 = q;
+      }
+      const size_t smem4 = asm_v4_smem_bytes(N, S, TJ, PG4);
+      const bool use_v4 = N <= 255 && smem4 <= 220 * 1024 && TJ * PG4 <= 256 && g_asm_kernel == 4;
       const int tiles_per_cta = 4;
-      if (use_v3)
+      if (use_v4) {
+        SG_CUDA(cudaFuncSetAttribute(k_assemble_v4, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem4));
+      } else if (use_v3)
         SG_CUDA(cudaFuncSetAttribute(k_assemble_v3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3));
       else
         SG_CUDA(cudaFuncSetAttribute(k_assemble, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -1109,7 +1405,10 @@ extern "C" int sgdml_b200_assemble_rows(const double* R_desc, const double* R_d_
         AsmArgs ac = a;
         ac.i0 = (int)m_begin + r0;
         ac.K = a.K + (int64_t)r0 * N3 * ldk;
-        if (use_v3) {
+        if (use_v4) {
+          dim3 grid((unsigned)ceil_div(ceil_div(nJ, TJ), tiles_per_cta), (unsigned)nr, (unsigned)n_chunks);
+          k_assemble_v4<<<grid, 256, smem4, s>>>(ac, PG4, tiles_per_cta);
+        } else if (use_v3) {
           dim3 grid((unsigned)ceil_div(ceil_div(nJ, TJ), tiles_per_cta), (unsigned)nr, (unsigned)n_chunks);
           k_assemble_v3<<<grid, 256, smem3, s>>>(ac, PG, tiles_per_cta);
         } else {

@@ -1007,18 +1007,22 @@ __global__ void k_transpose_pad(const double* __restrict__ src, int64_t rows, in
 // ============================================================== finishing kernel
 // F_desc[d] = sum_p G[b*S+p][perm_p[d]];  F = J_x^T F_desc (predict.py:240-243);
 // E = sum_p Erow;  outputs scaled by std, E += c (predict.py:1286-1288).
-// One CTA per query: threads over descriptor entries, then over force components.
+// One CTA per QPB queries (QPB = 128 / D for small molecules, else 1): threads over (query, descriptor entry), then
+// over (query, force component).
 __global__ void __launch_bounds__(128) k_predict_finish(const double* __restrict__ G, const double* __restrict__ Erow,
                                                         const double* __restrict__ gq, const int* __restrict__ perm,
                                                         int n_atoms, int D, int DP, int S, double std, double c,
-                                                        int n_splits, int64_t plane_rows,
+                                                        int n_splits, int64_t plane_rows, int64_t n_geo, int QPB,
                                                         double* __restrict__ E, double* __restrict__ F) {
-  extern __shared__ double fd[];  // D
-  const int64_t b = blockIdx.x;
+  extern __shared__ double fd[];  // QPB * D
+  const int64_t b0 = (int64_t)blockIdx.x * QPB;
+  const int nq = (int)min((int64_t)QPB, n_geo - b0);
   // fixed summation order (permutation-major, then split) with four independent accumulators so
   // that the L2 round trips of the gathered loads overlap (n_splits * S terms per descriptor entry)
   const int64_t stride = plane_rows * DP;
-  for (int d = threadIdx.x; d < D; d += blockDim.x) {
+  for (int e = threadIdx.x; e < nq * D; e += blockDim.x) {
+    const int ql = e / D, d = e - ql * D;
+    const int64_t b = b0 + ql;
     double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0, acc3 = 0.0;
     for (int pp = 0; pp < S; ++pp) {
       const double* gp = G + (b * S + pp) * DP + perm[pp * D + d];
@@ -1031,34 +1035,42 @@ __global__ void __launch_bounds__(128) k_predict_finish(const double* __restrict
       }
       for (; sp < n_splits; ++sp) acc0 += gp[(int64_t)sp * stride];
     }
-    fd[d] = (acc0 + acc1) + (acc2 + acc3);
+    fd[e] = (acc0 + acc1) + (acc2 + acc3);
   }
   __syncthreads();
-  const double* g = gq + b * (int64_t)D * 3;
-  for (int idx = threadIdx.x; idx < 3 * n_atoms; idx += blockDim.x) {
+  const int dimi = 3 * n_atoms;
+  for (int e = threadIdx.x; e < nq * dimi; e += blockDim.x) {
+    const int ql = e / dimi, idx = e - ql * dimi;
+    const int64_t b = b0 + ql;
+    const double* g = gq + b * (int64_t)D * 3;
+    const double* f = fd + ql * D;
     const int k = idx / 3, cc = idx - 3 * k;
     double s = 0.0;
     for (int o = 0; o < n_atoms; ++o) {
       if (o == k) continue;
       if (o > k) {
         const int d = pair_index(o, k);
-        s += g[d * 3 + cc] * fd[d];
+        s += g[d * 3 + cc] * f[d];
       } else {
         const int d = pair_index(k, o);
-        s -= g[d * 3 + cc] * fd[d];
+        s -= g[d * 3 + cc] * f[d];
       }
     }
-    F[b * 3 * n_atoms + idx] = s * std;
+    F[b * dimi + idx] = s * std;
   }
-  if (E != nullptr && threadIdx.x < 32) {
-    double s = 0.0;
-    for (int t = threadIdx.x; t < n_splits * S; t += 32) {
-      const int sp = t / S, pp = t - sp * S;
-      s += Erow[(int64_t)sp * plane_rows + b * S + pp];
-    }
+  if (E != nullptr) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int ql = warp; ql < nq; ql += (int)(blockDim.x >> 5)) {
+      const int64_t b = b0 + ql;
+      double s = 0.0;
+      for (int t = lane; t < n_splits * S; t += 32) {
+        const int sp = t / S, pp = t - sp * S;
+        s += Erow[(int64_t)sp * plane_rows + b * S + pp];
+      }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    if (threadIdx.x == 0) E[b] = s * std + c;
+      for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+      if (lane == 0) E[b] = s * std + c;
+    }
   }
 }
 
@@ -1512,7 +1524,8 @@ int run_queries(sgdml_b200_model* m, int slot, const double* xq, const double* g
   }
   {
     ProfScope ps(KID_PREDICT_AUX, s);
-    const size_t fd_bytes = sizeof(double) * (size_t)m->D;
+    const int QPB = std::max(1, 128 / m->D);  // small molecules: several queries per CTA
+    const size_t fd_bytes = sizeof(double) * (size_t)m->D * QPB;
     if (fd_bytes > 48 * 1024) {  // molecules above 111 atoms: opt in to more than the default dynamic shared memory
       if (fd_bytes > 200 * 1024) {
         set_last_error("sgdml_b200_predict: descriptor too long for the finishing kernel (n_atoms <= ~225 supported)");
@@ -1520,9 +1533,9 @@ int run_queries(sgdml_b200_model* m, int slot, const double* xq, const double* g
       }
       SG_CUDA(cudaFuncSetAttribute(k_predict_finish, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fd_bytes));
     }
-    k_predict_finish<<<(unsigned)n_geo, 128, fd_bytes, s>>>(w.G, w.Erow, gq, m->perm, m->N, m->D, m->DP,
-                                                                          m->S, std, c, n_splits, n_rows_pad, E_dev,
-                                                                          F_dev);
+    k_predict_finish<<<(unsigned)((n_geo + QPB - 1) / QPB), 128, fd_bytes, s>>>(w.G, w.Erow, gq, m->perm, m->N, m->D,
+                                                                               m->DP, m->S, std, c, n_splits,
+                                                                               n_rows_pad, n_geo, QPB, E_dev, F_dev);
     SG_CUDA(cudaGetLastError());
     count_launch(KID_PREDICT_AUX);
   }

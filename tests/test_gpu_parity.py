@@ -772,10 +772,12 @@ def test_ase_calculator_core_units(eng, golden):
     assert abs(_KCAL_PER_MOL_IN_EV - 0.0433641) < 1e-6
 
 
-# --------------------------------------------------------------------------- assembly kernel v3 (chunked permutations)
-def test_assemble_v3_kernel(eng, golden):
-    """k_assemble_v3 (permutation chunks, delta on the fly, resident row tables) against the reference's K: full
-    matrix (symmetric mode), a column subset, row ranges, and the multi-launch row path."""
+# --------------------------------------------------------------------------- assembly kernels v3 / v4 (chunked permutations)
+@pytest.mark.parametrize('variant', [3, 4])
+def test_assemble_v3_kernel(eng, golden, variant):
+    """k_assemble_v3 (permutation chunks, delta on the fly, resident row tables) and k_assemble_v4 (byte permutation
+    tables, odd table strides, type-major phase A over kept column atoms) against the reference's K: full matrix
+    (symmetric mode), a column subset, row ranges, and the multi-launch row path."""
     from sgdml_b200 import _lib
 
     N, M = int(golden['n_atoms']), golden['R_desc'].shape[0]
@@ -784,7 +786,7 @@ def test_assemble_v3_kernel(eng, golden):
     args = (golden['R_desc'], golden['R_d_desc'], golden['tril_perms_lin'], int(golden['sig']))
     cols = np.unique(np.random.default_rng(11).integers(0, n, size=37))
     L = _lib.lib()
-    L.sgdml_b200_set_assemble_variant(3)
+    L.sgdml_b200_set_assemble_variant(variant)
     try:
         K, _ = t._assemble_kernel_mat_device(*args)
         assert rel_err(K[:, :n].cpu().numpy(), golden['K']) < 1e-12
@@ -803,7 +805,7 @@ def test_assemble_v3_kernel(eng, golden):
 
 def test_assemble_v3_many_permutations(eng):
     """A permutation group too large for one chunk (S = 81, 12 atoms... PG < S) and a mid-sized molecule whose sub-blocks
-    are split over grid.z (N = 36): v3 against the per-permutation kernel."""
+    are split over grid.z (N = 36): v3 and v4 against the per-permutation kernel, full matrix and a column subset."""
     from sgdml_b200 import _lib, synth
     from sgdml_b200.desc import Desc, tril_perms_lin
 
@@ -814,16 +816,21 @@ def test_assemble_v3_many_permutations(eng):
         R = synth.geometries(N, M, 0).reshape(M, -1)
         x, g = Desc(N).from_R(R)
         lin = tril_perms_lin(perms)
-        out = {}
-        for v in (2, 3):
+        out, sub = {}, {}
+        cols = np.unique(np.random.default_rng(N).integers(0, 3 * N * M, size=3 * M))
+        for v in (2, 3, 4):
             L.sgdml_b200_set_assemble_variant(v)
             try:
                 K, nc = t._assemble_kernel_mat_device(x, g, lin, 25)
                 out[v] = K[:, :nc].cpu().numpy()
+                Kc, ncc = t._assemble_kernel_mat_device(x, g, lin, 25, col_idxs=cols)
+                sub[v] = Kc[:, :ncc].cpu().numpy()
             finally:
                 L.sgdml_b200_set_assemble_variant(0)
-        assert rel_err(out[3], out[2]) < 1e-12
-        assert rel_err(out[3], out[3].T) < 1e-12  # the mirrored blocks
+        for v in (3, 4):
+            assert rel_err(out[v], out[2]) < 1e-12
+            assert rel_err(out[v], out[v].T) < 1e-12  # the mirrored blocks
+            assert rel_err(sub[v], out[2][:, cols]) < 1e-12 and rel_err(sub[2], out[2][:, cols]) < 1e-12
 
 
 # --------------------------------------------------------------------------- (f)3: MD latency path (graph replay)

@@ -13,7 +13,7 @@ def run(name, N, M, perms, sig, cols):
     x, g = Desc(N).from_R(R)
     lin = tril_perms_lin(perms)
     ref = None
-    for v in (2, 3, 2, 3):
+    for v in (2, 3, 4, 2, 3, 4):
         L.sgdml_b200_set_assemble_variant(v)
         K, nc = t._assemble_kernel_mat_device(x, g, lin, sig, col_idxs=cols)  # warm-up + allocation
         torch.cuda.synchronize()
