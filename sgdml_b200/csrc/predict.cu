@@ -1282,8 +1282,15 @@ int launch_main(int cfg, const PredictArgs& a, int n_splits, cudaStream_t s) {
       case 4: return launch_main_t<Cfg224o>(a, n_splits, s);
     }
   }
-  if (g_predict_variant == 0) {  // default: the measured-fastest kernel per size (tools/predict_variants.py)
+  if (g_predict_variant == 0) {
+    // default: the measured-fastest kernel per size (tools/predict_variants.py, 65536 queries, M = 1000, S = 6, ms per
+    // call round-1 kernel -> one-barrier kernel): DP = 72: 9.09 -> 8.89, 112: 13.98 -> 12.73, 160: 20.07 -> 18.12,
+    // 224 (BASELINE config 2): 25.81 -> 24.01; DP = 40 (config 1) stays on the round-1 kernel (1.31 vs 1.51 ms: the
+    // doubled C1 / C2 buffers cost it its second CTA per SM)
     switch (cfg) {
+      case 1: return launch_main_t<Cfg72o>(a, n_splits, s);
+      case 2: return launch_main_t<Cfg112o>(a, n_splits, s);
+      case 3: return launch_main_t<Cfg160o>(a, n_splits, s);
       case 4: return launch_main_t<Cfg224o>(a, n_splits, s);
     }
   }
@@ -1726,9 +1733,6 @@ int predict_graph(sgdml_b200_model* m, const double* R, int64_t n_geo, double* E
   sgdml_b200_model::GraphSlot* g = nullptr;
   for (auto& c : m->graphs)
     if (c.exec != nullptr && c.n_geo == n_geo && c.with_E == with_E && c.generation == m->generation) g = &c;
-  // work queued on the caller's stream (set_alphas, ...) comes first
-  SG_CUDA(cudaEventRecord(m->graph_event, s));
-  SG_CUDA(cudaStreamWaitEvent(gs, m->graph_event, 0));
   // Three kernel nodes and no copy nodes: the first kernel reads the geometries straight from the pinned staging
   // buffer (unified addressing) and builds descriptors + query rows, the finishing kernel stores E and F straight
   // into pinned host memory.  SGDML_B200_GRAPH_ZEROCOPY=0: the earlier form (H2D copy, descriptor kernel, query-row
@@ -1756,6 +1760,10 @@ int predict_graph(sgdml_b200_model* m, const double* R, int64_t n_geo, double* E
     return 0;
   };
   if (g == nullptr) {
+    // capture happens on a private stream (the caller's may be the legacy stream, which cannot be captured); work
+    // queued on the caller's stream (set_alphas, ...) comes first
+    SG_CUDA(cudaEventRecord(m->graph_event, s));
+    SG_CUDA(cudaStreamWaitEvent(gs, m->graph_event, 0));
     g = &m->graphs[m->graph_next];
     m->graph_next = (m->graph_next + 1) % 4;
     free_graph_slot(*g);
@@ -1795,10 +1803,11 @@ int predict_graph(sgdml_b200_model* m, const double* R, int64_t n_geo, double* E
     g->with_E = with_E;
     g->generation = m->generation;
   } else {
+    // replay on the CALLER's stream: ordered after whatever it has queued, no event round trip
     std::copy(R, R + n_geo * dimi, g->hR);
-    SG_CUDA(cudaGraphLaunch(g->exec, gs));
+    SG_CUDA(cudaGraphLaunch(g->exec, s));
     count_launch(KID_PREDICT_AUX, g->n_kernels);  // the kernels of a replay are launches too
-    SG_CUDA(cudaStreamSynchronize(gs));
+    SG_CUDA(cudaStreamSynchronize(s));
   }
   std::copy(g->hF, g->hF + n_geo * dimi, F);
   if (with_E) std::copy(g->hE, g->hE + n_geo, E);

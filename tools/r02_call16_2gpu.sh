@@ -12,5 +12,5 @@ run c16_bench_n2 600 $TR --master-port 29517 bench.py --gpus 2 --steps 3 --warmu
 ls gpurun_out/nccl_* 2>/dev/null | head -4 | tee -a $O/call16.log; grep -h "nranks\|NVLS\|Connected all\|Channel 00/" gpurun_out/nccl_n2_* 2>/dev/null | head -6 | tee -a $O/call16.log
 export SGDML_B200_OZAKI_PREDICT_SLICES=5
 run c16_cg_acala_m2000_n2 420 $TR --master-port 29519 tools/cg_probe.py --workload ac-ala3-nhme --n-train 2000 --max-memory 170 --trace 50
-run c16_cg_c60_m3000_n2 780 $TR --master-port 29521 tools/cg_probe.py --workload c60 --n-train 3000 --max-memory 170 --trace 25
-run c16_cg_syn100_m5000_n2 480 $TR --master-port 29523 tools/cg_probe.py --workload synthetic100 --n-train 5000 --max-memory 170 --trace 25
+run c16_cg_c60_m3000_n2 600 $TR --master-port 29521 tools/cg_probe.py --workload c60 --n-train 3000 --max-memory 170 --trace 25
+run c16_cg_syn100_m5000_n2 360 $TR --master-port 29523 tools/cg_probe.py --workload synthetic100 --n-train 5000 --max-memory 170 --trace 25
