@@ -1074,6 +1074,70 @@ __global__ void __launch_bounds__(128) k_predict_finish(const double* __restrict
   }
 }
 
+// The same for batches of a few queries (the MD latency path: one geometry per call).  There the one-CTA-per-query form
+// is a chain of S * n_splits dependent L2 round trips per thread (126 at BASELINE config 2, B = 1: ~25 us); here 1024
+// threads split every descriptor entry's terms into `parts` interleaved partial sums (fixed order: bit-reproducible).
+__global__ void __launch_bounds__(1024) k_predict_finish_small(const double* __restrict__ G, const double* __restrict__ Erow,
+                                                               const double* __restrict__ gq, const int* __restrict__ perm,
+                                                               int n_atoms, int D, int DP, int S, double std, double c,
+                                                               int n_splits, int64_t plane_rows, int parts,
+                                                               double* __restrict__ E, double* __restrict__ F) {
+  extern __shared__ double fds[];  // parts * D partial sums, then D totals
+  double* fd = fds + parts * D;
+  const int64_t b = blockIdx.x;
+  const int64_t stride = plane_rows * DP;
+  const int n_terms = S * n_splits;
+  for (int e = threadIdx.x; e < parts * D; e += blockDim.x) {
+    const int part = e / D, d = e - part * D;
+    double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0, acc3 = 0.0;
+    int t = part;
+    for (; t + 3 * parts < n_terms; t += 4 * parts) {
+      const int t1 = t + parts, t2 = t + 2 * parts, t3 = t + 3 * parts;
+      acc0 += G[(b * S + t % S) * DP + perm[(t % S) * D + d] + (int64_t)(t / S) * stride];
+      acc1 += G[(b * S + t1 % S) * DP + perm[(t1 % S) * D + d] + (int64_t)(t1 / S) * stride];
+      acc2 += G[(b * S + t2 % S) * DP + perm[(t2 % S) * D + d] + (int64_t)(t2 / S) * stride];
+      acc3 += G[(b * S + t3 % S) * DP + perm[(t3 % S) * D + d] + (int64_t)(t3 / S) * stride];
+    }
+    for (; t < n_terms; t += parts) acc0 += G[(b * S + t % S) * DP + perm[(t % S) * D + d] + (int64_t)(t / S) * stride];
+    fds[e] = (acc0 + acc1) + (acc2 + acc3);
+  }
+  __syncthreads();
+  for (int d = threadIdx.x; d < D; d += blockDim.x) {
+    double sum = 0.0;
+    for (int part = 0; part < parts; ++part) sum += fds[part * D + d];
+    fd[d] = sum;
+  }
+  __syncthreads();
+  const int dimi = 3 * n_atoms;
+  const double* g = gq + b * (int64_t)D * 3;
+  for (int idx = threadIdx.x; idx < dimi; idx += blockDim.x) {
+    const int k = idx / 3, cc = idx - 3 * k;
+    double sum = 0.0;
+    for (int o = 0; o < n_atoms; ++o) {
+      if (o == k) continue;
+      if (o > k) {
+        const int d = pair_index(o, k);
+        sum += g[d * 3 + cc] * fd[d];
+      } else {
+        const int d = pair_index(k, o);
+        sum -= g[d * 3 + cc] * fd[d];
+      }
+    }
+    F[b * dimi + idx] = sum * std;
+  }
+  if (E != nullptr && threadIdx.x >= blockDim.x - 32) {  // last warp
+    const int lane = threadIdx.x & 31;
+    double sum = 0.0;
+    for (int t = lane; t < n_terms; t += 32) {
+      const int sp = t / S, pp = t - sp * S;
+      sum += Erow[(int64_t)sp * plane_rows + b * S + pp];
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    if (lane == 0) E[b] = sum * std + c;
+  }
+}
+
 // ============================================================== model maintenance kernels
 __global__ void k_col_mean(const double* __restrict__ X, int M, int D, double* __restrict__ mu, int DP) {
   // one block per column
@@ -1413,6 +1477,7 @@ int64_t chunk_geos(const sgdml_b200_model* m) {
 }
 
 // Runs the predictor on n_geo queries whose descriptors (xq, gq) are on the device.
+constexpr int64_t GRAPH_MAX_GEO = 16;  // batches up to this size with host buffers replay a captured graph
 // xq == nullptr: the query rows (w.Qg, w.qq) are already in place (k_desc_query_rows)
 int run_queries(sgdml_b200_model* m, int slot, const double* xq, const double* gq, int64_t n_geo, double std,
                 double c, double* E_dev, double* F_dev, cudaStream_t s) {
@@ -1540,9 +1605,17 @@ int run_queries(sgdml_b200_model* m, int slot, const double* xq, const double* g
       }
       SG_CUDA(cudaFuncSetAttribute(k_predict_finish, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fd_bytes));
     }
-    k_predict_finish<<<(unsigned)((n_geo + QPB - 1) / QPB), 128, fd_bytes, s>>>(w.G, w.Erow, gq, m->perm, m->N, m->D,
-                                                                               m->DP, m->S, std, c, n_splits,
-                                                                               n_rows_pad, n_geo, QPB, E_dev, F_dev);
+    const int parts = std::max(1, std::min(8, 1024 / m->D));
+    const size_t fds_bytes = sizeof(double) * (size_t)m->D * (parts + 1);
+    if (n_geo <= GRAPH_MAX_GEO && n_splits > 1 && parts > 1 && fds_bytes <= 48 * 1024) {
+      // a few queries, the sweep over the training points split across CTAs: the latency form
+      k_predict_finish_small<<<(unsigned)n_geo, 1024, fds_bytes, s>>>(w.G, w.Erow, gq, m->perm, m->N, m->D, m->DP, m->S, std, c,
+                                                                     n_splits, n_rows_pad, parts, E_dev, F_dev);
+    } else {
+      k_predict_finish<<<(unsigned)((n_geo + QPB - 1) / QPB), 128, fd_bytes, s>>>(w.G, w.Erow, gq, m->perm, m->N, m->D,
+                                                                                 m->DP, m->S, std, c, n_splits,
+                                                                                 n_rows_pad, n_geo, QPB, E_dev, F_dev);
+    }
     SG_CUDA(cudaGetLastError());
     count_launch(KID_PREDICT_AUX);
   }
@@ -1707,7 +1780,6 @@ bool g_graph_zero_copy() {
   const char* e = getenv("SGDML_B200_GRAPH_ZEROCOPY");
   return e != nullptr ? (e[0] == '1') : true;
 }
-constexpr int64_t GRAPH_MAX_GEO = 16;  // batches up to this size with host buffers replay a captured graph
 
 void free_graph_slot(sgdml_b200_model::GraphSlot& g) {
   if (g.exec) cudaGraphExecDestroy(g.exec);
