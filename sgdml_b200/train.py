@@ -240,8 +240,14 @@ class GDMLTrain(object):
         E_pred, _ = gdml_predict.predict()
         E_ref = np.squeeze(task['E_train'])
 
-        e_fact = np.linalg.lstsq(np.column_stack((E_pred, np.ones(E_ref.shape))), E_ref, rcond=-1)[0][0]
-        corrcoef = np.corrcoef(E_ref, E_pred)[0, 1]
+        # slope of the least-squares line E_ref ~ e_fact * E_pred + b and the correlation coefficient, in closed form
+        # (the reference calls np.linalg.lstsq / np.corrcoef, train.py:1150-1170; on a 128-thread host the LAPACK
+        # thread pool of that 1000 x 2 problem was measured at up to 0.6 s of a 1.3 s training run)
+        dp = E_pred - (E_pred.sum() / E_pred.size)
+        dr = E_ref - (E_ref.sum() / E_ref.size)
+        spp, srr, spr = float((dp * dp).sum()), float((dr * dr).sum()), float((dp * dr).sum())
+        e_fact = spr / spp if spp > 0 else 1.0
+        corrcoef = spr / np.sqrt(spp * srr) if spp > 0 and srr > 0 else 1.0
         if np.sign(e_fact) == -1:
             self.log.warning('The provided dataset may contain gradients instead of force labels (flipped sign).')
         if corrcoef < 0.95:
