@@ -629,12 +629,19 @@ def measure_workload(args, workload, batch, steps, warmup, world, rank, local_ra
             log('[%s] warm-up training run' % workload)
             trainer.train(synth.make_task(N, min(M, 40), perms, cfg['sig'], r0=r0))
             log('[%s] timed training run: n = %d' % (workload, n))
+            # clocks / power / throttle reasons during the training run too: the int8 trailing updates draw far more
+            # power than the FP64 DMMA kernels, so a power or thermal cap would show here and not in the predict phase
+            tsampler = ClockSampler(local_rank)
+            tsampler.start()
+            time.sleep(0.5)
+            tsampler.rows.clear()
             torch.cuda.synchronize()
             L.sgdml_b200_profile_reset()
             t0 = time.perf_counter()
             model0 = trainer.train(task)
             torch.cuda.synchronize()
             train_s = time.perf_counter() - t0
+            train_clocks = tsampler.stop()
             log('[%s] training done in %.3f s (%s)' % (workload, train_s, trainer.timings))
             snap = _lib.profile_snapshot()
             tm = trainer.timings
@@ -654,6 +661,7 @@ def measure_workload(args, workload, batch, steps, warmup, world, rank, local_ra
                 'n': n,
                 'K_bytes': 8 * n * n,
                 'total_s': train_s,
+                'clocks': train_clocks,
                 'assemble_s': tm['assemble_s'],
                 'solve_s': tm['solve_s'],
                 'what': 'GDMLTrain.train(task): host R/F/E in -> model dict out (descriptors, K assembly in HBM, '
@@ -1088,8 +1096,9 @@ def run_engine(args):
         # NCCL latches its debug settings at its first call.
         nccl_dir = os.path.join(ROOT, 'gpurun_out')
         os.makedirs(nccl_dir, exist_ok=True)
-        os.environ.setdefault('NCCL_DEBUG', 'INFO')
-        os.environ.setdefault('NCCL_DEBUG_SUBSYS', 'INIT,ENV')
+        if os.environ.get('NCCL_DEBUG', '').upper() not in ('INFO', 'TRACE'):
+            os.environ['NCCL_DEBUG'] = 'INFO'  # (a pre-set WARN / VERSION would leave the rank count unobservable)
+            os.environ.setdefault('NCCL_DEBUG_SUBSYS', 'INIT,ENV')
         os.environ.setdefault('NCCL_DEBUG_FILE', os.path.join(nccl_dir, 'nccl_n%d_%%h_%%p.log' % world))
         nccl_log = os.environ['NCCL_DEBUG_FILE']
     import torch
@@ -1102,6 +1111,18 @@ def run_engine(args):
         # a mismatched collective must fail in minutes, not in NCCL's default 10 (the slowest legitimate wait is rank > 0
         # waiting for rank 0's training legs: a few seconds)
         dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank), timeout=datetime.timedelta(seconds=240))
+        # the communicator, checked directly: a sum of ones over the ranks and the distinct devices behind them
+        ones = torch.ones(1, dtype=torch.float64, device='cuda')
+        dist.all_reduce(ones)
+        uuids = [None] * world
+        dist.all_gather_object(uuids, str(torch.cuda.get_device_properties(local_rank).uuid))
+        nccl_check = {
+            'backend': dist.get_backend(),
+            'world_size': dist.get_world_size(),
+            'allreduce_of_ones': float(ones.item()),
+            'distinct_devices': len(set(uuids)),
+            'nccl_version': '.'.join(str(v) for v in torch.cuda.nccl.version()),
+        }
 
     line = measure_workload(args, args.workload, args.batch, args.steps, args.warmup, world, rank, local_rank)
     default_run = args.workload == 'aspirin' and not args.no_train and args.n_train is None
@@ -1117,6 +1138,23 @@ def run_engine(args):
             line['sharded'] = sh
             if nccl_log:
                 line['sharded']['nccl_debug_file'] = nccl_log
+    if world > 1 and rank == 0:
+        # NCCL's own account of the communicator: the init lines of every rank's INFO log, echoed to stderr (stdout
+        # stays the one JSON line) and counted in the line
+        import glob
+
+        init_lines = []
+        for fn in sorted(glob.glob(os.path.join(ROOT, 'gpurun_out', 'nccl_n%d_*.log' % world))):
+            try:
+                with open(fn) as f:
+                    init_lines += [ln.strip() for ln in f if ('nranks' in ln or 'NVLS' in ln or 'Connected all' in ln)]
+            except OSError:
+                pass
+        for ln in init_lines[:24]:
+            print('[nccl] ' + ln, file=sys.stderr)
+        nccl_check['debug_file'] = nccl_log
+        nccl_check['init_lines_with_nranks'] = sum(1 for ln in init_lines if 'nranks %d' % world in ln or 'nranks=%d' % world in ln)
+        line['nccl'] = nccl_check
     if rank == 0:
         print(json.dumps(line))
         sys.stdout.flush()

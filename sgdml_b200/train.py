@@ -194,8 +194,16 @@ class GDMLTrain(object):
             alphas = analytic.solve(task, R_desc, R_d_desc, tril_perms_lin, y)
             self.timings = dict(analytic.timings)
         else:
+            # the Nystroem factor (n x m, the dominant term of iterative.py:845-866) is row-sharded over the ranks of a
+            # distributed run, so the budget that sizes the inducing set is the ranks' memory together
+            iter_bytes = max_bytes
+            if self.distributed:
+                import torch.distributed as tdist
+
+                if tdist.is_available() and tdist.is_initialized():
+                    iter_bytes = max_bytes * tdist.get_world_size()
             iterative = Iterative(
-                self, desc, max_bytes / 1024**3, self._max_processes, self._use_torch, callback=callback
+                self, desc, iter_bytes / 1024**3, self._max_processes, self._use_torch, callback=callback
             )
             (
                 alphas,
