@@ -1391,7 +1391,9 @@ extern "C" int sgdml_b200_assemble_rows(const double* R_desc, const double* R_d_
         if (asm_v4_smem_bytes(N, S, TJ, q) <= 110 * 1024) PG4 = q;
       }
       const size_t smem4 = asm_v4_smem_bytes(N, S, TJ, PG4);
-      const bool use_v4 = N <= 255 && smem4 <= 220 * 1024 && TJ * PG4 <= 256 && g_asm_kernel == 4;
+      // measured on B200 (tools/asm_variants.py): BASELINE config 2, full matrix: 42.4 (k_assemble) / 37.6 (v3) / 36.7 ms
+      // (v4); Ac-Ala3 shape, S = 243, 3000 random columns of M = 300 points: 616 / 805 / 312 ms -- v4 is the default
+      const bool use_v4 = N <= 255 && smem4 <= 220 * 1024 && TJ * PG4 <= 256 && (g_asm_kernel == 4 || g_asm_kernel == 0);
       const int tiles_per_cta = 4;
       if (use_v4) {
         SG_CUDA(cudaFuncSetAttribute(k_assemble_v4, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem4));
