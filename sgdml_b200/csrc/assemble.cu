@@ -844,6 +844,269 @@ __global__ void __launch_bounds__(256, 2) k_assemble_v4(const AsmArgs p, int PG,
 }
 
 // ---------------------------------------------------------------------------------------------
+// k_assemble_v5: k_assemble_v4 on the COMPRESSED pair arrays -- x (D) and g (D x 3) of the row point and of the column
+// point(s) sit in shared memory exactly as stored (4 D doubles per point instead of the 4 N^2 of the expanded
+// antisymmetric tables), looked up through the pair index d(a, g) = max(max - 1)/2 + min with the sign of a - g.  That
+// halves the table footprint: molecules up to ~64 atoms (BASELINE config 5: C60, N = 60, S = 120) keep everything on chip
+// with chunks of 11 permutations, where k_assemble_large walks per-CTA slabs in global memory one permutation at a time.
+__device__ __forceinline__ int pidx(int a, int g) { return a > g ? a * (a - 1) / 2 + g : g * (g - 1) / 2 + a; }
+
+__global__ void __launch_bounds__(256, 2) k_assemble_v5(const AsmArgs p, int PG, int tiles_per_cta) {
+  extern __shared__ __align__(16) double sm[];
+  const int N = p.N, S = p.S, TJ = p.TJ, NK = p.NK;
+  const int N3 = 3 * N, D = p.D, D3 = 3 * p.D;
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const int warp = tid >> 5, lane = tid & 31, nw = nt >> 5;
+  const int i = p.i0 + blockIdx.y;
+
+  double* gI = sm;                        // 3D   compressed pair vectors of the row point, as stored: g[d][0..2]
+  double* xI = gI + D3;                   // D    descriptor of the row point
+  double* gJ = xI + D;                    // TJ*3D
+  double* xJ = gJ + TJ * D3;              // TJ*D
+  double* uS = xJ + TJ * D;               // TJ*PG*N3
+  double* vS = uS + TJ * PG * N3;         // TJ*PG*N3   (rows of kept column atoms only)
+  double* DgS = vS + TJ * PG * N3;        // TJ*PG*3*N3 (rows a = P^-1 b of kept column atoms b only)
+  double* n2p = DgS + TJ * PG * 3 * N3;   // TJ*PG*N    per-u-row sums of squared deltas (each pair twice)
+  double* cc = n2p + TJ * PG * N;         // TJ*PG*2
+  int* klist = reinterpret_cast<int*>(cc + TJ * PG * 2);  // TJ*N: the kept column atoms of point t, compact
+  int* nk = klist + TJ * N;                                    // TJ: how many
+  unsigned char* sP = reinterpret_cast<unsigned char*>(nk + TJ);  // S*N
+  unsigned char* sPi = sP + S * N;                                     // S*N
+
+  for (int e = tid; e < D3; e += nt) gI[e] = p.R_d_desc[(int64_t)i * D3 + e];
+  for (int e = tid; e < D; e += nt) xI[e] = p.R_desc[(int64_t)i * D + e];
+  for (int idx = tid; idx < S * N; idx += nt) {
+    sP[idx] = (unsigned char)p.aperm[idx];
+    sPi[idx] = (unsigned char)p.apinv[idx];
+  }
+  const double sig = p.sig;
+  const double sig2 = sig * sig;
+  const double inv_div = 1.0 / (3.0 * sig2 * sig2);  // 1/mat52_base_div (train.py:179)
+
+  const int tile_begin = blockIdx.x * tiles_per_cta;
+  const int tile_end = min(tile_begin + tiles_per_cta, ceil_div_dev(p.nJ, TJ));
+  for (int tile = tile_begin; tile < tile_end; ++tile) {
+    const int jt0 = tile * TJ;
+    const int tj = min(TJ, p.nJ - jt0);
+    if (p.sym && jt0 + tj - 1 < i) continue;  // (sym: jpts is the identity) every column point of the tile is < i
+    __syncthreads();  // the previous tile's phase B has finished with Gj / the vectors
+    for (int t = 0; t < tj; ++t) {
+      const int j = p.jpts[jt0 + t];
+      for (int e = tid; e < D3; e += nt) gJ[t * D3 + e] = p.R_d_desc[(int64_t)j * D3 + e];
+      for (int e = tid; e < D; e += nt) xJ[t * D + e] = p.R_desc[(int64_t)j * D + e];
+    }
+    for (int tw = warp; tw < tj; tw += nw) {  // compact list of the kept column atoms of point tw (ballot over atoms)
+      int c = 0;
+      for (int b0 = 0; b0 < N; b0 += 32) {
+        const int b = b0 + lane;
+        bool kept = false;
+        if (b < N) {
+          const int64_t* dst = p.dest + (int64_t)(jt0 + tw) * N3 + 3 * b;
+          kept = dst[0] >= 0 || dst[1] >= 0 || dst[2] >= 0;
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, kept);
+        if (kept) klist[tw * N + c + __popc(m & ((1u << lane) - 1u))] = b;
+        c += __popc(m);
+      }
+      if (lane == 0) nk[tw] = c;
+    }
+    __syncthreads();
+    // this thread's output items: (t, a, b) = column point, row atom, kept column atom
+    int it_t[ASM_NI], it_a[ASM_NI], it_b[ASM_NI];
+    double acc[ASM_NI][9];
+#pragma unroll
+    for (int q = 0; q < ASM_NI; ++q) {
+      const int it = (int)blockIdx.z * ASM_NI * nt + tid + q * nt;  // grid.z splits the sub-blocks of large molecules
+      bool ok = it < tj * N * NK;
+      const int t = ok ? fastdiv(it, p.mNNK) : 0;
+      if (p.sym && jt0 + t < i) ok = false;  // mirrored from block (j, i) instead
+      const int ak = ok ? it - t * N * NK : 0;
+      it_a[q] = fastdiv(ak, p.mNK);
+      const int k = ak - it_a[q] * NK;
+      if (k >= nk[t]) ok = false;
+      it_b[q] = ok ? klist[t * N + k] : 0;
+      it_t[q] = ok ? t : -1;
+#pragma unroll
+      for (int e = 0; e < 9; ++e) acc[q][e] = 0.0;
+    }
+
+    for (int p0 = 0; p0 < S; p0 += PG) {
+      const int pg = min(PG, S - p0);
+      // ---- phase A, type-major over the chunk's (column point, permutation) slots
+      const int n_slots = tj * pg;
+      const int nU = n_slots * N, nV = n_slots * NK, nD = 3 * nV;
+      for (int idx = tid; idx < nU + nV + nD; idx += nt) {
+        if (idx < nU) {
+          // u[a] = -sum_g G_i[a][g] delta[a][g],  delta[a][g] = x_i[a][g] - x_j[Pa][Pg]  (i frame)
+          const int sl = fastdiv(idx, p.mN);
+          const int a = idx - sl * N;
+          const int t = sl / pg, pl = sl - t * pg;
+          const unsigned char* P = sP + (p0 + pl) * N;
+          const double* xj = xJ + t * D;
+          const int pa = P[a];
+          double s0 = 0.0, s1 = 0.0, s2 = 0.0, q2 = 0.0;
+          for (int g = 0; g < N; ++g) {
+            if (g == a) continue;
+            const int di = pidx(a, g), dj = pidx(pa, P[g]);
+            const double d = xI[di] - xj[dj];
+            q2 = fma(d, d, q2);
+            const double w = a > g ? d : -d;  // G_i[a][g] = sgn(a - g) g_i[d(a,g)]
+            const double* gi = gI + 3 * di;
+            s0 = fma(gi[0], w, s0);
+            s1 = fma(gi[1], w, s1);
+            s2 = fma(gi[2], w, s2);
+          }
+          const int slot = t * PG + pl;
+          double* u = uS + slot * N3 + 3 * a;
+          u[0] = -s0;
+          u[1] = -s1;
+          u[2] = -s2;
+          n2p[slot * N + a] = q2;
+        } else if (idx < nU + nV) {
+          // v[b] = -sum_g G_j[b][g] delta[P^-1 b][P^-1 g]  for the kept column atoms b
+          const int e = idx - nU;
+          const int sl = fastdiv(e, p.mNK);
+          const int k = e - sl * NK;
+          const int t = sl / pg, pl = sl - t * pg;
+          if (k >= nk[t]) continue;
+          const int b = klist[t * N + k];
+          const unsigned char* Pi = sPi + (p0 + pl) * N;
+          const double* xj = xJ + t * D;
+          const int pib = Pi[b];
+          double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+          for (int g = 0; g < N; ++g) {
+            if (g == b) continue;
+            const int dj = pidx(b, g), di = pidx(pib, Pi[g]);
+            const double d = xI[di] - xj[dj];
+            const double w = b > g ? d : -d;
+            const double* gj = gJ + t * D3 + 3 * dj;
+            s0 = fma(gj[0], w, s0);
+            s1 = fma(gj[1], w, s1);
+            s2 = fma(gj[2], w, s2);
+          }
+          double* v = vS + (t * PG + pl) * N3 + 3 * b;
+          v[0] = -s0;
+          v[1] = -s1;
+          v[2] = -s2;
+        } else {
+          // Dg[a][c][0..2] = sum_g G_i[a][g][c] G_j[Pa][Pg][0..2]  for a = P^-1 b, b a kept column atom
+          const int e = idx - nU - nV;
+          const int e3 = (int)__umulhi((unsigned)e, 0x55555556u), c = e - 3 * e3;
+          const int sl = fastdiv(e3, p.mNK);
+          const int k = e3 - sl * NK;
+          const int t = sl / pg, pl = sl - t * pg;
+          if (k >= nk[t]) continue;
+          const int b = klist[t * N + k];
+          const unsigned char* P = sP + (p0 + pl) * N;
+          const int a = sPi[(p0 + pl) * N + b];
+          double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+          for (int g = 0; g < N; ++g) {
+            if (g == a) continue;
+            const int pg = P[g];
+            const int di = pidx(a, g), dj = pidx(b, pg);  // b = P a
+            const double gic = gI[3 * di + c];
+            const double x = ((a > g) == (b > pg)) ? gic : -gic;  // sgn(a - g) sgn(Pa - Pg)
+            const double* y = gJ + t * D3 + 3 * dj;
+            s0 = fma(x, y[0], s0);
+            s1 = fma(x, y[1], s1);
+            s2 = fma(x, y[2], s2);
+          }
+          double* dg = DgS + (t * PG + pl) * 3 * N3 + (a * 3 + c) * 3;
+          dg[0] = s0;
+          dg[1] = s1;
+          dg[2] = s2;
+        }
+      }
+      __syncthreads();
+      // ---- Matern factors of the chunk (fixed-order sum of the row partials: bit-reproducible K)
+      if (tid < n_slots) {
+        const int t = tid / pg, pl = tid - t * pg;
+        const int slot = t * PG + pl;
+        double n2 = 0.0;
+        for (int a = 0; a < N; ++a) n2 += n2p[slot * N + a];
+        const double nrm = sqrt(5.0) * sqrt(0.5 * n2);  // every pair twice; train.py:201
+        const double base = exp(-nrm / sig) * inv_div * 5.0;          // train.py:202
+        cc[slot * 2 + 0] = base * 5.0;                                 // c1 (train.py:211)
+        cc[slot * 2 + 1] = (sig2 + sig * nrm) * base;                  // c2 (train.py:219)
+      }
+      __syncthreads();
+      // ---- phase B: acc[a][b] += c1 u[a] (x) v[b] - c2 T[a][b] for the permutations of the chunk
+      for (int pl = 0; pl < pg; ++pl) {
+        const unsigned char* P = sP + (p0 + pl) * N;
+        const unsigned char* Pi = sPi + (p0 + pl) * N;
+#pragma unroll
+        for (int q = 0; q < ASM_NI; ++q) {
+          const int t = it_t[q];
+          if (t < 0) continue;
+          const int slot = t * PG + pl;
+          const int a = it_a[q], b = it_b[q];
+          const double c1 = cc[slot * 2 + 0], c2 = cc[slot * 2 + 1];
+          const double* ua = uS + slot * N3 + 3 * a;
+          const double* vb = vS + slot * N3 + 3 * b;
+          const int pa = P[a];
+          if (b != pa) {
+            const int pib = Pi[b];
+            const double* gi = gI + 3 * pidx(a, pib);
+            const double* gj = gJ + t * D3 + 3 * pidx(pa, b);
+            const double sg = ((a > pib) == (pa > b)) ? c2 : -c2;  // sgn(a - P^-1 b) sgn(Pa - b) c2
+            double t0[3], t1[3];  // T[a][b] = -G_i[a][P^-1 b] (x) G_j[Pa][b]  ->  -c2 T = +c2 G_i (x) G_j
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+              t0[c] = sg * gi[c];
+              t1[c] = gj[c];
+            }
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+              const double cu = c1 * ua[c];
+#pragma unroll
+              for (int c2i = 0; c2i < 3; ++c2i)
+                acc[q][c * 3 + c2i] = fma(t0[c], t1[c2i], fma(cu, vb[c2i], acc[q][c * 3 + c2i]));
+            }
+          } else {
+            const double* dg = DgS + slot * 3 * N3 + 9 * a;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+              const double cu = c1 * ua[c];
+#pragma unroll
+              for (int c2i = 0; c2i < 3; ++c2i)
+                acc[q][c * 3 + c2i] = fma(-c2, dg[c * 3 + c2i], fma(cu, vb[c2i], acc[q][c * 3 + c2i]));
+            }
+          }
+        }
+      }
+      if (p0 + PG < S) __syncthreads();  // the next chunk overwrites the vectors
+    }
+
+    // ---- single store of the finished 3x3 sub-blocks (+ the mirrored block in symmetric mode)
+#pragma unroll
+    for (int q = 0; q < ASM_NI; ++q) {
+      const int t = it_t[q];
+      if (t < 0) continue;
+      const int a = it_a[q], b = it_b[q];
+      const int64_t* dst = p.dest + (int64_t)(jt0 + t) * N3 + 3 * b;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        double* Krow = p.K + ((int64_t)(i - p.i0) * N3 + 3 * a + c) * p.ldk;
+#pragma unroll
+        for (int c2i = 0; c2i < 3; ++c2i) {
+          const int64_t col = dst[c2i];
+          if (col >= 0) Krow[col] = p.scale * acc[q][c * 3 + c2i];
+        }
+      }
+      if (p.sym && jt0 + t > i) {  // (sym implies i0 == 0)
+        const int j = jt0 + t;
+#pragma unroll
+        for (int c2i = 0; c2i < 3; ++c2i) {
+          double* Krow = p.K + ((int64_t)j * N3 + 3 * b + c2i) * p.ldk + (int64_t)i * N3 + 3 * a;
+#pragma unroll
+          for (int c = 0; c < 3; ++c) Krow[c] = p.scale * acc[q][c * 3 + c2i];
+        }
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // Large molecules (N > ~50: the atom tables of one block no longer fit in shared memory; BASELINE
 // configs 4 and 5).  Same mathematics and the same summation order as k_assemble, but the tables
 // live in a private slab of global memory per CTA (L1/L2 resident), the CTAs are persistent
@@ -1139,6 +1402,12 @@ static size_t asm_v4_smem_bytes(int N, int S, int TJ, int PG) {
   return dbl * 8 + ((size_t)TJ * N + TJ) * 4 + 2 * (size_t)S * N + 16;
 }
 
+static size_t asm_v5_smem_bytes(int N, int S, int TJ, int PG) {
+  const size_t N3 = 3 * (size_t)N, D = (size_t)N * (N - 1) / 2;
+  const size_t dbl = 4 * D * (1 + TJ) + (size_t)TJ * PG * (2 * N3 + 3 * N3 + N + 2);
+  return dbl * 8 + ((size_t)TJ * N + TJ) * 4 + 2 * (size_t)S * N + 16;
+}
+
 static size_t asm_smem_bytes(int N, int D, int S, int TJ) {
   (void)D;
   const size_t N3 = 3 * (size_t)N, NN = (size_t)N * N;
@@ -1205,7 +1474,7 @@ extern "C" int sgdml_b200_set_assemble_variant(int variant) {
     g_asm_max_rowpts = variant - 1000;
     return 0;
   }
-  if (variant >= 2 && variant <= 4) {  // which small-molecule kernel
+  if (variant >= 2 && variant <= 5) {  // which small-molecule kernel
     g_asm_kernel = variant;
     return 0;
   }
@@ -1306,6 +1575,18 @@ extern "C" int sgdml_b200_assemble_rows(const double* R_desc, const double* R_d_
     n_chunks = (int)(((int64_t)N * NK + ASM_NI * 256 - 1) / (ASM_NI * 256));
     if (asm_smem_bytes(N, D, S, 1) > 220 * 1024) large = true;  // tables beyond shared memory: k_assemble_large
   }
+  // v5 kernel (compressed pair arrays on chip): for molecules whose expanded tables do not fit shared memory, up to
+  // ~64 atoms; one column point per CTA, chunks of up to 16 permutations
+  int PG5 = std::min(S, 16);
+  while (PG5 > 1 && asm_v5_smem_bytes(N, S, 1, PG5) > 220 * 1024) --PG5;
+  const size_t smem5 = asm_v5_smem_bytes(N, S, 1, PG5);
+  const bool fits5 = N <= 255 && smem5 <= 220 * 1024 && (PG5 >= 4 || PG5 == S);
+  const bool use_v5 = g_asm_variant != 1 && fits5 && (g_asm_kernel == 5 || (g_asm_kernel == 0 && large));
+  if (use_v5) {
+    large = false;
+    TJ = 1;
+    n_chunks = (int)(((int64_t)N * NK + ASM_NI * 256 - 1) / (ASM_NI * 256));
+  }
   if (large) TJ = 1;
   TJ = std::min(TJ, nJ);
   const size_t smem = asm_smem_bytes(N, D, S, TJ);
@@ -1395,7 +1676,9 @@ extern "C" int sgdml_b200_assemble_rows(const double* R_desc, const double* R_d_
       // (v4); Ac-Ala3 shape, S = 243, 3000 random columns of M = 300 points: 616 / 805 / 312 ms -- v4 is the default
       const bool use_v4 = N <= 255 && smem4 <= 220 * 1024 && TJ * PG4 <= 256 && (g_asm_kernel == 4 || g_asm_kernel == 0);
       const int tiles_per_cta = 4;
-      if (use_v4) {
+      if (use_v5) {
+        SG_CUDA(cudaFuncSetAttribute(k_assemble_v5, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem5));
+      } else if (use_v4) {
         SG_CUDA(cudaFuncSetAttribute(k_assemble_v4, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem4));
       } else if (use_v3)
         SG_CUDA(cudaFuncSetAttribute(k_assemble_v3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3));
@@ -1407,7 +1690,10 @@ extern "C" int sgdml_b200_assemble_rows(const double* R_desc, const double* R_d_
         AsmArgs ac = a;
         ac.i0 = (int)m_begin + r0;
         ac.K = a.K + (int64_t)r0 * N3 * ldk;
-        if (use_v4) {
+        if (use_v5) {
+          dim3 grid((unsigned)ceil_div(nJ, tiles_per_cta), (unsigned)nr, (unsigned)n_chunks);
+          k_assemble_v5<<<grid, 256, smem5, s>>>(ac, PG5, tiles_per_cta);
+        } else if (use_v4) {
           dim3 grid((unsigned)ceil_div(ceil_div(nJ, TJ), tiles_per_cta), (unsigned)nr, (unsigned)n_chunks);
           k_assemble_v4<<<grid, 256, smem4, s>>>(ac, PG4, tiles_per_cta);
         } else if (use_v3) {

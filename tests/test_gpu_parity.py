@@ -291,10 +291,13 @@ def test_assemble_large_kernel_matches_small(eng, golden):
     assert np.array_equal(K_full[iu][blk], K_small_full[iu][blk])
 
 
-@pytest.mark.parametrize('N,M,rot,swap,sig', [(60, 3, 1, 1, 50), (100, 2, 2, 0, 50), (53, 2, 0, 1, 30)])
-def test_assemble_large_molecules_vs_oracle(eng, N, M, rot, swap, sig):
-    """BASELINE configs 4-5 sizes (60 and 100 atoms): tables beyond shared memory."""
-    from sgdml_b200 import synth
+@pytest.mark.parametrize('variant', [0, 1])
+@pytest.mark.parametrize('N,M,rot,swap,sig', [(60, 3, 1, 1, 50), (100, 2, 2, 0, 50), (53, 2, 0, 1, 30), (64, 2, 2, 1, 40)])
+def test_assemble_large_molecules_vs_oracle(eng, N, M, rot, swap, sig, variant):
+    """BASELINE configs 4-5 sizes (60 and 100 atoms): expanded pair tables beyond shared memory.  variant 0: the default
+    routing (up to ~64 atoms k_assemble_v5, compressed pair arrays on chip; above that k_assemble_large), variant 1: the
+    large-molecule kernel (tables in global memory) for every size."""
+    from sgdml_b200 import _lib, synth
     from sgdml_b200.desc import Desc
 
     perms = synth.rotor_swap_group(N, rot, swap)
@@ -303,11 +306,17 @@ def test_assemble_large_molecules_vs_oracle(eng, N, M, rot, swap, sig):
     lin = odesc.tril_perms_lin(perms)
     K_ref = oassemble.assemble(x, g, lin, sig)
     t = eng.GDMLTrain()
-    K = t._assemble_kernel_mat(x, g, lin, sig, Desc(N))
-    assert rel_err(K, K_ref) < 1e-12
-    cols = np.unique(np.random.default_rng(2).integers(0, K_ref.shape[0], size=40))
-    K = t._assemble_kernel_mat(x, g, lin, sig, Desc(N), col_idxs=cols)
-    assert rel_err(K, K_ref[:, cols]) < 1e-12
+    _lib.lib().sgdml_b200_set_assemble_variant(variant)
+    try:
+        K = t._assemble_kernel_mat(x, g, lin, sig, Desc(N))
+        assert rel_err(K, K_ref) < 1e-12
+        cols = np.unique(np.random.default_rng(2).integers(0, K_ref.shape[0], size=40))
+        K = t._assemble_kernel_mat(x, g, lin, sig, Desc(N), col_idxs=cols)
+        assert rel_err(K, K_ref[:, cols]) < 1e-12
+        Kr, nc = t._assemble_kernel_mat_device(x, g, lin, sig, col_idxs=cols, rows=(1, M))
+        assert rel_err(Kr[:, :nc].cpu().numpy(), K_ref[3 * N :, cols]) < 1e-12
+    finally:
+        _lib.lib().sgdml_b200_set_assemble_variant(0)
 
 
 @pytest.mark.parametrize('large', [0, 1])
@@ -773,7 +782,7 @@ def test_ase_calculator_core_units(eng, golden):
 
 
 # --------------------------------------------------------------------------- assembly kernels v3 / v4 (chunked permutations)
-@pytest.mark.parametrize('variant', [3, 4])
+@pytest.mark.parametrize('variant', [3, 4, 5])
 def test_assemble_v3_kernel(eng, golden, variant):
     """k_assemble_v3 (permutation chunks, delta on the fly, resident row tables) and k_assemble_v4 (byte permutation
     tables, odd table strides, type-major phase A over kept column atoms) against the reference's K: full matrix
@@ -818,7 +827,7 @@ def test_assemble_v3_many_permutations(eng):
         lin = tril_perms_lin(perms)
         out, sub = {}, {}
         cols = np.unique(np.random.default_rng(N).integers(0, 3 * N * M, size=3 * M))
-        for v in (2, 3, 4):
+        for v in (2, 3, 4, 5):
             L.sgdml_b200_set_assemble_variant(v)
             try:
                 K, nc = t._assemble_kernel_mat_device(x, g, lin, 25)
@@ -827,7 +836,7 @@ def test_assemble_v3_many_permutations(eng):
                 sub[v] = Kc[:, :ncc].cpu().numpy()
             finally:
                 L.sgdml_b200_set_assemble_variant(0)
-        for v in (3, 4):
+        for v in (3, 4, 5):
             assert rel_err(out[v], out[2]) < 1e-12
             assert rel_err(out[v], out[v].T) < 1e-12  # the mirrored blocks
             assert rel_err(sub[v], out[2][:, cols]) < 1e-12 and rel_err(sub[2], out[2][:, cols]) < 1e-12
