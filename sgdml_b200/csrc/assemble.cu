@@ -1602,20 +1602,16 @@ extern "C" int sgdml_b200_assemble_rows(const double* R_desc, const double* R_d_
   int *d_dperm = nullptr, *d_aperm = nullptr, *d_apinv = nullptr, *d_jpts = nullptr;
   int64_t* d_dest = nullptr;
   double* d_slabs = nullptr;
-  auto cleanup = [&]() {
-    cudaFree(d_dperm);
-    cudaFree(d_aperm);
-    cudaFree(d_apinv);
-    cudaFree(d_jpts);
-    cudaFree(d_dest);
-    cudaFree(d_slabs);
-  };
+  // the integer tables (and the large-molecule kernel's slabs) live in persistent workspaces: a cudaMalloc / cudaFree
+  // pair per table costs milliseconds once the K buffer and the factorisation workspaces exist (measured: 36 ms of
+  // kernel inside a 74 ms assembly on the second training run of a process)
+  auto cleanup = [&]() {};
   auto body = [&]() -> int {
-    SG_CUDA(cudaMalloc(&d_dperm, sizeof(int) * dperm.size()));
-    SG_CUDA(cudaMalloc(&d_aperm, sizeof(int) * aperm.size()));
-    SG_CUDA(cudaMalloc(&d_apinv, sizeof(int) * apinv.size()));
-    SG_CUDA(cudaMalloc(&d_jpts, sizeof(int) * jpts.size()));
-    SG_CUDA(cudaMalloc(&d_dest, sizeof(int64_t) * dest.size()));
+    SG_TRY(ws_get(WS_ASM_DPERM, sizeof(int) * dperm.size(), (void**)&d_dperm));
+    SG_TRY(ws_get(WS_ASM_APERM, sizeof(int) * aperm.size(), (void**)&d_aperm));
+    SG_TRY(ws_get(WS_ASM_APINV, sizeof(int) * apinv.size(), (void**)&d_apinv));
+    SG_TRY(ws_get(WS_ASM_JPTS, sizeof(int) * jpts.size(), (void**)&d_jpts));
+    SG_TRY(ws_get(WS_ASM_DEST, sizeof(int64_t) * dest.size(), (void**)&d_dest));
     SG_CUDA(cudaMemcpyAsync(d_dperm, dperm.data(), sizeof(int) * dperm.size(), cudaMemcpyHostToDevice, s));
     SG_CUDA(cudaMemcpyAsync(d_aperm, aperm.data(), sizeof(int) * aperm.size(), cudaMemcpyHostToDevice, s));
     SG_CUDA(cudaMemcpyAsync(d_apinv, apinv.data(), sizeof(int) * apinv.size(), cudaMemcpyHostToDevice, s));
@@ -1715,7 +1711,7 @@ extern "C" int sgdml_b200_assemble_rows(const double* R_desc, const double* R_d_
       const size_t dl_bytes = sizeof(double) * (size_t)N * N;
       const int dl_in_smem = dl_bytes <= 100 * 1024 ? 1 : 0;  // two CTAs per SM keep their delta tables on chip
       const size_t slab = (asm_large_slab_doubles(N, S) + 1) / 2 * 2;
-      SG_CUDA(cudaMalloc(&d_slabs, sizeof(double) * slab * (size_t)n_cta));
+      SG_TRY(ws_get(WS_ASM_SLABS, sizeof(double) * slab * (size_t)n_cta, (void**)&d_slabs));
       if (dl_in_smem)
         SG_CUDA(cudaFuncSetAttribute(k_assemble_large, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dl_bytes));
       ProfScope ps(KID_ASSEMBLE, s);

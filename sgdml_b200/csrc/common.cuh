@@ -75,7 +75,8 @@ class Staged {
 // sgdml_b200_release_workspaces().  The caller must have finished with the buffer (stream synchronised) before the
 // next ws_get of the same slot -- true for every user: they all synchronise before returning.
 enum WsSlot { WS_POTRF_W0 = 0, WS_POTRF_W1 = 1, WS_OZ_PLANES = 2, WS_OZ_EXPS = 3, WS_POTRF_INFO = 4, WS_SOLVE_TMP = 5,
-              WS_SLOT_COUNT = 6 };
+              WS_ASM_DPERM = 6, WS_ASM_APERM = 7, WS_ASM_APINV = 8, WS_ASM_JPTS = 9, WS_ASM_DEST = 10, WS_ASM_SLABS = 11,
+              WS_SLOT_COUNT = 12 };
 int ws_get(int slot, size_t bytes, void** out);
 
 inline int ceil_div(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
