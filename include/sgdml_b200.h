@@ -127,7 +127,8 @@ int sgdml_b200_predict_train(sgdml_b200_model* model, int64_t m_begin, int64_t m
  * descriptor size); 1 = two warp groups running the sweep half a tile apart (72 < D; measured slower); 2 = no split
  * over k in the first contraction: Matern transform on the accumulator fragments, two CTA-wide barriers per tile
  * instead of three (72 < D <= 224); 3 = 2 with C1 / C2 double-buffered and ONE barrier per tile (D <= 224); 4 = the
- * round-1 kernels for every size.  A variant without a kernel for a size runs the round-1 kernel. */
+ * round-1 kernels for every size; 5 = the one-barrier form on 16-point tiles for D <= 40 (two CTAs per SM).  A variant
+ * without a kernel for a size runs the default kernel of that size. */
 int sgdml_b200_set_predict_variant(int variant);
 
 /* Shape of a model: n_atoms, n_train, n_perms (any pointer may be NULL). */

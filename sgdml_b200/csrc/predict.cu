@@ -98,6 +98,8 @@ struct PredictArgs {
   int64_t n_rows;       // B*S virtual rows
   int64_t n_rows_pad;   // rows rounded up to BQ (stride between the per-split output planes)
   int tiles_per_split;  // blockIdx.y handles training tiles [y*tps, (y+1)*tps): small batches split the sweep over M
+  int bm;               // training points per tile that tiles_per_split is counted in (the model's BM; a kernel with a
+                        // smaller tile converts)
   // outputs
   double* G;            // (n_rows, DP)
   double* Erow;         // (n_rows)
@@ -1282,6 +1284,8 @@ using Cfg72o = PCfg<72, 64, 32, 4, 2, 1, 8, 1, 1, 1, 1>;
 using Cfg112o = PCfg<112, 64, 16, 4, 2, 1, 4, 2, 1, 1, 1>;
 using Cfg160o = PCfg<160, 32, 16, 4, 2, 1, 2, 4, 1, 1, 1>;
 using Cfg224o = PCfg<224, 32, 16, 4, 2, 1, 2, 4, 1, 1, 1>;
+// variant 5 (DP = 40 only): the one-barrier form on 16-point tiles, which keeps two CTAs per SM (88 KB)
+using Cfg40o16 = PCfg<40, 64, 16, 4, 2, 1, 4, 1, 2, 2, 1>;
 
 struct CfgInfo {
   int DP, BQ, BM;
@@ -1314,7 +1318,9 @@ int launch_main_t(const PredictArgs& a, int n_splits, cudaStream_t s) {
     configured[dev] = true;
   }
   const int64_t grid = (a.n_rows + C::BQ - 1) / C::BQ;
-  k_predict_main<C><<<dim3((unsigned)grid, (unsigned)n_splits), C::NT, C::SMEM_BYTES, s>>>(a);
+  PredictArgs b = a;
+  if (a.bm > C::BM) b.tiles_per_split = a.tiles_per_split * (a.bm / C::BM);  // (a.bm is a multiple of C::BM)
+  k_predict_main<C><<<dim3((unsigned)grid, (unsigned)n_splits), C::NT, C::SMEM_BYTES, s>>>(b);
   SG_CUDA(cudaGetLastError());
   return 0;
 }
@@ -1346,6 +1352,7 @@ int launch_main(int cfg, const PredictArgs& a, int n_splits, cudaStream_t s) {
       case 4: return launch_main_t<Cfg224o>(a, n_splits, s);
     }
   }
+  if (g_predict_variant == 5 && cfg == 0) return launch_main_t<Cfg40o16>(a, n_splits, s);
   if (g_predict_variant == 0) {
     // default: the measured-fastest kernel per size (tools/predict_variants.py, 65536 queries, M = 1000, S = 6, ms per
     // call round-1 kernel -> one-barrier kernel): DP = 72: 9.09 -> 8.89, 112: 13.98 -> 12.73, 160: 20.07 -> 18.12,
@@ -1574,6 +1581,7 @@ int run_queries(sgdml_b200_model* m, int slot, const double* xq, const double* g
     a.qqg = w.qq;
     a.n_rows = n_rows;
     a.n_rows_pad = n_rows_pad;
+    a.bm = m->BM;
     a.G = w.G;
     a.Erow = w.Erow;
     // small batches: split the sweep over the training points across CTAs so that the grid fills the
@@ -2063,7 +2071,7 @@ int sgdml_b200_predict_train(sgdml_b200_model* m, int64_t m_begin, int64_t m_end
 }
 
 int sgdml_b200_set_predict_variant(int variant) {
-  SG_ARG(variant >= 0 && variant <= 4);
+  SG_ARG(variant >= 0 && variant <= 5);
   g_predict_variant = variant;
   return 0;
 }

@@ -875,7 +875,7 @@ def test_small_batch_graph_replay(eng, golden, monkeypatch, zero_copy):
     assert rel_err(F2, 2.0 * golden['F_query'][:1]) < 1e-10
 
 
-@pytest.mark.parametrize('variant', [1, 2, 3, 4])
+@pytest.mark.parametrize('variant', [1, 2, 3, 4, 5])
 @pytest.mark.parametrize(
     'N,M,rot,swap,sig', [(9, 70, 1, 1, 20), (12, 45, 2, 0, 20), (15, 40, 2, 0, 30), (18, 21, 1, 1, 40), (21, 50, 1, 1, 20), (23, 19, 0, 1, 20)]
 )
@@ -884,7 +884,7 @@ def test_predict_main_kernel_variants(eng, N, M, rot, swap, sig, variant):
     every tile configuration (DP = 40, 72, 112, 160, 224, 256; a variant without a kernel for a size runs the default):
     1 = two warp groups half a tile apart ("ping-pong"; measured slower), 2 = no split over k in GEMM1 (transform on
     the accumulator fragments, two barriers per tile), 3 = 2 with double-buffered C1 / C2 and one barrier per tile,
-    4 = the round-1 kernels."""
+    4 = the round-1 kernels, 5 = one barrier on 16-point tiles (DP = 40 only)."""
     from sgdml_b200 import _lib, synth
 
     perms = synth.rotor_swap_group(N, rot, swap)
