@@ -1,6 +1,9 @@
 // Error plumbing, host/device staging and misc entry points of the sgdml_b200 C ABI.
 #include "common.cuh"
 
+#include <map>
+#include <mutex>
+
 namespace sgdml {
 
 static thread_local std::string g_last_error;
@@ -151,6 +154,75 @@ int ws_get(int slot, size_t bytes, void** out) {
   return 0;
 }
 
+namespace {
+struct CacheKey {
+  int dev;
+  size_t bytes;
+  bool operator<(const CacheKey& o) const { return dev != o.dev ? dev < o.dev : bytes < o.bytes; }
+};
+std::mutex g_cache_mu;
+std::map<void*, CacheKey> g_cache_live;        // blocks handed out by cached_malloc
+std::multimap<CacheKey, void*> g_cache_free;   // blocks kept for reuse
+size_t g_cache_bytes = 0;
+constexpr size_t CACHE_LIMIT_BYTES = 8ull << 30;
+}  // namespace
+
+void cache_release_all() {
+  std::lock_guard<std::mutex> lk(g_cache_mu);
+  for (auto& kv : g_cache_free) cudaFree(kv.second);
+  g_cache_free.clear();
+  g_cache_bytes = 0;
+}
+
+cudaError_t cached_malloc_bytes(void** p, size_t bytes) {
+  *p = nullptr;
+  if (bytes == 0) return cudaSuccess;
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  const CacheKey key{dev, bytes};
+  {
+    std::lock_guard<std::mutex> lk(g_cache_mu);
+    auto it = g_cache_free.find(key);
+    if (it != g_cache_free.end()) {
+      *p = it->second;
+      g_cache_free.erase(it);
+      g_cache_bytes -= bytes;
+      g_cache_live[*p] = key;
+      return cudaSuccess;
+    }
+  }
+  e = cudaMalloc(p, bytes);
+  if (e == cudaErrorMemoryAllocation) {  // give the cached blocks back and try once more
+    cudaGetLastError();
+    cache_release_all();
+    e = cudaMalloc(p, bytes);
+  }
+  if (e == cudaSuccess) {
+    std::lock_guard<std::mutex> lk(g_cache_mu);
+    g_cache_live[*p] = key;
+  }
+  return e;
+}
+
+cudaError_t cached_free(void* p) {
+  if (p == nullptr) return cudaSuccess;
+  {
+    std::lock_guard<std::mutex> lk(g_cache_mu);
+    auto it = g_cache_live.find(p);
+    if (it != g_cache_live.end()) {
+      const CacheKey key = it->second;
+      g_cache_live.erase(it);
+      if (g_cache_bytes + key.bytes <= CACHE_LIMIT_BYTES) {
+        g_cache_free.emplace(key, p);
+        g_cache_bytes += key.bytes;
+        return cudaSuccess;
+      }
+    }
+  }
+  return cudaFree(p);
+}
+
 int num_sms() {
   static int cached[64] = {0};
   int dev = 0;
@@ -229,6 +301,7 @@ int sgdml_b200_release_workspaces(void) {
     if (sgdml::g_ws[dev][i].p != nullptr) cudaFree(sgdml::g_ws[dev][i].p);
     sgdml::g_ws[dev][i] = sgdml::WsBuf();
   }
+  sgdml::cache_release_all();
   return 0;
 }
 

@@ -1379,35 +1379,37 @@ int launch_main(int cfg, const PredictArgs& a, int n_splits, cudaStream_t s) {
 int64_t chunk_geos(const sgdml_b200_model* m);
 
 void free_oz(OzOperand& o) {
-  cudaFree(o.units);
-  cudaFree(o.exps);
+  cached_free(o.units);
+  cached_free(o.exps);
   o = OzOperand();
 }
 
 int alloc_oz(OzOperand& o, int64_t rows, int64_t k, int S) {
+  if (o.units != nullptr) cudaDeviceSynchronize();  // (blocks go back to the cache: nothing may still use them)
   free_oz(o);
-  SG_CUDA(cudaMalloc(&o.units, ozaki_units_bytes(rows, k, S)));
-  SG_CUDA(cudaMalloc(&o.exps, ozaki_exps_bytes(rows)));
+  SG_CUDA(cached_malloc(&o.units, ozaki_units_bytes(rows, k, S)));
+  SG_CUDA(cached_malloc(&o.exps, ozaki_exps_bytes(rows)));
   return 0;
 }
 
 void free_ws(sgdml_b200_model* m) {
+  cudaDeviceSynchronize();  // the blocks go back to the cache (no implicit synchronisation as in cudaFree)
   for (auto& w : m->ws) {
     free_oz(w.ozQ);
     free_oz(w.ozC1);
     free_oz(w.ozC2);
-    cudaFree(w.xq);
-    cudaFree(w.gq);
-    cudaFree(w.G);
-    cudaFree(w.Erow);
-    cudaFree(w.R);
-    cudaFree(w.E);
-    cudaFree(w.F);
-    cudaFree(w.Qg);
-    cudaFree(w.qq);
-    cudaFree(w.S1);
-    cudaFree(w.S2);
-    cudaFree(w.csum);
+    cached_free(w.xq);
+    cached_free(w.gq);
+    cached_free(w.G);
+    cached_free(w.Erow);
+    cached_free(w.R);
+    cached_free(w.E);
+    cached_free(w.F);
+    cached_free(w.Qg);
+    cached_free(w.qq);
+    cached_free(w.S1);
+    cached_free(w.S2);
+    cached_free(w.csum);
     w = sgdml_b200_model::WS();
   }
 }
@@ -1420,41 +1422,42 @@ int ensure_ws(sgdml_b200_model* m, int slot, int64_t n_geo) {
   }
   if (n_geo <= w.geo) return 0;
   ++m->generation;  // captured graphs hold the old workspace pointers
+  if (w.geo > 0) SG_CUDA(cudaDeviceSynchronize());  // earlier batches may still run on the old workspace
   free_oz(w.ozQ);
   free_oz(w.ozC1);
   free_oz(w.ozC2);
-  cudaFree(w.xq);
-  cudaFree(w.gq);
-  cudaFree(w.G);
-  cudaFree(w.Erow);
-  cudaFree(w.R);
-  cudaFree(w.E);
-  cudaFree(w.F);
-  cudaFree(w.Qg);
-  cudaFree(w.qq);
-  cudaFree(w.S1);
-  cudaFree(w.S2);
-  cudaFree(w.csum);
+  cached_free(w.xq);
+  cached_free(w.gq);
+  cached_free(w.G);
+  cached_free(w.Erow);
+  cached_free(w.R);
+  cached_free(w.E);
+  cached_free(w.F);
+  cached_free(w.Qg);
+  cached_free(w.qq);
+  cached_free(w.S1);
+  cached_free(w.S2);
+  cached_free(w.csum);
   w = sgdml_b200_model::WS();
-  SG_CUDA(cudaMalloc(&w.xq, sizeof(double) * n_geo * m->D));
-  SG_CUDA(cudaMalloc(&w.gq, sizeof(double) * n_geo * m->D * 3));
+  SG_CUDA(cached_malloc(&w.xq, sizeof(double) * n_geo * m->D));
+  SG_CUDA(cached_malloc(&w.gq, sizeof(double) * n_geo * m->D * 3));
   {
     // padded to whole row tiles: the per-split output planes of small batches are laid out with that stride
     const int64_t rows_cap = (n_geo * m->S + m->BQ - 1) / m->BQ * m->BQ;
-    SG_CUDA(cudaMalloc(&w.G, sizeof(double) * rows_cap * m->DP));
-    SG_CUDA(cudaMalloc(&w.Erow, sizeof(double) * rows_cap));
+    SG_CUDA(cached_malloc(&w.G, sizeof(double) * rows_cap * m->DP));
+    SG_CUDA(cached_malloc(&w.Erow, sizeof(double) * rows_cap));
   }
-  SG_CUDA(cudaMalloc(&w.R, sizeof(double) * n_geo * 3 * m->N));
-  SG_CUDA(cudaMalloc(&w.E, sizeof(double) * n_geo));
-  SG_CUDA(cudaMalloc(&w.F, sizeof(double) * n_geo * 3 * m->N));
+  SG_CUDA(cached_malloc(&w.R, sizeof(double) * n_geo * 3 * m->N));
+  SG_CUDA(cached_malloc(&w.E, sizeof(double) * n_geo));
+  SG_CUDA(cached_malloc(&w.F, sizeof(double) * n_geo * 3 * m->N));
   {
     const int64_t rows_pad = (n_geo * m->S + m->BQ - 1) / m->BQ * m->BQ;
-    SG_CUDA(cudaMalloc(&w.Qg, sizeof(double) * rows_pad * m->DS));
-    SG_CUDA(cudaMalloc(&w.qq, sizeof(double) * rows_pad));
+    SG_CUDA(cached_malloc(&w.Qg, sizeof(double) * rows_pad * m->DS));
+    SG_CUDA(cached_malloc(&w.qq, sizeof(double) * rows_pad));
     if (m->large) {
-      SG_CUDA(cudaMalloc(&w.S1, sizeof(double) * rows_pad * m->Mpad));
-      SG_CUDA(cudaMalloc(&w.S2, sizeof(double) * rows_pad * m->Mpad));
-      SG_CUDA(cudaMalloc(&w.csum, sizeof(double) * rows_pad));
+      SG_CUDA(cached_malloc(&w.S1, sizeof(double) * rows_pad * m->Mpad));
+      SG_CUDA(cached_malloc(&w.S2, sizeof(double) * rows_pad * m->Mpad));
+      SG_CUDA(cached_malloc(&w.csum, sizeof(double) * rows_pad));
       if (m->oz_s >= 2) {
         SG_TRY(alloc_oz(w.ozQ, rows_pad, m->DS, m->oz_s));
         SG_TRY(alloc_oz(w.ozC1, rows_pad, m->Mpad, m->oz_s));
@@ -1730,18 +1733,18 @@ int sgdml_b200_model_create(sgdml_b200_model** out, int64_t n_atoms, int64_t n_t
   int rc = 0;
   auto body = [&]() -> int {
     cudaStream_t s = 0;
-    SG_CUDA(cudaMalloc(&m->perm, sizeof(int) * perm.size()));
-    SG_CUDA(cudaMalloc(&m->pinv, sizeof(int) * pinv.size()));
+    SG_CUDA(cached_malloc(&m->perm, sizeof(int) * perm.size()));
+    SG_CUDA(cached_malloc(&m->pinv, sizeof(int) * pinv.size()));
     SG_CUDA(cudaMemcpy(m->perm, perm.data(), sizeof(int) * perm.size(), cudaMemcpyHostToDevice));
     SG_CUDA(cudaMemcpy(m->pinv, pinv.data(), sizeof(int) * pinv.size(), cudaMemcpyHostToDevice));
-    SG_CUDA(cudaMalloc(&m->X, sizeof(double) * n_train * D));
-    SG_CUDA(cudaMalloc(&m->Xc, sizeof(double) * m->Mpad * m->DS));
-    SG_CUDA(cudaMalloc(&m->JA, sizeof(double) * m->Mpad * m->DS));
-    SG_CUDA(cudaMalloc(&m->mm, sizeof(double) * m->Mpad));
-    SG_CUDA(cudaMalloc(&m->xja, sizeof(double) * m->Mpad));
-    SG_CUDA(cudaMalloc(&m->ae, sizeof(double) * m->Mpad));
+    SG_CUDA(cached_malloc(&m->X, sizeof(double) * n_train * D));
+    SG_CUDA(cached_malloc(&m->Xc, sizeof(double) * m->Mpad * m->DS));
+    SG_CUDA(cached_malloc(&m->JA, sizeof(double) * m->Mpad * m->DS));
+    SG_CUDA(cached_malloc(&m->mm, sizeof(double) * m->Mpad));
+    SG_CUDA(cached_malloc(&m->xja, sizeof(double) * m->Mpad));
+    SG_CUDA(cached_malloc(&m->ae, sizeof(double) * m->Mpad));
     SG_CUDA(cudaMemset(m->ae, 0, sizeof(double) * m->Mpad));
-    SG_CUDA(cudaMalloc(&m->mu, sizeof(double) * m->DS));
+    SG_CUDA(cached_malloc(&m->mu, sizeof(double) * m->DS));
     SG_CUDA(cudaMemset(m->mu, 0, sizeof(double) * m->DS));
     Staged sJA;
     SG_CUDA(cudaMemcpy(m->X, R_desc, sizeof(double) * n_train * D, cudaMemcpyDefault));
@@ -1756,8 +1759,8 @@ int sgdml_b200_model_create(sgdml_b200_model** out, int64_t n_atoms, int64_t n_t
     SG_CUDA(cudaGetLastError());
     SG_TRY(refresh_row_dots(m, true, s));
     if (m->large) {
-      SG_CUDA(cudaMalloc(&m->XcT, sizeof(double) * (size_t)m->DP * m->Mpad));
-      SG_CUDA(cudaMalloc(&m->JAT, sizeof(double) * (size_t)m->DP * m->Mpad));
+      SG_CUDA(cached_malloc(&m->XcT, sizeof(double) * (size_t)m->DP * m->Mpad));
+      SG_CUDA(cached_malloc(&m->JAT, sizeof(double) * (size_t)m->DP * m->Mpad));
       SG_TRY(refresh_transposes(m, true, s));
       const char* ozp = getenv("SGDML_B200_OZAKI_PREDICT_SLICES");
       const int oz_s = (ozp != nullptr) ? std::max(0, std::min(7, atoi(ozp))) : 0;
@@ -1898,21 +1901,22 @@ int predict_graph(sgdml_b200_model* m, const double* R, int64_t n_geo, double* E
 
 int sgdml_b200_model_destroy(sgdml_b200_model* m) {
   if (m == nullptr) return 0;
+  cudaDeviceSynchronize();  // the device blocks go back to the cache: no kernel of this model may still run
   for (auto& g : m->graphs) free_graph_slot(g);
   if (m->graph_stream) cudaStreamDestroy(m->graph_stream);
   if (m->graph_event) cudaEventDestroy(m->graph_event);
-  cudaFree(m->X);
-  cudaFree(m->Xc);
-  cudaFree(m->JA);
-  cudaFree(m->mm);
-  cudaFree(m->xja);
-  cudaFree(m->ae);
-  cudaFree(m->mu);
-  cudaFree(m->perm);
-  cudaFree(m->pinv);
-  cudaFree(m->R_d_desc);
-  cudaFree(m->XcT);
-  cudaFree(m->JAT);
+  cached_free(m->X);
+  cached_free(m->Xc);
+  cached_free(m->JA);
+  cached_free(m->mm);
+  cached_free(m->xja);
+  cached_free(m->ae);
+  cached_free(m->mu);
+  cached_free(m->perm);
+  cached_free(m->pinv);
+  cached_free(m->R_d_desc);
+  cached_free(m->XcT);
+  cached_free(m->JAT);
   free_oz(m->ozXc);
   free_oz(m->ozJA);
   free_oz(m->ozXcT);
@@ -2008,7 +2012,7 @@ int sgdml_b200_model_set_R_d_desc(sgdml_b200_model* m, const double* R_d_desc) {
   // this entry point has no stream argument: order it against work the caller may have in flight on ANY
   // stream (k_set_alphas / predict kernels of a non-blocking torch stream read m->R_d_desc)
   SG_CUDA(cudaDeviceSynchronize());
-  if (m->R_d_desc == nullptr) SG_CUDA(cudaMalloc(&m->R_d_desc, bytes));
+  if (m->R_d_desc == nullptr) SG_CUDA(cached_malloc(&m->R_d_desc, bytes));
   SG_CUDA(cudaMemcpy(m->R_d_desc, R_d_desc, bytes, cudaMemcpyDefault));
   SG_CUDA(cudaDeviceSynchronize());
   return 0;

@@ -901,3 +901,34 @@ def test_predict_main_kernel_variants(eng, N, M, rot, swap, sig, variant):
         _lib.lib().sgdml_b200_set_predict_variant(0)
     assert rel_err(F1, F0) < 1e-12 and rel_err(E1, E0) < 1e-12
     assert rel_err(F1s, F0[:1]) < 1e-12
+
+
+# --------------------------------------------------------------------------- device-block cache of the predictor
+def test_predictor_block_cache_reuse(eng, golden):
+    """Model arrays and workspaces of a destroyed predictor are kept for the next one of the same shape
+    (csrc/core.cu cached_malloc / cached_free).  Destroying a predictor whose kernels are still in flight (CUDA tensors
+    in and out: nothing synchronises), creating another one on the recycled blocks with DIFFERENT coefficients and
+    predicting again must give each model's own results; releasing the cache in between changes nothing."""
+    import torch
+
+    from sgdml_b200 import _lib
+
+    model = golden_model(golden)
+    model2 = dict(model)
+    model2['R_d_desc_alpha'] = 3.0 * np.asarray(model['R_d_desc_alpha'])
+    Rq = np.repeat(golden['R_query'], 200, axis=0)
+    Rd = torch.from_numpy(Rq).cuda()
+    ref = eng.GDMLPredict(model).predict(golden['R_query'])[1]
+    for rep in range(4):
+        p = eng.GDMLPredict(model)
+        E1, F1 = p.predict(Rd)  # asynchronous: outputs are CUDA tensors
+        del p  # blocks go back to the cache while the kernels may still run
+        p2 = eng.GDMLPredict(model2)  # same shapes: recycled blocks
+        E2, F2 = p2.predict(Rd)
+        torch.cuda.synchronize()
+        n = golden['R_query'].shape[0]
+        assert rel_err(F1.cpu().numpy()[::200][:n], ref) < 1e-12
+        assert rel_err(F2.cpu().numpy()[::200][:n], 3.0 * ref) < 1e-12
+        del p2
+        if rep == 1:
+            assert _lib.lib().sgdml_b200_release_workspaces() == 0
