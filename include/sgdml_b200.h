@@ -123,6 +123,13 @@ int sgdml_b200_model_set_alphas(sgdml_b200_model* model, const double* alphas_F,
 int sgdml_b200_predict_train(sgdml_b200_model* model, int64_t m_begin, int64_t m_end, int scaled,
                              double* E, double* F, void* stream);
 
+/* Large-descriptor models (D > 256: the predictor is four GEMMs around two element-wise kernels): run those GEMMs on
+ * the tcgen05 tensor cores through `slices` exact int8 slices per operand (2..7; csrc/ozaki.cu) or in FP64 DMMA (0, the
+ * default unless SGDML_B200_OZAKI_PREDICT_SLICES is set when the model is created).  Forces against the FP64 form:
+ * 8.8e-9 / 6.5e-11 / 5.4e-13 relative for 4 / 5 / 6 slices.  The iterative solver sets 5 for its K.v products
+ * (iterative.py:183-204: tolerance 1e-4).  No effect for D <= 256. */
+int sgdml_b200_model_set_contraction_slices(sgdml_b200_model* model, int slices, void* stream);
+
 /* Test / tuning hook: main kernel of the fused predictor (D <= 256).  0 = default (the measured-fastest kernel per
  * descriptor size); 1 = two warp groups running the sweep half a tile apart (72 < D; measured slower); 2 = no split
  * over k in the first contraction: Matern transform on the accumulator fragments, two CTA-wide barriers per tile

@@ -2074,6 +2074,26 @@ int sgdml_b200_predict_train(sgdml_b200_model* m, int64_t m_begin, int64_t m_end
   return 0;
 }
 
+int sgdml_b200_model_set_contraction_slices(sgdml_b200_model* m, int slices, void* stream) {
+  SG_ARG(m != nullptr && (slices == 0 || (slices >= 2 && slices <= 7)));
+  if (!m->large) return 0;  // D <= 256: the fused FP64 kernel, nothing to choose
+  if (slices >= 2 && !(m->DS <= (1 << 14) && m->Mpad <= (1 << 14))) slices = 0;
+  if (slices == m->oz_s) return 0;
+  cudaStream_t s = (cudaStream_t)stream;
+  free_ws(m);  // (synchronises) the per-batch workspaces carry slice buffers sized for the old setting
+  ++m->generation;
+  m->oz_s = slices;
+  if (slices >= 2) {
+    SG_TRY(refresh_oz_model(m, true, s));
+  } else {
+    free_oz(m->ozXc);
+    free_oz(m->ozJA);
+    free_oz(m->ozXcT);
+    free_oz(m->ozJAT);
+  }
+  return 0;
+}
+
 int sgdml_b200_set_predict_variant(int variant) {
   SG_ARG(variant >= 0 && variant <= 5);
   g_predict_variant = variant;

@@ -103,6 +103,14 @@ class GDMLPredict(object):
                 pass
             self._handle = None
 
+    def set_contraction_slices(self, slices):
+        """Extension (large descriptors, D > 256): run the predictor's four GEMMs on the tcgen05 tensor cores through
+        `slices` exact int8 slices per operand (4..7) instead of FP64 DMMA (0).  See include/sgdml_b200.h."""
+        _lib.check(
+            _lib.lib().sgdml_b200_model_set_contraction_slices(self._handle, int(slices), _lib.current_stream()),
+            'model_set_contraction_slices',
+        )
+
     # ------------------------------------------------------------------ training-mode hooks
     def set_R_desc(self, R_desc):
         """predict.py:511-525."""

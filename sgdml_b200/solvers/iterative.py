@@ -268,6 +268,12 @@ class Iterative(object):
         v_F = np.zeros(n)
         model = self.gdml_train.create_model(task, 'cg', R_desc, R_d_desc, tril_perms_lin, 1.0, v_F)
         self.gdml_predict = GDMLPredict(model, max_memory=self._max_memory, max_processes=self._max_processes)
+        # K.v on the tcgen05 tensor cores for large descriptors (5 exact int8 slices: forces within 6.5e-11 of the FP64
+        # contractions, CG tolerance 1e-4); SGDML_B200_OZAKI_PREDICT_SLICES (0 = FP64) overrides
+        import os
+
+        if 'SGDML_B200_OZAKI_PREDICT_SLICES' not in os.environ:
+            self.gdml_predict.set_contraction_slices(5)
         self.gdml_predict.set_R_desc(R_desc)
         self.gdml_predict.set_R_d_desc(R_d_desc)
 

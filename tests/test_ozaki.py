@@ -216,3 +216,14 @@ def test_large_descriptor_kmatvec_on_int8_path(monkeypatch):
         p.set_alphas(2.0 * v)  # a second set of coefficients through the same handle
         assert rel_err(p.kmatvec_train(), 2.0 * out[S]) < 1e-9
     assert rel_err(out['5'], out['0']) < 1e-8
+    # the same through the model-level switch (what the iterative solver uses), back and forth on one handle
+    monkeypatch.delenv('SGDML_B200_OZAKI_PREDICT_SLICES')
+    p = sgdml_b200.GDMLPredict(model)
+    p.set_R_d_desc(R_d_desc)
+    p.set_alphas(v)
+    kv_fp64 = p.kmatvec_train().copy()
+    p.set_contraction_slices(5)
+    kv_i8 = p.kmatvec_train().copy()
+    p.set_contraction_slices(0)
+    assert np.array_equal(p.kmatvec_train(), kv_fp64)
+    assert rel_err(kv_i8, out['5']) < 1e-12 and rel_err(kv_fp64, out['0']) < 1e-12
